@@ -1,0 +1,182 @@
+/* srfrd_b200.h -- C ABI of libsrfrd_b200.so: the B200 (sm_100a) kernels behind the SRFRD hot path.
+ *
+ * The reference (oss0430/SRFRD) has no native code and no FFI: every native instruction on its hot
+ * path is reached through torch.nn modules.  Each entry point below therefore cites the reference
+ * *Python* lines whose ATen/cuBLAS/cuDNN launches it replaces ("replaces: file:line", paths relative
+ * to the upstream checkout).  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into memory owned by the caller (torch-allocated); the
+ *     library never allocates, frees or retains device memory between calls;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - return 0 = ok; non-zero = error, message via srfrd_last_error() (thread-local);
+ *     invalid shapes / alignment are rejected before any launch.  There is NO CPU fallback;
+ *   - activations are bf16 row-major with an explicit leading dimension (elements); ids are int64
+ *     (the reference feeds torch.LongTensor, trainer.py:29); parameters, statistics, logits,
+ *     gradients of parameters and the final hidden state are fp32;
+ *   - "T" = B*L tokens, "H" = encoder width, "D" = item-table width, "F" = fake-embedding width.
+ */
+#ifndef SRFRD_B200_H
+#define SRFRD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRFRD_ABI_VERSION 1
+#if defined(__GNUC__)
+#define SRFRD_API __attribute__((visibility("default")))
+#else
+#define SRFRD_API
+#endif
+
+SRFRD_API const char* srfrd_last_error(void);
+SRFRD_API int srfrd_abi_version(void);
+/* 0 if the current device is an sm_100 part; error otherwise (called once by the Python loader). */
+SRFRD_API int srfrd_device_check(void);
+
+/* ---- K1: embedding gather + positional add + fake concat / user-label add + pad mask + LayerNorm ----
+ * replaces: SRFR_model.py:17-34 (SRFR_Embedding.forward), :98-99 (pad mask), :111 (first attention LN);
+ *           :411-424 (SRFU_Embedding.forward); :620-628 (SASRec.log2feats head).
+ * mode 0: x = E[seq]*item_scale + P[l]                         (SASRec, item_scale = sqrt(D))
+ * mode 1: x = [E[seq] + P[l] || Fe[aux_ids[t]]]                (SRFR/SRFRN; aux_ids NULL -> all 0)
+ * mode 2: x = E[seq] + P[l] + Ul[aux_ids[b]]                   (SRFU_*; aux_ids = per-sequence labels)
+ * then x *= (seq != 0); optional outputs: x0_bf16 (T, ldx), x0_f32 (T, H) [bit-identical to torch],
+ * q_bf16 = LayerNorm(x) (T, ldx) with stats (T, 2) = {mean, rstd} when ln_w != NULL. */
+SRFRD_API int srfrd_embed_ln_fwd(const float* item_table, int64_t n_rows, int D, const float* pos_table,
+                       const float* aux_table, int64_t n_aux, int F, int mode, const int64_t* seq,
+                       const int64_t* aux_ids, int64_t B, int L, float item_scale, const float* ln_w,
+                       const float* ln_b, float eps, void* x0_bf16, float* x0_f32, void* q_bf16, float* stats,
+                       int ldx, float drop_p, uint64_t drop_seed, uint32_t drop_stream, const float* drop_step,
+                       void* stream);
+
+/* SRFU_B/F/R.get_Labels -- replaces SRFR_model.py:546-570.  kind 0 = B, 1 = F, 2 = R. */
+SRFRD_API int srfrd_srfu_labels(const int64_t* fake_ids, int64_t B, int L, int kind, int64_t* labels, void* stream);
+
+/* K5: gradient of the input-sequence lookups into the item table (and fake / user-label table).
+ * replaces: the embedding_dense_backward launches autograd issues for SRFR_model.py:22,31 / :415,421. */
+SRFRD_API int srfrd_embed_bwd(const void* dx0_bf16, int ldx, const int64_t* seq, const int64_t* aux_ids, int64_t B, int L,
+                    int D, int F, int mode, float item_scale, float* d_item, float* d_aux, void* stream);
+
+/* ---- LayerNorm (eps 1e-8 in the reference, SRFR_model.py:77,80,86) ----
+ * fwd: y[t] = LN(x[t*row_stride + row_offset]); row_stride/offset select e.g. only the last position.
+ * bwd: dx = LN'(dy) (+ add) (* (row_ids != 0)); dw/db accumulated with atomics. */
+SRFRD_API int srfrd_layernorm_fwd(const void* x_bf16, int ldx, const float* w, const float* b, float eps, void* y_bf16,
+                        float* y_f32, int ldy, float* stats, int64_t T, int H, int64_t row_stride,
+                        int64_t row_offset, void* stream);
+SRFRD_API int srfrd_layernorm_bwd(const void* dy_bf16, const float* dy_f32, int lddy, const void* x_bf16, int ldx,
+                        const float* stats, const float* w, const void* add_bf16, int ldadd,
+                        const int64_t* row_ids, void* dx_bf16, int lddx, float* dw, float* db, int64_t T, int H,
+                        void* stream);
+
+/* ---- tcgen05 GEMMs ----
+ * replaces: the cuBLAS / cuDNN launches behind nn.MultiheadAttention's in/out projections
+ * (SRFR_model.py:83,112), PointWiseFeedForward's two 1x1 Conv1d (:41,44,47-51) and last_conv (:76,123),
+ * plus their autograd backward. */
+typedef struct {
+  const float* bias;       /* [N] or NULL */
+  const void* residual;    /* bf16 [M, ldr] or NULL: added after bias/dropout/relu/gate */
+  const void* gate;        /* bf16 [M, ldg] or NULL: v *= (gate > 0)   (ReLU backward) */
+  const int64_t* row_ids;  /* [M] or NULL: v *= (row_ids[m] != 0)       (pad re-mask) */
+  void* out_bf16;          /* [M, ldc] or NULL */
+  float* out_f32;          /* [M, ldc] or NULL */
+  int ldr, ldg, ldc;
+  int relu;
+  float drop_p;            /* 0 = no dropout; keep = hash(drop_seed ^ step, drop_stream, m*N+n) >= p */
+  uint32_t drop_stream;
+  uint64_t drop_seed;
+  const float* drop_step;  /* device scalar mixed into the seed (the Adam step counter) or NULL: lets a
+                              captured CUDA graph draw a fresh mask on every replay */
+} srfrd_gemm_epilogue_t;
+
+/* C[M,N] = epilogue(A[M,K] . B[N,K]^T), A and B bf16 K-major. */
+SRFRD_API int srfrd_gemm_tn(const void* A_bf16, int lda, const void* B_bf16, int ldb, int M, int N, int K,
+                  const srfrd_gemm_epilogue_t* ep, void* stream);
+/* dW[Mo,No] += sum_t dY[t,Mo] * X[t,No]  (fp32 atomics into dW; split over tokens). */
+SRFRD_API int srfrd_gemm_wgrad(const void* dY_bf16, int lda, const void* X_bf16, int ldb, int64_t T, int Mo, int No,
+                     float* dW, int ldw, void* stream);
+/* SIMT cross-check used by the GPU tests only. */
+SRFRD_API int srfrd_gemm_ref(const void* A, int lda, const void* B, int ldb, float* C, int ldc, int M, int N, int K,
+                   int a_mn_major, int b_mn_major, void* stream);
+
+/* out[n] += sum_m X[m, n]   (bias gradients; positional-table gradient through the (B, L*ld) view) */
+SRFRD_API int srfrd_colsum(const void* X_bf16, int64_t M, int N, int64_t ld, float* out, void* stream);
+/* out[(n / seg_in) * seg_out + n % seg_in] += in[n] for n % seg_in < seg_out */
+SRFRD_API int srfrd_add_segments(const float* in, int64_t n, int seg_in, int seg_out, float* out, void* stream);
+
+/* out = keep(seed ^ step, stream_id, m*N+n) ? x / (1-p) : 0  -- re-applies a forward dropout mask to a
+ * gradient (same hash as the forward kernels, nothing is stored). */
+SRFRD_API int srfrd_dropout_apply(const void* x_bf16, int ldx, void* out_bf16, int ldo, int64_t M, int N, float drop_p,
+                        uint64_t seed, uint32_t stream_id, const float* drop_step, void* stream);
+
+/* fp32 master weights -> bf16 GEMM operands (W and W^T), one launch for the whole table of matrices. */
+typedef struct {
+  const float* src; int src_ld;   /* (rows, cols) fp32 */
+  void* dst; int dst_ld;          /* bf16 (rows, cols) or NULL */
+  void* dst_t; int dst_t_ld;      /* bf16 (cols, rows) or NULL */
+  int rows, cols;
+} srfrd_cast_desc_t;
+SRFRD_API int srfrd_cast_weights(const srfrd_cast_desc_t* descs_dev, int n, void* stream);
+/* hi[r] = bf16(src[row_index ? row_index[r] : r]); lo = bf16(src - hi) (lo, row_index may be NULL).
+ * With row_index this is the candidate-row gather of predict() (SRFR_model.py:148). */
+SRFRD_API int srfrd_f32_to_bf16_split(const float* src, int64_t src_ld, const int64_t* row_index, void* hi, void* lo,
+                            int64_t rows, int cols, int dst_ld, void* stream);
+
+/* ---- causal self-attention, one (sequence, head) per CTA ----
+ * replaces: F.multi_head_attention_forward need_weights branch reached from SRFR_model.py:112
+ * (q scaling, baddbmm, softmax, dropout, bmm) and its backward.  k and v share ldkv. */
+SRFRD_API int srfrd_attention_fwd(const void* q, int ldq, const void* k, const void* v, int ldkv, void* o, int ldo,
+                        int64_t B, int L, int H, int heads, float drop_p, uint64_t seed, uint32_t stream_id,
+                        const float* drop_step, void* stream);
+SRFRD_API int srfrd_attention_bwd(const void* dout, int lddo, const void* q, int ldq, const void* k, const void* v, int ldkv,
+                        void* dq, int lddq, void* dk, void* dv, int lddkv, int64_t B, int L, int H, int heads,
+                        float drop_p, uint64_t seed, uint32_t stream_id, const float* drop_step, void* stream);
+
+/* ---- K4: pos/neg scoring + (discriminator-weighted) BCE ----
+ * replaces: SRFR_model.py:129-136 (SRFRN :225-233, SASRec :657-661) and trainer.py:31-38.
+ * fake_table != NULL selects SRFRN rows E[id] || Fe[fake_id].
+ * score_loss_fused: z+- (optional out), loss_acc[0] += sum w+ softplus(-z+), loss_acc[1] += sum w- softplus(z-),
+ *   dz+ = w+ (sigmoid(z+) - 1) / norm[0], dz- = w- sigmoid(z-) / norm[1], dh = dz+ E[pos] + dz- E[neg],
+ *   d_item[pos] += dz+ h, d_item[neg] += dz- h (row 0 never written: padding_idx).  w NULL -> 1[pos != 0]
+ *   which reproduces trainer.py:36-38 exactly. */
+SRFRD_API int srfrd_score_fwd(const float* h, int ldh, const float* item_table, const float* fake_table, const int64_t* pos,
+                    const int64_t* neg, const int64_t* prs, const int64_t* nrs, int64_t T, int D, int F, float* zp,
+                    float* zn, void* stream);
+SRFRD_API int srfrd_score_bwd(const float* h, int ldh, const float* item_table, const float* fake_table, const int64_t* pos,
+                    const int64_t* neg, const int64_t* prs, const int64_t* nrs, const float* dzp, const float* dzn,
+                    int64_t T, int D, int F, float* dh, int lddh, float* d_item, float* d_fake, void* stream);
+SRFRD_API int srfrd_score_loss_fused(const float* h, int ldh, const float* item_table, const float* fake_table,
+                           const int64_t* pos, const int64_t* neg, const int64_t* prs, const int64_t* nrs,
+                           const float* w_pos, const float* w_neg, const float* norm, int64_t T, int D, int F,
+                           float* zp, float* zn, float* loss_acc, float* dh, int lddh, float* d_item, float* d_fake,
+                           void* stream);
+SRFRD_API int srfrd_weight_sums(const int64_t* pos, const float* w_pos, const float* w_neg, int64_t T, float* out2,
+                      void* stream);
+SRFRD_API int srfrd_loss_finalize(const float* acc2, const float* norm2, float* loss, void* stream);
+
+/* ---- K7: Adam(lr, betas, eps), dense, torch.optim.Adam arithmetic (trainer.py:390) ----
+ * state3 = {step, 1-beta1^step, 1-beta2^step} lives on the device (CUDA-graph replayable). */
+SRFRD_API int srfrd_adam_tick(float* state3, float beta1, float beta2, void* stream);
+SRFRD_API int srfrd_adam_step(float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                    const float* state3, int zero_grad, void* stream);
+
+/* ---- K8/K9: full-catalogue scoring fused with a streaming per-row top-10 ----
+ * replaces: SRFR_model.py:144-152 predict() called with label = arange(1, N+1) + the double argsort of
+ * utils.py:591, i.e. rank by (score desc, item id asc).
+ * feats: bf16 (n_split stacked blocks of u_pad rows, D); table: bf16 (n_rows, D); candidates are local
+ * rows [row_lo, n_rows) with global id = id_base + row.  Writes (U, chunks*2, 10) partial lists that
+ * srfrd_merge_topk reduces (also used for the cross-GPU all-gather merge). */
+SRFRD_API int srfrd_catalogue_topk_plan(int64_t U, int64_t n_rows, int64_t row_lo, int* chunks_out);
+SRFRD_API int srfrd_catalogue_topk(const void* feats_bf16, int64_t U, int64_t u_pad, int n_split, const void* table_bf16,
+                         int64_t n_rows, int64_t row_lo, int64_t id_base, int D, int ld_feats, int ld_table,
+                         int chunks, float* part_scores, int* part_ids, void* stream);
+SRFRD_API int srfrd_merge_topk(const float* scores, const int* ids, int64_t U, int nlists, int k, float* out_scores,
+                     int64_t* out_ids, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRFRD_B200_H */

@@ -1,0 +1,363 @@
+// HBM/atomic-bound kernels around the encoder:
+//   K4  fused gather-dot scoring + discriminator-weighted BCE forward AND backward
+//   K5  sparse embedding-gradient scatter-add for the input sequence (row A8, k7)
+//   K7  flat fused Adam with device-resident step state (row A8, k8)
+#include "common.cuh"
+#include "srfrd_b200.h"
+
+namespace srfrd {
+
+static constexpr int MAXC = 16;
+
+struct ScoreParams {
+  const float* h; int ldh;              // (T, W) final hidden state, W = D (+F for SRFRN)
+  const float* item_table;              // (n_rows, D)
+  const float* fake_table;              // (3, F) or null (SRFRN only)
+  const int64_t *pos, *neg, *prs, *nrs; // (T)
+  const float *w_pos, *w_neg;           // (T) or null -> 1[pos != 0]
+  const float* norm;                    // device [2]: sum(w_pos), sum(w_neg)    (fused mode)
+  const float *dzp_in, *dzn_in;         // (T) upstream logit gradients          (bwd mode)
+  float *zp, *zn;                       // (T) logits out or null
+  float* loss_acc;                      // device [2] += sum w*softplus(-z+), sum w*softplus(z-)
+  float* dh; int lddh;                  // (T, W) or null
+  float* d_item; float* d_fake;         // gradient tables (red.add) or null
+  int64_t T; int D, F;
+  int mode;                             // 0 = logits only, 1 = fused loss fwd+bwd, 2 = bwd from dz
+};
+
+__device__ __forceinline__ float softplus(float x) { return fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x))); }
+__device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + __expf(-x)); }
+
+__global__ void __launch_bounds__(256) score_kernel(ScoreParams p) {
+  __shared__ float red[2][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int64_t warp0 = (int64_t)blockIdx.x * nw + warp, nwarps = (int64_t)gridDim.x * nw;
+  const int W = p.D + (p.fake_table ? p.F : 0);
+  float lp_acc = 0.f, ln_acc = 0.f;
+  float inv_np = 0.f, inv_nn = 0.f;
+  if (p.mode == 1) {
+    const float a = __ldg(p.norm), b = __ldg(p.norm + 1);
+    inv_np = a > 0.f ? 1.f / a : 0.f;
+    inv_nn = b > 0.f ? 1.f / b : 0.f;
+  }
+  for (int64_t t = warp0; t < p.T; t += nwarps) {
+    const int64_t pid = __ldg(p.pos + t), nid = __ldg(p.neg + t);
+    float wp = 0.f, wn = 0.f, dzp = 0.f, dzn = 0.f;
+    bool active = true;
+    if (p.mode == 1) {
+      wp = p.w_pos ? __ldg(p.w_pos + t) : (pid != 0 ? 1.f : 0.f);
+      wn = p.w_neg ? __ldg(p.w_neg + t) : wp;
+      active = (wp != 0.f) || (wn != 0.f) || p.zp;
+    } else if (p.mode == 2) {
+      dzp = __ldg(p.dzp_in + t);
+      dzn = __ldg(p.dzn_in + t);
+      active = (dzp != 0.f) || (dzn != 0.f);
+    }
+    if (!active) {
+      if (p.dh) {
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) {
+          const int c = lane + 32 * i;
+          if (c < W) p.dh[t * p.lddh + c] = 0.f;
+        }
+      }
+      continue;
+    }
+    int64_t pf = 0, nf = 0;
+    if (p.fake_table) { pf = __ldg(p.prs + t); nf = __ldg(p.nrs + t); }
+    float hv[MAXC], ep[MAXC], en[MAXC];
+    float sp = 0.f, sn = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+      const int c = lane + 32 * i;
+      hv[i] = ep[i] = en[i] = 0.f;
+      if (c < W) {
+        hv[i] = p.h[t * p.ldh + c];
+        if (c < p.D) {
+          ep[i] = __ldg(p.item_table + pid * p.D + c);
+          en[i] = __ldg(p.item_table + nid * p.D + c);
+        } else {
+          ep[i] = __ldg(p.fake_table + pf * p.F + (c - p.D));
+          en[i] = __ldg(p.fake_table + nf * p.F + (c - p.D));
+        }
+        sp = fmaf(hv[i], ep[i], sp);
+        sn = fmaf(hv[i], en[i], sn);
+      }
+    }
+    const float zp = warp_sum(sp), zn = warp_sum(sn);
+    if (p.zp && lane == 0) { p.zp[t] = zp; p.zn[t] = zn; }
+    if (p.mode == 0) continue;
+    if (p.mode == 1) {
+      lp_acc += wp * softplus(-zp);
+      ln_acc += wn * softplus(zn);
+      dzp = wp * (sigmoidf(zp) - 1.f) * inv_np;
+      dzn = wn * sigmoidf(zn) * inv_nn;
+    }
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+      const int c = lane + 32 * i;
+      if (c < W) {
+        if (p.dh) p.dh[t * p.lddh + c] = dzp * ep[i] + dzn * en[i];
+        if (c < p.D) {
+          // padding_idx = 0: the pad row never receives gradient (SRFR_model.py:10)
+          if (p.d_item && pid != 0 && dzp != 0.f) red_add_f32(p.d_item + pid * p.D + c, dzp * hv[i]);
+          if (p.d_item && nid != 0 && dzn != 0.f) red_add_f32(p.d_item + nid * p.D + c, dzn * hv[i]);
+        } else if (p.d_fake) {
+          if (pf != 0 && dzp != 0.f) red_add_f32(p.d_fake + pf * p.F + (c - p.D), dzp * hv[i]);
+          if (nf != 0 && dzn != 0.f) red_add_f32(p.d_fake + nf * p.F + (c - p.D), dzn * hv[i]);
+        }
+      }
+    }
+  }
+  if (p.mode == 1 && p.loss_acc) {
+    if (lane == 0) { red[0][warp] = lp_acc; red[1][warp] = ln_acc; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float a = 0.f, b = 0.f;
+      for (int w = 0; w < nw; ++w) { a += red[0][w]; b += red[1][w]; }
+      red_add_f32(p.loss_acc, a);
+      red_add_f32(p.loss_acc + 1, b);
+    }
+  }
+}
+
+// out[0] = sum w_pos (or #pos != 0), out[1] = sum w_neg
+__global__ void __launch_bounds__(256) weight_sums_kernel(const int64_t* pos, const float* w_pos, const float* w_neg,
+                                                          int64_t T, float* out) {
+  __shared__ float red[2][8];
+  float a = 0.f, b = 0.f;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += (int64_t)gridDim.x * blockDim.x) {
+    const float wp = w_pos ? w_pos[t] : (pos[t] != 0 ? 1.f : 0.f);
+    a += wp;
+    b += w_neg ? w_neg[t] : wp;
+  }
+  a = warp_sum(a); b = warp_sum(b);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { red[0][warp] = a; red[1][warp] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a = b = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += red[0][w]; b += red[1][w]; }
+    red_add_f32(out, a);
+    red_add_f32(out + 1, b);
+  }
+}
+
+__global__ void loss_finalize_kernel(const float* acc, const float* norm, float* loss) {
+  const float a = norm[0] > 0.f ? acc[0] / norm[0] : 0.f;
+  const float b = norm[1] > 0.f ? acc[1] / norm[1] : 0.f;
+  loss[0] = a + b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5: gradient of the input-sequence lookups.  One CTA per sequence, one thread per feature column.
+struct EmbedBwdParams {
+  const bf16* dx0; int ldx;          // (T, ldx), already pad-masked
+  const int64_t* seq;                // (B, L)
+  const int64_t* aux_ids;            // mode 1: (B, L) fake ids or null; mode 2: (B,) labels
+  int L, D, F, mode;
+  float item_scale;
+  float* d_item;                     // (n_rows, D)
+  float* d_aux;                      // mode 1: (3, F); mode 2: (labels, D)
+};
+
+__global__ void embed_bwd_kernel(EmbedBwdParams p) {
+  extern __shared__ int64_t ids[];   // [L] seq ids, [L] fake ids
+  const int64_t b = blockIdx.x;
+  const int c = threadIdx.x;
+  const int H = p.D + (p.mode == 1 ? p.F : 0);
+  for (int l = threadIdx.x; l < p.L; l += blockDim.x) {
+    ids[l] = p.seq[b * p.L + l];
+    ids[p.L + l] = (p.mode == 1 && p.aux_ids) ? p.aux_ids[b * p.L + l] : 0;
+  }
+  __syncthreads();
+  if (c >= H) return;
+  float acc1 = 0.f, acc2 = 0.f, accu = 0.f;
+  for (int l = 0; l < p.L; ++l) {
+    const int64_t id = ids[l];
+    if (id == 0) continue;
+    const float v = bf2f(p.dx0[(b * p.L + l) * p.ldx + c]);
+    if (c < p.D) {
+      red_add_f32(p.d_item + id * p.D + c, v * p.item_scale);
+      accu += v;
+    } else {
+      const int64_t f = ids[p.L + l];
+      if (f == 1) acc1 += v;
+      else if (f == 2) acc2 += v;
+    }
+  }
+  if (p.mode == 1 && c >= p.D && p.d_aux) {        // fake_embed padding_idx = 0: row 0 gets nothing
+    if (acc1 != 0.f) red_add_f32(p.d_aux + 1 * p.F + (c - p.D), acc1);
+    if (acc2 != 0.f) red_add_f32(p.d_aux + 2 * p.F + (c - p.D), acc2);
+  }
+  if (p.mode == 2 && c < p.D && p.d_aux && accu != 0.f)
+    red_add_f32(p.d_aux + p.aux_ids[b] * p.D + c, accu);
+}
+
+// out[(n / seg_in) * seg_out + n % seg_in] += in[n] where n % seg_in < seg_out
+__global__ void add_segments_kernel(const float* in, int64_t n, int seg_in, int seg_out, float* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = (int)(i % seg_in);
+  if (c < seg_out) out[(i / seg_in) * seg_out + c] += in[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7: Adam.  state = {step, 1 - beta1^step, 1 - beta2^step}; kept on device so a captured CUDA
+// graph can replay the whole training step.
+__global__ void adam_tick_kernel(float* state, float beta1, float beta2) {
+  const float step = state[0] + 1.f;
+  state[0] = step;
+  state[1] = (float)(1.0 - pow((double)beta1, (double)step));
+  state[2] = (float)(1.0 - pow((double)beta2, (double)step));
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, int64_t n, float lr, float beta1, float beta2,
+                                                   float eps, const float* __restrict__ state, int zero_grad) {
+  // torch.optim.Adam (trainer.py:390): step_size = lr / bc1; denom = sqrt(v) / sqrt(bc2) + eps
+  const float step_size = lr / state[1];
+  const float inv_sqrt_bc2 = rsqrtf(state[2]);
+  const int64_t n4 = n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i], gg = reinterpret_cast<float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    float* pa = &pp.x; float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      ma[j] = beta1 * ma[j] + (1.f - beta1) * ga[j];
+      va[j] = beta2 * va[j] + (1.f - beta2) * ga[j] * ga[j];
+      pa[j] -= step_size * ma[j] / (sqrtf(va[j]) * inv_sqrt_bc2 + eps);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    m[i] = beta1 * m[i] + (1.f - beta1) * g[i];
+    v[i] = beta2 * v[i] + (1.f - beta2) * g[i] * g[i];
+    p[i] -= step_size * m[i] / (sqrtf(v[i]) * inv_sqrt_bc2 + eps);
+    if (zero_grad) g[i] = 0.f;
+  }
+}
+
+}  // namespace srfrd
+
+using namespace srfrd;
+
+static int score_launch(ScoreParams& p, void* stream) {
+  const int W = p.D + (p.fake_table ? p.F : 0);
+  SRFRD_REQUIRE(W <= 32 * MAXC, "score: width %d unsupported", W);
+  if (p.T == 0) return 0;
+  int64_t blocks = (p.T + 7) / 8;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  score_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  SRFRD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int srfrd_score_fwd(const float* h, int ldh, const float* item_table, const float* fake_table,
+                               const int64_t* pos, const int64_t* neg, const int64_t* prs, const int64_t* nrs,
+                               int64_t T, int D, int F, float* zp, float* zn, void* stream) {
+  SRFRD_REQUIRE(h && item_table && pos && neg && zp && zn, "score_fwd: null pointer");
+  SRFRD_REQUIRE(!fake_table || (prs && nrs), "score_fwd: fake ids required with a fake table");
+  ScoreParams p = {};
+  p.h = h; p.ldh = ldh; p.item_table = item_table; p.fake_table = fake_table; p.pos = pos; p.neg = neg; p.prs = prs;
+  p.nrs = nrs; p.T = T; p.D = D; p.F = F; p.zp = zp; p.zn = zn; p.mode = 0;
+  return score_launch(p, stream);
+}
+
+extern "C" int srfrd_score_bwd(const float* h, int ldh, const float* item_table, const float* fake_table,
+                               const int64_t* pos, const int64_t* neg, const int64_t* prs, const int64_t* nrs,
+                               const float* dzp, const float* dzn, int64_t T, int D, int F, float* dh, int lddh,
+                               float* d_item, float* d_fake, void* stream) {
+  SRFRD_REQUIRE(h && item_table && pos && neg && dzp && dzn && dh, "score_bwd: null pointer");
+  SRFRD_REQUIRE(!fake_table || (prs && nrs), "score_bwd: fake ids required with a fake table");
+  ScoreParams p = {};
+  p.h = h; p.ldh = ldh; p.item_table = item_table; p.fake_table = fake_table; p.pos = pos; p.neg = neg; p.prs = prs;
+  p.nrs = nrs; p.T = T; p.D = D; p.F = F; p.dzp_in = dzp; p.dzn_in = dzn; p.dh = dh; p.lddh = lddh; p.d_item = d_item;
+  p.d_fake = d_fake; p.mode = 2;
+  return score_launch(p, stream);
+}
+
+extern "C" int srfrd_score_loss_fused(const float* h, int ldh, const float* item_table, const float* fake_table,
+                                      const int64_t* pos, const int64_t* neg, const int64_t* prs, const int64_t* nrs,
+                                      const float* w_pos, const float* w_neg, const float* norm, int64_t T, int D,
+                                      int F, float* zp, float* zn, float* loss_acc, float* dh, int lddh, float* d_item,
+                                      float* d_fake, void* stream) {
+  SRFRD_REQUIRE(h && item_table && pos && neg && norm && loss_acc, "score_loss_fused: null pointer");
+  SRFRD_REQUIRE(!fake_table || (prs && nrs), "score_loss_fused: fake ids required with a fake table");
+  SRFRD_REQUIRE((zp == nullptr) == (zn == nullptr), "score_loss_fused: pass both logit outputs or neither");
+  ScoreParams p = {};
+  p.h = h; p.ldh = ldh; p.item_table = item_table; p.fake_table = fake_table; p.pos = pos; p.neg = neg; p.prs = prs;
+  p.nrs = nrs; p.w_pos = w_pos; p.w_neg = w_neg; p.norm = norm; p.T = T; p.D = D; p.F = F; p.zp = zp; p.zn = zn;
+  p.loss_acc = loss_acc; p.dh = dh; p.lddh = lddh; p.d_item = d_item; p.d_fake = d_fake; p.mode = 1;
+  return score_launch(p, stream);
+}
+
+extern "C" int srfrd_weight_sums(const int64_t* pos, const float* w_pos, const float* w_neg, int64_t T, float* out2,
+                                 void* stream) {
+  SRFRD_REQUIRE(pos && out2, "weight_sums: null pointer");
+  SRFRD_CUDA(cudaMemsetAsync(out2, 0, 2 * sizeof(float), (cudaStream_t)stream));
+  if (T == 0) return 0;
+  int64_t blocks = (T + 2047) / 2048;
+  if (blocks > num_sms() * 2) blocks = num_sms() * 2;
+  weight_sums_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(pos, w_pos, w_neg, T, out2);
+  SRFRD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int srfrd_loss_finalize(const float* acc2, const float* norm2, float* loss, void* stream) {
+  SRFRD_REQUIRE(acc2 && norm2 && loss, "loss_finalize: null pointer");
+  loss_finalize_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(acc2, norm2, loss);
+  SRFRD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int srfrd_embed_bwd(const void* dx0, int ldx, const int64_t* seq, const int64_t* aux_ids, int64_t B, int L,
+                               int D, int F, int mode, float item_scale, float* d_item, float* d_aux, void* stream) {
+  SRFRD_REQUIRE(dx0 && seq && d_item, "embed_bwd: null pointer");
+  SRFRD_REQUIRE(mode >= 0 && mode <= 2, "embed_bwd: bad mode");
+  SRFRD_REQUIRE(mode != 2 || aux_ids, "embed_bwd: labels required for mode 2");
+  const int H = D + (mode == 1 ? F : 0);
+  SRFRD_REQUIRE(H <= 1024, "embed_bwd: width %d unsupported", H);
+  if (B == 0) return 0;
+  EmbedBwdParams p;
+  p.dx0 = (const bf16*)dx0; p.ldx = ldx; p.seq = seq; p.aux_ids = aux_ids; p.L = L; p.D = D; p.F = F; p.mode = mode;
+  p.item_scale = item_scale; p.d_item = d_item; p.d_aux = d_aux;
+  const int threads = (H + 31) & ~31;
+  embed_bwd_kernel<<<(unsigned)B, threads, 2 * L * sizeof(int64_t), (cudaStream_t)stream>>>(p);
+  SRFRD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int srfrd_add_segments(const float* in, int64_t n, int seg_in, int seg_out, float* out, void* stream) {
+  SRFRD_REQUIRE(in && out && seg_in > 0 && seg_out <= seg_in, "add_segments: bad arguments");
+  if (n == 0) return 0;
+  add_segments_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, n, seg_in, seg_out, out);
+  SRFRD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int srfrd_adam_tick(float* state3, float beta1, float beta2, void* stream) {
+  SRFRD_REQUIRE(state3, "adam_tick: null state");
+  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state3, beta1, beta2);
+  SRFRD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int srfrd_adam_step(float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                               float eps, const float* state3, int zero_grad, void* stream) {
+  SRFRD_REQUIRE(p && g && m && v && state3, "adam_step: null pointer");
+  SRFRD_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "adam_step: buffers must be 16-byte aligned");
+  if (n == 0) return 0;
+  int64_t blocks = (n / 4 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+  adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, state3, zero_grad);
+  SRFRD_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,358 @@
+"""Host-side orchestration of the hot path: parameter layout, workspaces and the kernel sequence
+for forward, backward, the fused loss and Adam.  Pure plumbing: every arithmetic step is a call
+into libsrfrd_b200.so (see ops.py); there is no eager-PyTorch fallback for any of them.
+
+The block wiring reproduces the reference's non-standard encoder (SRFR_model.py:109-121):
+  Q = LN1(x); q = Q Wq^T + bq;  [k, v] = x Wkv^T + bkv  (UN-normalised x);  o = causal_attn(q, k, v)
+  r = Q + o Wo^T + bo;  y = LN2(r);  z = relu(y W1^T + b1) W2^T + b2 + y;  x' = z * (seq != 0)
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+
+bf16 = torch.bfloat16
+LN_EPS = 1e-8  # SRFR_model.py:77,80,86
+
+KINDS = ("SRFR", "SRFRN", "SRFU_B", "SRFU_F", "SRFU_R", "SASRec")
+
+
+@dataclass
+class ModelSpec:
+    kind: str
+    item_number: int
+    max_len: int
+    D: int                       # item_embedding_size / hidden_units
+    F: int = 0                   # fake_embedding_size (SRFR / SRFRN)
+    n_labels: int = 0            # SRFU_*: rows of user_label_embed
+    num_blocks: int = 2
+    num_heads: int = 1
+    dropout: float = 0.0
+
+    def __post_init__(self):
+        if self.kind not in KINDS:
+            raise ValueError(f"unknown model kind {self.kind}")
+        if self.H % 16 or self.D % 16:
+            raise ValueError(
+                f"srfrd_b200: encoder width H={self.H} and item width D={self.D} must be multiples of 16 "
+                "(tcgen05 N granularity / 16-byte TMA pitch); pad the embedding sizes")
+        if self.H % self.num_heads:
+            raise ValueError("hidden size must be divisible by num_heads")
+
+    @property
+    def H(self) -> int:
+        return self.D + self.F if self.kind in ("SRFR", "SRFRN") else self.D
+
+    @property
+    def Dout(self) -> int:       # width of the hidden state the model returns
+        return self.H if self.kind == "SRFRN" else self.D
+
+    @property
+    def mode(self) -> int:       # K1 mode
+        return 1 if self.kind in ("SRFR", "SRFRN") else (2 if self.kind.startswith("SRFU") else 0)
+
+    @property
+    def item_scale(self) -> float:   # SASRec scales embeddings by sqrt(d), SRFR_model.py:622
+        return float(self.D ** 0.5) if self.kind == "SASRec" else 1.0
+
+    @property
+    def item_key(self) -> str:
+        return "item_emb.weight" if self.kind == "SASRec" else "embedding_layer.item_embed.weight"
+
+    @property
+    def pos_key(self) -> str:
+        return "pos_emb.weight" if self.kind == "SASRec" else "embedding_layer.pos_embed.weight"
+
+    @property
+    def aux_key(self) -> Optional[str]:
+        if self.mode == 1:
+            return "embedding_layer.fake_embed.weight"
+        if self.mode == 2:
+            return "embedding_layer.user_label_embed.weight"
+        return None
+
+    def param_shapes(self) -> List[Tuple[str, Tuple[int, ...]]]:
+        """state_dict names and shapes in the reference's registration order."""
+        H, D, L, N = self.H, self.D, self.max_len, self.item_number
+        out: List[Tuple[str, Tuple[int, ...]]] = []
+        if self.kind == "SASRec":
+            out += [("item_emb.weight", (N + 1, D)), ("pos_emb.weight", (L, D))]
+        elif self.mode == 1:
+            out += [("embedding_layer.item_embed.weight", (N + 1, D)),
+                    ("embedding_layer.fake_embed.weight", (3, self.F)),
+                    ("embedding_layer.pos_embed.weight", (L, D))]
+        else:
+            out += [("embedding_layer.item_embed.weight", (N + 1, D)),
+                    ("embedding_layer.user_label_embed.weight", (self.n_labels, D)),
+                    ("embedding_layer.pos_embed.weight", (L, D))]
+        for i in range(self.num_blocks):
+            out += [(f"attention_layernorms.{i}.weight", (H,)), (f"attention_layernorms.{i}.bias", (H,))]
+        for i in range(self.num_blocks):
+            out += [(f"attention_layers.{i}.in_proj_weight", (3 * H, H)), (f"attention_layers.{i}.in_proj_bias", (3 * H,)),
+                    (f"attention_layers.{i}.out_proj.weight", (H, H)), (f"attention_layers.{i}.out_proj.bias", (H,))]
+        for i in range(self.num_blocks):
+            out += [(f"forward_layernorms.{i}.weight", (H,)), (f"forward_layernorms.{i}.bias", (H,))]
+        for i in range(self.num_blocks):
+            out += [(f"forward_layers.{i}.conv1.weight", (H, H, 1)), (f"forward_layers.{i}.conv1.bias", (H,)),
+                    (f"forward_layers.{i}.conv2.weight", (H, H, 1)), (f"forward_layers.{i}.conv2.bias", (H,))]
+        if self.kind == "SRFR":
+            out += [("last_conv.weight", (D, H, 1)), ("last_conv.bias", (D,))]
+        out += [("last_layernorm.weight", (self.Dout,)), ("last_layernorm.bias", (self.Dout,))]
+        return out
+
+
+class FlatParams:
+    """All parameters in ONE fp32 buffer (plus a same-shaped gradient buffer): the Adam kernel, the
+    gradient all-reduce and the bf16 shadow refresh each touch it in a single launch."""
+
+    def __init__(self, spec: ModelSpec, device):
+        self.spec = spec
+        self.offsets: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
+        off = 0
+        for name, shape in spec.param_shapes():
+            n = int(math.prod(shape))
+            self.offsets[name] = (off, shape)
+            off += (n + 3) // 4 * 4                      # keep every view 16-byte aligned
+        self.numel = off
+        self.data = torch.zeros(off, dtype=torch.float32, device=device)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=device)
+
+    def view(self, name: str, grad: bool = False) -> torch.Tensor:
+        off, shape = self.offsets[name]
+        buf = self.grad if grad else self.data
+        return buf[off:off + int(math.prod(shape))].view(shape)
+
+    def mat(self, name: str, grad: bool = False) -> torch.Tensor:
+        """2-D view (conv weights (out, in, 1) -> (out, in))."""
+        v = self.view(name, grad)
+        return v.view(v.shape[0], -1)
+
+
+class HotPath:
+    """Forward / backward kernel sequences over a FlatParams store."""
+
+    def __init__(self, spec: ModelSpec, params: FlatParams):
+        self.spec, self.P = spec, params
+        self.device = params.data.device
+        self._ws_tokens = 0
+        self._ws: Dict[str, torch.Tensor] = {}
+        self._build_shadows()
+        self.step_state = torch.zeros(4, dtype=torch.float32, device=self.device)   # Adam {step, bc1, bc2}
+        self.drop_seed = 0x5EED5EED
+        self.saved: Optional[dict] = None
+
+    # ------------------------------------------------------------------ bf16 operand shadows
+    def _build_shadows(self):
+        s, P, dev = self.spec, self.P, self.device
+        H, D = s.H, s.D
+        self.sh: Dict[str, torch.Tensor] = {}
+        entries = []
+        for i in range(s.num_blocks):
+            win = P.mat(f"attention_layers.{i}.in_proj_weight")
+            self.sh[f"win{i}"] = torch.zeros(3 * H, H, dtype=bf16, device=dev)        # rows [0,H) = Wq, [H,3H) = Wkv
+            self.sh[f"wqT{i}"] = torch.zeros(H, H, dtype=bf16, device=dev)
+            self.sh[f"wkvT{i}"] = torch.zeros(H, 2 * H, dtype=bf16, device=dev)
+            entries.append((win[:H], self.sh[f"win{i}"][:H], self.sh[f"wqT{i}"]))
+            entries.append((win[H:], self.sh[f"win{i}"][H:], self.sh[f"wkvT{i}"]))
+            for tag, key in (("wo", f"attention_layers.{i}.out_proj.weight"), ("w1", f"forward_layers.{i}.conv1.weight"),
+                             ("w2", f"forward_layers.{i}.conv2.weight")):
+                self.sh[f"{tag}{i}"] = torch.zeros(H, H, dtype=bf16, device=dev)
+                self.sh[f"{tag}T{i}"] = torch.zeros(H, H, dtype=bf16, device=dev)
+                entries.append((P.mat(key), self.sh[f"{tag}{i}"], self.sh[f"{tag}T{i}"]))
+        if s.kind == "SRFR":
+            self.sh["wc"] = torch.zeros(D, H, dtype=bf16, device=dev)
+            self.sh["wcT"] = torch.zeros(H, D, dtype=bf16, device=dev)
+            entries.append((P.mat("last_conv.weight"), self.sh["wc"], self.sh["wcT"]))
+        self._cast_table, self._cast_n = ops.make_cast_table(entries, dev)
+        self.shadows_version = -1
+
+    def refresh_shadows(self):
+        """fp32 master weights -> bf16 GEMM operands (W and W^T); one launch."""
+        ops.cast_weights(self._cast_table, self._cast_n)
+
+    # ------------------------------------------------------------------ workspaces
+    def _workspace(self, T: int, L: int) -> Dict[str, torch.Tensor]:
+        if T <= self._ws_tokens:
+            return self._ws
+        s, dev = self.spec, self.device
+        H, nb = s.H, s.num_blocks
+        ws: Dict[str, torch.Tensor] = {}
+
+        def act(name, w=H, dtype=bf16):
+            ws[name] = torch.empty(T, w, dtype=dtype, device=dev)
+
+        for i in range(nb + 1):
+            act(f"x{i}")
+        for i in range(nb):
+            for n in ("Q", "q", "o", "r", "y", "h1"):
+                act(f"{n}{i}")
+            act(f"kv{i}", 2 * H)
+            act(f"st1_{i}", 2, torch.float32)
+            act(f"st2_{i}", 2, torch.float32)
+        if s.kind == "SRFR":
+            act("c", s.D)
+        act("stF", 2, torch.float32)
+        act("hfin", s.Dout, torch.float32)
+        act("dh", s.Dout, torch.float32)
+        for n in ("gA", "gB", "gC", "gD"):
+            act(n)
+        act("gKV", 2 * H)
+        if s.kind == "SRFR":
+            act("gc", s.D)
+        if s.dropout > 0:
+            act("gE")
+        ws["pos_tmp"] = torch.zeros(L * H, dtype=torch.float32, device=dev)
+        self._ws, self._ws_tokens = ws, T
+        return ws
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, seq: torch.Tensor, fake_ids: Optional[torch.Tensor], training: bool,
+                last_only: bool = False, save: Optional[bool] = None) -> torch.Tensor:
+        """Encoder forward.  Returns hidden (B, L, Dout) fp32 -- or (B, Dout) for last_only (predict uses
+        hidden[:, -1, :] only, SRFR_model.py:147).  Saves what backward needs when training."""
+        s, P = self.spec, self.P
+        B, L = seq.shape
+        if L > s.max_len:
+            raise RuntimeError(f"sequence length {L} exceeds max_len {s.max_len} (pos_embed rows, SRFR_model.py:12)")
+        T, H, nb = B * L, s.H, s.num_blocks
+        ws = self._workspace(T, L)
+        p_drop = s.dropout if training else 0.0
+        step = self.step_state[0:1] if p_drop > 0 else None
+        seed = self.drop_seed
+        seq = seq.contiguous()
+        aux_ids = None
+        if s.mode == 1:
+            aux_ids = None if fake_ids is None else fake_ids.contiguous()
+        elif s.mode == 2:
+            aux_ids = torch.empty(B, dtype=torch.int64, device=self.device)
+            ops.srfu_labels(fake_ids.contiguous(), {"SRFU_B": 0, "SRFU_F": 1, "SRFU_R": 2}[s.kind], aux_ids)
+        aux_table = P.view(s.aux_key) if s.aux_key else None
+        x = [ws[f"x{i}"][:T] for i in range(nb + 1)]
+        ops.embed_ln_fwd(P.view(s.item_key), P.view(s.pos_key), aux_table, s.mode, seq, aux_ids, s.item_scale,
+                         P.view("attention_layernorms.0.weight"), P.view("attention_layernorms.0.bias"), LN_EPS,
+                         x0_bf16=x[0], q_bf16=ws["Q0"][:T], stats=ws["st1_0"][:T],
+                         drop_p=p_drop if s.kind == "SASRec" else 0.0, drop_seed=seed, drop_stream=1, drop_step=step)
+        seq_flat = seq.view(-1)
+        for i in range(nb):
+            Q, q, kv, o, r, y, h1 = (ws[f"{n}{i}"][:T] for n in ("Q", "q", "kv", "o", "r", "y", "h1"))
+            if i > 0:
+                ops.layernorm_fwd(x[i], P.view(f"attention_layernorms.{i}.weight"), P.view(f"attention_layernorms.{i}.bias"),
+                                  LN_EPS, y_bf16=Q, stats=ws[f"st1_{i}"][:T])
+            bias_in = P.view(f"attention_layers.{i}.in_proj_bias")
+            ops.gemm_tn(Q, self.sh[f"win{i}"][:H], out_bf16=q, bias=bias_in[:H])
+            ops.gemm_tn(x[i], self.sh[f"win{i}"][H:], out_bf16=kv, bias=bias_in[H:])
+            ops.attention_fwd(q, kv[:, :H], kv[:, H:], o, B, L, H, s.num_heads, p_drop, seed, 10 + 4 * i, step)
+            ops.gemm_tn(o, self.sh[f"wo{i}"], out_bf16=r, bias=P.view(f"attention_layers.{i}.out_proj.bias"), residual=Q)
+            ops.layernorm_fwd(r, P.view(f"forward_layernorms.{i}.weight"), P.view(f"forward_layernorms.{i}.bias"), LN_EPS,
+                              y_bf16=y, stats=ws[f"st2_{i}"][:T])
+            ops.gemm_tn(y, self.sh[f"w1{i}"], out_bf16=h1, bias=P.view(f"forward_layers.{i}.conv1.bias"), relu=True,
+                        drop_p=p_drop, drop_seed=seed, drop_stream=11 + 4 * i, drop_step=step)
+            ops.gemm_tn(h1, self.sh[f"w2{i}"], out_bf16=x[i + 1], bias=P.view(f"forward_layers.{i}.conv2.bias"),
+                        residual=y, row_ids=seq_flat, drop_p=p_drop, drop_seed=seed, drop_stream=12 + 4 * i, drop_step=step)
+        fin_in = x[nb]
+        if s.kind == "SRFR":      # last_conv H -> D (SRFR_model.py:123)
+            ops.gemm_tn(x[nb], self.sh["wc"], out_bf16=ws["c"][:T], bias=P.view("last_conv.bias"))
+            fin_in = ws["c"][:T]
+        hfin = ws["hfin"][:T]
+        if last_only:
+            out = ws["hfin"][:B]
+            ops.layernorm_fwd(fin_in, P.view("last_layernorm.weight"), P.view("last_layernorm.bias"), LN_EPS, y_f32=out,
+                              T=B, H=s.Dout, row_stride=L, row_offset=L - 1)
+            return out
+        ops.layernorm_fwd(fin_in, P.view("last_layernorm.weight"), P.view("last_layernorm.bias"), LN_EPS, y_f32=hfin,
+                          stats=ws["stF"][:T], H=s.Dout)
+        if training if save is None else save:
+            self.saved = dict(seq=seq, aux_ids=aux_ids, B=B, L=L, p_drop=p_drop, seed=seed, step=step)
+        return hfin.view(B, L, s.Dout)
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, dh: torch.Tensor) -> None:
+        """Given dL/dhidden (T, Dout) fp32, accumulate every parameter gradient into P.grad
+        (the score kernels have already added the pos/neg rows of the item table)."""
+        s, P, sv = self.spec, self.P, self.saved
+        if sv is None:
+            raise RuntimeError("backward() without a training forward()")
+        B, L = sv["B"], sv["L"]
+        T, H, nb = B * L, s.H, s.num_blocks
+        ws = self._ws
+        seq_flat = sv["seq"].view(-1)
+        p_drop, seed, step = sv["p_drop"], sv["seed"], sv["step"]
+        gA, gB, gC, gD, gKV = (ws[n][:T] for n in ("gA", "gB", "gC", "gD", "gKV"))
+        G = lambda name: P.view(name, grad=True)
+        GM = lambda name: P.mat(name, grad=True)
+        x = [ws[f"x{i}"][:T] for i in range(nb + 1)]
+
+        # final LayerNorm (+ last_conv) -> dz = dL/dx[nb], pad rows zeroed
+        if s.kind == "SRFR":
+            gc = ws["gc"][:T]
+            ops.layernorm_bwd(dh, ws["c"][:T], ws["stF"][:T], P.view("last_layernorm.weight"), gc,
+                              G("last_layernorm.weight"), G("last_layernorm.bias"))
+            ops.gemm_wgrad(gc, x[nb], GM("last_conv.weight"))
+            ops.colsum(gc, G("last_conv.bias"))
+            ops.gemm_tn(gc, self.sh["wcT"], out_bf16=gA, row_ids=seq_flat)
+        else:
+            ops.layernorm_bwd(dh, x[nb], ws["stF"][:T], P.view("last_layernorm.weight"), gA,
+                              G("last_layernorm.weight"), G("last_layernorm.bias"), row_ids=seq_flat)
+
+        for i in reversed(range(nb)):
+            Q, q, kv, o, r, y, h1 = (ws[f"{n}{i}"][:T] for n in ("Q", "q", "kv", "o", "r", "y", "h1"))
+            dz = gA
+            dz2 = dz
+            if p_drop > 0:      # da2 = dz * mask2 (dropout2 sits between conv2 and the residual add)
+                dz2 = ws["gE"][:T]
+                ops.dropout_apply(dz, dz2, H, p_drop, seed, 12 + 4 * i, step)
+            # FFN: z = drop2(h1 W2^T + b2) + y ; h1 = relu(drop1(y W1^T + b1))
+            ops.gemm_wgrad(dz2, h1, GM(f"forward_layers.{i}.conv2.weight"))
+            ops.colsum(dz2, G(f"forward_layers.{i}.conv2.bias"))
+            ops.gemm_tn(dz2, self.sh[f"w2T{i}"], out_bf16=gB, gate=h1, drop_p=p_drop, drop_seed=seed,
+                        drop_stream=11 + 4 * i, drop_step=step)                                   # da1
+            ops.gemm_wgrad(gB, y, GM(f"forward_layers.{i}.conv1.weight"))
+            ops.colsum(gB, G(f"forward_layers.{i}.conv1.bias"))
+            ops.gemm_tn(gB, self.sh[f"w1T{i}"], out_bf16=gC, residual=dz)                          # dy
+            # LN2
+            ops.layernorm_bwd(gC, r, ws[f"st2_{i}"][:T], P.view(f"forward_layernorms.{i}.weight"), gB,
+                              G(f"forward_layernorms.{i}.weight"), G(f"forward_layernorms.{i}.bias"))   # dr
+            # r = Q + o Wo^T + bo
+            ops.gemm_wgrad(gB, o, GM(f"attention_layers.{i}.out_proj.weight"))
+            ops.colsum(gB, G(f"attention_layers.{i}.out_proj.bias"))
+            ops.gemm_tn(gB, self.sh[f"woT{i}"], out_bf16=gC)                                       # do
+            ops.attention_bwd(gC, q, kv[:, :H], kv[:, H:], gD, gKV[:, :H], gKV[:, H:], B, L, H, s.num_heads, p_drop,
+                              seed, 10 + 4 * i, step)                                             # dq, dk|dv
+            gin = GM(f"attention_layers.{i}.in_proj_weight")
+            gbin = G(f"attention_layers.{i}.in_proj_bias")
+            ops.gemm_wgrad(gD, Q, gin[:H])
+            ops.colsum(gD, gbin[:H])
+            ops.gemm_tn(gD, self.sh[f"wqT{i}"], out_bf16=gC, residual=gB)                          # dQ = dr + dq Wq
+            ops.gemm_wgrad(gKV, x[i], gin[H:])
+            ops.colsum(gKV, gbin[H:])
+            ops.gemm_tn(gKV, self.sh[f"wkvT{i}"], out_bf16=gD)                                     # dx via k, v
+            # LN1 + the un-normalised k/v path; pad rows zeroed (x_i was masked, SRFR_model.py:99,121)
+            ops.layernorm_bwd(gC, x[i], ws[f"st1_{i}"][:T], P.view(f"attention_layernorms.{i}.weight"), gA,
+                              G(f"attention_layernorms.{i}.weight"), G(f"attention_layernorms.{i}.bias"),
+                              add=gD, row_ids=seq_flat)
+
+        # embedding tables
+        dx0 = gA
+        if s.kind == "SASRec" and p_drop > 0:
+            ops.dropout_apply(gA, gB, H, p_drop, seed, 1, step)
+            dx0 = gB
+        aux_grad = G(s.aux_key) if s.aux_key else None
+        ops.embed_bwd(dx0, sv["seq"], sv["aux_ids"], s.D, s.F if s.mode == 1 else 0, s.mode, s.item_scale,
+                      G(s.item_key), aux_grad)
+        pos_tmp = ws["pos_tmp"][:L * H]
+        pos_tmp.zero_()
+        ops.colsum(dx0, pos_tmp, M=B, N=L * H, ld=L * H)
+        ops.add_segments(pos_tmp, L * H, H, s.D, G(s.pos_key))
+        self.saved = None
+
+    # ------------------------------------------------------------------ scoring helpers
+    def fake_table(self) -> Optional[torch.Tensor]:
+        return self.P.view("embedding_layer.fake_embed.weight") if self.spec.kind == "SRFRN" else None
+
+    def fake_table_grad(self) -> Optional[torch.Tensor]:
+        return self.P.view("embedding_layer.fake_embed.weight", grad=True) if self.spec.kind == "SRFRN" else None

@@ -1,0 +1,222 @@
+"""Thin tensor-level wrappers over the C ABI (include/srfrd_b200.h).
+
+Every function takes CUDA torch tensors, passes raw device pointers plus the caller's current
+stream, and returns nothing (outputs are pre-allocated by the caller).  PyTorch is used only for
+device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import CastDesc, GemmEpilogue, call
+
+bf16 = torch.bfloat16
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"srfrd_b200: {name} must be a CUDA tensor (there is no CPU fallback)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"srfrd_b200: {name} must be {dtype}, got {t.dtype}")
+    if t.stride(-1) != 1:
+        raise RuntimeError(f"srfrd_b200: {name} must be contiguous in its last dimension")
+
+
+def embed_ln_fwd(item_table, pos_table, aux_table, mode, seq, aux_ids, item_scale, ln_w, ln_b, eps,
+                 x0_bf16=None, x0_f32=None, q_bf16=None, stats=None, drop_p=0.0, drop_seed=0, drop_stream=0,
+                 drop_step=None):
+    _lib.require_device()
+    B, L = seq.shape
+    D = item_table.shape[1]
+    F = aux_table.shape[1] if (aux_table is not None and mode == 1) else 0
+    _chk(item_table, torch.float32, "item_table"); _chk(seq, torch.int64, "seq")
+    ldx = (x0_bf16 if x0_bf16 is not None else q_bf16).stride(0) if (x0_bf16 is not None or q_bf16 is not None) else D + F
+    call("srfrd_embed_ln_fwd", _p(item_table), item_table.shape[0], D, _p(pos_table), _p(aux_table),
+         0 if aux_table is None else aux_table.shape[0], F, mode, _p(seq), _p(aux_ids), B, L, float(item_scale),
+         _p(ln_w), _p(ln_b), float(eps), _p(x0_bf16), _p(x0_f32), _p(q_bf16), _p(stats), ldx, float(drop_p),
+         int(drop_seed), int(drop_stream), _p(drop_step), _stream())
+
+
+def srfu_labels(fake_ids, kind: int, labels):
+    _lib.require_device()
+    B, L = fake_ids.shape
+    call("srfrd_srfu_labels", _p(fake_ids), B, L, kind, _p(labels), _stream())
+
+
+def embed_bwd(dx0, seq, aux_ids, D, F, mode, item_scale, d_item, d_aux):
+    B, L = seq.shape
+    call("srfrd_embed_bwd", _p(dx0), dx0.stride(0), _p(seq), _p(aux_ids), B, L, D, F, mode, float(item_scale),
+         _p(d_item), _p(d_aux), _stream())
+
+
+def layernorm_fwd(x, w, b, eps, y_bf16=None, y_f32=None, stats=None, T=None, H=None, row_stride=1, row_offset=0):
+    _lib.require_device()
+    T = x.shape[0] if T is None else T
+    H = x.shape[1] if H is None else H
+    y = y_bf16 if y_bf16 is not None else y_f32
+    call("srfrd_layernorm_fwd", _p(x), x.stride(0), _p(w), _p(b), float(eps), _p(y_bf16), _p(y_f32), y.stride(0),
+         _p(stats), T, H, row_stride, row_offset, _stream())
+
+
+def layernorm_bwd(dy, x, stats, w, dx, dw, db, add=None, row_ids=None):
+    T, H = x.shape
+    dyb = dy if dy.dtype == bf16 else None
+    dyf = dy if dy.dtype == torch.float32 else None
+    call("srfrd_layernorm_bwd", _p(dyb), _p(dyf), dy.stride(0), _p(x), x.stride(0), _p(stats), _p(w), _p(add),
+         0 if add is None else add.stride(0), _p(row_ids), _p(dx), dx.stride(0), _p(dw), _p(db), T, H, _stream())
+
+
+def gemm_tn(A, B, out_bf16=None, out_f32=None, bias=None, residual=None, gate=None, row_ids=None, relu=False,
+            drop_p=0.0, drop_seed=0, drop_stream=0, drop_step=None, M=None):
+    """out[M,N] = epilogue(A[M,K] @ B[N,K]^T)."""
+    _lib.require_device()
+    M = A.shape[0] if M is None else M
+    K = A.shape[1]
+    N = B.shape[0]
+    out = out_bf16 if out_bf16 is not None else out_f32
+    ep = GemmEpilogue(_p(bias), _p(residual), _p(gate), _p(row_ids), _p(out_bf16), _p(out_f32),
+                      0 if residual is None else residual.stride(0), 0 if gate is None else gate.stride(0),
+                      out.stride(0), int(relu), float(drop_p), int(drop_stream), int(drop_seed), _p(drop_step))
+    call("srfrd_gemm_tn", _p(A), A.stride(0), _p(B), B.stride(0), M, N, K, C.byref(ep), _stream())
+
+
+def gemm_wgrad(dY, X, dW):
+    """dW[Mo,No] += dY[T,Mo]^T @ X[T,No]  (dW fp32, atomically accumulated)."""
+    T, Mo = dY.shape
+    No = X.shape[1]
+    call("srfrd_gemm_wgrad", _p(dY), dY.stride(0), _p(X), X.stride(0), T, Mo, No, _p(dW), dW.stride(0), _stream())
+
+
+def gemm_ref(A, B, Cout, a_mn_major=False, b_mn_major=False):
+    _lib.require_device()
+    M, N = Cout.shape
+    K = A.shape[0] if a_mn_major else A.shape[1]
+    call("srfrd_gemm_ref", _p(A), A.stride(0), _p(B), B.stride(0), _p(Cout), Cout.stride(0), M, N, K,
+         int(a_mn_major), int(b_mn_major), _stream())
+
+
+def colsum(X, out, M=None, N=None, ld=None):
+    M = X.shape[0] if M is None else M
+    N = X.shape[1] if N is None else N
+    ld = X.stride(0) if ld is None else ld
+    call("srfrd_colsum", _p(X), M, N, ld, _p(out), _stream())
+
+
+def add_segments(src, n, seg_in, seg_out, out):
+    call("srfrd_add_segments", _p(src), n, seg_in, seg_out, _p(out), _stream())
+
+
+def dropout_apply(x, out, N, drop_p, seed, stream_id, drop_step=None):
+    call("srfrd_dropout_apply", _p(x), x.stride(0), _p(out), out.stride(0), x.shape[0], N, float(drop_p), int(seed),
+         int(stream_id), _p(drop_step), _stream())
+
+
+def cast_weights(descs_dev, n):
+    call("srfrd_cast_weights", _p(descs_dev), n, _stream())
+
+
+def make_cast_table(entries, device):
+    """entries: list of (src fp32 2-D view, dst bf16 or None, dst_t bf16 or None) -> uint8 device tensor."""
+    arr = (CastDesc * len(entries))()
+    for i, (src, dst, dst_t) in enumerate(entries):
+        arr[i] = CastDesc(src.data_ptr(), src.stride(0), _p(dst), 0 if dst is None else dst.stride(0), _p(dst_t),
+                          0 if dst_t is None else dst_t.stride(0), src.shape[0], src.shape[1])
+    raw = bytes(arr)
+    host = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+    return host.to(device), len(entries)
+
+
+def f32_to_bf16_split(src, hi, lo=None, row_index=None):
+    _lib.require_device()
+    rows = src.shape[0] if row_index is None else row_index.numel()
+    cols = src.shape[1]
+    call("srfrd_f32_to_bf16_split", _p(src), src.stride(0), _p(row_index), _p(hi), _p(lo), rows, cols, hi.stride(0),
+         _stream())
+
+
+def attention_fwd(q, k, v, o, B, L, H, heads, drop_p=0.0, seed=0, stream_id=0, drop_step=None):
+    _lib.require_device()
+    call("srfrd_attention_fwd", _p(q), q.stride(0), _p(k), _p(v), k.stride(0), _p(o), o.stride(0), B, L, H, heads,
+         float(drop_p), int(seed), int(stream_id), _p(drop_step), _stream())
+
+
+def attention_bwd(dout, q, k, v, dq, dk, dv, B, L, H, heads, drop_p=0.0, seed=0, stream_id=0, drop_step=None):
+    call("srfrd_attention_bwd", _p(dout), dout.stride(0), _p(q), q.stride(0), _p(k), _p(v), k.stride(0), _p(dq),
+         dq.stride(0), _p(dk), _p(dv), dk.stride(0), B, L, H, heads, float(drop_p), int(seed), int(stream_id),
+         _p(drop_step), _stream())
+
+
+def score_fwd(h, item_table, fake_table, pos, neg, prs, nrs, zp, zn):
+    _lib.require_device()
+    T = pos.numel()
+    D = item_table.shape[1]
+    F = 0 if fake_table is None else fake_table.shape[1]
+    call("srfrd_score_fwd", _p(h), h.stride(0), _p(item_table), _p(fake_table), _p(pos), _p(neg), _p(prs), _p(nrs), T,
+         D, F, _p(zp), _p(zn), _stream())
+
+
+def score_bwd(h, item_table, fake_table, pos, neg, prs, nrs, dzp, dzn, dh, d_item, d_fake):
+    T = pos.numel()
+    D = item_table.shape[1]
+    F = 0 if fake_table is None else fake_table.shape[1]
+    call("srfrd_score_bwd", _p(h), h.stride(0), _p(item_table), _p(fake_table), _p(pos), _p(neg), _p(prs), _p(nrs),
+         _p(dzp), _p(dzn), T, D, F, _p(dh), dh.stride(0), _p(d_item), _p(d_fake), _stream())
+
+
+def score_loss_fused(h, item_table, fake_table, pos, neg, prs, nrs, w_pos, w_neg, norm, loss_acc, dh, d_item, d_fake,
+                     zp=None, zn=None):
+    T = pos.numel()
+    D = item_table.shape[1]
+    F = 0 if fake_table is None else fake_table.shape[1]
+    call("srfrd_score_loss_fused", _p(h), h.stride(0), _p(item_table), _p(fake_table), _p(pos), _p(neg), _p(prs),
+         _p(nrs), _p(w_pos), _p(w_neg), _p(norm), T, D, F, _p(zp), _p(zn), _p(loss_acc), _p(dh),
+         0 if dh is None else dh.stride(0), _p(d_item), _p(d_fake), _stream())
+
+
+def weight_sums(pos, w_pos, w_neg, out2):
+    _lib.require_device()
+    call("srfrd_weight_sums", _p(pos), _p(w_pos), _p(w_neg), pos.numel(), _p(out2), _stream())
+
+
+def loss_finalize(acc2, norm2, loss):
+    call("srfrd_loss_finalize", _p(acc2), _p(norm2), _p(loss), _stream())
+
+
+def adam_tick(state3, beta1, beta2):
+    call("srfrd_adam_tick", _p(state3), float(beta1), float(beta2), _stream())
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, state3, zero_grad=True):
+    _lib.require_device()
+    call("srfrd_adam_step", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
+         _p(state3), int(zero_grad), _stream())
+
+
+def catalogue_topk_plan(U, n_rows, row_lo) -> int:
+    out = C.c_int(0)
+    call("srfrd_catalogue_topk_plan", U, n_rows, row_lo, C.byref(out))
+    return out.value
+
+
+def catalogue_topk(feats, U, u_pad, n_split, table, row_lo, id_base, chunks, part_scores, part_ids):
+    _lib.require_device()
+    D = table.shape[1]
+    call("srfrd_catalogue_topk", _p(feats), U, u_pad, n_split, _p(table), table.shape[0], row_lo, id_base, D,
+         feats.stride(0), table.stride(0), chunks, _p(part_scores), _p(part_ids), _stream())
+
+
+def merge_topk(scores, ids, U, nlists, k, out_scores, out_ids):
+    _lib.require_device()
+    call("srfrd_merge_topk", _p(scores), _p(ids), U, nlists, k, _p(out_scores), _p(out_ids), _stream())

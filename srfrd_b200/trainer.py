@@ -1,0 +1,206 @@
+"""Training loops for the hot path.
+
+``simulate``      -- drop-in for the reference's ``simulate(model, optimizer, criterion, sampler, config,
+                     wandb, model_index=0)`` (trainer.py:15-68): same batches, same masked BCE, any torch
+                     criterion / optimizer; the model's forward/backward run on the sm_100a kernels.
+``FusedTrainer``  -- the B200-first step: ids and discriminator weights are copied to static device buffers,
+                     then ONE captured CUDA graph runs forward -> fused weighted BCE (forward+backward, no
+                     ``nonzero`` sync, trainer.py:36) -> backward -> [gradient all-reduce] -> flat Adam ->
+                     bf16 shadow refresh.  The loss stays on the device until the caller asks for it.
+"""
+from __future__ import annotations
+
+import time
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import ops
+from .engine import HotPath
+
+__all__ = ["simulate", "FusedTrainer", "discriminator_weights"]
+
+
+def discriminator_weights(pos: torch.Tensor, p_fake: Optional[torch.Tensor], policy: str = "none") -> torch.Tensor:
+    """w = 1[pos != 0] * g(p_fake): 'none' g = 1 (the reference's loss, trainer.py:36-38), 'mask'
+    g = 1[p_fake < 0.5] (== the hard label prs == 2 the BERT discriminator emits,
+    data/userDiscriminator.py:68,117-122), 'soft' g = 1 - p_fake.  Tiny elementwise plumbing on the
+    batch's (B, L) weights; the weighted loss itself is the fused CUDA kernel."""
+    valid = (pos != 0).to(torch.float32)
+    if policy == "none" or p_fake is None:
+        return valid
+    if policy == "mask":
+        return valid * (p_fake < 0.5).to(torch.float32)
+    if policy == "soft":
+        return valid * (1.0 - p_fake.to(torch.float32))
+    raise ValueError(f"unknown discriminator weighting policy {policy!r}")
+
+
+class FusedTrainer:
+    """One data-parallel replica of the fused training step.
+
+    model        : a srfrd_b200.SRFR_model module already on the CUDA device
+    lr, betas, eps: Adam hyper-parameters (reference: lr 1e-3, betas (0.9, 0.98), trainer.py:390)
+    process_group: torch.distributed group for batch-sharded data parallelism (None = single GPU).
+                   Gradients are SUM-all-reduced and the loss is normalised by the all-reduced weight
+                   sums, so N ranks on B/N sequences each reproduce one rank on B sequences.
+    use_graph    : capture the step in a CUDA graph after the first (eager) step.
+    """
+
+    def __init__(self, model, lr: float = 1e-3, betas=(0.9, 0.98), eps: float = 1e-8, process_group=None,
+                 use_graph: bool = True, l2_emb: float = 0.0):
+        if l2_emb != 0.0:
+            raise NotImplementedError("FusedTrainer implements the reference default l2_emb = 0.0 (trainer.py:123); "
+                                      "use simulate() with a torch optimizer for l2_emb != 0")
+        self.model = model
+        self.eng: HotPath = model._sync_flat()
+        self.P = self.eng.P
+        self.spec = self.eng.spec
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.pg = process_group
+        self.use_graph = use_graph
+        dev = self.eng.device
+        self.m = torch.zeros_like(self.P.data)
+        self.v = torch.zeros_like(self.P.data)
+        self.scal = torch.zeros(8, dtype=torch.float32, device=dev)   # [0:2] norm, [2:4] loss acc, [4] loss
+        self._static: Optional[Dict[str, torch.Tensor]] = None
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._graph_key = None
+        self._has_w = (False, False)
+        self.P.grad.zero_()
+        self.eng.refresh_shadows()
+        self.steps = 0
+
+    # ------------------------------------------------------------------
+    def _alloc_static(self, B: int, L: int):
+        dev = self.eng.device
+        z = lambda dt=torch.int64: torch.zeros(B, L, dtype=dt, device=dev)
+        self._static = dict(seq=z(), rsq=z(), pos=z(), prs=z(), neg=z(), nrs=z(), w_pos=z(torch.float32),
+                            w_neg=z(torch.float32))
+        self._graph = None
+
+    def _step_body(self, has_wp: bool, has_wn: bool):
+        """The kernel sequence of one step, on static buffers (captured once, replayed forever)."""
+        st, eng, P, s = self._static, self.eng, self.P, self.spec
+        B, L = st["seq"].shape
+        T = B * L
+        pos, neg = st["pos"].view(-1), st["neg"].view(-1)
+        w_pos = st["w_pos"].view(-1) if has_wp else None
+        w_neg = st["w_neg"].view(-1) if has_wn else None
+        norm, acc, loss = self.scal[0:2], self.scal[2:4], self.scal[4:5]
+        ops.weight_sums(pos, w_pos, w_neg, norm)
+        acc.zero_()
+        if self.pg is not None:
+            torch.distributed.all_reduce(norm, group=self.pg)             # global sum of weights
+        hidden = eng.forward(st["seq"], st["rsq"], training=True)
+        ws = eng._ws
+        ft = eng.fake_table()
+        ops.score_loss_fused(ws["hfin"][:T], P.view(s.item_key), ft, pos, neg,
+                             st["prs"].view(-1) if ft is not None else None,
+                             st["nrs"].view(-1) if ft is not None else None, w_pos, w_neg, norm, acc, ws["dh"][:T],
+                             P.view(s.item_key, grad=True), eng.fake_table_grad())
+        eng.backward(ws["dh"][:T])
+        if self.pg is not None:
+            torch.distributed.all_reduce(P.grad, group=self.pg)           # NCCL sum over NVLink
+            torch.distributed.all_reduce(acc, group=self.pg)
+        ops.loss_finalize(acc, norm, loss)
+        ops.adam_tick(eng.step_state, self.betas[0], self.betas[1])
+        ops.adam_step(P.data, P.grad, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, eng.step_state,
+                      zero_grad=True)
+        eng.refresh_shadows()
+
+    # ------------------------------------------------------------------
+    def load_batch(self, batch: Dict[str, torch.Tensor], w_pos=None, w_neg=None, non_blocking: bool = True):
+        """Copy one batch (host pinned or device tensors, int64 (B, L)) into the static buffers."""
+        B, L = batch["seq"].shape
+        if self._static is None or self._static["seq"].shape != (B, L):
+            self._alloc_static(B, L)
+        st = self._static
+        for k in ("seq", "rsq", "pos", "prs", "neg", "nrs"):
+            src = batch.get(k)
+            if src is None:
+                st[k].zero_()
+            else:
+                st[k].copy_(torch.as_tensor(src), non_blocking=non_blocking)
+        if w_pos is not None:
+            st["w_pos"].copy_(torch.as_tensor(w_pos), non_blocking=non_blocking)
+        if w_neg is not None:
+            st["w_neg"].copy_(torch.as_tensor(w_neg), non_blocking=non_blocking)
+        self._has_w = (w_pos is not None, w_neg is not None)
+
+    def run_step(self) -> torch.Tensor:
+        """Run one step on the loaded batch; returns the device scalar holding the loss (no sync)."""
+        key = (tuple(self._static["seq"].shape), self._has_w)
+        if self.use_graph and self._graph is not None and self._graph_key == key:
+            self._graph.replay()
+        elif self.use_graph and self.steps >= 1 and self.pg is None:
+            # capture after one eager step has sized the workspaces and set kernel attributes
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                self._step_body(*self._has_w)
+            self._graph, self._graph_key = g, key
+            g.replay()
+        else:
+            self._step_body(*self._has_w)
+        self.steps += 1
+        return self.scal[4]
+
+    def step(self, batch, w_pos=None, w_neg=None) -> torch.Tensor:
+        self.load_batch(batch, w_pos, w_neg)
+        return self.run_step()
+
+    def state_dict(self):
+        return {k: v.detach().clone() for k, v in self.model.state_dict().items()}
+
+
+# ---------------------------------------------------------------------------------------------
+def simulate(model, optimizer, criterion, sampler, config, wandb=None, model_index=0, num_batch=None, device=None,
+             dataset=None, evaluation=None, log_every: int = 1):
+    """The reference loop (trainer.py:15-68) with its module globals (num_batch, device, dataset) made
+    explicit keyword arguments.  ``wandb`` is duck-typed (anything with .log(dict)) or None.
+    ``log_every`` strides the per-step ``loss.item()`` sync the reference performs every step."""
+    T, t0 = 0.0, time.time()
+    metricsbyepoch = dict()
+    device = device if device is not None else next(model.parameters()).device
+    num_batch = num_batch if num_batch is not None else getattr(config, "num_batch")
+    for epoch in range(config.num_epochs):
+        if config.inference_only:
+            break
+        epoch_loss = 0.0
+        model.train()
+        for step in range(num_batch):
+            u, seq, rsq, pos, prs, neg, nrs = sampler.next_batch()
+            seq, rsq, pos, prs, neg, nrs = (torch.as_tensor(np.array(a)).long().to(device)
+                                            for a in (seq, rsq, pos, prs, neg, nrs))
+            hidden_state, pos_logits, neg_logits = model(user_ids=None, input_ids=seq, fake_ids=rsq, positive_ids=pos,
+                                                         positive_fake_ids=prs, negative_ids=neg, negative_fake_ids=nrs)
+            pos_labels = torch.ones(pos_logits.shape, device=device)
+            neg_labels = torch.zeros(neg_logits.shape, device=device)
+            optimizer.zero_grad()
+            indices = torch.where(pos != 0)
+            loss = criterion(pos_logits[indices], pos_labels[indices])
+            loss += criterion(neg_logits[indices], neg_labels[indices])
+            if getattr(config, "l2_emb", 0.0):
+                for param in model.parameters():
+                    loss += config.l2_emb * torch.norm(param)
+            loss.backward()
+            optimizer.step()
+            if step % log_every == 0:
+                li = loss.item()
+                if wandb is not None:
+                    wandb.log({"Training Loss by iteration": li})
+                epoch_loss += li
+        if wandb is not None:
+            wandb.log({"Training Loss by Epoch": epoch_loss, "Epochs": epoch + 1})
+        if (epoch + 1) % 10 == 0 and evaluation is not None and dataset is not None:
+            model.eval()
+            T += time.time() - t0
+            t_test = evaluation(model, dataset, config.maxlen, device)
+            if wandb is not None:
+                wandb.log({"NDCG@10": t_test[0], "HT@10": t_test[1]})
+            metricsbyepoch[epoch + 1] = {"NDCG@10": t_test[0], "HT@10": t_test[1]}
+            t0 = time.time()
+            model.train()
+    return metricsbyepoch

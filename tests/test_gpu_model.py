@@ -1,0 +1,242 @@
+"""End-to-end parity of the drop-in models / trainer on the B200 against (a) the committed golden
+fixtures produced by the unmodified reference and (b) the CPU oracle on larger seeded inputs.
+
+Tolerances (bf16 activations and GEMM operands, fp32 accumulation / statistics / parameters):
+  hidden, logits : rtol 2e-2, atol 2e-2           loss : 5e-3
+  gradients      : 5e-2 of the tensor's max |g| (bf16 activation gradients)
+  HR@10 / NDCG@10: 1e-3
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("SRFR", "SRFR"), ("SRFRN", "SRFRN"), ("SRFU_B", "SRFU_B"), ("SRFU_F", "SRFU_F"), ("SRFU_R", "SRFU_R"),
+         ("SASRec", "SASRec"), ("SRFR_heads2", "SRFR"), ("SASRec_heads4", "SASRec")]
+
+
+def build_from_golden(name, kind, dropout=0.0):
+    from srfrd_b200 import SRFR_model as M
+    fx = load_golden(name)
+    N, L, D, Fw, nb, heads, B = (int(v) for v in fx["meta"])
+    if kind in ("SRFR", "SRFRN"):
+        m = getattr(M, kind)(N, L, D, Fw, dropout, nb, heads, "cuda")
+    elif kind.startswith("SRFU"):
+        nlab = fx["param"]["embedding_layer.user_label_embed.weight"].shape[0]
+        m = getattr(M, kind)(N, L, D, nlab, dropout, nb, heads, "cuda")
+    else:
+        m = M.SASRec(N, L, D, dropout, nb, heads, "cuda")
+    m.load_state_dict(fx["param"])
+    return m.to("cuda"), fx
+
+
+def cuda_batch(fx):
+    return {k: v.cuda() for k, v in fx["in"].items()}
+
+
+@pytest.mark.parametrize("name,kind", CASES)
+def test_forward_matches_reference_golden(name, kind):
+    m, fx = build_from_golden(name, kind)
+    b = cuda_batch(fx)
+    m.eval()
+    with torch.no_grad():
+        h, zp, zn = m(None, b["seq"], b["rsq"], b["pos"], b["prs"], b["neg"], b["nrs"])
+    np.testing.assert_allclose(h.cpu().numpy(), fx["hidden"], rtol=2e-2, atol=2e-2)
+    np.testing.assert_allclose(zp.cpu().numpy(), fx["pos_logits"], rtol=2e-2, atol=2e-2)
+    np.testing.assert_allclose(zn.cpu().numpy(), fx["neg_logits"], rtol=2e-2, atol=2e-2)
+    # the reference's loss (trainer.py:36-38) through torch's own criterion on our logits
+    idx = torch.where(b["pos"] != 0)
+    crit = torch.nn.BCEWithLogitsLoss()
+    loss = crit(zp[idx], torch.ones_like(zp[idx])) + crit(zn[idx], torch.zeros_like(zn[idx]))
+    assert abs(float(loss) - float(fx["loss"])) < 5e-3
+
+
+@pytest.mark.parametrize("name,kind", CASES)
+def test_autograd_gradients_match_reference_golden(name, kind):
+    m, fx = build_from_golden(name, kind)
+    b = cuda_batch(fx)
+    m.train()
+    h, zp, zn = m(None, b["seq"], b["rsq"], b["pos"], b["prs"], b["neg"], b["nrs"])
+    idx = torch.where(b["pos"] != 0)
+    crit = torch.nn.BCEWithLogitsLoss()
+    loss = crit(zp[idx], torch.ones_like(zp[idx])) + crit(zn[idx], torch.zeros_like(zn[idx]))
+    loss.backward()
+    for k, p in m.named_parameters():
+        ref = fx["grad"][k]
+        if k.endswith("in_proj_bias"):       # d/d b_k == 0 analytically: compare q and v thirds only
+            H = ref.shape[0] // 3
+            sel = torch.cat([torch.arange(0, H), torch.arange(2 * H, 3 * H)])
+            got, ref = p.grad.cpu()[sel], ref[sel]
+        else:
+            got = p.grad.cpu()
+        scale = float(ref.abs().max()) + 1e-6
+        err = float((got - ref).abs().max())
+        assert err <= 5e-2 * scale + 1e-5, f"{k}: max err {err:.3e} vs scale {scale:.3e}"
+
+
+@pytest.mark.parametrize("name,kind", CASES)
+def test_drop_in_training_loop_matches_reference_golden(name, kind):
+    """Three steps of the reference loop with torch.optim.Adam(lr 1e-3, betas (0.9, 0.98)) on our model."""
+    m, fx = build_from_golden(name, kind)
+    b = cuda_batch(fx)
+    m.train()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3, betas=(0.9, 0.98))
+    crit = torch.nn.BCEWithLogitsLoss()
+    losses = []
+    for _ in range(3):
+        h, zp, zn = m(None, b["seq"], b["rsq"], b["pos"], b["prs"], b["neg"], b["nrs"])
+        idx = torch.where(b["pos"] != 0)
+        loss = crit(zp[idx], torch.ones_like(zp[idx])) + crit(zn[idx], torch.zeros_like(zn[idx]))
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    np.testing.assert_allclose(losses, fx["loss_steps"], atol=5e-3)
+
+
+@pytest.mark.parametrize("name,kind", CASES)
+def test_fused_trainer_matches_reference_golden(name, kind):
+    """FusedTrainer (fused weighted BCE, flat Adam, CUDA graph) with policy 'none' == the reference steps."""
+    from srfrd_b200.trainer import FusedTrainer
+    m, fx = build_from_golden(name, kind)
+    tr = FusedTrainer(m, lr=1e-3, betas=(0.9, 0.98), use_graph=True)
+    losses = [float(tr.step(cuda_batch(fx))) for _ in range(3)]
+    np.testing.assert_allclose(losses, fx["loss_steps"], atol=5e-3)
+    sd = m.state_dict()
+    for k, ref in fx["after"].items():
+        if k.endswith("in_proj_bias"):
+            continue
+        d = float((sd[k].cpu() - ref).abs().max())
+        assert d < 2.5e-3, f"{k}: parameter drift {d:.2e} after 3 Adam steps (lr 1e-3)"
+
+
+@pytest.mark.parametrize("name,kind", [c for c in CASES if c[1] != "SRFRN"])
+def test_predict_matches_reference_golden(name, kind):
+    m, fx = build_from_golden(name, kind)
+    b = cuda_batch(fx)
+    N = int(fx["meta"][0])
+    m.eval()
+    out = m.predict(None, b["seq"], b["rsq"], torch.arange(1, N + 1).cuda())
+    np.testing.assert_allclose(out.cpu().numpy(), fx["predict_all"], rtol=2e-2, atol=2e-2)
+    # 101-candidate call shape (utils.py:589): (1, L) sequence, squeezed (I,) output
+    one = m.predict(None, b["seq"][:1], b["rsq"][:1], torch.arange(1, 34).cuda())
+    assert one.shape == (33,)
+
+
+def test_srfrn_predict_single_user_matches_reference_golden():
+    m, fx = build_from_golden("SRFRN", "SRFRN")
+    b = cuda_batch(fx)
+    N = int(fx["meta"][0])
+    m.eval()
+    for u in range(b["seq"].shape[0]):
+        out = m.predict(None, b["seq"][u:u + 1], b["rsq"][u:u + 1], torch.arange(1, N + 1).cuda())
+        np.testing.assert_allclose(out.cpu().numpy(), fx["predict_all"][u], rtol=2e-2, atol=2e-2)
+
+
+def test_legacy_numpy_sasrec_matches_reference_golden():
+    import types
+    from srfrd_b200 import model as legacy
+    fx = load_golden("legacy_SASRec")
+    N, L, D, _, nb, heads, B = (int(v) for v in fx["meta"])
+    args = types.SimpleNamespace(device="cuda", hidden_units=D, maxlen=L, dropout_rate=0.0, num_blocks=nb, num_heads=heads)
+    m = legacy.SASRec(10, N, args)
+    m.load_state_dict(fx["param"])
+    m = m.to("cuda").eval()
+    i = {k: v.numpy() for k, v in fx["in"].items()}
+    with torch.no_grad():
+        zp, zn = m(None, i["seq"], i["pos"], i["neg"])
+    np.testing.assert_allclose(zp.cpu().numpy(), fx["pos_logits"], rtol=2e-2, atol=2e-2)
+    np.testing.assert_allclose(zn.cpu().numpy(), fx["neg_logits"], rtol=2e-2, atol=2e-2)
+    p = m.predict(None, i["seq"], np.arange(1, N + 1))
+    np.testing.assert_allclose(p.cpu().numpy(), fx["predict_all"], rtol=2e-2, atol=2e-2)
+
+
+# ---------------------------------------------------------------------------------------------
+def _c2_like(B=512, N=3000, seed=7):
+    from srfrd_b200 import synth
+    data = synth.make_interactions(seed, 4000, N, 5, 4.0, 50)
+    return data, synth.BatchSampler(data, 50, seed).next_batch(B)
+
+
+def test_training_vs_oracle_beauty_shaped_with_discriminator_weights():
+    """C1/C2-shaped data (L=50, D=64, F=16, 2 blocks), 'soft' discriminator weights: 5 fused steps vs the
+    CPU oracle (autograd + torch Adam) on the same batches; then the policy 'none' parity point."""
+    from oracle import srfrd_oracle as O
+    from srfrd_b200 import SRFR_model as M
+    from srfrd_b200.trainer import FusedTrainer, discriminator_weights
+    data, _ = _c2_like()
+    torch.manual_seed(0)
+    m = M.SRFR(data.itemnum, 50, 64, 16, 0.0, 2, 1, "cuda")
+    for _, p in m.named_parameters():                      # trainer.py:364-369
+        if p.dim() >= 2:
+            torch.nn.init.xavier_normal_(p.data)
+    m = m.to("cuda")
+    sd0 = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    orc = O.OracleTrainer(sd0, "SRFR", 1)
+    tr = FusedTrainer(m, use_graph=True)
+    from srfrd_b200 import synth
+    smp = synth.BatchSampler(data, 50, 3)
+    for step in range(5):
+        nb = smp.next_batch(256)
+        tb = {k: torch.from_numpy(v) for k, v in nb.items()}
+        policy = "soft" if step < 3 else "none"
+        w_cpu = O.discriminator_weights(tb["pos"], tb["p_fake"], policy)
+        ref_loss = orc.step(tb, w_cpu if policy != "none" else None)
+        cb = {k: v.cuda() for k, v in tb.items()}
+        w = discriminator_weights(cb["pos"], cb["p_fake"], policy)
+        loss = float(tr.step(cb, w_pos=w if policy != "none" else None))
+        assert abs(loss - ref_loss) < 5e-3, f"step {step}: {loss} vs oracle {ref_loss}"
+
+
+def test_full_catalogue_metrics_match_oracle():
+    """HR@10 / NDCG@10 over the full catalogue: GPU top-10 vs the oracle's exact ranking, |delta| <= 1e-3."""
+    from oracle import srfrd_oracle as O
+    from srfrd_b200 import SRFR_model as M, evaluation as EV, synth
+    data = synth.make_interactions(21, 3000, 5000, 5, 4.0, 50)
+    torch.manual_seed(1)
+    m = M.SRFR(data.itemnum, 50, 64, 16, 0.0, 2, 1, "cuda")
+    for _, p in m.named_parameters():
+        if p.dim() >= 2:
+            torch.nn.init.xavier_normal_(p.data)
+    m = m.to("cuda").eval()
+    users0 = np.nonzero(data.test_item > 0)[0][:2000]
+    seq, rsq, tgt = synth.eval_sequences(data, 50, users0)
+    ndcg, hr, ids = EV.evaluate_full_catalogue(m, torch.from_numpy(seq).cuda(), torch.from_numpy(rsq).cuda(),
+                                               torch.from_numpy(tgt), n_split=3)
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    h = O.encode(sd, "SRFR", torch.from_numpy(seq), torch.from_numpy(rsq), 1)[:, -1, :]
+    rank = O.full_catalogue_rank(h, sd["embedding_layer.item_embed.weight"], tgt)
+    ndcg_ref, hr_ref = O.hr_ndcg_from_rank(rank)
+    assert abs(hr - hr_ref) <= 1e-3 and abs(ndcg - ndcg_ref) <= 1e-3, (hr, hr_ref, ndcg, ndcg_ref)
+
+
+def test_dropout_training_step_runs_and_is_stochastic():
+    from srfrd_b200 import SRFR_model as M
+    from srfrd_b200.trainer import FusedTrainer
+    data, batch = _c2_like(B=128)
+    for kind in ("SRFR", "SASRec"):
+        torch.manual_seed(2)
+        m = (M.SRFR(data.itemnum, 50, 64, 16, 0.5, 2, 1, "cuda") if kind == "SRFR"
+             else M.SASRec(data.itemnum, 50, 64, 0.5, 2, 1, "cuda")).to("cuda")
+        tr = FusedTrainer(m, use_graph=True)
+        cb = {k: torch.from_numpy(v).cuda() for k, v in batch.items()}
+        losses = [float(tr.step(cb)) for _ in range(6)]
+        assert all(np.isfinite(losses)) and len(set(losses)) == len(losses)
+        assert losses[-1] < losses[0] + 0.5
+
+
+def test_state_dict_round_trip_and_device_errors():
+    from srfrd_b200 import SRFR_model as M
+    m, fx = build_from_golden("SRFR", "SRFR")
+    sd = m.state_dict()
+    assert set(sd) == set(fx["param"])
+    for k in sd:
+        assert torch.equal(sd[k].cpu(), fx["param"][k])
+    cpu_model = M.SRFR(10, 4, 16, 16, 0.0, 1, 1, "cpu")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cpu_model(None, torch.ones(1, 4, dtype=torch.long), torch.ones(1, 4, dtype=torch.long))
+    with pytest.raises(ValueError, match="multiples of 16"):
+        M.SRFR(10, 4, 45, 5)
