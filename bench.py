@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""Benchmark of the SRFRD hot path on B200 (contract: see the task statement / DESIGN.md section "Measurement").
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (torchrun launches N ranks for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port) on host cores
+
+A "step" is one training step (forward + discriminator-weighted BCE + backward + gradient all-reduce +
+Adam) of the reference SRFR model on Beauty-shaped synthetic data, config C2 of BASELINE.json:
+22 363 users, 12 101 items, maxlen 50, D=64, F=16, 2 blocks, batch 4096 per GPU (weak scaling).
+`value` = global sequences / second with the batch already resident in HBM; `e2e` = the same step driven
+through FusedTrainer.step() from pinned HOST batches (H2D copies + a D2H read of the loss every step).
+A second object, "catalogue", reports full-catalogue top-10 users/s (C3: 1 M items, row-sharded).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "training seqs/sec; full-catalogue top-10 users/sec"
+CFG = dict(kind="SRFR", usernum=22363, itemnum=12101, L=50, D=64, F=16, blocks=2, heads=1, batch=4096)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+# ---------------------------------------------------------------------------------------------
+def algorithmic_bytes(name, a, valid_frac):
+    """Algorithmic (minimum) HBM bytes of one C-ABI call, from its arguments (DESIGN.md 'bytes per unit')."""
+    g = lambda i: a[i] or 0
+    if name == "srfrd_gemm_tn":
+        M, N, K = a[4], a[5], a[6]
+        ep = a[7]._obj
+        b = M * K * 2 + N * K * 2 + M * N * (2 if ep.out_bf16 else 4)
+        b += (M * N * 2 if ep.residual else 0) + (M * N * 2 if ep.gate else 0) + (M * 8 if ep.row_ids else 0)
+        return b, 2.0 * M * N * K
+    if name == "srfrd_gemm_wgrad":
+        T, Mo, No = a[4], a[5], a[6]
+        return T * (Mo + No) * 2 + Mo * No * 4, 2.0 * T * Mo * No
+    if name == "srfrd_attention_fwd":
+        B, L, H = a[7], a[8], a[9]
+        return 4 * B * L * H * 2, 2.0 * B * L * L * H           # causal half of 2 x (2 L^2 H)
+    if name == "srfrd_attention_bwd":
+        B, L, H = a[12], a[13], a[14]
+        return 7 * B * L * H * 2, 5.0 * B * L * L * H
+    if name == "srfrd_layernorm_fwd":
+        T, H = a[9], a[10]
+        return T * H * 2 + T * H * (2 if a[5] else 4) + T * 8, 0.0
+    if name == "srfrd_layernorm_bwd":
+        T, H = a[14], a[15]
+        return T * H * (2 if a[0] else 4) + 2 * T * H * 2 + T * 8 + (T * H * 2 if a[7] else 0) + (T * 8 if a[9] else 0), 0.0
+    if name == "srfrd_embed_ln_fwd":
+        D, F, mode, T = a[2], a[6], a[7], a[10] * a[11]
+        H = D + (F if mode == 1 else 0)
+        return T * 16 + valid_frac * T * D * 4 + 2 * T * H * 2 + T * 8, 0.0
+    if name == "srfrd_score_loss_fused":
+        T, D, F = a[11], a[12], a[13]
+        return T * 16 + valid_frac * T * (D * 4 + 2 * D * 4 + D * 4 + 2 * 2 * D * 4) + (1 - valid_frac) * T * D * 4, 0.0
+    if name == "srfrd_colsum":
+        return a[1] * a[2] * 2 + a[2] * 4, 0.0
+    if name == "srfrd_adam_step":
+        return a[4] * 32, 0.0
+    if name == "srfrd_embed_bwd":
+        T, D, F, mode = a[4] * a[5], a[6], a[7], a[8]
+        return T * 16 + valid_frac * T * ((D + (F if mode == 1 else 0)) * 2 + D * 8), 0.0
+    if name == "srfrd_dropout_apply":
+        return a[4] * a[5] * 4, 0.0
+    return 0, 0.0
+
+
+def kernel_breakdown(tr, steps, valid_frac):
+    """Eager, event-bracketed pass over `steps` steps: per entry point total ms, launches, algorithmic bytes."""
+    from srfrd_b200 import _lib
+    recs = []
+    tr_graph, tr.use_graph = tr.use_graph, False
+    _lib.set_profile(recs)
+    for _ in range(steps):
+        tr.run_step()
+    torch.cuda.synchronize()
+    _lib.set_profile(None)
+    tr.use_graph = tr_graph
+    agg = {}
+    for name, args, e0, e1 in recs:
+        ms = e0.elapsed_time(e1)
+        by, fl = algorithmic_bytes(name, args, valid_frac)
+        d = agg.setdefault(name, dict(ms=0.0, n=0, bytes=0.0, flops=0.0))
+        d["ms"] += ms; d["n"] += 1; d["bytes"] += by; d["flops"] += fl
+    return agg, len(recs) // max(steps, 1)
+
+
+# ---------------------------------------------------------------------------------------------
+def make_model_and_data(device, seed=1236):
+    from srfrd_b200 import SRFR_model as M, synth
+    c = CFG
+    data = synth.make_interactions(seed, c["usernum"], c["itemnum"], 5, 4.0, c["L"])
+    torch.manual_seed(seed)
+    m = M.SRFR(c["itemnum"], c["L"], c["D"], c["F"], 0.0, c["blocks"], c["heads"], device)
+    for _, p in m.named_parameters():          # trainer.py:364-369
+        if p.dim() >= 2:
+            torch.nn.init.xavier_normal_(p.data)
+    return m.to(device), data
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from srfrd_b200 import _lib, evaluation as EV, synth
+    from srfrd_b200.trainer import FusedTrainer, discriminator_weights
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    c = CFG
+    B, L = c["batch"], c["L"]
+    m, data = make_model_and_data(dev)
+    if world > 1:                               # identical replicas
+        dist.broadcast(m.flat_parameters().data, 0)
+    tr = FusedTrainer(m, lr=1e-3, betas=(0.9, 0.98), process_group=pg, use_graph=(world == 1))
+    smp = synth.BatchSampler(data, L, seed=100 + rank)
+    npool = 8
+    host, dev_batches = [], []
+    for _ in range(npool):
+        nb = smp.next_batch(B)
+        hb = {k: torch.from_numpy(nb[k]).pin_memory() for k in ("seq", "rsq", "pos", "prs", "neg", "nrs", "p_fake")}
+        host.append(hb)
+        dev_batches.append({k: v.to(dev) for k, v in hb.items()})
+    valid_frac = float(np.mean([float((hb["pos"] != 0).float().mean()) for hb in host]))
+    h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in ("seq", "rsq", "pos", "prs", "neg", "nrs")) + B * L * 4
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warm):
+        for i in range(warm):
+            fn(i)
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warm + i)
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    # ---- value: batch resident in HBM (device->device copy into the step's static buffers; weights 'soft') ----
+    def dev_step(i):
+        b = dev_batches[i % npool]
+        tr.step(b, w_pos=discriminator_weights(b["pos"], b["p_fake"], "soft"))
+
+    # ---- e2e: pinned host batch -> H2D -> step -> D2H loss ----
+    wbuf = [discriminator_weights(hb["pos"], hb["p_fake"], "soft").pin_memory() for hb in host]
+
+    def host_step(i):
+        tr.step(host[i % npool], w_pos=wbuf[i % npool])
+        return float(tr.scal[4].item())
+
+    clk = ClockSampler(local)
+    W = max(args.warmup, 3)
+    timed(dev_step, 2, W)                       # sizes workspaces, captures the graph
+    clk.start()
+    ms = timed(dev_step, args.steps, W)
+    clocks = clk.stop()
+    ms_e2e = timed(host_step, args.steps, W)
+    value = world * B * args.steps / (ms / 1e3)
+    e2e = world * B * args.steps / (ms_e2e / 1e3)
+
+    # ---- per-kernel breakdown + roofline of the dominant kernel (rank 0) ----
+    pk = peaks()
+    agg, calls_per_step = kernel_breakdown(tr, 3, valid_frac)
+    tot = sum(d["ms"] for d in agg.values())
+    top = max(agg.items(), key=lambda kv: kv[1]["ms"])
+    tname, td = top
+    per_ms = td["ms"] / td["n"]
+    if td["flops"] > 0 and tname in ("srfrd_attention_fwd", "srfrd_attention_bwd"):
+        bound, ach, peak, unit = "hbm", td["bytes"] / td["n"] / (per_ms * 1e-3) / 1e9, pk["hbm"], "GB/s"
+    else:
+        bound, ach, peak, unit = "hbm", td["bytes"] / td["n"] / (per_ms * 1e-3) / 1e9, pk["hbm"], "GB/s"
+    roofline = dict(bound=bound, kernel=tname, achieved=round(ach, 1), peak=peak, unit=unit, frac=round(ach / peak, 4),
+                    traffic=None, peak_source=pk["src"] + ", sustained figure not needed for HBM", avg_launch_ms=round(per_ms, 4),
+                    share_of_step=round(td["ms"] / tot, 3),
+                    how="eager event-bracketed pass of 3 steps right after the timed region (the timed region replays a CUDA graph)",
+                    kernels={k: dict(ms_per_step=round(v["ms"] / 3, 4), launches_per_step=v["n"] // 3,
+                                     gbs=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None,
+                                     tflops=round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["flops"] else None)
+                             for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])})
+
+    # ---- catalogue: C3, 1 M items row-sharded, U = 16384 users ----
+    cat = None
+    if not args.no_catalogue:
+        cat = bench_catalogue(dev, rank, world, pg, args, pk, timed)
+
+    # ---- CPU baseline (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(sample_steps=2)
+
+    if rank == 0:
+        line = dict(metric=METRIC, value=round(value, 1), unit="seqs/s", n_gpus=world, steps=args.steps, warmup=W,
+                    ms_per_step=round(ms / args.steps, 4), higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="bf16", data="synthetic",
+                    config=dict(workload="C2: SRFR D=64 F=16 L=50 2 blocks 1 head, 12101 items, 22363 users, batch 4096/GPU, "
+                                         "discriminator-weighted (soft) BCE, dropout 0.0, Adam(1e-3,(0.9,0.98))",
+                                global_batch=world * B, maxlen=L, parallelism=f"dp{world}", valid_slot_fraction=round(valid_frac, 4),
+                                l2="per-step working set ~0.7 GB of activations > 126 MB L2; 8 distinct batches rotate"),
+                    e2e=dict(value=round(e2e, 1), unit="seqs/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4,
+                             ms_per_step=round(ms_e2e / args.steps, 4)),
+                    gpu_launches=int(calls_per_step * args.steps), clocks=clocks, roofline=roofline)
+        if cat is not None:
+            line["catalogue"] = cat
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_catalogue(dev, rank, world, pg, args, pk, timed):
+    from srfrd_b200 import evaluation as EV
+    N, D, U = 1_000_000, 64, 16384
+    lo, hi = EV.CatalogueIndex.shard_bounds(N + 1, rank, world)
+    g = torch.Generator(device="cpu").manual_seed(1237)
+    std = (2.0 / (N + 1 + D)) ** 0.5            # xavier_normal_ on an (N+1, D) weight
+    table = torch.randn(N + 1, D, generator=g)[lo:hi].mul_(std).to(torch.bfloat16).float().to(dev)
+    index = EV.CatalogueIndex(table, lo)
+    del table
+    feats = torch.randn(U, D, generator=g).to(dev)
+    out = {}
+
+    def step(i):
+        out["r"] = EV.sharded_topk(feats, index, pg, 1)
+
+    steps = max(3, min(args.steps, 10))
+    ms = timed(step, steps, 3)
+    users_s = U * steps / (ms / 1e3)
+    flops = 2.0 * U * (hi - lo) * D
+    # kernel-only time of the scoring kernel on this rank
+    from srfrd_b200 import _lib
+    recs = []
+    _lib.set_profile(recs)
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
+    _lib.set_profile(None)
+    kms = np.mean([e0.elapsed_time(e1) for n, a, e0, e1 in recs if n == "srfrd_catalogue_topk"])
+    tf = flops / (kms * 1e-3) / 1e12
+    return dict(value=round(users_s, 1), unit="users/s", users=U, items=N, D=D, shards=world, ms_per_pass=round(ms / steps, 4),
+                config="C3: 1M items x D=64 bf16 table row-sharded, 16384 users, top-10, all-gather merge",
+                roofline=dict(bound="tensor", kernel="srfrd_catalogue_topk", achieved=round(tf, 1), peak=pk["tf_burst"],
+                              unit="TFLOP/s", frac=round(tf / pk["tf_burst"], 4), avg_launch_ms=round(float(kms), 4),
+                              traffic=None, peak_source=pk["src"] + ", burst figure (kernel timed alone)"))
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_baseline(sample_steps=2, batch=None):
+    """The reference's CPU path (oracle port: same arithmetic as SRFR_model.py + trainer.py:27-41 through torch's
+    CPU kernels) on this box's host cores, on a bounded sample of the SAME workload (C2 batches of 4096)."""
+    from oracle import srfrd_oracle as O
+    from srfrd_b200 import SRFR_model as M, synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    c = CFG
+    B = batch or c["batch"]
+    data = synth.make_interactions(1236, c["usernum"], c["itemnum"], 5, 4.0, c["L"])
+    torch.manual_seed(1236)
+    m = M.SRFR(c["itemnum"], c["L"], c["D"], c["F"], 0.0, c["blocks"], c["heads"], "cpu")
+    for _, p in m.named_parameters():
+        if p.dim() >= 2:
+            torch.nn.init.xavier_normal_(p.data)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    orc = O.OracleTrainer(sd, "SRFR", 1)
+    smp = synth.BatchSampler(data, c["L"], seed=100)
+    batches = [{k: torch.from_numpy(v) for k, v in smp.next_batch(B).items()} for _ in range(sample_steps + 1)]
+    ws = [O.discriminator_weights(b["pos"], b["p_fake"], "soft") for b in batches]
+    orc.step(batches[0], ws[0])                 # warm-up
+    t0 = time.perf_counter()
+    for b, w in zip(batches[1:], ws[1:]):
+        orc.step(b, w)
+    dt = time.perf_counter() - t0
+    return dict(value=round(B * sample_steps / dt, 1), unit="seqs/s", cores=cores, kind="port",
+                sample=f"{sample_steps} steps of batch {B} (C2 workload, fp32, dropout 0.0, soft discriminator weights), "
+                       f"torch {torch.__version__} CPU with {cores} threads", seconds=round(dt, 2))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    W = 1
+    from oracle import srfrd_oracle as O  # noqa: F401  (checker doubles as the timed CPU port here)
+    t0 = time.perf_counter()
+    cpu = cpu_baseline(sample_steps=min(steps, 4))
+    line = dict(impl="reference", metric=METRIC, value=cpu["value"], unit="seqs/s", n_gpus=args.gpus, steps=min(steps, 4),
+                warmup=W, ms_per_step=round(1e3 * CFG["batch"] / cpu["value"], 2), higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload="C2: SRFR D=64 F=16 L=50 2 blocks 1 head, 12101 items, batch 4096, soft discriminator "
+                                     "weights, dropout 0.0, Adam(1e-3,(0.9,0.98)) -- reference CPU path (oracle port: the "
+                                     "upstream checkout is Python and does not exist on the GPU box)"),
+                cpu_baseline=cpu, e2e=dict(value=cpu["value"], unit="seqs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                wall_s=round(time.perf_counter() - t0, 1))
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-catalogue", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -53,7 +53,8 @@ SRFRD_API int srfrd_embed_ln_fwd(const float* item_table, int64_t n_rows, int D,
                        int ldx, float drop_p, uint64_t drop_seed, uint32_t drop_stream, const float* drop_step,
                        void* stream);
 
-/* SRFU_B/F/R.get_Labels -- replaces SRFR_model.py:546-570.  kind 0 = B, 1 = F, 2 = R. */
+/* SRFU_B/F/R.get_Labels -- replaces SRFR_model.py:546-570.  kind 0 = B, 1 = F, 2 = R,
+ * 3 = the truncating variant SRFRN.predict uses (SRFR_model.py:244). */
 SRFRD_API int srfrd_srfu_labels(const int64_t* fake_ids, int64_t B, int L, int kind, int64_t* labels, void* stream);
 
 /* K5: gradient of the input-sequence lookups into the item table (and fake / user-label table).

@@ -48,7 +48,7 @@ class _EncodeAndScore(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, seq, rsq, pos, prs, neg, nrs, *params):
         eng: HotPath = model._engine
-        train = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        train = any(ctx.needs_input_grad)    # (grad mode is always off inside Function.forward)
         with torch.no_grad():
             hidden = eng.forward(seq, rsq, training=model.training, save=train)
             B, L = seq.shape
@@ -189,7 +189,7 @@ class _HotPathModule(nn.Module):
         if self.spec.kind == "SRFRN":       # rows are E[label] || Fe[user_label] (SRFR_model.py:244-257)
             fid = torch.as_tensor(fake_ids, device=eng.device).long()
             lab = torch.empty(fid.shape[0], dtype=torch.int64, device=eng.device)
-            ops.srfu_labels(fid.contiguous(), 0, lab)
+            ops.srfu_labels(fid.contiguous(), 3, lab)
             fe = eng.P.view("embedding_layer.fake_embed.weight")[lab]
             logits = logits + (feats[:, self.spec.D:] * fe).sum(-1, keepdim=True)
         return logits.squeeze()

@@ -95,11 +95,27 @@ def require_device() -> None:
     _device_ok = True
 
 
+_profile = None    # when a list: (name, args, start_event, end_event) per call (bench.py's per-kernel timing)
+
+
+def set_profile(records) -> None:
+    global _profile
+    _profile = records
+
+
 def call(name: str, *args) -> None:
     """Invoke a kernel entry point; a non-zero return code becomes RuntimeError(srfrd_last_error())."""
     global launch_count
     lib = _lib or load()
-    rc = getattr(lib, name)(*args)
+    if _profile is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        _profile.append((name, args, e0, e1))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name}: {lib.srfrd_last_error().decode()}")
     launch_count += 1

@@ -274,6 +274,7 @@ __global__ void srfu_labels_kernel(const int64_t* fake_ids, int64_t B, int L, in
   if (lane == 0) {
     int64_t lab;
     if (kind == 0) lab = nf < nr ? 1 : 2;                      // round(sign(nf-nr)*0.5+1.5), tie -> 2
+    else if (kind == 3) lab = nf > nr ? 2 : 1;                 // SRFRN.predict: (sign(..)*0.5+1.5).int(), tie -> 1 (:244)
     else if (kind == 1) lab = nf;
     else {
       const float r = __fmul_rn(__fdiv_rn((float)nf, (float)(nf + nr)), 10.f);
@@ -409,7 +410,7 @@ extern "C" int srfrd_cast_weights(const srfrd_cast_desc_t* descs_dev, int n, voi
 
 extern "C" int srfrd_srfu_labels(const int64_t* fake_ids, int64_t B, int L, int kind, int64_t* labels, void* stream) {
   SRFRD_REQUIRE(fake_ids && labels, "srfu_labels: null pointer");
-  SRFRD_REQUIRE(kind >= 0 && kind <= 2, "srfu_labels: kind must be 0 (B), 1 (F) or 2 (R)");
+  SRFRD_REQUIRE(kind >= 0 && kind <= 3, "srfu_labels: kind must be 0 (B), 1 (F), 2 (R) or 3 (SRFRN.predict)");
   if (B == 0) return 0;
   srfu_labels_kernel<<<(unsigned)((B + 7) / 8), 256, 0, (cudaStream_t)stream>>>(fake_ids, B, L, kind, labels);
   SRFRD_LAUNCH_CHECK();
