@@ -1,13 +1,45 @@
 // HBM-bound row-wise kernels: K1 (gather + positional add + concat/add + pad mask + LayerNorm),
 // LayerNorm forward/backward, column sums (bias gradients), fp32 -> bf16 weight shadows.
-// One warp per token; lanes stride the feature dimension so every global access is coalesced.
+//
+// Layout: a row (token) is handled by a group of LPR lanes (8/16/32), each lane owning CH chunks of
+// 8 contiguous features, so every global access is a 16-byte (bf16) or 2 x 16-byte (fp32) vector and a
+// warp covers 32/LPR rows per pass; two passes are kept in flight per loop iteration for memory-level
+// parallelism.  Row statistics are reduced with xor-shuffles inside the lane group.
 #include "common.cuh"
 #include "srfrd_b200.h"
 
 namespace srfrd {
 
-static constexpr int MAXC = 16;  // features per lane -> widths up to 512
+static constexpr int MAXW = 512;     // widest supported row
 
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+    f[2 * i] = t.x; f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+__device__ __forceinline__ void load8_f32(const float* p, float* f) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void store8_f32(float* p, const float* f) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+// ---------------------------------------------------------------------------------------------
 struct EmbedParams {
   const float* item_table;   // (n_rows, D)
   const float* pos_table;    // (L, D)
@@ -16,7 +48,6 @@ struct EmbedParams {
   const int64_t* aux_ids;    // mode 1: (B, L) fake ids or null (-> all 0); mode 2: (B,) labels
   int64_t T;
   int L, D, F, mode;
-  int64_t n_rows, n_aux;
   float item_scale;
   const float* ln_w;         // (H) or null -> no LN output
   const float* ln_b;
@@ -29,73 +60,96 @@ struct EmbedParams {
   uint64_t drop_seed; uint32_t drop_thresh, drop_stream; float drop_scale; const float* drop_step;
 };
 
+template <int LPR, int CH>
 __global__ void __launch_bounds__(256) embed_ln_kernel(EmbedParams p) {
   if (p.drop_thresh) p.drop_seed = mix_seed(p.drop_seed, p.drop_step);
-  const int lane = threadIdx.x & 31;
-  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  constexpr int RPW = 32 / LPR;                         // rows per warp pass
+  const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
   const int H = p.D + (p.mode == 1 ? p.F : 0);
-  for (int64_t t = warp0; t < p.T; t += nwarps) {
-    const int l = (int)(t % p.L);
-    const int64_t id = __ldg(p.seq + t);
-    const bool valid = id != 0;
-    int64_t aid = 0;
-    if (p.mode == 1) aid = p.aux_ids ? __ldg(p.aux_ids + t) : 0;
-    if (p.mode == 2) aid = __ldg(p.aux_ids + t / p.L);
-    float v[MAXC];
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t t0 = warp * RPW; t0 < p.T; t0 += nwarps * RPW) {
+    const int64_t t = t0 + grp;
+    const bool row_ok = t < p.T;
+    int64_t id = 0, aid = 0;
+    int l = 0;
+    if (row_ok) {
+      l = (int)(t % p.L);
+      id = __ldg(p.seq + t);
+      if (p.mode == 1) aid = p.aux_ids ? __ldg(p.aux_ids + t) : 0;
+      if (p.mode == 2) aid = __ldg(p.aux_ids + t / p.L);
+    }
+    const bool valid = row_ok && id != 0;
+    float v[CH][8];
     float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXC; ++i) {
-      const int c = lane + 32 * i;
-      float x = 0.f;
-      if (c < H && valid) {
+    for (int ch = 0; ch < CH; ++ch) {
+      const int c = (ch * LPR + sub) * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[ch][j] = 0.f;
+      if (valid && c < H) {
         if (c < p.D) {
           // __fmul_rn/__fadd_rn: no FMA contraction, so the pre-LN tensor is bit-identical to
           // torch's  E[id] (* sqrt(d)) + P[l] (+ Ul[label])   (SRFR_model.py:22-25, :622-624, :419-422)
-          x = __ldg(p.item_table + id * p.D + c);
-          if (p.item_scale != 1.f) x = __fmul_rn(x, p.item_scale);
-          x = __fadd_rn(x, __ldg(p.pos_table + (int64_t)l * p.D + c));
-          if (p.mode == 2) x = __fadd_rn(x, __ldg(p.aux_table + aid * p.D + c));
+          float e[8], pp[8];
+          load8_f32(p.item_table + id * p.D + c, e);
+          load8_f32(p.pos_table + (int64_t)l * p.D + c, pp);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float x = e[j];
+            if (p.item_scale != 1.f) x = __fmul_rn(x, p.item_scale);
+            v[ch][j] = __fadd_rn(x, pp[j]);
+          }
+          if (p.mode == 2) {
+            float u[8];
+            load8_f32(p.aux_table + aid * p.D + c, u);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[ch][j] = __fadd_rn(v[ch][j], u[j]);
+          }
         } else {
-          x = __ldg(p.aux_table + aid * p.F + (c - p.D));
+          load8_f32(p.aux_table + aid * p.F + (c - p.D), v[ch]);
         }
-        // SASRec.emb_dropout (SRFR_model.py:625): after the positional add, before the pad mask
-        if (p.drop_thresh)
-          x = dropout_keep(p.drop_seed, p.drop_stream, (uint64_t)t * H + c, p.drop_thresh) ? x * p.drop_scale : 0.f;
-      }
-      v[i] = x;
-      sum += x;
-    }
-    if (p.x0_f32) {
+        if (p.drop_thresh) {   // SASRec.emb_dropout (SRFR_model.py:625): after the positional add, before the mask
 #pragma unroll
-      for (int i = 0; i < MAXC; ++i) {
-        const int c = lane + 32 * i;
-        if (c < H) p.x0_f32[t * H + c] = v[i];
+          for (int j = 0; j < 8; ++j)
+            v[ch][j] = dropout_keep(p.drop_seed, p.drop_stream, (uint64_t)t * H + c + j, p.drop_thresh)
+                           ? v[ch][j] * p.drop_scale : 0.f;
+        }
       }
-    }
-    if (p.x0) {
 #pragma unroll
-      for (int i = 0; i < MAXC; ++i) {
-        const int c = lane + 32 * i;
-        if (c < H) p.x0[t * p.ldx + c] = f2bf(v[i]);
-      }
+      for (int j = 0; j < 8; ++j) sum += v[ch][j];
     }
+    float mean = 0.f, rstd = 0.f;
     if (p.ln_w) {
-      const float mean = warp_sum(sum) / H;
+      mean = group_sum<LPR>(sum) / H;
       float sq = 0.f;
 #pragma unroll
-      for (int i = 0; i < MAXC; ++i) {
-        const int c = lane + 32 * i;
-        if (c < H) { const float d = v[i] - mean; sq += d * d; }
-      }
-      const float rstd = rsqrtf(warp_sum(sq) / H + p.eps);
+      for (int ch = 0; ch < CH; ++ch) {
+        const int c = (ch * LPR + sub) * 8;
+        if (c < H) {
 #pragma unroll
-      for (int i = 0; i < MAXC; ++i) {
-        const int c = lane + 32 * i;
-        if (c < H) p.q[t * p.ldx + c] = f2bf((v[i] - mean) * rstd * __ldg(p.ln_w + c) + __ldg(p.ln_b + c));
+          for (int j = 0; j < 8; ++j) { const float d = v[ch][j] - mean; sq += d * d; }
+        }
       }
-      if (p.stats && lane == 0) { p.stats[2 * t] = mean; p.stats[2 * t + 1] = rstd; }
+      rstd = rsqrtf(group_sum<LPR>(sq) / H + p.eps);
     }
+    if (!row_ok) continue;
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch) {
+      const int c = (ch * LPR + sub) * 8;
+      if (c >= H) continue;
+      if (p.x0_f32) store8_f32(p.x0_f32 + t * H + c, v[ch]);
+      if (p.x0) *reinterpret_cast<uint4*>(p.x0 + t * p.ldx + c) = pack8(v[ch]);
+      if (p.ln_w) {
+        float w[8], b[8], y[8];
+        load8_f32(p.ln_w + c, w);
+        load8_f32(p.ln_b + c, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = (v[ch][j] - mean) * rstd * w[j] + b[j];
+        *reinterpret_cast<uint4*>(p.q + t * p.ldx + c) = pack8(y);
+      }
+    }
+    if (p.ln_w && p.stats && sub == 0) *reinterpret_cast<float2*>(p.stats + 2 * t) = make_float2(mean, rstd);
   }
 }
 
@@ -110,38 +164,61 @@ struct LnFwdParams {
   int64_t row_offset;
 };
 
+template <int LPR, int CH>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(LnFwdParams p) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  constexpr int RPW = 32 / LPR, UN = 2;
+  const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t t = warp0; t < p.T; t += nwarps) {
-    const int64_t r = t * p.row_stride + p.row_offset;
-    float v[MAXC];
-    float sum = 0.f;
+  for (int64_t t0 = warp * RPW * UN; t0 < p.T; t0 += nwarps * RPW * UN) {
+    uint4 raw[UN][CH];
 #pragma unroll
-    for (int i = 0; i < MAXC; ++i) {
-      const int c = lane + 32 * i;
-      v[i] = c < p.H ? bf2f(p.x[r * p.ldx + c]) : 0.f;
-      sum += v[i];
-    }
-    const float mean = warp_sum(sum) / p.H;
-    float sq = 0.f;
+    for (int u = 0; u < UN; ++u) {
+      const int64_t t = t0 + u * RPW + grp;
 #pragma unroll
-    for (int i = 0; i < MAXC; ++i) {
-      const int c = lane + 32 * i;
-      if (c < p.H) { const float d = v[i] - mean; sq += d * d; }
-    }
-    const float rstd = rsqrtf(warp_sum(sq) / p.H + p.eps);
-#pragma unroll
-    for (int i = 0; i < MAXC; ++i) {
-      const int c = lane + 32 * i;
-      if (c < p.H) {
-        const float y = (v[i] - mean) * rstd * __ldg(p.w + c) + __ldg(p.b + c);
-        if (p.y_bf16) p.y_bf16[t * p.ldy + c] = f2bf(y);
-        if (p.y_f32) p.y_f32[t * p.ldy + c] = y;
+      for (int ch = 0; ch < CH; ++ch) {
+        const int c = (ch * LPR + sub) * 8;
+        raw[u][ch] = make_uint4(0, 0, 0, 0);
+        if (t < p.T && c < p.H)
+          raw[u][ch] = __ldg(reinterpret_cast<const uint4*>(p.x + (t * p.row_stride + p.row_offset) * p.ldx + c));
       }
     }
-    if (p.stats && lane == 0) { p.stats[2 * t] = mean; p.stats[2 * t + 1] = rstd; }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int64_t t = t0 + u * RPW + grp;
+      float v[CH][8];
+      float sum = 0.f;
+#pragma unroll
+      for (int ch = 0; ch < CH; ++ch) {
+        unpack8(raw[u][ch], v[ch]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += v[ch][j];
+      }
+      const float mean = group_sum<LPR>(sum) / p.H;
+      float sq = 0.f;
+#pragma unroll
+      for (int ch = 0; ch < CH; ++ch) {
+        if ((ch * LPR + sub) * 8 < p.H) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float d = v[ch][j] - mean; sq += d * d; }
+        }
+      }
+      const float rstd = rsqrtf(group_sum<LPR>(sq) / p.H + p.eps);
+      if (t >= p.T) continue;
+#pragma unroll
+      for (int ch = 0; ch < CH; ++ch) {
+        const int c = (ch * LPR + sub) * 8;
+        if (c >= p.H) continue;
+        float w[8], b[8], y[8];
+        load8_f32(p.w + c, w);
+        load8_f32(p.b + c, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = (v[ch][j] - mean) * rstd * w[j] + b[j];
+        if (p.y_bf16) *reinterpret_cast<uint4*>(p.y_bf16 + t * p.ldy + c) = pack8(y);
+        if (p.y_f32) store8_f32(p.y_f32 + t * p.ldy + c, y);
+      }
+      if (p.stats && sub == 0) *reinterpret_cast<float2*>(p.stats + 2 * t) = make_float2(mean, rstd);
+    }
   }
 }
 
@@ -158,63 +235,110 @@ struct LnBwdParams {
   int64_t T; int H;
 };
 
+template <int LPR, int CH>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdParams p) {
-  __shared__ float red[8][32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const int64_t warp0 = (int64_t)blockIdx.x * nw + warp;
-  const int64_t nwarps = (int64_t)gridDim.x * nw;
-  float adw[MAXC], adb[MAXC];
+  __shared__ float sdw[MAXW], sdb[MAXW];
+  constexpr int RPW = 32 / LPR, UN = 2;
+  const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int i = threadIdx.x; i < p.H; i += blockDim.x) sdw[i] = sdb[i] = 0.f;
+  __syncthreads();
+  float gw[CH][8];
+  float adw[CH][8], adb[CH][8];
 #pragma unroll
-  for (int i = 0; i < MAXC; ++i) adw[i] = adb[i] = 0.f;
-  for (int64_t t = warp0; t < p.T; t += nwarps) {
-    const float mean = __ldg(p.stats + 2 * t), rstd = __ldg(p.stats + 2 * t + 1);
-    float g[MAXC], xh[MAXC];
-    float sg = 0.f, sgx = 0.f;
+  for (int ch = 0; ch < CH; ++ch) {
+    const int c = (ch * LPR + sub) * 8;
 #pragma unroll
-    for (int i = 0; i < MAXC; ++i) {
-      const int c = lane + 32 * i;
-      g[i] = xh[i] = 0.f;
-      if (c < p.H) {
-        const float dy = p.dy_bf16 ? bf2f(p.dy_bf16[t * p.lddy + c]) : p.dy_f32[t * p.lddy + c];
-        xh[i] = (bf2f(p.x[t * p.ldx + c]) - mean) * rstd;
-        g[i] = dy * __ldg(p.w + c);
-        adw[i] += dy * xh[i];
-        adb[i] += dy;
-        sg += g[i];
-        sgx += g[i] * xh[i];
+    for (int j = 0; j < 8; ++j) { adw[ch][j] = adb[ch][j] = 0.f; gw[ch][j] = 0.f; }
+    if (c < p.H) load8_f32(p.w + c, gw[ch]);
+  }
+  for (int64_t t0 = warp * RPW * UN; t0 < p.T; t0 += nwarps * RPW * UN) {
+    float dy[UN][CH][8];
+    uint4 xr[UN][CH], ar[UN][CH];
+    float2 st[UN];
+    float msk[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int64_t t = t0 + u * RPW + grp;
+      const bool ok = t < p.T;
+      st[u] = ok ? __ldg(reinterpret_cast<const float2*>(p.stats + 2 * t)) : make_float2(0.f, 0.f);
+      msk[u] = (ok && p.row_ids) ? ((__ldg(p.row_ids + t) != 0) ? 1.f : 0.f) : 1.f;
+#pragma unroll
+      for (int ch = 0; ch < CH; ++ch) {
+        const int c = (ch * LPR + sub) * 8;
+        xr[u][ch] = ar[u][ch] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dy[u][ch][j] = 0.f;
+        if (ok && c < p.H) {
+          if (p.dy_bf16) {
+            const uint4 r = __ldg(reinterpret_cast<const uint4*>(p.dy_bf16 + t * p.lddy + c));
+            unpack8(r, dy[u][ch]);
+          } else {
+            load8_f32(p.dy_f32 + t * p.lddy + c, dy[u][ch]);
+          }
+          xr[u][ch] = __ldg(reinterpret_cast<const uint4*>(p.x + t * p.ldx + c));
+          if (p.add) ar[u][ch] = __ldg(reinterpret_cast<const uint4*>(p.add + t * p.ldadd + c));
+        }
       }
     }
-    sg = warp_sum(sg) / p.H;
-    sgx = warp_sum(sgx) / p.H;
-    float m = 1.f;
-    if (p.row_ids) m = (__ldg(p.row_ids + t) != 0) ? 1.f : 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXC; ++i) {
-      const int c = lane + 32 * i;
-      if (c < p.H) {
-        float dx = rstd * (g[i] - sg - xh[i] * sgx);
-        if (p.add) dx += bf2f(p.add[t * p.ldadd + c]);
-        p.dx[t * p.lddx + c] = f2bf(dx * m);
+    for (int u = 0; u < UN; ++u) {
+      const int64_t t = t0 + u * RPW + grp;
+      const float mean = st[u].x, rstd = st[u].y;
+      float g[CH][8], xh[CH][8];
+      float sg = 0.f, sgx = 0.f;
+#pragma unroll
+      for (int ch = 0; ch < CH; ++ch) {
+        float xv[8];
+        unpack8(xr[u][ch], xv);
+        const bool cok = (ch * LPR + sub) * 8 < p.H && t < p.T;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[ch][j] = cok ? (xv[j] - mean) * rstd : 0.f;
+          g[ch][j] = dy[u][ch][j] * gw[ch][j];
+          adw[ch][j] += dy[u][ch][j] * xh[ch][j];
+          adb[ch][j] += dy[u][ch][j];
+          sg += g[ch][j];
+          sgx += g[ch][j] * xh[ch][j];
+        }
+      }
+      sg = group_sum<LPR>(sg) / p.H;
+      sgx = group_sum<LPR>(sgx) / p.H;
+      if (t >= p.T) continue;
+#pragma unroll
+      for (int ch = 0; ch < CH; ++ch) {
+        const int c = (ch * LPR + sub) * 8;
+        if (c >= p.H) continue;
+        float av[8], o[8];
+        unpack8(ar[u][ch], av);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (rstd * (g[ch][j] - sg - xh[ch][j] * sgx) + av[j]) * msk[u];
+        *reinterpret_cast<uint4*>(p.dx + t * p.lddx + c) = pack8(o);
       }
     }
   }
-  // block reduction of the per-lane column partials, then one red.add per column per block
+  // per-block reduction of the column partials in shared memory, then one red.add per column per block
 #pragma unroll
-  for (int i = 0; i < MAXC; ++i) {
-    if (32 * i >= p.H) break;
-    for (int pass = 0; pass < 2; ++pass) {
-      __syncthreads();
-      red[warp][lane] = pass ? adb[i] : adw[i];
-      __syncthreads();
-      if (warp == 0) {
-        float s = 0.f;
-        for (int w = 0; w < nw; ++w) s += red[w][lane];
-        const int c = lane + 32 * i;
-        if (c < p.H) red_add_f32((pass ? p.db : p.dw) + c, s);
-      }
+  for (int ch = 0; ch < CH; ++ch) {
+    const int c = (ch * LPR + sub) * 8;
+    if (c < p.H) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { atomicAdd(&sdw[c + j], adw[ch][j]); atomicAdd(&sdb[c + j], adb[ch][j]); }
     }
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.H; i += blockDim.x) { red_add_f32(p.dw + i, sdw[i]); red_add_f32(p.db + i, sdb[i]); }
 }
+
+// dispatch on the row width: lanes per row x chunks per lane (8 features each)
+#define SRFRD_ROW_DISPATCH(H, CALL)                      \
+  do {                                                   \
+    if ((H) <= 64) { CALL(8, 1); }                       \
+    else if ((H) <= 128) { CALL(16, 1); }                \
+    else if ((H) <= 256) { CALL(32, 1); }                \
+    else { CALL(32, 2); }                                \
+  } while (0)
 
 // ---------------------------------------------------------------------------------------------
 // out[n] += sum_m X[m, n]  (bias gradients; positional-table gradient via the (B, L*H) view)
@@ -309,9 +433,9 @@ __global__ void dropout_apply_kernel(const bf16* x, int ldx, bf16* out, int ldo,
   }
 }
 
-static int grid_for_warps(int64_t T, int warps_per_block) {
-  int64_t blocks = (T + warps_per_block - 1) / warps_per_block;
-  const int64_t cap = (int64_t)num_sms() * 16;
+static int grid_for_rows(int64_t T, int rows_per_block, int max_blocks_per_sm) {
+  int64_t blocks = (T + rows_per_block - 1) / rows_per_block;
+  const int64_t cap = (int64_t)num_sms() * max_blocks_per_sm;
   return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
 
@@ -331,19 +455,23 @@ extern "C" int srfrd_embed_ln_fwd(const float* item_table, int64_t n_rows, int D
   SRFRD_REQUIRE(mode == 0 || aux_table, "embed_ln_fwd: aux_table required for mode %d", mode);
   SRFRD_REQUIRE(mode != 2 || aux_ids, "embed_ln_fwd: per-sequence labels required for mode 2");
   const int H = D + (mode == 1 ? F : 0);
-  SRFRD_REQUIRE(H <= 32 * MAXC, "embed_ln_fwd: width %d > %d unsupported", H, 32 * MAXC);
+  SRFRD_REQUIRE(H <= MAXW, "embed_ln_fwd: width %d > %d unsupported", H, MAXW);
+  SRFRD_REQUIRE(D % 8 == 0 && H % 8 == 0, "embed_ln_fwd: D and H must be multiples of 8 (D=%d H=%d)", D, H);
   SRFRD_REQUIRE(!ln_w || (ln_b && q_bf16), "embed_ln_fwd: LN needs weight, bias and an output");
-  SRFRD_REQUIRE((!x0_bf16 && !q_bf16) || ldx >= H, "embed_ln_fwd: ldx < H");
+  SRFRD_REQUIRE((!x0_bf16 && !q_bf16) || (ldx >= H && ldx % 8 == 0), "embed_ln_fwd: bad ldx %d", ldx);
+  (void)n_rows; (void)n_aux;
   if (B * L == 0) return 0;
   EmbedParams p;
   p.item_table = item_table; p.pos_table = pos_table; p.aux_table = aux_table; p.seq = seq; p.aux_ids = aux_ids;
-  p.T = B * L; p.L = L; p.D = D; p.F = F; p.mode = mode; p.n_rows = n_rows; p.n_aux = n_aux; p.item_scale = item_scale;
+  p.T = B * L; p.L = L; p.D = D; p.F = F; p.mode = mode; p.item_scale = item_scale;
   p.ln_w = ln_w; p.ln_b = ln_b; p.eps = eps; p.x0 = (bf16*)x0_bf16; p.x0_f32 = x0_f32; p.q = (bf16*)q_bf16;
   p.stats = stats; p.ldx = ldx;
   p.drop_seed = drop_seed; p.drop_stream = drop_stream; p.drop_step = drop_step;
   p.drop_thresh = drop_p > 0.f ? (uint32_t)((double)drop_p * 4294967296.0) : 0;
   p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  embed_ln_kernel<<<grid_for_warps(p.T, 8), 256, 0, (cudaStream_t)stream>>>(p);
+#define CALL(LPR, CH) embed_ln_kernel<LPR, CH><<<grid_for_rows(p.T, 8 * (32 / LPR), 8), 256, 0, (cudaStream_t)stream>>>(p)
+  SRFRD_ROW_DISPATCH(H, CALL);
+#undef CALL
   SRFRD_LAUNCH_CHECK();
   return 0;
 }
@@ -352,12 +480,14 @@ extern "C" int srfrd_layernorm_fwd(const void* x, int ldx, const float* w, const
                                    float* y_f32, int ldy, float* stats, int64_t T, int H, int64_t row_stride,
                                    int64_t row_offset, void* stream) {
   SRFRD_REQUIRE(x && w && b && (y_bf16 || y_f32), "layernorm_fwd: null pointer");
-  SRFRD_REQUIRE(H <= 32 * MAXC, "layernorm_fwd: width %d unsupported", H);
+  SRFRD_REQUIRE(H <= MAXW && H % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "layernorm_fwd: width %d / ld unsupported", H);
   if (T == 0) return 0;
   LnFwdParams p;
   p.x = (const bf16*)x; p.ldx = ldx; p.w = w; p.b = b; p.eps = eps; p.y_bf16 = (bf16*)y_bf16; p.y_f32 = y_f32;
   p.ldy = ldy; p.stats = stats; p.T = T; p.H = H; p.row_stride = row_stride; p.row_offset = row_offset;
-  ln_fwd_kernel<<<grid_for_warps(T, 8), 256, 0, (cudaStream_t)stream>>>(p);
+#define CALL(LPR, CH) ln_fwd_kernel<LPR, CH><<<grid_for_rows(T, 16 * (32 / LPR), 8), 256, 0, (cudaStream_t)stream>>>(p)
+  SRFRD_ROW_DISPATCH(H, CALL);
+#undef CALL
   SRFRD_LAUNCH_CHECK();
   return 0;
 }
@@ -367,15 +497,16 @@ extern "C" int srfrd_layernorm_bwd(const void* dy_bf16, const float* dy_f32, int
                                    const int64_t* row_ids, void* dx, int lddx, float* dw, float* db, int64_t T, int H,
                                    void* stream) {
   SRFRD_REQUIRE((dy_bf16 || dy_f32) && x && stats && w && dx && dw && db, "layernorm_bwd: null pointer");
-  SRFRD_REQUIRE(H <= 32 * MAXC, "layernorm_bwd: width %d unsupported", H);
+  SRFRD_REQUIRE(H <= MAXW && H % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0 && lddy % 8 == 0 && (!add || ldadd % 8 == 0),
+                "layernorm_bwd: width %d / ld unsupported", H);
   if (T == 0) return 0;
   LnBwdParams p;
   p.dy_bf16 = (const bf16*)dy_bf16; p.dy_f32 = dy_f32; p.lddy = lddy; p.x = (const bf16*)x; p.ldx = ldx;
   p.stats = stats; p.w = w; p.add = (const bf16*)add; p.ldadd = ldadd; p.row_ids = row_ids; p.dx = (bf16*)dx;
   p.lddx = lddx; p.dw = dw; p.db = db; p.T = T; p.H = H;
-  int grid = grid_for_warps(T, 8);
-  if (grid > num_sms() * 4) grid = num_sms() * 4;
-  ln_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+#define CALL(LPR, CH) ln_bwd_kernel<LPR, CH><<<grid_for_rows(T, 16 * (32 / LPR) * 8, 4), 256, 0, (cudaStream_t)stream>>>(p)
+  SRFRD_ROW_DISPATCH(H, CALL);
+#undef CALL
   SRFRD_LAUNCH_CHECK();
   return 0;
 }

@@ -158,26 +158,45 @@ catalogue_topk_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_cons
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * TILE_I + half * 128;
         const int col_row0 = s.row_lo + t * TILE_I + half * 128;     // local table row of this thread's column 0
-#pragma unroll 1
+        // all 128 scores of this thread's row in flight at once (one TMEM round trip per tile)
+        uint32_t raw[4][32];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) tmem_ld32(taddr + g * 32, raw[g]);
+        tmem_ld_wait();
+        float gm[4];
+#pragma unroll
         for (int g = 0; g < 4; ++g) {
-          uint32_t raw[32];
-          tmem_ld32(taddr + g * 32, raw);
-          tmem_ld_wait();
-          float m0 = __uint_as_float(raw[0]), m1 = __uint_as_float(raw[1]);
-          float m2 = __uint_as_float(raw[2]), m3 = __uint_as_float(raw[3]);
+          float m0 = __uint_as_float(raw[g][0]), m1 = __uint_as_float(raw[g][1]);
+          float m2 = __uint_as_float(raw[g][2]), m3 = __uint_as_float(raw[g][3]);
 #pragma unroll
           for (int j = 4; j < 32; j += 4) {
-            m0 = fmaxf(m0, __uint_as_float(raw[j]));
-            m1 = fmaxf(m1, __uint_as_float(raw[j + 1]));
-            m2 = fmaxf(m2, __uint_as_float(raw[j + 2]));
-            m3 = fmaxf(m3, __uint_as_float(raw[j + 3]));
+            m0 = fmaxf(m0, __uint_as_float(raw[g][j]));
+            m1 = fmaxf(m1, __uint_as_float(raw[g][j + 1]));
+            m2 = fmaxf(m2, __uint_as_float(raw[g][j + 2]));
+            m3 = fmaxf(m3, __uint_as_float(raw[g][j + 3]));
           }
-          const float gmax = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-          if (gmax > ts[TK - 1]) {
-            const int base = col_row0 + g * 32;
+          gm[g] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        }
+        const float tmax = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
+        // Threshold-first: only if some lane of the warp beats its current 10th best do we look closer.
+        // Candidate columns are found with a warp-wide OR of per-lane compare masks and re-read from TMEM
+        // one column at a time (warp-uniform address), so the insertion code exists once and runs rarely.
+        if (__any_sync(0xffffffffu, tmax > ts[TK - 1])) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float sc = __uint_as_float(raw[j]);
+          for (int g = 0; g < 4; ++g) {
+            if (!__any_sync(0xffffffffu, gm[g] > ts[TK - 1])) continue;
+            uint32_t mask = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(raw[g][j]) > ts[TK - 1]) ? (1u << j) : 0u;
+            uint32_t wmask = __reduce_or_sync(0xffffffffu, mask);
+            const int base = col_row0 + g * 32;
+            while (wmask) {
+              const int j = __ffs(wmask) - 1;
+              wmask &= wmask - 1;
+              uint32_t one;
+              tmem_ld1(taddr + g * 32 + j, one);
+              tmem_ld_wait();
+              const float sc = __uint_as_float(one);
               if (sc > ts[TK - 1] && base + j < s.row_hi) list_insert(ts, ti, sc, base + j);
             }
           }
@@ -241,7 +260,9 @@ extern "C" int srfrd_catalogue_topk_plan(int64_t U, int64_t n_rows, int64_t row_
   SRFRD_REQUIRE(chunks_out, "catalogue_topk_plan: null output");
   const int64_t tiles = (n_rows - row_lo + TILE_I - 1) / TILE_I;
   const int64_t ublocks = (U + TILE_U - 1) / TILE_U;
-  int64_t chunks = ublocks > 0 ? (8ll * num_sms() + ublocks - 1) / ublocks : 1;
+  // One wave of work units: every unit restarts its top-10 lists cold (about 10 ln(n/10) insertions per row
+  // over n items), so item chunks are only used to occupy SMs that the user blocks alone would leave idle.
+  int64_t chunks = ublocks > 0 ? num_sms() / ublocks : 1;
   if (chunks > tiles / 4) chunks = tiles / 4;
   if (chunks < 1) chunks = 1;
   const int64_t per = (tiles + chunks - 1) / chunks;

@@ -77,8 +77,9 @@ def test_autograd_gradients_match_reference_golden(name, kind):
         err = float((got - ref).abs().max())
         cos = float(torch.dot(got.flatten(), ref.flatten()) / (got.norm() * ref.norm() + 1e-30))
         # 6-sequence batches: no averaging of the bf16 activation-gradient rounding noise.  Direction must
-        # agree to 1 % (cos >= 0.99); the worst single element within 15 % of the tensor's largest gradient.
-        assert cos >= 0.99 and err <= 0.15 * scale + 1e-5, f"{k}: cos {cos:.4f}, max err {err:.3e} vs scale {scale:.3e}"
+        # agree to 1 % (cos >= 0.99); the worst single element within 25 % of the tensor's largest gradient
+        # (test_gradients_match_oracle_at_scale below is the tight check, where the noise averages out).
+        assert cos >= 0.99 and err <= 0.25 * scale + 1e-5, f"{k}: cos {cos:.4f}, max err {err:.3e} vs scale {scale:.3e}"
 
 
 @pytest.mark.parametrize("name,kind", CASES)
@@ -201,6 +202,44 @@ def test_training_vs_oracle_beauty_shaped_with_discriminator_weights():
         w = discriminator_weights(cb["pos"], cb["p_fake"], policy)
         loss = float(tr.step(cb, w_pos=w if policy != "none" else None))
         assert abs(loss - ref_loss) < 5e-3, f"step {step}: {loss} vs oracle {ref_loss}"
+
+
+@pytest.mark.parametrize("kind", ["SRFR", "SRFRN", "SASRec", "SRFU_F"])
+def test_gradients_match_oracle_at_scale(kind):
+    """256 Beauty-shaped sequences (L=50, D=64): every parameter gradient vs the fp32 oracle's autograd.
+    bf16 activations -> relative L2 error <= 3 % and cosine >= 0.999 per tensor."""
+    from oracle import srfrd_oracle as O
+    from srfrd_b200 import SRFR_model as M
+    data, batch = _c2_like(B=256)
+    torch.manual_seed(3)
+    N = data.itemnum
+    m = {"SRFR": lambda: M.SRFR(N, 50, 64, 16, 0.0, 2, 1, "cuda"), "SRFRN": lambda: M.SRFRN(N, 50, 64, 16, 0.0, 2, 1, "cuda"),
+         "SASRec": lambda: M.SASRec(N, 50, 64, 0.0, 2, 2, "cuda"), "SRFU_F": lambda: M.SRFU_F(N, 50, 64, 51, 0.0, 2, 1, "cuda")}[kind]()
+    for _, p in m.named_parameters():
+        if p.dim() >= 2:
+            torch.nn.init.xavier_normal_(p.data)
+        else:
+            p.data.add_(0.1 * torch.randn_like(p))
+    m = m.to("cuda").train()
+    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    tb = {k: torch.from_numpy(v) for k, v in batch.items()}
+    heads = 2 if kind == "SASRec" else 1
+    ref_loss, ref = O.OracleTrainer(sd, kind, heads).grads(tb)
+    cb = {k: v.cuda() for k, v in tb.items()}
+    h, zp, zn = m(None, cb["seq"], cb["rsq"], cb["pos"], cb["prs"], cb["neg"], cb["nrs"])
+    idx = torch.where(cb["pos"] != 0)
+    crit = torch.nn.BCEWithLogitsLoss()
+    loss = crit(zp[idx], torch.ones_like(zp[idx])) + crit(zn[idx], torch.zeros_like(zn[idx]))
+    loss.backward()
+    assert abs(float(loss) - ref_loss) < 5e-3
+    for k, p in m.named_parameters():
+        g, r = p.grad.cpu().flatten(), ref[k].flatten()
+        if k.endswith("in_proj_bias"):
+            H = r.numel() // 3
+            g, r = torch.cat([g[:H], g[2 * H:]]), torch.cat([r[:H], r[2 * H:]])
+        rel = float((g - r).norm() / (r.norm() + 1e-30))
+        cos = float(torch.dot(g, r) / (g.norm() * r.norm() + 1e-30))
+        assert rel <= 0.03 and cos >= 0.999, f"{k}: rel L2 err {rel:.4f}, cos {cos:.5f}"
 
 
 def test_full_catalogue_metrics_match_oracle():
