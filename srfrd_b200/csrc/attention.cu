@@ -246,13 +246,10 @@ static int fill_common(AttnParams& p, int L, int H, int heads, float drop_p, uin
   return 0;
 }
 
-}  // namespace srfrd
-
-using namespace srfrd;
-
-extern "C" int srfrd_attention_fwd(const void* q, int ldq, const void* k, const void* v, int ldkv, void* o, int ldo,
-                                   int64_t B, int L, int H, int heads, float drop_p, uint64_t seed,
-                                   uint32_t stream_id, const float* drop_step, void* stream) {
+// SIMT path: shapes the tcgen05 kernels (attention_tc.cu) do not cover -- maxlen > 128 or head_dim % 16 != 0.
+int attn_fwd_simt(const void* q, int ldq, const void* k, const void* v, int ldkv, void* o, int ldo, int64_t B, int L,
+                  int H, int heads, float drop_p, uint64_t seed, uint32_t stream_id, const float* drop_step,
+                  void* stream) {
   SRFRD_REQUIRE(q && k && v && o, "attention_fwd: null pointer");
   SRFRD_REQUIRE(ldq % 2 == 0 && ldkv % 2 == 0 && ldo % 2 == 0, "attention_fwd: leading dims must be even");
   if (B == 0 || L == 0) return 0;
@@ -272,10 +269,9 @@ extern "C" int srfrd_attention_fwd(const void* q, int ldq, const void* k, const 
   return 0;
 }
 
-extern "C" int srfrd_attention_bwd(const void* dout, int lddo, const void* q, int ldq, const void* k, const void* v,
-                                   int ldkv, void* dq, int lddq, void* dk, void* dv, int lddkv, int64_t B, int L,
-                                   int H, int heads, float drop_p, uint64_t seed, uint32_t stream_id,
-                                   const float* drop_step, void* stream) {
+int attn_bwd_simt(const void* dout, int lddo, const void* q, int ldq, const void* k, const void* v, int ldkv, void* dq,
+                  int lddq, void* dk, void* dv, int lddkv, int64_t B, int L, int H, int heads, float drop_p,
+                  uint64_t seed, uint32_t stream_id, const float* drop_step, void* stream) {
   SRFRD_REQUIRE(dout && q && k && v && dq && dk && dv, "attention_bwd: null pointer");
   SRFRD_REQUIRE(lddo % 2 == 0 && ldq % 2 == 0 && ldkv % 2 == 0 && lddq % 2 == 0 && lddkv % 2 == 0,
                 "attention_bwd: leading dims must be even");
@@ -296,3 +292,5 @@ extern "C" int srfrd_attention_bwd(const void* dout, int lddo, const void* q, in
   SRFRD_LAUNCH_CHECK();
   return 0;
 }
+
+}  // namespace srfrd

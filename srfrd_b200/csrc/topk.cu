@@ -166,16 +166,15 @@ catalogue_topk_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_cons
         float gm[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          float m0 = __uint_as_float(raw[g][0]), m1 = __uint_as_float(raw[g][1]);
-          float m2 = __uint_as_float(raw[g][2]), m3 = __uint_as_float(raw[g][3]);
+          // FMNMX3: two scores folded per ALU instruction (the half-rate ALU pipe is the epilogue's limiter)
+          float m0 = fmax3(__uint_as_float(raw[g][0]), __uint_as_float(raw[g][1]), __uint_as_float(raw[g][2]));
+          float m1 = fmax3(__uint_as_float(raw[g][3]), __uint_as_float(raw[g][4]), __uint_as_float(raw[g][5]));
 #pragma unroll
-          for (int j = 4; j < 32; j += 4) {
-            m0 = fmaxf(m0, __uint_as_float(raw[g][j]));
-            m1 = fmaxf(m1, __uint_as_float(raw[g][j + 1]));
-            m2 = fmaxf(m2, __uint_as_float(raw[g][j + 2]));
-            m3 = fmaxf(m3, __uint_as_float(raw[g][j + 3]));
+          for (int j = 6; j < 30; j += 4) {
+            m0 = fmax3(m0, __uint_as_float(raw[g][j]), __uint_as_float(raw[g][j + 1]));
+            m1 = fmax3(m1, __uint_as_float(raw[g][j + 2]), __uint_as_float(raw[g][j + 3]));
           }
-          gm[g] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+          gm[g] = fmax3(fmaxf(m0, m1), __uint_as_float(raw[g][30]), __uint_as_float(raw[g][31]));
         }
         const float tmax = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
         // Threshold-first: only if some lane of the warp beats its current 10th best do we look closer.

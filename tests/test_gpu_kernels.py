@@ -169,7 +169,8 @@ def _attn_ref(q, k, v, heads):
 
 
 @pytest.mark.parametrize("B,L,H,heads", [(3, 12, 32, 1), (5, 50, 80, 1), (2, 50, 80, 2), (2, 200, 272, 1), (4, 7, 16, 4),
-                                         (64, 50, 64, 1)])
+                                         (64, 50, 64, 1), (7, 50, 64, 2), (3, 128, 64, 1), (5, 100, 128, 1),
+                                         (300, 50, 80, 1), (9, 33, 96, 3)])
 def test_attention_fwd_bwd(ops, B, L, H, heads):
     T = B * L
     q, kv = rnd((T, H), 30, 0.7, bf16), rnd((T, 2 * H), 31, 0.7, bf16)
