@@ -3,11 +3,13 @@
 // (SURVEY.md rows A9/A10 + full-catalogue extension: == predict(..., label = arange(1, N+1)) + stable top-k
 //  with the tie-break (score desc, item id asc).)
 //
-// Tile = 128 users (TMEM lanes) x 256 items (TMEM columns); the user tile stays in smem for a whole
-// work unit (user block x item chunk) while item tiles stream through a TMA ring; accumulators are
-// double-buffered in TMEM so the tensor pipe runs ahead of the scan.  Each epilogue thread owns one
-// user row x 128 columns and keeps that row's running top-10 in registers: a group max over 32 scores
-// is compared with the current 10th best first, so the insertion path is rare after warm-up.
+// A work unit is (256 users) x (a chunk of the item rows).  The two 128-user tiles (TMEM lanes) stay in smem
+// for the whole unit while 128-item tiles stream through a TMA ring and are multiplied against BOTH user
+// tiles, which halves the L2 -> SM traffic per score (with one user tile per CTA the kernel was L2-bound at
+// ~5 TB/s: every CTA streams the whole table).  Accumulators (2 user tiles x 128 columns) are double-buffered
+// in TMEM so the tensor pipe runs ahead of the scan.  Each epilogue thread owns one user row x 128 columns
+// and keeps that row's running top-10 in registers: group maxima are compared with the current 10th best
+// first, so the insertion path is rare after warm-up.
 // n_split = 2/3 feeds hi/lo bf16 splits of the fp32 user features as extra K (near-fp32 scores).
 #include <math.h>
 
@@ -17,12 +19,15 @@
 namespace srfrd {
 
 static constexpr int TK = 10;               // list length kept per row
-static constexpr int TILE_U = 128;
-static constexpr int TILE_I = 256;
+static constexpr int TILE_U = 128;          // users per MMA (TMEM lanes)
+static constexpr int UBS = 2;               // user blocks per work unit: each item tile is reused for 256 users
+static constexpr int GROUP_U = TILE_U * UBS;
+static constexpr int TILE_I = 128;          // items per tile (TMEM columns per user block)
 static constexpr int KB = 64;               // k-block (bf16 elements)
-static constexpr int TOPK_THREADS = 320;    // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+static constexpr int TOPK_THREADS = 320;    // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (4 per user block)
 static constexpr int A_TILE_BYTES = TILE_U * KB * 2;   // 16 KB
-static constexpr int B_TILE_BYTES = TILE_I * KB * 2;   // 32 KB
+static constexpr int B_TILE_BYTES = TILE_I * KB * 2;   // 16 KB
+static constexpr int ACC_STRIDE = UBS * TILE_I;        // TMEM columns per accumulator stage (256)
 
 struct TopkShape {
   int U, D;
@@ -32,10 +37,10 @@ struct TopkShape {
   int64_t id_base;        // global item id of local row 0
   int kblocks;            // ceil(D / 64)
   int tiles_total;        // item tiles over [row_lo, row_hi)
-  int chunks, tiles_per_chunk, ublocks;
+  int chunks, tiles_per_chunk, ugroups;
   int stages;
-  float* out_scores;      // (U, chunks*2, TK)
-  int* out_ids;           // (U, chunks*2, TK)  global ids (int32), -1 = empty
+  float* out_scores;      // (U, chunks, TK)
+  int* out_ids;           // (U, chunks, TK)  global ids (int32), -1 = empty
 };
 
 __device__ __forceinline__ void list_insert(float (&ts)[TK], int (&ti)[TK], float s, int id) {
@@ -53,8 +58,9 @@ __global__ void __launch_bounds__(TOPK_THREADS, 1)
 catalogue_topk_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmE, TopkShape s) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int a_bytes = s.n_split * s.kblocks * A_TILE_BYTES;
-  uint8_t* smA = smem;
+  const int a_tiles = UBS * s.n_split * s.kblocks;
+  const int a_bytes = a_tiles * A_TILE_BYTES;
+  uint8_t* smA = smem;                                  // [ub][split][kblock] tiles of 128 users x 64 features
   uint8_t* smB = smem + a_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smB + s.stages * B_TILE_BYTES);
   uint64_t* full = bars;
@@ -66,7 +72,7 @@ catalogue_topk_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_units = s.ublocks * s.chunks;
+  const int n_units = s.ugroups * s.chunks;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmF);
@@ -87,14 +93,15 @@ catalogue_topk_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_cons
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0, uphase = 0;
       for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-        const int ub = unit / s.chunks, ch = unit % s.chunks;
+        const int ug = unit / s.chunks, ch = unit % s.chunks;
         const int t0 = ch * s.tiles_per_chunk, t1 = min(s.tiles_total, t0 + s.tiles_per_chunk);
-        mbar_wait(aempty, uphase ^ 1);                    // previous unit's MMAs no longer read the user tile
+        mbar_wait(aempty, uphase ^ 1);                    // previous unit's MMAs no longer read the user tiles
         mbar_expect_tx(afull, a_bytes);
-        for (int sp = 0; sp < s.n_split; ++sp)
-          for (int kb = 0; kb < s.kblocks; ++kb)
-            tma_load_2d(smA + (sp * s.kblocks + kb) * A_TILE_BYTES, &tmF, afull, kb * KB,
-                        sp * s.u_pad + ub * TILE_U, SRFRD_EVICT_LAST);
+        for (int ub = 0; ub < UBS; ++ub)
+          for (int sp = 0; sp < s.n_split; ++sp)
+            for (int kb = 0; kb < s.kblocks; ++kb)
+              tma_load_2d(smA + ((ub * s.n_split + sp) * s.kblocks + kb) * A_TILE_BYTES, &tmF, afull, kb * KB,
+                          sp * s.u_pad + ug * GROUP_U + ub * TILE_U, SRFRD_EVICT_LAST);
         uphase ^= 1;
         for (int t = t0; t < t1; ++t) {
           for (int kb = 0; kb < s.kblocks; ++kb) {
@@ -121,18 +128,19 @@ catalogue_topk_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_cons
         for (int t = t0; t < t1; ++t) {
           mbar_wait(&tempty[as], aphase ^ 1);
           tc_fence_after();
-          const uint32_t tacc = tmem_base + as * TILE_I;
+          const uint32_t tacc = tmem_base + as * ACC_STRIDE;
           for (int kb = 0; kb < s.kblocks; ++kb) {
             mbar_wait(&full[stage], phase);
             tc_fence_after();
             const uint32_t b0 = smem_u32(smB + stage * B_TILE_BYTES);
             const int ksteps = min(KB / 16, (s.D - kb * KB + 15) / 16);
-            for (int sp = 0; sp < s.n_split; ++sp) {
-              const uint32_t a0 = smem_u32(smA + (sp * s.kblocks + kb) * A_TILE_BYTES);
-              for (int k = 0; k < ksteps; ++k)
-                umma_bf16(tacc, umma_smem_desc(a0 + k * 32, 0, 1024), umma_smem_desc(b0 + k * 32, 0, 1024), idesc,
-                          (kb | sp | k) != 0);
-            }
+            for (int ub = 0; ub < UBS; ++ub)               // the item tile is read from smem once per user block
+              for (int sp = 0; sp < s.n_split; ++sp) {
+                const uint32_t a0 = smem_u32(smA + ((ub * s.n_split + sp) * s.kblocks + kb) * A_TILE_BYTES);
+                for (int k = 0; k < ksteps; ++k)
+                  umma_bf16(tacc + ub * TILE_I, umma_smem_desc(a0 + k * 32, 0, 1024),
+                            umma_smem_desc(b0 + k * 32, 0, 1024), idesc, (kb | sp | k) != 0);
+              }
             umma_commit(&empty[stage]);
             if (++stage == s.stages) { stage = 0; phase ^= 1; }
           }
@@ -144,20 +152,20 @@ catalogue_topk_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_cons
     }
   } else {
     const int e = warp - 2;
-    const int quarter = warp & 3, half = e >> 2;
+    const int quarter = warp & 3, ub = e >> 2;
     int as = 0; uint32_t aphase = 0;
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-      const int ub = unit / s.chunks, ch = unit % s.chunks;
+      const int ug = unit / s.chunks, ch = unit % s.chunks;
       const int t0 = ch * s.tiles_per_chunk, t1 = min(s.tiles_total, t0 + s.tiles_per_chunk);
-      const int urow = ub * TILE_U + quarter * 32 + lane;
+      const int urow = ug * GROUP_U + ub * TILE_U + quarter * 32 + lane;
       float ts[TK]; int ti[TK];
 #pragma unroll
       for (int r = 0; r < TK; ++r) { ts[r] = -INFINITY; ti[r] = -1; }
       for (int t = t0; t < t1; ++t) {
         mbar_wait(&tfull[as], aphase);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * TILE_I + half * 128;
-        const int col_row0 = s.row_lo + t * TILE_I + half * 128;     // local table row of this thread's column 0
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * ACC_STRIDE + ub * TILE_I;
+        const int col_row0 = s.row_lo + t * TILE_I;                  // local table row of column 0
         // all 128 scores of this thread's row in flight at once (one TMEM round trip per tile)
         uint32_t raw[4][32];
 #pragma unroll
@@ -166,7 +174,7 @@ catalogue_topk_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_cons
         float gm[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          // FMNMX3: two scores folded per ALU instruction (the half-rate ALU pipe is the epilogue's limiter)
+          // FMNMX3: two scores folded per ALU instruction
           float m0 = fmax3(__uint_as_float(raw[g][0]), __uint_as_float(raw[g][1]), __uint_as_float(raw[g][2]));
           float m1 = fmax3(__uint_as_float(raw[g][3]), __uint_as_float(raw[g][4]), __uint_as_float(raw[g][5]));
 #pragma unroll
@@ -206,7 +214,7 @@ catalogue_topk_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_cons
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
       if (urow < s.U) {
-        const size_t o = ((size_t)urow * (s.chunks * 2) + ch * 2 + half) * TK;
+        const size_t o = ((size_t)urow * s.chunks + ch) * TK;
 #pragma unroll
         for (int r = 0; r < TK; ++r) {
           s.out_scores[o + r] = ts[r];
@@ -258,7 +266,7 @@ using namespace srfrd;
 extern "C" int srfrd_catalogue_topk_plan(int64_t U, int64_t n_rows, int64_t row_lo, int* chunks_out) {
   SRFRD_REQUIRE(chunks_out, "catalogue_topk_plan: null output");
   const int64_t tiles = (n_rows - row_lo + TILE_I - 1) / TILE_I;
-  const int64_t ublocks = (U + TILE_U - 1) / TILE_U;
+  const int64_t ublocks = (U + GROUP_U - 1) / GROUP_U;
   // One wave of work units: every unit restarts its top-10 lists cold (about 10 ln(n/10) insertions per row
   // over n items), so item chunks are only used to occupy SMs that the user blocks alone would leave idle.
   int64_t chunks = ublocks > 0 ? num_sms() / ublocks : 1;
@@ -288,11 +296,11 @@ extern "C" int srfrd_catalogue_topk(const void* feats_bf16, int64_t U, int64_t u
   s.tiles_total = (int)((n_rows - row_lo + TILE_I - 1) / TILE_I);
   s.chunks = chunks;
   s.tiles_per_chunk = (s.tiles_total + chunks - 1) / chunks;
-  s.ublocks = (int)((U + TILE_U - 1) / TILE_U);
-  const int a_bytes = n_split * s.kblocks * A_TILE_BYTES;
+  s.ugroups = (int)((U + GROUP_U - 1) / GROUP_U);
+  const int a_bytes = UBS * n_split * s.kblocks * A_TILE_BYTES;
   s.stages = (int)((210 * 1024 - a_bytes) / B_TILE_BYTES);
   SRFRD_REQUIRE(s.stages >= 2, "catalogue_topk: D=%d with n_split=%d does not fit shared memory", D, n_split);
-  if (s.stages > 6) s.stages = 6;
+  if (s.stages > 8) s.stages = 8;
   s.out_scores = part_scores; s.out_ids = part_ids;
   const size_t smem = (size_t)a_bytes + (size_t)s.stages * B_TILE_BYTES + 1024 + 256;
   CUtensorMap tmF, tmE;
@@ -303,7 +311,7 @@ extern "C" int srfrd_catalogue_topk(const void* feats_bf16, int64_t U, int64_t u
     SRFRD_CUDA(cudaFuncSetAttribute(catalogue_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  int grid = s.ublocks * s.chunks;
+  int grid = s.ugroups * s.chunks;
   if (grid > num_sms()) grid = num_sms();
   catalogue_topk_kernel<<<grid, TOPK_THREADS, smem, stream>>>(tmF, tmE, s);
   SRFRD_LAUNCH_CHECK();

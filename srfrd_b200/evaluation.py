@@ -60,12 +60,12 @@ def local_topk(feats_f32: torch.Tensor, index: CatalogueIndex, n_split: int = 1)
     if index.n_rows <= index.row_lo:                      # empty shard
         return (torch.full((U, TK), float("-inf"), device=dev), torch.full((U, TK), -1, dtype=torch.int64, device=dev))
     chunks = ops.catalogue_topk_plan(U, index.n_rows, index.row_lo)
-    ps = torch.empty(U, chunks * 2, TK, dtype=torch.float32, device=dev)
-    pi = torch.empty(U, chunks * 2, TK, dtype=torch.int32, device=dev)
+    ps = torch.empty(U, chunks, TK, dtype=torch.float32, device=dev)
+    pi = torch.empty(U, chunks, TK, dtype=torch.int32, device=dev)
     ops.catalogue_topk(fb, U, u_pad, n_split, index.table, index.row_lo, index.id_base, chunks, ps, pi)
     out_s = torch.empty(U, TK, dtype=torch.float32, device=dev)
     out_i = torch.empty(U, TK, dtype=torch.int64, device=dev)
-    ops.merge_topk(ps, pi, U, chunks * 2, TK, out_s, out_i)
+    ops.merge_topk(ps, pi, U, chunks, TK, out_s, out_i)
     return out_s, out_i
 
 
