@@ -170,7 +170,7 @@ SRFRD_API int srfrd_adam_step(float* p, float* g, float* m, float* v, int64_t n,
  * feats: bf16 (n_split stacked blocks of u_pad rows, D); table: bf16 (n_rows, D); candidates are local
  * rows [row_lo, n_rows) with global id = id_base + row.  Writes (U, chunks, 10) partial lists that
  * srfrd_merge_topk reduces (also used for the cross-GPU all-gather merge). */
-SRFRD_API int srfrd_catalogue_topk_plan(int64_t U, int64_t n_rows, int64_t row_lo, int* chunks_out);
+SRFRD_API int srfrd_catalogue_topk_plan(int64_t U, int64_t n_rows, int64_t row_lo, int D, int n_split, int* chunks_out);
 SRFRD_API int srfrd_catalogue_topk(const void* feats_bf16, int64_t U, int64_t u_pad, int n_split, const void* table_bf16,
                          int64_t n_rows, int64_t row_lo, int64_t id_base, int D, int ld_feats, int ld_table,
                          int chunks, float* part_scores, int* part_ids, void* stream);

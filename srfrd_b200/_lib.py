@@ -53,7 +53,7 @@ SIGNATURES = {
     "srfrd_loss_finalize": [vp, vp, vp, vp],
     "srfrd_adam_tick": [vp, f32, f32, vp],
     "srfrd_adam_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, i32, vp],
-    "srfrd_catalogue_topk_plan": [i64, i64, i64, C.POINTER(i32)],
+    "srfrd_catalogue_topk_plan": [i64, i64, i64, i32, i32, C.POINTER(i32)],
     "srfrd_catalogue_topk": [vp, i64, i64, i32, vp, i64, i64, i64, i32, i32, i32, i32, vp, vp, vp],
     "srfrd_merge_topk": [vp, vp, i64, i32, i32, vp, vp, vp],
 }

@@ -149,49 +149,59 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tO = tmem_base + 128;
 
+  // warps 0 / 1 stay converged; issuing instructions sit under elect.sync (uniform-register operands)
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t ph = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ph ^= 1) {
-        const int tile = it / p.heads, h = it % p.heads;
-        const int row0 = tile * p.spt * p.L, col0 = h * p.hd;
-        mbar_wait(qk_empty, ph ^ 1);
+    uint32_t ph = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ph ^= 1) {
+      const int tile = it / p.heads, h = it % p.heads;
+      const int row0 = tile * p.spt * p.L, col0 = h * p.hd;
+      mbar_wait(qk_empty, ph ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(qk_full, 2 * opbytes);
         for (int kb = 0; kb < p.kblocks; ++kb) {
           tma_load_2d(Qs + kb * OPB, &tmQ, qk_full, col0 + kb * 64, row0, SRFRD_EVICT_FIRST);
           tma_load_2d(Ks + kb * OPB, &tmK, qk_full, col0 + kb * 64, row0, SRFRD_EVICT_FIRST);
         }
-        mbar_wait(v_empty, ph ^ 1);
+      }
+      __syncwarp();
+      mbar_wait(v_empty, ph ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(v_full, opbytes);
         for (int kb = 0; kb < p.kblocks; ++kb)
           tma_load_2d(Vs + kb * OPB, &tmV, v_full, col0 + kb * 64, row0, SRFRD_EVICT_FIRST);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idS = umma_idesc_bf16(TILE, TILE, 0, 0);
-      const uint32_t idO = umma_idesc_bf16(TILE, p.hd, 0, 1);
-      uint32_t ph = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ph ^= 1) {
-        mbar_wait(qk_full, ph);
-        tc_fence_after();
+    const uint32_t idS = umma_idesc_bf16(TILE, TILE, 0, 0);
+    const uint32_t idO = umma_idesc_bf16(TILE, p.hd, 0, 1);
+    const uint64_t dQ = umma_smem_desc(smem_u32(Qs), 0, 1024), dK = umma_smem_desc(smem_u32(Ks), 0, 1024);
+    const uint64_t dP = umma_smem_desc(smem_u32(Ps), 0, 1024), dV = umma_smem_desc(smem_u32(Vs), OPB, 1024);
+    uint32_t ph = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ph ^= 1) {
+      mbar_wait(qk_full, ph);
+      tc_fence_after();
+      if (elect_one()) {
         for (int kb = 0; kb < p.kblocks; ++kb) {
           const int ksteps = min(4, (p.hd - kb * 64) / 16);
           for (int k = 0; k < ksteps; ++k)
-            umma_bf16(tS, umma_smem_desc(smem_u32(Qs + kb * OPB) + k * 32, 0, 1024),
-                      umma_smem_desc(smem_u32(Ks + kb * OPB) + k * 32, 0, 1024), idS, (kb | k) != 0);
+            umma_bf16(tS, dQ + (uint64_t)(kb * (OPB >> 4) + 2 * k), dK + (uint64_t)(kb * (OPB >> 4) + 2 * k), idS, (kb | k) != 0);
         }
         umma_commit(qk_empty);
         umma_commit(s_full);
-        mbar_wait(p_full, ph);
-        mbar_wait(v_full, ph);
-        tc_fence_after();
+      }
+      __syncwarp();
+      mbar_wait(p_full, ph);
+      mbar_wait(v_full, ph);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
         for (int ks = 0; ks < 8; ++ks)     // K = 128 keys; V tile read MN-major (rows = K): 16 rows = 2048 B
-          umma_bf16(tO, umma_smem_desc(smem_u32(Ps + (ks >> 2) * OPB) + (ks & 3) * 32, 0, 1024),
-                    umma_smem_desc(smem_u32(Vs) + ks * 2048, OPB, 1024), idO, ks != 0);
+          umma_bf16(tO, dP + (uint64_t)((ks >> 2) * (OPB >> 4) + (ks & 3) * 2), dV + (uint64_t)(ks * 128), idO, ks != 0);
         umma_commit(v_empty);
         umma_commit(o_full);
       }
+      __syncwarp();
     }
   } else {
     const int quarter = warp & 3;
@@ -276,12 +286,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDK = tmem_base, tDV = tmem_base + 128, tDQ = tmem_base + 256;
 
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t ph = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ph ^= 1) {
-        const int tile = it / p.heads, h = it % p.heads;
-        const int row0 = tile * p.spt * p.L, col0 = h * p.hd;
-        mbar_wait(in_empty, ph ^ 1);
+    uint32_t ph = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ph ^= 1) {
+      const int tile = it / p.heads, h = it % p.heads;
+      const int row0 = tile * p.spt * p.L, col0 = h * p.hd;
+      mbar_wait(in_empty, ph ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(in_full, 4 * opbytes);
         for (int kb = 0; kb < p.kblocks; ++kb) {
           tma_load_2d(Qs + kb * OPB, &tmQ, in_full, col0 + kb * 64, row0, SRFRD_EVICT_FIRST);
@@ -290,43 +300,51 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           tma_load_2d(Ds + kb * OPB, &tmDO, in_full, col0 + kb * 64, row0, SRFRD_EVICT_FIRST);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idKK = umma_idesc_bf16(TILE, TILE, 0, 0);      // S, dP : both operands K-major
-      const uint32_t idKM = umma_idesc_bf16(TILE, p.hd, 0, 1);      // dQ    : A = dS K-major, B = K MN-major
-      const uint32_t idMM = umma_idesc_bf16(TILE, p.hd, 1, 1);      // dK, dV: A = dS^T / P^T MN-major, B MN-major
-      uint32_t ph = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ph ^= 1) {
-        mbar_wait(in_full, ph);
-        mbar_wait(out_empty, ph ^ 1);          // the previous item's dK/dV (same TMEM columns as S/dP) were read out
-        tc_fence_after();
+    const uint32_t idKK = umma_idesc_bf16(TILE, TILE, 0, 0);      // S, dP : both operands K-major
+    const uint32_t idKM = umma_idesc_bf16(TILE, p.hd, 0, 1);      // dQ    : A = dS K-major, B = K MN-major
+    const uint32_t idMM = umma_idesc_bf16(TILE, p.hd, 1, 1);      // dK, dV: A = dS^T / P^T MN-major, B MN-major
+    // K-major views (+2 per 16-column K step, +OPB>>4 per 64-column block) and MN-major views (+128 per 16-row K step)
+    const uint64_t kQ = umma_smem_desc(smem_u32(Qs), 0, 1024), kK = umma_smem_desc(smem_u32(Ks), 0, 1024);
+    const uint64_t kV = umma_smem_desc(smem_u32(Vs), 0, 1024), kD = umma_smem_desc(smem_u32(Ds), 0, 1024);
+    const uint64_t kG = umma_smem_desc(smem_u32(Gs), 0, 1024);
+    const uint64_t mK = umma_smem_desc(smem_u32(Ks), OPB, 1024), mQ = umma_smem_desc(smem_u32(Qs), OPB, 1024);
+    const uint64_t mD = umma_smem_desc(smem_u32(Ds), OPB, 1024), mG = umma_smem_desc(smem_u32(Gs), OPB, 1024);
+    const uint64_t mP = umma_smem_desc(smem_u32(Ps), OPB, 1024);
+    uint32_t ph = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ph ^= 1) {
+      mbar_wait(in_full, ph);
+      mbar_wait(out_empty, ph ^ 1);          // the previous item's dK/dV (same TMEM columns as S/dP) were read out
+      tc_fence_after();
+      if (elect_one()) {
         for (int kb = 0; kb < p.kblocks; ++kb) {
           const int ksteps = min(4, (p.hd - kb * 64) / 16);
           for (int k = 0; k < ksteps; ++k) {
-            umma_bf16(tS, umma_smem_desc(smem_u32(Qs + kb * OPB) + k * 32, 0, 1024),
-                      umma_smem_desc(smem_u32(Ks + kb * OPB) + k * 32, 0, 1024), idKK, (kb | k) != 0);
-            umma_bf16(tDP, umma_smem_desc(smem_u32(Ds + kb * OPB) + k * 32, 0, 1024),
-                      umma_smem_desc(smem_u32(Vs + kb * OPB) + k * 32, 0, 1024), idKK, (kb | k) != 0);
+            const uint64_t o = (uint64_t)(kb * (OPB >> 4) + 2 * k);
+            umma_bf16(tS, kQ + o, kK + o, idKK, (kb | k) != 0);
+            umma_bf16(tDP, kD + o, kV + o, idKK, (kb | k) != 0);
           }
         }
         umma_commit(sdp_full);
-        mbar_wait(ds_full, ph);
-        tc_fence_after();
+      }
+      __syncwarp();
+      mbar_wait(ds_full, ph);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-          const uint32_t k_off = (ks >> 2) * OPB + (ks & 3) * 32;      // K-major A: key block, then 32 B per step
-          // dQ[i, :] += dS[i, keys] K[keys, :]
-          umma_bf16(tDQ, umma_smem_desc(smem_u32(Gs) + k_off, 0, 1024), umma_smem_desc(smem_u32(Ks) + ks * 2048, OPB, 1024),
-                    idKM, ks != 0);
-          // dK[j, :] += dS[rows, j]^T Q[rows, :]      dV[j, :] += P[rows, j]^T dO[rows, :]
-          umma_bf16(tDK, umma_smem_desc(smem_u32(Gs) + ks * 2048, OPB, 1024), umma_smem_desc(smem_u32(Qs) + ks * 2048, OPB, 1024),
-                    idMM, ks != 0);
-          umma_bf16(tDV, umma_smem_desc(smem_u32(Ps) + ks * 2048, OPB, 1024), umma_smem_desc(smem_u32(Ds) + ks * 2048, OPB, 1024),
-                    idMM, ks != 0);
+          const uint64_t ko = (uint64_t)((ks >> 2) * (OPB >> 4) + (ks & 3) * 2);   // K-major A: key block, 32 B per step
+          const uint64_t mo = (uint64_t)(ks * 128);                                // MN-major: 16 rows = 2048 B
+          umma_bf16(tDQ, kG + ko, mK + mo, idKM, ks != 0);      // dQ[i, :] += dS[i, keys] K[keys, :]
+          umma_bf16(tDK, mG + mo, mQ + mo, idMM, ks != 0);      // dK[j, :] += dS[rows, j]^T Q[rows, :]
+          umma_bf16(tDV, mP + mo, mD + mo, idMM, ks != 0);      // dV[j, :] += P[rows, j]^T dO[rows, :]
         }
         umma_commit(in_empty);
         umma_commit(out_full);
       }
+      __syncwarp();
     }
   } else {
     const int quarter = warp & 3;

@@ -98,6 +98,16 @@ __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint32_t stream, uin
 // ---------------------------------------------------------------------------------------------
 // mbarrier / TMA / tcgen05 PTX wrappers
 // ---------------------------------------------------------------------------------------------
+// one lane of a converged warp (warp-uniform control flow around the single-thread tcgen05 / TMA issue)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }

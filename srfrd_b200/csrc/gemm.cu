@@ -94,48 +94,51 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Warps 0 and 1 stay converged; only the issuing instructions are predicated on elect.sync so that barrier
+  // addresses and descriptors live in uniform registers (see topk.cu for the measurement behind this).
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int m0 = (t / s.n_tiles) * BLOCK_M, n0 = (t % s.n_tiles) * s.block_n;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
+    int stage = 0; uint32_t phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int m0 = (t / s.n_tiles) * BLOCK_M, n0 = (t % s.n_tiles) * s.block_n;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(&full[stage], A_STAGE_BYTES + b_stage_bytes);
           tma_load_2d(smA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BLOCK_K, m0, SRFRD_EVICT_FIRST);
           tma_load_2d(smB + stage * b_stage_bytes, &tmB, &full[stage], kb * BLOCK_K, n0, SRFRD_EVICT_LAST);
-          if (++stage == s.stages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == s.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      int as = 0; uint32_t aphase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int n0 = (t % s.n_tiles) * s.block_n;
-        int bn = min(s.block_n, s.N - n0);
-        bn = (bn + 15) & ~15;
-        const uint32_t idesc = umma_idesc_bf16(BLOCK_M, bn, 0, 0);
-        mbar_wait(&tempty[as], aphase ^ 1);
+    int stage = 0; uint32_t phase = 0;
+    int as = 0; uint32_t aphase = 0;
+    const uint64_t adesc0 = umma_smem_desc(smem_u32(smA), 0, 1024), bdesc0 = umma_smem_desc(smem_u32(smB), 0, 1024);
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int n0 = (t % s.n_tiles) * s.block_n;
+      int bn = min(s.block_n, s.N - n0);
+      bn = (bn + 15) & ~15;
+      const uint32_t idesc = umma_idesc_bf16(BLOCK_M, bn, 0, 0);
+      mbar_wait(&tempty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + as * 256;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t tacc = tmem_base + as * 256;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t a0 = smem_u32(smA + stage * A_STAGE_BYTES), b0 = smem_u32(smB + stage * b_stage_bytes);
-          const int ksteps = min(BLOCK_K / 16, (s.K - kb * BLOCK_K + 15) / 16);
-          for (int k = 0; k < ksteps; ++k) {
-            // K-major SW128: 8-row groups are 1024 B apart (SBO); +32 B per UMMA_K=16 inside the swizzle row
-            umma_bf16(tacc, umma_smem_desc(a0 + k * 32, 0, 1024), umma_smem_desc(b0 + k * 32, 0, 1024), idesc,
-                      (kb | k) != 0);
-          }
+        // K-major SW128: 8-row groups are 1024 B apart (SBO); +32 B (= 2 in descriptor units) per UMMA_K = 16
+        const uint64_t ad = adesc0 + (uint64_t)(stage * (A_STAGE_BYTES >> 4));
+        const uint64_t bd = bdesc0 + (uint64_t)(stage * (b_stage_bytes >> 4));
+        const int ksteps = min(BLOCK_K / 16, (s.K - kb * BLOCK_K + 15) / 16);
+        if (elect_one()) {
+          for (int k = 0; k < ksteps; ++k) umma_bf16(tacc, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
           umma_commit(&empty[stage]);
           if (kb == kblocks - 1) umma_commit(&tfull[as]);
-          if (++stage == s.stages) { stage = 0; phase ^= 1; }
         }
-        if (++as == 2) { as = 0; aphase ^= 1; }
+        __syncwarp();
+        if (++stage == s.stages) { stage = 0; phase ^= 1; }
       }
+      if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else {
     const int quarter = warp & 3;
@@ -244,10 +247,10 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (nkb > 0) {
     if (warp == 0) {
-      if (lane == 0) {
-        int stage = 0; uint32_t phase = 0;
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(&full[stage], a_bytes + b_bytes);
           for (int a = 0; a < s.a_atoms; ++a)
             tma_load_2d(smA + stage * a_bytes + a * ATOM_BYTES, &tmA, &full[stage], m0 + a * 64, kb * BLOCK_K,
@@ -255,30 +258,32 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int b = 0; b < s.b_atoms; ++b)
             tma_load_2d(smB + stage * b_bytes + b * ATOM_BYTES, &tmB, &full[stage], n0 + b * 64, kb * BLOCK_K,
                         SRFRD_EVICT_FIRST);
-          if (++stage == s.stages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == s.stages) { stage = 0; phase ^= 1; }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        int bn = min(s.block_n, s.No - n0);
-        bn = (bn + 15) & ~15;
-        const uint32_t idesc = umma_idesc_bf16(BLOCK_M, bn, 1, 1);
-        int stage = 0; uint32_t phase = 0;
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t a0 = smem_u32(smA + stage * a_bytes), b0 = smem_u32(smB + stage * b_bytes);
+      int bn = min(s.block_n, s.No - n0);
+      bn = (bn + 15) & ~15;
+      const uint32_t idesc = umma_idesc_bf16(BLOCK_M, bn, 1, 1);
+      // MN-major SW128: 64-wide MN atoms are ATOM_BYTES apart (LBO); 8 k-rows = 1024 B (SBO);
+      // one UMMA_K = 16 k-rows = 2048 B (= 128 in descriptor units)
+      const uint64_t adesc0 = umma_smem_desc(smem_u32(smA), ATOM_BYTES, 1024);
+      const uint64_t bdesc0 = umma_smem_desc(smem_u32(smB), ATOM_BYTES, 1024);
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint64_t ad = adesc0 + (uint64_t)(stage * (a_bytes >> 4)), bd = bdesc0 + (uint64_t)(stage * (b_bytes >> 4));
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            // MN-major SW128: 64-wide MN atoms are ATOM_BYTES apart (LBO); 8 k-rows = 1024 B (SBO);
-            // one UMMA_K = 16 k-rows = 2048 B
-            umma_bf16(tmem_base, umma_smem_desc(a0 + k * 2048, ATOM_BYTES, 1024),
-                      umma_smem_desc(b0 + k * 2048, ATOM_BYTES, 1024), idesc, (kb > kb_begin) || (k > 0));
-          }
+          for (int k = 0; k < BLOCK_K / 16; ++k)
+            umma_bf16(tmem_base, ad + 128 * k, bd + 128 * k, idesc, (kb > kb_begin) || (k > 0));
           umma_commit(&empty[stage]);
           if (kb == kb_end - 1) umma_commit(tfull);
-          if (++stage == s.stages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == s.stages) { stage = 0; phase ^= 1; }
       }
     } else {
       const int quarter = warp & 3;

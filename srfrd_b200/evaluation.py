@@ -44,7 +44,7 @@ def local_topk(feats_f32: torch.Tensor, index: CatalogueIndex, n_split: int = 1)
     """Per-user top-10 of feats (U, D) against the local shard -> (scores (U,10) fp32, ids (U,10) int64)."""
     U, D = feats_f32.shape
     dev = feats_f32.device
-    u_pad = (U + 127) // 128 * 128
+    u_pad = (U + 383) // 384 * 384          # whole user groups (up to 3 tiles of 128) per split
     fb = torch.zeros(n_split * u_pad, D, dtype=bf16, device=dev)
     f = feats_f32.contiguous()
     if n_split == 1:
@@ -59,7 +59,7 @@ def local_topk(feats_f32: torch.Tensor, index: CatalogueIndex, n_split: int = 1)
         ops.f32_to_bf16_split(rest.contiguous(), fb[2 * u_pad:2 * u_pad + U], None)
     if index.n_rows <= index.row_lo:                      # empty shard
         return (torch.full((U, TK), float("-inf"), device=dev), torch.full((U, TK), -1, dtype=torch.int64, device=dev))
-    chunks = ops.catalogue_topk_plan(U, index.n_rows, index.row_lo)
+    chunks = ops.catalogue_topk_plan(U, index.n_rows, index.row_lo, D, n_split)
     ps = torch.empty(U, chunks, TK, dtype=torch.float32, device=dev)
     pi = torch.empty(U, chunks, TK, dtype=torch.int32, device=dev)
     ops.catalogue_topk(fb, U, u_pad, n_split, index.table, index.row_lo, index.id_base, chunks, ps, pi)

@@ -204,9 +204,9 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, state3, zero_grad=True):
          _p(state3), int(zero_grad), _stream())
 
 
-def catalogue_topk_plan(U, n_rows, row_lo) -> int:
+def catalogue_topk_plan(U, n_rows, row_lo, D, n_split) -> int:
     out = C.c_int(0)
-    call("srfrd_catalogue_topk_plan", U, n_rows, row_lo, C.byref(out))
+    call("srfrd_catalogue_topk_plan", U, n_rows, row_lo, D, n_split, C.byref(out))
     return out.value
 
 
