@@ -236,7 +236,7 @@ struct LnBwdParams {
 };
 
 template <int LPR, int CH>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdParams p) {
+__global__ void __launch_bounds__(256, 2) ln_bwd_kernel(LnBwdParams p) {
   __shared__ float sdw[MAXW], sdb[MAXW];
   constexpr int RPW = 32 / LPR, UN = 2;
   const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
