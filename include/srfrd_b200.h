@@ -96,9 +96,10 @@ typedef struct {
 /* C[M,N] = epilogue(A[M,K] . B[N,K]^T), A and B bf16 K-major. */
 SRFRD_API int srfrd_gemm_tn(const void* A_bf16, int lda, const void* B_bf16, int ldb, int M, int N, int K,
                   const srfrd_gemm_epilogue_t* ep, void* stream);
-/* dW[Mo,No] += sum_t dY[t,Mo] * X[t,No]  (fp32 atomics into dW; split over tokens). */
+/* dW[Mo,No] += sum_t dY[t,Mo] * X[t,No]  (fp32 atomics into dW; split over tokens).
+ * dbias (nullable): dbias[Mo] += sum_t dY[t,Mo], from one extra N=16 MMA per K step against an all-ones operand. */
 SRFRD_API int srfrd_gemm_wgrad(const void* dY_bf16, int lda, const void* X_bf16, int ldb, int64_t T, int Mo, int No,
-                     float* dW, int ldw, void* stream);
+                     float* dW, int ldw, float* dbias, void* stream);
 /* SIMT cross-check used by the GPU tests only. */
 SRFRD_API int srfrd_gemm_ref(const void* A, int lda, const void* B, int ldb, float* C, int ldc, int M, int N, int K,
                    int a_mn_major, int b_mn_major, void* stream);

@@ -209,6 +209,8 @@ struct WgradShape {
   int stages, k_splits;
   float* out;          // [Mo, ldw] fp32, accumulated with red.add
   int ldw;
+  float* dbias;        // [Mo] or null: column sums of dY, computed by one extra N=16 MMA per K step against a
+                       // constant all-ones operand (the bias gradient for free, no second pass over dY)
 };
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -224,9 +226,15 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* empty = bars + s.stages;
   uint64_t* tfull = bars + 2 * s.stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+  uint8_t* ones = smem + s.stages * (a_bytes + b_bytes) + 1024;      // 64 k-rows x 128 B of bf16 1.0 (after the barriers)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BLOCK_M, n0 = blockIdx.z * s.block_n;
+  const bool do_bias = s.dbias != nullptr && blockIdx.z == 0;
+  if (do_bias) {
+    for (int i = threadIdx.x; i < ATOM_BYTES / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
+    fence_proxy_async();
+  }
   const int kblocks_total = (s.T + BLOCK_K - 1) / BLOCK_K;
   const int per = (kblocks_total + s.k_splits - 1) / s.k_splits;
   const int kb_begin = blockIdx.x * per, kb_end = min(kblocks_total, kb_begin + per);
@@ -270,6 +278,8 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // one UMMA_K = 16 k-rows = 2048 B (= 128 in descriptor units)
       const uint64_t adesc0 = umma_smem_desc(smem_u32(smA), ATOM_BYTES, 1024);
       const uint64_t bdesc0 = umma_smem_desc(smem_u32(smB), ATOM_BYTES, 1024);
+      const uint64_t onesdesc = umma_smem_desc(smem_u32(ones), ATOM_BYTES, 1024);
+      const uint32_t idesc_ones = umma_idesc_bf16(BLOCK_M, 16, 1, 1);
       int stage = 0; uint32_t phase = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&full[stage], phase);
@@ -279,6 +289,11 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k)
             umma_bf16(tmem_base, ad + 128 * k, bd + 128 * k, idesc, (kb > kb_begin) || (k > 0));
+          if (do_bias) {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / 16; ++k)
+              umma_bf16(tmem_base + 240, ad + 128 * k, onesdesc + 128 * k, idesc_ones, (kb > kb_begin) || (k > 0));
+          }
           umma_commit(&empty[stage]);
           if (kb == kb_end - 1) umma_commit(tfull);
         }
@@ -302,6 +317,12 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int j = 0; j < 16; ++j)
             if (n0 + c + j < s.No) red_add_f32(o + j, __uint_as_float(raw[j]));
         }
+      }
+      if (do_bias) {                       // columns [240, 256) all hold sum_t dY[t, row]
+        uint32_t raw[16];
+        tmem_ld16(taddr + 240, raw);
+        tmem_ld_wait();
+        if (row < s.Mo) red_add_f32(s.dbias + row, __uint_as_float(raw[0]));
       }
     }
   }
@@ -383,7 +404,7 @@ extern "C" int srfrd_gemm_tn(const void* A, int lda, const void* B, int ldb, int
 }
 
 extern "C" int srfrd_gemm_wgrad(const void* dY, int lda, const void* X, int ldb, int64_t T, int Mo, int No,
-                                float* dW, int ldw, void* stream_) {
+                                float* dW, int ldw, float* dbias, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SRFRD_REQUIRE(dY && X && dW, "gemm_wgrad: null operand");
   SRFRD_REQUIRE(T > 0 && Mo > 0 && No > 0, "gemm_wgrad: empty shape");
@@ -396,15 +417,16 @@ extern "C" int srfrd_gemm_wgrad(const void* dY, int lda, const void* X, int ldb,
   s.a_atoms = 2;
   s.b_atoms = (s.block_n + 63) / 64;
   const int stage_bytes = (s.a_atoms + s.b_atoms) * BLOCK_K * 128;
-  s.stages = (200 * 1024) / stage_bytes;
+  s.stages = (190 * 1024) / stage_bytes;
   if (s.stages > 6) s.stages = 6;
   const int kblocks = (s.T + BLOCK_K - 1) / BLOCK_K;
   int splits = num_sms() / (n_tiles * m_tiles);
   if (splits < 1) splits = 1;
   if (splits > kblocks) splits = kblocks;
   s.k_splits = splits;
-  s.out = dW; s.ldw = ldw;
-  const size_t smem = (size_t)s.stages * stage_bytes + 1024 + 256;
+  s.out = dW; s.ldw = ldw; s.dbias = dbias;
+  SRFRD_REQUIRE(!dbias || s.block_n <= 240, "gemm_wgrad: fused bias gradient needs a column tile <= 240");
+  const size_t smem = (size_t)s.stages * stage_bytes + 1024 + 1024 + BLOCK_K * 128;
   CUtensorMap tmA, tmB;
   // MN-major: the TMA box is [64 tokens (rows), 64 features (cols)]
   if (int rc = make_tmap_bf16_2d(&tmA, dY, T, Mo, lda, BLOCK_K, 64)) return rc;

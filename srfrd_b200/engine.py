@@ -292,8 +292,7 @@ class HotPath:
             gc = ws["gc"][:T]
             ops.layernorm_bwd(dh, ws["c"][:T], ws["stF"][:T], P.view("last_layernorm.weight"), gc,
                               G("last_layernorm.weight"), G("last_layernorm.bias"))
-            ops.gemm_wgrad(gc, x[nb], GM("last_conv.weight"))
-            ops.colsum(gc, G("last_conv.bias"))
+            ops.gemm_wgrad(gc, x[nb], GM("last_conv.weight"), G("last_conv.bias"))
             ops.gemm_tn(gc, self.sh["wcT"], out_bf16=gA, row_ids=seq_flat)
         else:
             ops.layernorm_bwd(dh, x[nb], ws["stF"][:T], P.view("last_layernorm.weight"), gA,
@@ -307,29 +306,24 @@ class HotPath:
                 dz2 = ws["gE"][:T]
                 ops.dropout_apply(dz, dz2, H, p_drop, seed, 12 + 4 * i, step)
             # FFN: z = drop2(h1 W2^T + b2) + y ; h1 = relu(drop1(y W1^T + b1))
-            ops.gemm_wgrad(dz2, h1, GM(f"forward_layers.{i}.conv2.weight"))
-            ops.colsum(dz2, G(f"forward_layers.{i}.conv2.bias"))
+            ops.gemm_wgrad(dz2, h1, GM(f"forward_layers.{i}.conv2.weight"), G(f"forward_layers.{i}.conv2.bias"))
             ops.gemm_tn(dz2, self.sh[f"w2T{i}"], out_bf16=gB, gate=h1, drop_p=p_drop, drop_seed=seed,
                         drop_stream=11 + 4 * i, drop_step=step)                                   # da1
-            ops.gemm_wgrad(gB, y, GM(f"forward_layers.{i}.conv1.weight"))
-            ops.colsum(gB, G(f"forward_layers.{i}.conv1.bias"))
+            ops.gemm_wgrad(gB, y, GM(f"forward_layers.{i}.conv1.weight"), G(f"forward_layers.{i}.conv1.bias"))
             ops.gemm_tn(gB, self.sh[f"w1T{i}"], out_bf16=gC, residual=dz)                          # dy
             # LN2
             ops.layernorm_bwd(gC, r, ws[f"st2_{i}"][:T], P.view(f"forward_layernorms.{i}.weight"), gB,
                               G(f"forward_layernorms.{i}.weight"), G(f"forward_layernorms.{i}.bias"))   # dr
             # r = Q + o Wo^T + bo
-            ops.gemm_wgrad(gB, o, GM(f"attention_layers.{i}.out_proj.weight"))
-            ops.colsum(gB, G(f"attention_layers.{i}.out_proj.bias"))
+            ops.gemm_wgrad(gB, o, GM(f"attention_layers.{i}.out_proj.weight"), G(f"attention_layers.{i}.out_proj.bias"))
             ops.gemm_tn(gB, self.sh[f"woT{i}"], out_bf16=gC)                                       # do
             ops.attention_bwd(gC, q, kv[:, :H], kv[:, H:], gD, gKV[:, :H], gKV[:, H:], B, L, H, s.num_heads, p_drop,
                               seed, 10 + 4 * i, step)                                             # dq, dk|dv
             gin = GM(f"attention_layers.{i}.in_proj_weight")
             gbin = G(f"attention_layers.{i}.in_proj_bias")
-            ops.gemm_wgrad(gD, Q, gin[:H])
-            ops.colsum(gD, gbin[:H])
+            ops.gemm_wgrad(gD, Q, gin[:H], gbin[:H])
             ops.gemm_tn(gD, self.sh[f"wqT{i}"], out_bf16=gC, residual=gB)                          # dQ = dr + dq Wq
-            ops.gemm_wgrad(gKV, x[i], gin[H:])
-            ops.colsum(gKV, gbin[H:])
+            ops.gemm_wgrad(gKV, x[i], gin[H:], gbin[H:])
             ops.gemm_tn(gKV, self.sh[f"wkvT{i}"], out_bf16=gD)                                     # dx via k, v
             # LN1 + the un-normalised k/v path; pad rows zeroed (x_i was masked, SRFR_model.py:99,121)
             ops.layernorm_bwd(gC, x[i], ws[f"st1_{i}"][:T], P.view(f"attention_layernorms.{i}.weight"), gA,

@@ -92,11 +92,12 @@ def gemm_tn(A, B, out_bf16=None, out_f32=None, bias=None, residual=None, gate=No
     call("srfrd_gemm_tn", _p(A), A.stride(0), _p(B), B.stride(0), M, N, K, C.byref(ep), _stream())
 
 
-def gemm_wgrad(dY, X, dW):
-    """dW[Mo,No] += dY[T,Mo]^T @ X[T,No]  (dW fp32, atomically accumulated)."""
+def gemm_wgrad(dY, X, dW, dbias=None):
+    """dW[Mo,No] += dY[T,Mo]^T @ X[T,No]  (dW fp32, atomically accumulated); dbias[Mo] += column sums of dY."""
     T, Mo = dY.shape
     No = X.shape[1]
-    call("srfrd_gemm_wgrad", _p(dY), dY.stride(0), _p(X), X.stride(0), T, Mo, No, _p(dW), dW.stride(0), _stream())
+    call("srfrd_gemm_wgrad", _p(dY), dY.stride(0), _p(X), X.stride(0), T, Mo, No, _p(dW), dW.stride(0), _p(dbias),
+         _stream())
 
 
 def gemm_ref(A, B, Cout, a_mn_major=False, b_mn_major=False):

@@ -73,8 +73,10 @@ def test_gemm_wgrad(ops, T, Mo, No):
     simt = torch.empty_like(dW)
     ops.gemm_ref(dY, X, simt, a_mn_major=True, b_mn_major=True)
     torch.testing.assert_close(simt, ref, rtol=1e-3, atol=2e-3 * math.sqrt(T))
-    ops.gemm_wgrad(dY, X, dW)             # accumulates
+    db = torch.zeros(Mo, device="cuda")
+    ops.gemm_wgrad(dY, X, dW, db)         # accumulates; bias gradient from the fused all-ones MMA
     torch.testing.assert_close(dW, 2 * ref, rtol=1e-3, atol=4e-3 * math.sqrt(T))
+    torch.testing.assert_close(db, dY.float().sum(0), rtol=1e-3, atol=2e-3 * math.sqrt(T))
 
 
 # ------------------------------------------------------------------------------------------- K1
