@@ -35,8 +35,11 @@ __device__ __forceinline__ void load_chunk(bf16* dst, const bf16* src, int ld, i
   }
 }
 
+// The causal (L x L) matrices are stored as packed lower triangles: row i starts at i (i + 1) / 2.
+__device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
+
 // S[i][j] += sum_c a[i][c] * b[j][c] for j <= i  (strips of 1 x 4)
-__device__ __forceinline__ void accum_scores(float* S, int LP, const bf16* a, const bf16* b, int L) {
+__device__ __forceinline__ void accum_scores(float* S, const bf16* a, const bf16* b, int L) {
   const int strips = (L + 3) / 4;
   for (int w = threadIdx.x; w < L * strips; w += blockDim.x) {
     const int i = w / strips, j0 = (w % strips) * 4;
@@ -55,7 +58,7 @@ __device__ __forceinline__ void accum_scores(float* S, int LP, const bf16* a, co
     }
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj)
-      if (j0 + jj <= i) S[i * LP + j0 + jj] += acc[jj];
+      if (j0 + jj <= i) S[tri(i) + j0 + jj] += acc[jj];
   }
 }
 
@@ -64,21 +67,21 @@ __device__ __forceinline__ void zero_f32(float* p, int n) {
 }
 
 // rows of S -> softmax probabilities (pre-dropout), one warp per row
-__device__ __forceinline__ void softmax_rows(float* S, int LP, int L, float scale) {
+__device__ __forceinline__ void softmax_rows(float* S, int L, float scale) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int i = warp; i < L; i += nw) {
     float m = -INFINITY;
-    for (int j = lane; j <= i; j += 32) m = fmaxf(m, S[i * LP + j] * scale);
+    for (int j = lane; j <= i; j += 32) m = fmaxf(m, S[tri(i) + j] * scale);
     m = warp_max(m);
     float sum = 0.f;
     for (int j = lane; j <= i; j += 32) {
-      const float e = __expf(S[i * LP + j] * scale - m);
-      S[i * LP + j] = e;
+      const float e = __expf(S[tri(i) + j] * scale - m);
+      S[tri(i) + j] = e;
       sum += e;
     }
     sum = warp_sum(sum);
     const float inv = 1.f / sum;
-    for (int j = lane; j <= i; j += 32) S[i * LP + j] *= inv;
+    for (int j = lane; j <= i; j += 32) S[tri(i) + j] *= inv;
   }
 }
 
@@ -90,9 +93,9 @@ __device__ __forceinline__ float drop_factor(const AttnParams& p, int bh, int i,
 
 __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(AttnParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
-  const int L = p.L, LP = L + 1;
+  const int L = p.L, NTRI = (tri(L) + 3) & ~3;
   float* S = reinterpret_cast<float*>(smem);
-  bf16* bufA = reinterpret_cast<bf16*>(S + L * LP);
+  bf16* bufA = reinterpret_cast<bf16*>(S + NTRI);
   bf16* bufB = bufA + L * CHP;
   const int bh = blockIdx.x, b = bh / p.heads, h = bh % p.heads;
   const bf16* q = p.q + (size_t)b * L * p.ldq + h * p.hd;
@@ -101,21 +104,21 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(AttnParams p) {
   bf16* o = p.o + (size_t)b * L * p.ldo + h * p.hd;
   if (p.drop_thresh) p.drop_seed = mix_seed(p.drop_seed, p.drop_step);
 
-  zero_f32(S, L * LP);
+  zero_f32(S, NTRI);
   for (int c0 = 0; c0 < p.hd; c0 += CH) {
     __syncthreads();
     load_chunk(bufA, q, p.ldq, L, c0, p.hd);
     load_chunk(bufB, k, p.ldkv, L, c0, p.hd);
     __syncthreads();
-    accum_scores(S, LP, bufA, bufB, L);
+    accum_scores(S, bufA, bufB, L);
   }
   __syncthreads();
-  softmax_rows(S, LP, L, p.scale);
+  softmax_rows(S, L, p.scale);
   __syncthreads();
   if (p.drop_thresh) {
     for (int w = threadIdx.x; w < L * L; w += blockDim.x) {
       const int i = w / L, j = w % L;
-      if (j <= i) S[i * LP + j] *= drop_factor(p, bh, i, j);
+      if (j <= i) S[tri(i) + j] *= drop_factor(p, bh, i, j);
     }
   }
   // O[i][c] = sum_{j<=i} P[i][j] v[j][c]
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(AttnParams p) {
       if (c0 + c >= p.hd) continue;
       float a0 = 0.f, a1 = 0.f;
       for (int j = 0; j <= i; ++j) {
-        const float pij = S[i * LP + j];
+        const float pij = S[tri(i) + j];
         const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(bufA + j * CHP + c));
         a0 = fmaf(pij, vv.x, a0);
         a1 = fmaf(pij, vv.y, a1);
@@ -142,10 +145,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(AttnParams p) {
 //           dV = Ad^T dO; dq = dS k; dk = dS^T q.
 __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(AttnParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
-  const int L = p.L, LP = L + 1;
+  const int L = p.L, NTRI = (tri(L) + 3) & ~3;
   float* A = reinterpret_cast<float*>(smem);        // probabilities, later Ad = A * M
-  float* G = A + L * LP;                            // dAd, later dS
-  bf16* bufA = reinterpret_cast<bf16*>(G + L * LP);
+  float* G = A + NTRI;                              // dAd, later dS
+  bf16* bufA = reinterpret_cast<bf16*>(G + NTRI);
   bf16* bufB = bufA + L * CHP;
   const int bh = blockIdx.x, b = bh / p.heads, h = bh % p.heads;
   const bf16* q = p.q + (size_t)b * L * p.ldq + h * p.hd;
@@ -157,21 +160,21 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(AttnParams p) {
   bf16* dv = p.dv + (size_t)b * L * p.lddkv + h * p.hd;
   if (p.drop_thresh) p.drop_seed = mix_seed(p.drop_seed, p.drop_step);
 
-  zero_f32(A, 2 * L * LP);
+  zero_f32(A, 2 * NTRI);
   for (int c0 = 0; c0 < p.hd; c0 += CH) {
     __syncthreads();
     load_chunk(bufA, q, p.ldq, L, c0, p.hd);
     load_chunk(bufB, k, p.ldkv, L, c0, p.hd);
     __syncthreads();
-    accum_scores(A, LP, bufA, bufB, L);
+    accum_scores(A, bufA, bufB, L);
     __syncthreads();
     load_chunk(bufA, dout, p.lddo, L, c0, p.hd);
     load_chunk(bufB, v, p.ldkv, L, c0, p.hd);
     __syncthreads();
-    accum_scores(G, LP, bufA, bufB, L);
+    accum_scores(G, bufA, bufB, L);
   }
   __syncthreads();
-  softmax_rows(A, LP, L, p.scale);
+  softmax_rows(A, L, p.scale);
   __syncthreads();
   {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -179,16 +182,16 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(AttnParams p) {
       float delta = 0.f;
       for (int j = lane; j <= i; j += 32) {
         const float m = drop_factor(p, bh, i, j);
-        const float gm = G[i * LP + j] * m;
-        G[i * LP + j] = gm;                    // dA = dAd * M
-        delta += gm * A[i * LP + j];
+        const float gm = G[tri(i) + j] * m;
+        G[tri(i) + j] = gm;                    // dA = dAd * M
+        delta += gm * A[tri(i) + j];
         // keep A (undropped) until dS is formed; Ad is rebuilt below
       }
       delta = warp_sum(delta);
       for (int j = lane; j <= i; j += 32) {
-        const float a = A[i * LP + j];
-        G[i * LP + j] = a * (G[i * LP + j] - delta) * p.scale;   // dS (scale folded: S = scale * q k^T)
-        A[i * LP + j] = a * drop_factor(p, bh, i, j);            // Ad
+        const float a = A[tri(i) + j];
+        G[tri(i) + j] = a * (G[tri(i) + j] - delta) * p.scale;   // dS (scale folded: S = scale * q k^T)
+        A[tri(i) + j] = a * drop_factor(p, bh, i, j);            // Ad
       }
     }
   }
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(AttnParams p) {
       if (c0 + c >= p.hd) continue;
       float v0 = 0.f, v1 = 0.f, k0 = 0.f, k1 = 0.f;
       for (int i = j; i < L; ++i) {
-        const float ad = A[i * LP + j], ds = G[i * LP + j];
+        const float ad = A[tri(i) + j], ds = G[tri(i) + j];
         const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(bufA + i * CHP + c));
         const float2 qq = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(bufB + i * CHP + c));
         v0 = fmaf(ad, d.x, v0); v1 = fmaf(ad, d.y, v1);
@@ -221,7 +224,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(AttnParams p) {
       if (c0 + c >= p.hd) continue;
       float a0 = 0.f, a1 = 0.f;
       for (int j = 0; j <= i; ++j) {
-        const float ds = G[i * LP + j];
+        const float ds = G[tri(i) + j];
         const float2 kk = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(bufA + j * CHP + c));
         a0 = fmaf(ds, kk.x, a0); a1 = fmaf(ds, kk.y, a1);
       }
@@ -229,6 +232,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(AttnParams p) {
     }
   }
 }
+
+static int host_ntri(int L) { return ((L * (L + 1) / 2) + 3) & ~3; }
 
 static int fill_common(AttnParams& p, int L, int H, int heads, float drop_p, uint64_t seed, uint32_t stream_id,
                        const float* drop_step) {
@@ -247,6 +252,7 @@ static int fill_common(AttnParams& p, int L, int H, int heads, float drop_p, uin
 }
 
 // SIMT path: shapes the tcgen05 kernels (attention_tc.cu) do not cover -- maxlen > 128 or head_dim % 16 != 0.
+// Packed-triangle score storage keeps maxlen 200 (C4) inside 227 KB: forward up to L ~ 305, backward up to L = 223.
 int attn_fwd_simt(const void* q, int ldq, const void* k, const void* v, int ldkv, void* o, int ldo, int64_t B, int L,
                   int H, int heads, float drop_p, uint64_t seed, uint32_t stream_id, const float* drop_step,
                   void* stream) {
@@ -257,7 +263,7 @@ int attn_fwd_simt(const void* q, int ldq, const void* k, const void* v, int ldkv
   if (int rc = fill_common(p, L, H, heads, drop_p, seed, stream_id, drop_step)) return rc;
   p.q = (const bf16*)q; p.k = (const bf16*)k; p.v = (const bf16*)v; p.ldq = ldq; p.ldkv = ldkv;
   p.o = (bf16*)o; p.ldo = ldo;
-  const size_t smem = (size_t)L * (L + 1) * 4 + 2 * (size_t)L * CHP * 2;
+  const size_t smem = (size_t)host_ntri(L) * 4 + 2 * (size_t)L * CHP * 2;
   SRFRD_REQUIRE(smem <= 227 * 1024, "attention_fwd: maxlen %d needs %zu B of shared memory (> 227 KB)", L, smem);
   static size_t smem_set = 48 * 1024;
   if (smem > smem_set) {
@@ -281,7 +287,7 @@ int attn_bwd_simt(const void* dout, int lddo, const void* q, int ldq, const void
   p.q = (const bf16*)q; p.k = (const bf16*)k; p.v = (const bf16*)v; p.ldq = ldq; p.ldkv = ldkv;
   p.dout = (const bf16*)dout; p.lddo = lddo; p.dq = (bf16*)dq; p.dk = (bf16*)dk; p.dv = (bf16*)dv;
   p.lddq = lddq; p.lddkv = lddkv;
-  const size_t smem = 2 * (size_t)L * (L + 1) * 4 + 2 * (size_t)L * CHP * 2;
+  const size_t smem = 2 * (size_t)host_ntri(L) * 4 + 2 * (size_t)L * CHP * 2;
   SRFRD_REQUIRE(smem <= 227 * 1024, "attention_bwd: maxlen %d needs %zu B of shared memory (> 227 KB)", L, smem);
   static size_t smem_set = 48 * 1024;
   if (smem > smem_set) {
