@@ -8,6 +8,8 @@
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
 // warps 2..5 = epilogue (TMEM lane quarter = warp_idx & 3).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "srfrd_b200.h"
 
@@ -16,8 +18,12 @@ namespace srfrd {
 static constexpr int BLOCK_M = 128;
 static constexpr int BLOCK_K = 64;                       // 64 bf16 = one 128-byte swizzle row
 static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
-static constexpr int GEMM_THREADS = 192;
+static constexpr int GEMM_THREADS = 192;                 // gemm_wgrad
+static constexpr int TN_THREADS = 640;                   // gemm_tn: 2 epilogue sets of 8 warps + 4 control warps
 static constexpr int TMEM_COLS = 512;
+static constexpr int EPI_BLK_BYTES = BLOCK_M * 64 * 2;   // one [128 rows x 64 cols] bf16 epilogue block, 16 KB
+static constexpr int TN_MAX_BLOCK_N = 192;               // <= 3 epilogue blocks per tile and per set
+static constexpr int MAX_BIAS = 1024;
 
 struct GemmEpilogue {
   const float* bias;        // [N] or null
@@ -34,76 +40,114 @@ struct GemmEpilogue {
   const float* drop_step;
 };
 
+// profiling experiments only (SRFRD_GEMM_DEBUG=5): clock64 timeline of CTA 0, [event][tile], read by srfrd_gemm_debug_read
+__device__ long long g_gemm_dbg[32 * 16];
+#define TN_STAMP(ev, tile) do { if (s.debug == 5 && blockIdx.x == 0 && (tile) < 16) { if (elect_one()) g_gemm_dbg[(ev) * 16 + (tile)] = clock64(); } } while (0)
+
 struct GemmShape {
   int M, N, K;
   int block_n, m_tiles, n_tiles, stages;
+  int has_aux;              // residual or gate present: the tile's aux block(s) arrive by TMA in the set's tile buffer
+  int tma_out;              // bf16 output written IN PLACE over the aux block(s) and stored with TMA
+  int buf_blocks;           // 64-column blocks per set's tile buffer (0 if neither aux nor TMA output)
+  int debug;                // SRFRD_GEMM_DEBUG (profiling experiments only): 1 = no TMA store, 2 = no epilogue math, 5 = timeline
 };
 
-__device__ __forceinline__ float apply_epilogue(float v, int j, const GemmEpilogue& e, const float* bias_v,
-                                                const float* res_v, const float* gate_v, float rowm,
-                                                uint64_t elem_idx) {
-  if (e.bias) v += bias_v[j];
-  if (e.drop_thresh) v = dropout_keep(e.drop_seed, e.drop_stream, elem_idx, e.drop_thresh) ? v * e.drop_scale : 0.f;
-  if (e.relu) v = fmaxf(v, 0.f);
-  if (e.gate) v = gate_v[j] > 0.f ? v : 0.f;
-  if (e.residual) v += res_v[j];
-  return v * rowm;
-}
+// byte offset of the 16-byte chunk j (8 bf16 columns) of row r inside a 128-byte-swizzled [128 x 64] bf16 block
+__device__ __forceinline__ uint32_t sw128_chunk(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
 
-__device__ __forceinline__ void load16_bf16(const bf16* p, float* out) {
-  const uint4* q = reinterpret_cast<const uint4*>(p);
-  uint4 a = __ldg(q), b = __ldg(q + 1);
-  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+__device__ __forceinline__ void unpack_bf16x8(const uint4& u, float* f) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
-    out[2 * i] = __low2float(t);
-    out[2 * i + 1] = __high2float(t);
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+    f[2 * i] = __low2float(t);
+    f[2 * i + 1] = __high2float(t);
   }
 }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmShape s,
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+// C = epilogue(A B^T).  Persistent CTAs over 128-row tiles.  All global traffic is asynchronous bulk copies:
+// A / B tiles and the residual-or-gate ("aux") tile arrive by TMA, the bf16 result is written IN PLACE over the
+// aux tile (same thread, same 16-byte chunk) and leaves by TMA stores, so the epilogue threads only touch TMEM
+// and shared memory and nothing in the per-tile critical path waits on an HBM round trip.
+//   warps 0..7 / 8..15: epilogue set 0 / 1.  Set s owns accumulator stage s and tile buffer s (tiles alternate between
+//     the sets); warp (quarter q, half h) owns TMEM lanes [32q, 32q+32) and the 32-column chunks with chunk % 2 == h.
+//     Four epilogue warps per scheduler: measured, the epilogue is a chain of TMEM / barrier latencies, not bandwidth.
+//   warp 16: TMA producer for A/B   warp 17: TMEM allocator + MMA issuer   warp 18: TMA producer for aux
+//     The control warps have the HIGHEST warp ids: the scheduler favours high ids, and with low ids the MMA issuer
+//     took ~700 cycles to issue five MMAs while the epilogue warps of its scheduler were busy (clock64 timeline).
+// AUX: 0 none, 1 residual (v += aux), 2 gate (v = aux > 0 ? v : 0).  bias / ReLU / row mask are branch-free.
+template <int AUX, bool DROP>
+__global__ void __launch_bounds__(TN_THREADS, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmAux, const __grid_constant__ CUtensorMap tmOut, GemmShape s,
                GemmEpilogue e) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int b_stage_bytes = s.block_n * BLOCK_K * 2;
+  const int b_stage_bytes = ((s.block_n * BLOCK_K * 2) + 1023) & ~1023;
   uint8_t* smA = smem;
-  uint8_t* smB = smem + s.stages * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + s.stages * b_stage_bytes);
+  uint8_t* smB = smA + s.stages * A_STAGE_BYTES;
+  uint8_t* smBuf = smB + s.stages * b_stage_bytes;       // [set][buf_blocks][16 KB]
+  float* sbias = reinterpret_cast<float*>(smBuf + 2 * s.buf_blocks * EPI_BLK_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + MAX_BIAS);
   uint64_t* full = bars;
   uint64_t* empty = bars + s.stages;
   uint64_t* tfull = bars + 2 * s.stages;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* xfull = tempty + 2;                          // [set] aux tile landed
+  uint64_t* bfree = xfull + 2;                           // [set] tile buffer free again (TMA store has read it)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfree + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = s.m_tiles * s.n_tiles;
   const int kblocks = (s.K + BLOCK_K - 1) / BLOCK_K;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (s.has_aux) tma_prefetch_desc(&tmAux);
+    if (s.tma_out) tma_prefetch_desc(&tmOut);
     for (int i = 0; i < s.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); mbar_init(&xfull[i], 1); mbar_init(&bfree[i], 1);
+    }
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+  if (s.debug == 5 && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    g_gemm_dbg[10 * 16] = (long long)gt; g_gemm_dbg[10 * 16 + 1] = clock64();
+  }
+  if (warp == 17) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+  for (int i = threadIdx.x; i < MAX_BIAS; i += blockDim.x) sbias[i] = (e.bias && i < s.N) ? __ldg(e.bias + i) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // Warps 0 and 1 stay converged; only the issuing instructions are predicated on elect.sync so that barrier
+  // Warps 16..18 stay converged; only the issuing instructions are predicated on elect.sync so that barrier
   // addresses and descriptors live in uniform registers (see topk.cu for the measurement behind this).
-  if (warp == 0) {
+  if (warp == 16) {
     int stage = 0; uint32_t phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    int tl = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
       const int m0 = (t / s.n_tiles) * BLOCK_M, n0 = (t % s.n_tiles) * s.block_n;
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
+        if (kb == 0) TN_STAMP(0, tl);
         if (elect_one()) {
-          mbar_expect_tx(&full[stage], A_STAGE_BYTES + b_stage_bytes);
+          mbar_expect_tx(&full[stage], A_STAGE_BYTES + s.block_n * BLOCK_K * 2);
           tma_load_2d(smA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BLOCK_K, m0, SRFRD_EVICT_FIRST);
           tma_load_2d(smB + stage * b_stage_bytes, &tmB, &full[stage], kb * BLOCK_K, n0, SRFRD_EVICT_LAST);
         }
@@ -111,27 +155,33 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++stage == s.stages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 17) {
     int stage = 0; uint32_t phase = 0;
     int as = 0; uint32_t aphase = 0;
     const uint64_t adesc0 = umma_smem_desc(smem_u32(smA), 0, 1024), bdesc0 = umma_smem_desc(smem_u32(smB), 0, 1024);
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    int tl = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
       const int n0 = (t % s.n_tiles) * s.block_n;
       int bn = min(s.block_n, s.N - n0);
       bn = (bn + 15) & ~15;
       const uint32_t idesc = umma_idesc_bf16(BLOCK_M, bn, 0, 0);
       mbar_wait(&tempty[as], aphase ^ 1);
       tc_fence_after();
+      TN_STAMP(1, tl);
       const uint32_t tacc = tmem_base + as * 256;
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
+        if (kb == 0) TN_STAMP(2, tl);
+        if (kb == kblocks - 1) TN_STAMP(3, tl);
         // K-major SW128: 8-row groups are 1024 B apart (SBO); +32 B (= 2 in descriptor units) per UMMA_K = 16
         const uint64_t ad = adesc0 + (uint64_t)(stage * (A_STAGE_BYTES >> 4));
         const uint64_t bd = bdesc0 + (uint64_t)(stage * (b_stage_bytes >> 4));
         const int ksteps = min(BLOCK_K / 16, (s.K - kb * BLOCK_K + 15) / 16);
         if (elect_one()) {
-          for (int k = 0; k < ksteps; ++k) umma_bf16(tacc, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k)
+            if (k < ksteps) umma_bf16(tacc, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
           umma_commit(&empty[stage]);
           if (kb == kblocks - 1) umma_commit(&tfull[as]);
         }
@@ -140,63 +190,135 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
-  } else {
-    const int quarter = warp & 3;
-    int as = 0; uint32_t aphase = 0;
-    if (e.drop_thresh) e.drop_seed = mix_seed(e.drop_seed, e.drop_step);
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+  } else if (warp == 18) {
+    if (AUX) {
+      uint32_t bph0 = 0, bph1 = 0;                       // parity of the bfree phase each set's NEXT load waits for
+      int n_local = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++n_local) {
+        const int m0 = (t / s.n_tiles) * BLOCK_M, n0 = (t % s.n_tiles) * s.block_n;
+        const int nblk = (min(s.block_n, s.N - n0) + 63) >> 6;
+        const int set = n_local & 1;
+        const uint32_t bph = set ? bph1 : bph0;
+        mbar_wait(&bfree[set], bph ^ 1);                 // first tile of a set: passes at once (fresh barrier)
+        if (elect_one()) {
+          mbar_expect_tx(&xfull[set], nblk * EPI_BLK_BYTES);
+          for (int blk = 0; blk < nblk; ++blk)
+            tma_load_2d(smBuf + (set * s.buf_blocks + blk) * EPI_BLK_BYTES, &tmAux, &xfull[set], n0 + blk * 64, m0,
+                        SRFRD_EVICT_FIRST);
+        }
+        __syncwarp();
+        if (set) bph1 ^= 1; else bph0 ^= 1;
+      }
+    }
+  } else if (warp < 16) {
+    const int set = warp >> 3, quarter = warp & 3, half = (warp >> 2) & 1;
+    const int r = quarter * 32 + lane;                   // row inside the tile == TMEM lane
+    const bool issuer = (quarter == 0) && (half == 0) && (lane == 0);
+    const bool stamp = (quarter == 0) && (half == 0);
+    uint8_t* buf = smBuf + set * s.buf_blocks * EPI_BLK_BYTES;
+    const bool use_buf = AUX || s.tma_out;
+    uint32_t tph = 0;                                    // parity for this set's tfull / xfull / bfree
+    if (DROP) e.drop_seed = mix_seed(e.drop_seed, e.drop_step);
+    const float relu_floor = e.relu ? 0.f : -INFINITY;
+    int n_local = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++n_local) {
+      if ((n_local & 1) != set) continue;                // the other set's tile
       const int m0 = (t / s.n_tiles) * BLOCK_M, n0 = (t % s.n_tiles) * s.block_n;
-      const int bn = min(s.block_n, s.N - n0);
-      const int row = m0 + quarter * 32 + lane;
+      const int bn = min(s.block_n, s.N - n0);           // multiple of 16
+      const int nblk = (bn + 63) >> 6;
+      const int row = m0 + r;
       const bool row_ok = row < s.M;
       float rowm = 1.f;
       if (e.row_ids && row_ok) rowm = (__ldg(e.row_ids + row) != 0) ? 1.f : 0.f;
-      mbar_wait(&tfull[as], aphase);
+      mbar_wait(&tfull[set], tph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * 256;
-      for (int c = 0; c < bn; c += 16) {
-        uint32_t raw[16];
-        tmem_ld16(taddr + c, raw);
-        tmem_ld_wait();
-        if (row_ok) {
-          const int n = n0 + c;
-          float bias_v[16], res_v[16], gate_v[16], v[16];
-          if (e.bias) {
+      if (stamp) TN_STAMP(4, n_local);
+      if (AUX) mbar_wait(&xfull[set], tph);              // aux tile landed (implies the buffer was free)
+      else if (s.tma_out) mbar_wait(&bfree[set], tph ^ 1);   // previous store of this set has read the buffer
+      if (stamp) TN_STAMP(5, n_local);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + set * 256;
+      if (s.debug != 2) {
+#pragma unroll 1
+        for (int c = half * 32; c < bn; c += 64) {       // this warp's 32-column chunks of the tile
+          uint8_t* blkp = buf + (c >> 6) * EPI_BLK_BYTES;
+          const int cj = (c & 63) >> 3;                  // first 16-byte chunk inside the 64-column block
+          uint32_t raw[32];
+          tmem_ld32(taddr + c, raw);
+          uint4 ax[4];
+          if (AUX) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias + n + j));
-              bias_v[j] = b4.x; bias_v[j + 1] = b4.y; bias_v[j + 2] = b4.z; bias_v[j + 3] = b4.w;
+            for (int j = 0; j < 4; ++j) ax[j] = *reinterpret_cast<const uint4*>(blkp + sw128_chunk(r, cj + j));
+          }
+          const int nc = n0 + c;
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (c + 8 * j >= bn) break;                  // bn is a multiple of 16: chunks come in pairs
+            float v[8], a[8];
+            if (AUX) unpack_bf16x8(ax[j], a);
+            const float4 b0 = *reinterpret_cast<const float4*>(sbias + nc + 8 * j);
+            const float4 b1 = *reinterpret_cast<const float4*>(sbias + nc + 8 * j + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float x = __uint_as_float(raw[8 * j + i]) + bb[i];
+              if (DROP) {
+                const int n = nc + 8 * j + i;
+                x = dropout_keep(e.drop_seed, e.drop_stream, (uint64_t)row * (uint64_t)s.N + (uint64_t)n, e.drop_thresh)
+                        ? x * e.drop_scale : 0.f;
+              }
+              x = fmaxf(x, relu_floor);
+              if (AUX == 2) x = a[i] > 0.f ? x : 0.f;
+              if (AUX == 1) x += a[i];
+              v[i] = x * rowm;
             }
-          }
-          if (e.residual) load16_bf16(e.residual + (size_t)row * e.ldr + n, res_v);
-          if (e.gate) load16_bf16(e.gate + (size_t)row * e.ldg + n, gate_v);
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            v[j] = apply_epilogue(__uint_as_float(raw[j]), j, e, bias_v, res_v, gate_v, rowm,
-                                  (uint64_t)row * (uint64_t)s.N + (uint64_t)(n + j));
-          if (e.out_bf16) {
-            uint4* o = reinterpret_cast<uint4*>(e.out_bf16 + (size_t)row * e.ldc + n);
-            o[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                              pack_bf16x2(v[6], v[7]));
-            o[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
-                              pack_bf16x2(v[14], v[15]));
-          }
-          if (e.out_f32) {
-            float4* o = reinterpret_cast<float4*>(e.out_f32 + (size_t)row * e.ldc + n);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            if (s.tma_out) {
+              *reinterpret_cast<uint4*>(blkp + sw128_chunk(r, cj + j)) =
+                  make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+            } else if (row_ok) {
+              const int n = nc + 8 * j;
+              if (e.out_bf16)
+                *reinterpret_cast<uint4*>(e.out_bf16 + (size_t)row * e.ldc + n) =
+                    make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+              if (e.out_f32) {
+                float4* o = reinterpret_cast<float4*>(e.out_f32 + (size_t)row * e.ldc + n);
+                o[0] = make_float4(v[0], v[1], v[2], v[3]);
+                o[1] = make_float4(v[4], v[5], v[6], v[7]);
+              }
+            }
           }
         }
       }
-      tc_fence_before();
+      if (stamp) TN_STAMP(6, n_local);
+      tc_fence_before();                                 // accumulator fully read: hand the TMEM stage back
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
-      if (++as == 2) { as = 0; aphase ^= 1; }
+      if (lane == 0) mbar_arrive(&tempty[set]);
+      if (use_buf) {
+        if (s.tma_out) fence_proxy_async();              // generic-proxy smem writes -> visible to the TMA store
+        if (stamp) TN_STAMP(7, n_local);
+        named_bar_sync(1 + set, 256);                    // every warp of the set is done with the tile buffer
+        if (stamp) TN_STAMP(8, n_local);
+        if (issuer) {
+          if (s.tma_out && s.debug != 1) {
+            for (int blk = 0; blk < nblk; ++blk) tma_store_2d(&tmOut, buf + blk * EPI_BLK_BYTES, n0 + blk * 64, m0);
+            bulk_commit();
+            bulk_wait_read<0>();                         // smem has been read: the buffer may be refilled
+          }
+          mbar_arrive(&bfree[set]);
+        }
+        __syncwarp();
+      }
+      if (stamp) TN_STAMP(9, n_local);
+      tph ^= 1;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+  if (s.debug == 5 && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    g_gemm_dbg[11 * 16] = (long long)gt; g_gemm_dbg[11 * 16 + 1] = clock64();
+  }
+  if (warp == 17) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -352,6 +474,14 @@ static int pick_block_n(int N) {
   int bn = ((N + tiles - 1) / tiles + 15) & ~15;
   return bn;
 }
+// gemm_tn: with more than one column tile the tile width is a multiple of 64, so the 64-column TMA store boxes of
+// one tile never reach into its neighbour's columns
+static int pick_block_n_tn(int N) {
+  if (N <= TN_MAX_BLOCK_N) return (N + 15) & ~15;
+  const int tiles = (N + TN_MAX_BLOCK_N - 1) / TN_MAX_BLOCK_N;
+  const int bn = ((N + tiles - 1) / tiles + 63) & ~63;
+  return bn > TN_MAX_BLOCK_N ? TN_MAX_BLOCK_N : bn;
+}
 
 }  // namespace srfrd
 
@@ -368,18 +498,34 @@ extern "C" int srfrd_gemm_tn(const void* A, int lda, const void* B, int ldb, int
   SRFRD_REQUIRE(ep->ldc % 8 == 0 && ep->ldc >= N, "gemm_tn: bad ldc=%d", ep->ldc);
   SRFRD_REQUIRE(!ep->residual || ep->ldr % 8 == 0, "gemm_tn: bad ldr");
   SRFRD_REQUIRE(!ep->gate || ep->ldg % 8 == 0, "gemm_tn: bad ldg");
+  SRFRD_REQUIRE(!(ep->residual && ep->gate), "gemm_tn: residual and gate cannot be combined (one aux operand)");
+  SRFRD_REQUIRE(!ep->bias || N <= MAX_BIAS, "gemm_tn: bias with N=%d > %d unsupported", N, MAX_BIAS);
   GemmShape s;
   s.M = M; s.N = N; s.K = K;
-  s.block_n = pick_block_n(N);
+  s.block_n = pick_block_n_tn(N);
   s.n_tiles = (N + s.block_n - 1) / s.block_n;
   s.m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
-  const int stage_bytes = A_STAGE_BYTES + s.block_n * BLOCK_K * 2;
-  s.stages = (200 * 1024) / stage_bytes;
+  const void* aux = ep->residual ? ep->residual : ep->gate;
+  const int ldaux = ep->residual ? ep->ldr : ep->ldg;
+  s.has_aux = aux != nullptr;
+  // TMA store needs a 16-byte aligned bf16 output; the fp32 output (predict logits, tests) is stored directly
+  s.tma_out = ep->out_bf16 && !ep->out_f32 && (((uintptr_t)ep->out_bf16 & 15) == 0);
+  SRFRD_REQUIRE(!aux || (((uintptr_t)aux & 15) == 0), "gemm_tn: residual / gate must be 16-byte aligned");
+  const int b_stage_bytes = ((s.block_n * BLOCK_K * 2) + 1023) & ~1023;
+  const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+  { const char* dbg = getenv("SRFRD_GEMM_DEBUG"); s.debug = dbg ? atoi(dbg) : 0; }
+  s.buf_blocks = (s.has_aux || s.tma_out) ? (s.block_n + 63) / 64 : 0;
+  const int fixed = 1024 + 2 * s.buf_blocks * EPI_BLK_BYTES + MAX_BIAS * 4 + 512;
+  s.stages = (227 * 1024 - fixed) / stage_bytes;
   if (s.stages > 6) s.stages = 6;
-  const size_t smem = (size_t)s.stages * stage_bytes + 1024 + 256;
-  CUtensorMap tmA, tmB;
+  SRFRD_REQUIRE(s.stages >= 2, "gemm_tn: tile does not fit shared memory");
+  const size_t smem = (size_t)s.stages * stage_bytes + fixed;
+  CUtensorMap tmA, tmB, tmAux, tmOut;
   if (int rc = make_tmap_bf16_2d(&tmA, A, M, K, lda, BLOCK_M, BLOCK_K)) return rc;
   if (int rc = make_tmap_bf16_2d(&tmB, B, N, K, ldb, s.block_n, BLOCK_K)) return rc;
+  tmAux = tmA; tmOut = tmA;
+  if (s.has_aux) if (int rc = make_tmap_bf16_2d(&tmAux, aux, M, N, ldaux, BLOCK_M, 64)) return rc;
+  if (s.tma_out) if (int rc = make_tmap_bf16_2d(&tmOut, ep->out_bf16, M, N, ep->ldc, BLOCK_M, 64)) return rc;
   GemmEpilogue e;
   e.bias = ep->bias; e.residual = (const bf16*)ep->residual; e.gate = (const bf16*)ep->gate;
   e.row_ids = ep->row_ids; e.out_bf16 = (bf16*)ep->out_bf16; e.out_f32 = ep->out_f32;
@@ -391,15 +537,31 @@ extern "C" int srfrd_gemm_tn(const void* A, int lda, const void* B, int ldb, int
     e.drop_thresh = (uint32_t)((double)ep->drop_p * 4294967296.0);
     e.drop_scale = 1.f / (1.f - ep->drop_p);
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    SRFRD_CUDA(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
   int grid = s.m_tiles * s.n_tiles;
   if (grid > num_sms()) grid = num_sms();
-  gemm_tn_kernel<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, s, e);
+  const int aux_mode = ep->residual ? 1 : (ep->gate ? 2 : 0);
+#define SRFRD_TN_LAUNCH(AUXM, DROPF)                                                                                  \
+  do {                                                                                                                \
+    static bool attr_set = false;                                                                                     \
+    if (!attr_set) {                                                                                                  \
+      SRFRD_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<AUXM, DROPF>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                      227 * 1024));                                                                   \
+      attr_set = true;                                                                                                \
+    }                                                                                                                 \
+    gemm_tn_kernel<AUXM, DROPF><<<grid, TN_THREADS, smem, stream>>>(tmA, tmB, tmAux, tmOut, s, e);                    \
+  } while (0)
+  const bool drop = e.drop_thresh != 0;
+  if (aux_mode == 0) { if (drop) SRFRD_TN_LAUNCH(0, true); else SRFRD_TN_LAUNCH(0, false); }
+  else if (aux_mode == 1) { if (drop) SRFRD_TN_LAUNCH(1, true); else SRFRD_TN_LAUNCH(1, false); }
+  else { if (drop) SRFRD_TN_LAUNCH(2, true); else SRFRD_TN_LAUNCH(2, false); }
+#undef SRFRD_TN_LAUNCH
   SRFRD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int srfrd_gemm_debug_read(long long* host_dst) {
+  SRFRD_CUDA(cudaDeviceSynchronize());
+  SRFRD_CUDA(cudaMemcpyFromSymbol(host_dst, g_gemm_dbg, sizeof(long long) * 32 * 16));
   return 0;
 }
 
