@@ -100,6 +100,8 @@ SRFRD_API int srfrd_gemm_tn(const void* A_bf16, int lda, const void* B_bf16, int
  * dbias (nullable): dbias[Mo] += sum_t dY[t,Mo], from one extra N=16 MMA per K step against an all-ones operand. */
 /* profiling experiments only: with SRFRD_GEMM_DEBUG=5 gemm_tn records a clock64 timeline of CTA 0 (32 x 16 int64). */
 SRFRD_API int srfrd_gemm_debug_read(long long* host_dst);
+/* same for attention_fwd with SRFRD_ATTN_DEBUG=5 (16 x 16 int64). */
+SRFRD_API int srfrd_attn_debug_read(long long* host_dst);
 
 SRFRD_API int srfrd_gemm_wgrad(const void* dY_bf16, int lda, const void* X_bf16, int ldb, int64_t T, int Mo, int No,
                      float* dW, int ldw, float* dbias, void* stream);
