@@ -235,94 +235,113 @@ struct LnBwdParams {
   int64_t T; int H;
 };
 
-template <int LPR, int CH>
+// Lean register layout: the per-lane column accumulators (dw, db: 2 x CH x 8) are the only persistent state; the LN
+// weight is re-read from shared memory, dy / x / add stay packed (bf16) until used, and g = dy * w and
+// xh = (x - mean) * rstd are recomputed in the output pass instead of being kept.
+template <int LPR, int CH, bool F32DY>
 __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(LnBwdParams p) {
   __shared__ float sdw[MAXW], sdb[MAXW];
-  constexpr int RPW = 32 / LPR, UN = 2;
+  __shared__ __align__(16) float sw[MAXW];
+  constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int i = threadIdx.x; i < p.H; i += blockDim.x) sdw[i] = sdb[i] = 0.f;
+  for (int i = threadIdx.x; i < MAXW; i += blockDim.x) { sdw[i] = sdb[i] = 0.f; sw[i] = i < p.H ? __ldg(p.w + i) : 0.f; }
   __syncthreads();
-  float gw[CH][8];
   float adw[CH][8], adb[CH][8];
 #pragma unroll
-  for (int ch = 0; ch < CH; ++ch) {
-    const int c = (ch * LPR + sub) * 8;
+  for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { adw[ch][j] = adb[ch][j] = 0.f; gw[ch][j] = 0.f; }
-    if (c < p.H) load8_f32(p.w + c, gw[ch]);
-  }
-  for (int64_t t0 = warp * RPW * UN; t0 < p.T; t0 += nwarps * RPW * UN) {
-    float dy[UN][CH][8];
-    uint4 xr[UN][CH], ar[UN][CH];
-    float2 st[UN];
-    float msk[UN];
+    for (int j = 0; j < 8; ++j) adw[ch][j] = adb[ch][j] = 0.f;
+  const float invH = 1.f / p.H;
+  for (int64_t t0 = warp * RPW; t0 < p.T; t0 += nwarps * RPW) {
+    const int64_t t = t0 + grp;
+    const bool ok = t < p.T;
+    uint4 xr[CH], ar[CH], dr[CH];
+    float df[F32DY ? CH : 1][8];
+    const float2 st = ok ? __ldg(reinterpret_cast<const float2*>(p.stats + 2 * t)) : make_float2(0.f, 0.f);
+    const float msk = (ok && p.row_ids) ? ((__ldg(p.row_ids + t) != 0) ? 1.f : 0.f) : 1.f;
 #pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const int64_t t = t0 + u * RPW + grp;
-      const bool ok = t < p.T;
-      st[u] = ok ? __ldg(reinterpret_cast<const float2*>(p.stats + 2 * t)) : make_float2(0.f, 0.f);
-      msk[u] = (ok && p.row_ids) ? ((__ldg(p.row_ids + t) != 0) ? 1.f : 0.f) : 1.f;
+    for (int ch = 0; ch < CH; ++ch) {
+      const int c = (ch * LPR + sub) * 8;
+      xr[ch] = ar[ch] = dr[ch] = make_uint4(0, 0, 0, 0);
+      if (F32DY) {
 #pragma unroll
-      for (int ch = 0; ch < CH; ++ch) {
-        const int c = (ch * LPR + sub) * 8;
-        xr[u][ch] = ar[u][ch] = make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dy[u][ch][j] = 0.f;
-        if (ok && c < p.H) {
-          if (p.dy_bf16) {
-            const uint4 r = __ldg(reinterpret_cast<const uint4*>(p.dy_bf16 + t * p.lddy + c));
-            unpack8(r, dy[u][ch]);
-          } else {
-            load8_f32(p.dy_f32 + t * p.lddy + c, dy[u][ch]);
-          }
-          xr[u][ch] = __ldg(reinterpret_cast<const uint4*>(p.x + t * p.ldx + c));
-          if (p.add) ar[u][ch] = __ldg(reinterpret_cast<const uint4*>(p.add + t * p.ldadd + c));
-        }
+        for (int j = 0; j < 8; ++j) df[ch][j] = 0.f;
+      }
+      if (ok && c < p.H) {
+        if (F32DY) load8_f32(p.dy_f32 + t * p.lddy + c, df[ch]);
+        else dr[ch] = __ldg(reinterpret_cast<const uint4*>(p.dy_bf16 + t * p.lddy + c));
+        xr[ch] = __ldg(reinterpret_cast<const uint4*>(p.x + t * p.ldx + c));
+        if (p.add) ar[ch] = __ldg(reinterpret_cast<const uint4*>(p.add + t * p.ldadd + c));
       }
     }
+    const float mean = st.x, rstd = st.y;
+    float sg = 0.f, sgx = 0.f;
 #pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const int64_t t = t0 + u * RPW + grp;
-      const float mean = st[u].x, rstd = st[u].y;
-      float g[CH][8], xh[CH][8];
-      float sg = 0.f, sgx = 0.f;
+    for (int ch = 0; ch < CH; ++ch) {
+      const int c = (ch * LPR + sub) * 8;
+      const bool cok = c < p.H && ok;
+      float xv[8], dv[8];
+      unpack8(xr[ch], xv);
+      if (F32DY) {
 #pragma unroll
-      for (int ch = 0; ch < CH; ++ch) {
-        float xv[8];
-        unpack8(xr[u][ch], xv);
-        const bool cok = (ch * LPR + sub) * 8 < p.H && t < p.T;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          xh[ch][j] = cok ? (xv[j] - mean) * rstd : 0.f;
-          g[ch][j] = dy[u][ch][j] * gw[ch][j];
-          adw[ch][j] += dy[u][ch][j] * xh[ch][j];
-          adb[ch][j] += dy[u][ch][j];
-          sg += g[ch][j];
-          sgx += g[ch][j] * xh[ch][j];
-        }
+        for (int j = 0; j < 8; ++j) dv[j] = df[ch][j];
+      } else {
+        unpack8(dr[ch], dv);
       }
-      sg = group_sum<LPR>(sg) / p.H;
-      sgx = group_sum<LPR>(sgx) / p.H;
-      if (t >= p.T) continue;
+      const float4 w0 = *reinterpret_cast<const float4*>(sw + (cok ? c : 0)), w1 = *reinterpret_cast<const float4*>(sw + (cok ? c : 0) + 4);
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-      for (int ch = 0; ch < CH; ++ch) {
-        const int c = (ch * LPR + sub) * 8;
-        if (c >= p.H) continue;
-        float av[8], o[8];
-        unpack8(ar[u][ch], av);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (rstd * (g[ch][j] - sg - xh[ch][j] * sgx) + av[j]) * msk[u];
-        *reinterpret_cast<uint4*>(p.dx + t * p.lddx + c) = pack8(o);
+      for (int j = 0; j < 8; ++j) {
+        const float xh = cok ? (xv[j] - mean) * rstd : 0.f;
+        const float g = dv[j] * wv[j];
+        adw[ch][j] = fmaf(dv[j], xh, adw[ch][j]);
+        adb[ch][j] += dv[j];
+        sg += g;
+        sgx = fmaf(g, xh, sgx);
       }
     }
+    sg = group_sum<LPR>(sg) * invH;
+    sgx = group_sum<LPR>(sgx) * invH;
+    if (!ok) continue;
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch) {
+      const int c = (ch * LPR + sub) * 8;
+      if (c >= p.H) continue;
+      float xv[8], dv[8], av[8], o[8];
+      unpack8(xr[ch], xv);
+      unpack8(ar[ch], av);
+      if (F32DY) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dv[j] = df[ch][j];
+      } else {
+        unpack8(dr[ch], dv);
+      }
+      const float4 w0 = *reinterpret_cast<const float4*>(sw + c), w1 = *reinterpret_cast<const float4*>(sw + c + 4);
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (xv[j] - mean) * rstd;
+        o[j] = (rstd * (dv[j] * wv[j] - sg - xh * sgx) + av[j]) * msk;
+      }
+      *reinterpret_cast<uint4*>(p.dx + t * p.lddx + c) = pack8(o);
+    }
   }
-  // per-block reduction of the column partials in shared memory, then one red.add per column per block
+  // column partials: first across the row groups of the warp (lanes with equal `sub` hold the same columns), then one
+  // shared-memory atomic per column per warp, then one red.add per column per block
 #pragma unroll
   for (int ch = 0; ch < CH; ++ch) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int o = LPR; o < 32; o <<= 1) {
+        adw[ch][j] += __shfl_xor_sync(0xffffffffu, adw[ch][j], o);
+        adb[ch][j] += __shfl_xor_sync(0xffffffffu, adb[ch][j], o);
+      }
+    }
     const int c = (ch * LPR + sub) * 8;
-    if (c < p.H) {
+    if (grp == 0 && c < p.H) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) { atomicAdd(&sdw[c + j], adw[ch][j]); atomicAdd(&sdb[c + j], adb[ch][j]); }
     }
@@ -332,11 +351,25 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(LnBwdParams p) {
 }
 
 // dispatch on the row width: lanes per row x chunks per lane (8 features each)
-#define SRFRD_ROW_DISPATCH(H, CALL)                      \
+// backward keeps more per-lane state (column accumulators): one chunk per lane up to 256 columns
+#define SRFRD_ROW_DISPATCH_BWD(H, CALL)                  \
   do {                                                   \
     if ((H) <= 64) { CALL(8, 1); }                       \
     else if ((H) <= 128) { CALL(16, 1); }                \
     else if ((H) <= 256) { CALL(32, 1); }                \
+    else { CALL(32, 2); }                                \
+  } while (0)
+// (the capacity LPR * CH * 8 closest above H wins: H = 80 runs as 4 lanes x 3 chunks = 96 columns, 83 % of the
+//  lanes busy and two shuffle steps per reduction, instead of 16 x 1 = 128 columns at 62 %)
+#define SRFRD_ROW_DISPATCH(H, CALL)                      \
+  do {                                                   \
+    if ((H) <= 32) { CALL(4, 1); }                       \
+    else if ((H) <= 64) { CALL(8, 1); }                  \
+    else if ((H) <= 96) { CALL(4, 3); }                  \
+    else if ((H) <= 128) { CALL(16, 1); }                \
+    else if ((H) <= 192) { CALL(8, 3); }                 \
+    else if ((H) <= 256) { CALL(32, 1); }                \
+    else if ((H) <= 384) { CALL(16, 3); }                \
     else { CALL(32, 2); }                                \
   } while (0)
 
@@ -504,7 +537,12 @@ extern "C" int srfrd_layernorm_bwd(const void* dy_bf16, const float* dy_f32, int
   p.dy_bf16 = (const bf16*)dy_bf16; p.dy_f32 = dy_f32; p.lddy = lddy; p.x = (const bf16*)x; p.ldx = ldx;
   p.stats = stats; p.w = w; p.add = (const bf16*)add; p.ldadd = ldadd; p.row_ids = row_ids; p.dx = (bf16*)dx;
   p.lddx = lddx; p.dw = dw; p.db = db; p.T = T; p.H = H;
-#define CALL(LPR, CH) ln_bwd_kernel<LPR, CH><<<grid_for_rows(T, 16 * (32 / LPR) * 8, 4), 256, 0, (cudaStream_t)stream>>>(p)
+#define CALL(LPR, CH)                                                                                             \
+  do {                                                                                                            \
+    const int grid = grid_for_rows(T, 8 * (32 / LPR) * 8, 2);                                                     \
+    if (dy_f32) ln_bwd_kernel<LPR, CH, true><<<grid, 256, 0, (cudaStream_t)stream>>>(p);                          \
+    else ln_bwd_kernel<LPR, CH, false><<<grid, 256, 0, (cudaStream_t)stream>>>(p);                                \
+  } while (0)
   SRFRD_ROW_DISPATCH(H, CALL);
 #undef CALL
   SRFRD_LAUNCH_CHECK();

@@ -83,3 +83,13 @@ if what in ("ln", "all"):
     dw, dbb = torch.zeros(H, device="cuda"), torch.zeros(H, device="cuda")
     timeit("layernorm_bwd", lambda i: ops.layernorm_bwd(res[i % NBUF], acts[i % NBUF], st, w, outs[i % NBUF], dw, dbb), 3 * A + T * 8)
     timeit("layernorm_bwd +add+rowmask", lambda i: ops.layernorm_bwd(res[i % NBUF], acts[i % NBUF], st, w, outs[i % NBUF], dw, dbb, add=acts[(i + 1) % NBUF], row_ids=ids), 4 * A + T * 16)
+
+if what in ("k1", "all"):
+    N = 12101
+    E, P, Fe = rnd(N + 1, 64, dtype=torch.float32), rnd(L, 64, dtype=torch.float32), rnd(3, H - 64, dtype=torch.float32)
+    seq = torch.randint(0, N + 1, (B, L), device="cuda")
+    seq[:, : L // 2] = 0
+    rsq = torch.randint(0, 3, (B, L), device="cuda")
+    w, b = rnd(H, dtype=torch.float32), rnd(H, dtype=torch.float32)
+    st = torch.empty(T, 2, device="cuda")
+    timeit("embed_ln_fwd (K1) 50% valid", lambda i: ops.embed_ln_fwd(E, P, Fe, 1, seq, rsq, 1.0, w, b, 1e-8, x0_bf16=outs[i % NBUF], q_bf16=acts[i % NBUF], stats=st), 2 * A + T * 24 + T * 128)
