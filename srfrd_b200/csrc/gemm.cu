@@ -42,6 +42,7 @@ struct GemmEpilogue {
 
 // profiling experiments only (SRFRD_GEMM_DEBUG=5): clock64 timeline of CTA 0, [event][tile], read by srfrd_gemm_debug_read
 __device__ long long g_gemm_dbg[32 * 16];
+__device__ long long g_gemm_cta[2 * 160];     // per-CTA start / end globaltimer (SRFRD_GEMM_DEBUG=5)
 #define TN_STAMP(ev, tile) do { if (s.debug == 5 && blockIdx.x == 0 && (tile) < 16) { if (elect_one()) g_gemm_dbg[(ev) * 16 + (tile)] = clock64(); } } while (0)
 
 struct GemmShape {
@@ -125,9 +126,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     fence_barrier_init();
   }
-  if (s.debug == 5 && blockIdx.x == 0 && threadIdx.x == 0) {
+  if (s.debug == 5 && threadIdx.x == 0) {
     unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-    g_gemm_dbg[10 * 16] = (long long)gt; g_gemm_dbg[10 * 16 + 1] = clock64();
+    if (blockIdx.x == 0) { g_gemm_dbg[10 * 16] = (long long)gt; g_gemm_dbg[10 * 16 + 1] = clock64(); }
+    if (blockIdx.x < 160) g_gemm_cta[2 * blockIdx.x] = (long long)gt;
   }
   if (warp == 17) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
   for (int i = threadIdx.x; i < MAX_BIAS; i += blockDim.x) sbias[i] = (e.bias && i < s.N) ? __ldg(e.bias + i) : 0.f;
@@ -314,9 +316,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
-  if (s.debug == 5 && blockIdx.x == 0 && threadIdx.x == 0) {
+  if (s.debug == 5 && threadIdx.x == 0) {
     unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-    g_gemm_dbg[11 * 16] = (long long)gt; g_gemm_dbg[11 * 16 + 1] = clock64();
+    if (blockIdx.x == 0) { g_gemm_dbg[11 * 16] = (long long)gt; g_gemm_dbg[11 * 16 + 1] = clock64(); }
+    if (blockIdx.x < 160) g_gemm_cta[2 * blockIdx.x + 1] = (long long)gt;
   }
   if (warp == 17) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
@@ -562,6 +565,7 @@ extern "C" int srfrd_gemm_tn(const void* A, int lda, const void* B, int ldb, int
 extern "C" int srfrd_gemm_debug_read(long long* host_dst) {
   SRFRD_CUDA(cudaDeviceSynchronize());
   SRFRD_CUDA(cudaMemcpyFromSymbol(host_dst, g_gemm_dbg, sizeof(long long) * 32 * 16));
+  SRFRD_CUDA(cudaMemcpyFromSymbol(host_dst + 32 * 16, g_gemm_cta, sizeof(long long) * 2 * 160));
   return 0;
 }
 

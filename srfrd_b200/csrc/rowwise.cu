@@ -34,6 +34,15 @@ __device__ __forceinline__ void load8_f32(const float* p, float* f) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
   f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
+// item-table rows are read once per lookup: no L1 allocation, 256-byte L2 fetch granularity (a D = 64 row is 256 B)
+__device__ __forceinline__ void load8_f32_stream(const float* p, float* f) {
+  float4 a, b;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p + 4));
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
 __device__ __forceinline__ void store8_f32(float* p, const float* f) {
   reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
   reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
@@ -61,7 +70,7 @@ struct EmbedParams {
 };
 
 template <int LPR, int CH>
-__global__ void __launch_bounds__(256) embed_ln_kernel(EmbedParams p) {
+__global__ void __launch_bounds__(256, 4) embed_ln_kernel(EmbedParams p) {
   if (p.drop_thresh) p.drop_seed = mix_seed(p.drop_seed, p.drop_step);
   constexpr int RPW = 32 / LPR;                         // rows per warp pass
   const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
@@ -92,7 +101,7 @@ __global__ void __launch_bounds__(256) embed_ln_kernel(EmbedParams p) {
           // __fmul_rn/__fadd_rn: no FMA contraction, so the pre-LN tensor is bit-identical to
           // torch's  E[id] (* sqrt(d)) + P[l] (+ Ul[label])   (SRFR_model.py:22-25, :622-624, :419-422)
           float e[8], pp[8];
-          load8_f32(p.item_table + id * p.D + c, e);
+          load8_f32_stream(p.item_table + id * p.D + c, e);
           load8_f32(p.pos_table + (int64_t)l * p.D + c, pp);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {

@@ -36,25 +36,18 @@ struct TopkShape {
   int row_lo, row_hi;     // candidate rows of the (local) table: [row_lo, row_hi)
   int64_t id_base;        // global item id of local row 0
   int kblocks;            // ceil(D / 64)
+  int nt;                 // item rows per tile
   int tiles_total;        // item tiles over [row_lo, row_hi)
-  int chunks, tiles_per_chunk, ugroups;
+  int ugroups;            // user groups of UBS * 128 rows
+  int64_t share;          // (user group, item tile) pairs per CTA: CTA i owns the linear range [i * share, (i + 1) * share)
+  int slots;              // tile-maxima lists per row = 2 epilogue sets x max pieces a user group is cut into
   int stages;
-  int debug;              // SRFRD_TOPK_DEBUG (profiling experiments only): 1 = no scan, 2 = no TMEM loads either
+  int debug;              // SRFRD_TOPK_DEBUG (profiling experiments only): 1 = never insert
   const bf16* feats; int ld_feats;
-  float* out_scores;      // (U, chunks, TK)
-  int* out_ids;           // (U, chunks, TK)  global ids (int32), -1 = empty
+  const bf16* table; int ld_table;
+  float* out_scores;      // (U, slots, TK)  phase 1: tile maxima; phase 2 writes the row's exact top-10 into slot 0
+  int* out_ids;           // (U, slots, TK)  phase 1: tile indices (-1 = empty); phase 2: global item ids in slot 0
 };
-
-__device__ __forceinline__ void list_insert(float (&ts)[TK], int (&ti)[TK], float s, int id) {
-  ts[TK - 1] = s; ti[TK - 1] = id;
-#pragma unroll
-  for (int r = TK - 1; r > 0; --r) {
-    if (ts[r] > ts[r - 1]) {          // strict: an equal score never overtakes an earlier (lower) id
-      const float fs = ts[r]; ts[r] = ts[r - 1]; ts[r - 1] = fs;
-      const int is = ti[r]; ti[r] = ti[r - 1]; ti[r - 1] = is;
-    }
-  }
-}
 
 // D[tmem] (+)= A[tmem] * B[smem]
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
@@ -72,53 +65,107 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
                : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync_t(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
-template <int UBS, int NT>
-__global__ void __launch_bounds__(96 + 128 * UBS, 1)
-catalogue_topk_kernel(const __grid_constant__ CUtensorMap tmE, TopkShape s) {
-  constexpr int NG = NT / 32;                         // 32-column groups per thread per tile
+// Sorted (value desc) list of TK entries per thread in shared memory, entry k of thread x at [k * stride + x].
+// Keys reach a thread in increasing order, so the strict comparison keeps the lower key ahead on ties.
+// All TK entries are loaded at once (one shared-memory latency instead of a dependent walk), the insertion
+// position is a count of compares and the shift is a chain of selects.  Returns the new 10th best value.
+__device__ __forceinline__ float list_insert_smem(float* ls, int* li, int stride, float sc, int id) {
+  float v[TK]; int ix[TK];
+#pragma unroll
+  for (int k = 0; k < TK; ++k) { v[k] = ls[k * stride]; ix[k] = li[k * stride]; }
+  int r = 0;                                   // entries that stay ahead of the new one
+#pragma unroll
+  for (int k = 0; k < TK; ++k) r += (v[k] >= sc) ? 1 : 0;
+#pragma unroll
+  for (int k = TK - 1; k >= 1; --k) {
+    const bool shift = k > r, here = k == r;
+    const float nv = shift ? v[k - 1] : (here ? sc : v[k]);
+    const int ni = shift ? ix[k - 1] : (here ? id : ix[k]);
+    if (k >= r) { ls[k * stride] = nv; li[k * stride] = ni; }
+    v[k] = nv;
+  }
+  if (r == 0) { ls[0] = sc; li[0] = id; }
+  return v[TK - 1];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Phase 1 (tcgen05): per user row, the TK item tiles with the largest TILE MAXIMUM score.
+//
+// Why tile maxima are enough: order tiles by (max desc, tile index asc) and items by (score desc, id asc).  If an item
+// x of tile T were in the row's top TK without T being among the TK best tiles, each of those TK tiles C would hold an
+// item at least as good as x (its maximum: a larger score, or an equal score at a lower id because C < T and tiles are
+// contiguous id ranges) -- TK items ahead of x, a contradiction.  So the exact top TK items all live in the TK best
+// tiles, and phase 2 re-scores just those TK x NT items per row.  The streaming epilogue therefore needs ONE value per
+// (row, tile) -- a chain of FMNMX3 over the row's NT scores -- and ONE compare against the row's current TK-th best
+// tile maximum; an insertion handles a (value, tile index) pair, never a column search.
+//
+// One CTA per SM; every CTA owns an equal share of the linear (user group, item tile) space, cut into "pieces" at
+// user-group boundaries (a piece = one user group x a run of item tiles; its user tiles are staged into TMEM once).
+//   NACC accumulator stages (UBS x NT fp32 columns each) with ONE ISSUER WARP PER STAGE: a tile's MMAs cost a few
+//     hundred cycles of barrier waits, fences and commits on the issuing thread, so the tensor pipe only stays busy
+//     with three issuers working on consecutive tiles.
+//   Two epilogue sets of 4 * UBS warps take alternate tiles.  A thread reads its row's NT scores out of TMEM in one
+//     round trip and hands the accumulator back at once.  (Measured on this part: tcgen05.ld sustains > 800 B/clk/SM
+//     with enough loads in flight, but a lone warp sees ~160 cycles per round trip -- the epilogue is a latency chain,
+//     so it is split over many warps and kept off the accumulator's critical path.)  The per-thread lists live in
+//     shared memory and are only touched on the rare insertion; the two threads that serve the same row (one per set)
+//     publish their current threshold to each other: a tile below EITHER list's TK-th best cannot be a top-TK tile.
+//   Control warps have the highest warp ids (the scheduler favours them).
+// Barriers are never shared by waiters that would skip phases: smem stage s is always consumed by issuer
+// (tile % NACC) because the ring length is a multiple of NACC * kblocks, and tfull is indexed [stage][set].
+template <int UBS, int NT, int NACC>
+__global__ void __launch_bounds__(32 * (8 * UBS + 4), 1)
+catalogue_tilemax_kernel(const __grid_constant__ CUtensorMap tmE, TopkShape s) {
+  constexpr int NEPI = 8 * UBS;                       // epilogue warps
   constexpr int ACC_STRIDE = UBS * NT;                // TMEM columns per accumulator stage
   constexpr int B_TILE_BYTES = NT * KB * 2;
+  constexpr int LSTR = NEPI * 32;                     // list stride (threads)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smB = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + s.stages * B_TILE_BYTES);
+  float* lsc = reinterpret_cast<float*>(smB + s.stages * B_TILE_BYTES);       // [TK][LSTR]
+  int* lid = reinterpret_cast<int*>(lsc + TK * LSTR);
+  float* lthr = reinterpret_cast<float*>(lid + TK * LSTR);                    // [LSTR] current TK-th best per thread
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lthr + LSTR);
   uint64_t* full = bars;
   uint64_t* empty = bars + s.stages;
-  uint64_t* tfull = bars + 2 * s.stages;
-  uint64_t* tempty = tfull + 2;
-  uint64_t* afull = tempty + 2;
+  uint64_t* tfull = bars + 2 * s.stages;              // [NACC][2 sets]
+  uint64_t* tempty = tfull + 2 * NACC;                // [NACC]
+  uint64_t* afull = tempty + NACC;
   uint64_t* aempty = afull + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_units = s.ugroups * s.chunks;
   const int a_cols = s.n_split * (s.D / 2);           // 32-bit TMEM columns of one user tile
+  const int64_t total = (int64_t)s.ugroups * s.tiles_total;
+  const int64_t lin0 = (int64_t)blockIdx.x * s.share, lin1 = min(total, lin0 + s.share);
 
-  if (warp == 0 && lane == 0) {
+  if (warp == NEPI && lane == 0) {
     tma_prefetch_desc(&tmE);
     for (int i = 0; i < s.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * UBS); }
+    for (int i = 0; i < 2 * NACC; ++i) mbar_init(&tfull[i], 1);
+    for (int i = 0; i < NACC; ++i) mbar_init(&tempty[i], 4 * UBS);
     mbar_init(afull, 4 * UBS);
-    mbar_init(aempty, 2);
+    mbar_init(aempty, NACC);
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == NEPI + 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tA = tmem_base + 2 * ACC_STRIDE;     // user tiles live after the two accumulator stages
+  const uint32_t tA = tmem_base + NACC * ACC_STRIDE;  // user tiles live after the accumulator stages
 
-  // Warps 0 and 1 run their loops CONVERGED and only the issuing instructions sit under elect.sync: barrier
-  // addresses, descriptors and TMEM addresses then stay in uniform registers (inside an `if (lane == 0)`
-  // region the compiler wraps every operand in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop, which made each
-  // tcgen05.mma cost > 100 issue cycles).
-  if (warp == 0) {
+  if (warp == NEPI) {
+    // ------------------------------------------------------------------ TMA producer (item tiles)
     int stage = 0; uint32_t phase = 0;
-    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-      const int ch = unit % s.chunks;
-      const int t0 = ch * s.tiles_per_chunk, t1 = min(s.tiles_total, t0 + s.tiles_per_chunk);
+    for (int64_t lin = lin0; lin < lin1;) {
+      const int t0 = (int)(lin % s.tiles_total);
+      const int t1 = (int)min((int64_t)s.tiles_total, t0 + (lin1 - lin));
       for (int t = t0; t < t1; ++t) {
         for (int kb = 0; kb < s.kblocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
@@ -130,31 +177,30 @@ catalogue_topk_kernel(const __grid_constant__ CUtensorMap tmE, TopkShape s) {
           if (++stage == s.stages) { stage = 0; phase ^= 1; }
         }
       }
+      lin += t1 - t0;
     }
-  } else if (warp == 1 || warp == 2) {
-    // TWO issuing warps, one per accumulator stage: with K = 64 a tile is only a few hundred MMA cycles, about
-    // as long as one warp needs for its barrier waits, fences and commits (measured ~350 cycles per tile), so
-    // a single issuer leaves the tensor pipe idle half of the time.  Warp w issues tiles n with n % 2 == w.
-    const int w = warp - 1;
+  } else if (warp > NEPI && warp <= NEPI + NACC) {
+    // ------------------------------------------------------------------ MMA issuer w: tiles with n % NACC == w
+    const int w = warp - NEPI - 1;
     const uint32_t idesc = umma_idesc_bf16(TILE_U, NT, 0, 0);
     const uint64_t bdesc0 = umma_smem_desc(smem_u32(smB), 0, 1024);
     const bool fast = s.D == 64 && s.n_split == 1;
     const uint32_t tacc = tmem_base + w * ACC_STRIDE;
     int stage = 0; uint32_t phase = 0, uphase = 0, aphase = 0;
-    int n = 0;
-    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-      const int ch = unit % s.chunks;
-      const int t0 = ch * s.tiles_per_chunk, t1 = min(s.tiles_total, t0 + s.tiles_per_chunk);
-      mbar_wait(afull, uphase);                         // user tiles of this unit are in TMEM
+    int n = 0;                                          // tiles seen by this CTA so far
+    for (int64_t lin = lin0; lin < lin1;) {
+      const int t0 = (int)(lin % s.tiles_total);
+      const int t1 = (int)min((int64_t)s.tiles_total, t0 + (lin1 - lin));
+      mbar_wait(afull, uphase);                         // user tiles of this piece are in TMEM
       uphase ^= 1;
       tc_fence_after();
       for (int t = t0; t < t1; ++t, ++n) {
-        if ((n & 1) != w) {                             // the other warp's tile: just advance the smem ring
+        if (n % NACC != w) {                            // another issuer's tile: just advance the smem ring
           stage += s.kblocks;
           if (stage >= s.stages) { stage -= s.stages; phase ^= 1; }
           continue;
         }
-        if (s.debug != 3) mbar_wait(&tempty[w], aphase ^ 1);
+        mbar_wait(&tempty[w], aphase ^ 1);
         aphase ^= 1;
         tc_fence_after();
         for (int kb = 0; kb < s.kblocks; ++kb) {
@@ -177,128 +223,235 @@ catalogue_topk_kernel(const __grid_constant__ CUtensorMap tmE, TopkShape s) {
                                  bd + 2 * k, idesc, (kb | sp | k) != 0);
             }
             umma_commit(&empty[stage]);
-            if (kb == s.kblocks - 1) umma_commit(&tfull[w]);
+            if (kb == s.kblocks - 1) umma_commit(&tfull[w * 2 + (n & 1)]);
           }
           __syncwarp();
           if (++stage == s.stages) { stage = 0; phase ^= 1; }
         }
       }
-      if (elect_one()) umma_commit(aempty);             // this warp's MMAs of the unit are done with the user tiles
+      if (elect_one()) umma_commit(aempty);             // this warp's MMAs of the piece are done with the user tiles
       __syncwarp();
+      lin += t1 - t0;
     }
-  } else {
-    const int e = warp - 3;
-    const int quarter = warp & 3, ub = e >> 2;
+  } else if (warp < NEPI) {
+    // ------------------------------------------------------------------ epilogue: set = tile parity
+    const int quarter = warp & 3, ub = (warp >> 2) % UBS, set = warp / (4 * UBS);
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    int as = 0; uint32_t aphase = 0, uphase = 0;
-    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-      const int ug = unit / s.chunks, ch = unit % s.chunks;
-      const int t0 = ch * s.tiles_per_chunk, t1 = min(s.tiles_total, t0 + s.tiles_per_chunk);
+    float* thr_mine = lthr + warp * 32 + lane;
+    const float* thr_other = lthr + ((warp + 4 * UBS) % NEPI) * 32 + lane;   // same user row, other set
+    uint32_t cnt[NACC];                                 // uses of tfull[a][set] so far -> wait parity
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) cnt[a] = 0;
+    uint32_t uphase = 0;
+    int n = 0;
+    for (int64_t lin = lin0; lin < lin1;) {
+      const int ug = (int)(lin / s.tiles_total);
+      const int t0 = (int)(lin % s.tiles_total);
+      const int t1 = (int)min((int64_t)s.tiles_total, t0 + (lin1 - lin));
+      const int piece = (int)(lin / s.share - ((int64_t)ug * s.tiles_total) / s.share);
       const int urow = (ug * UBS + ub) * TILE_U + quarter * 32 + lane;
-      // ---- stage this thread's user row into tensor memory (A operand, K-major, 2 bf16 per column) ----
-      mbar_wait(aempty, uphase ^ 1);                      // previous unit's MMAs no longer read the user tiles
-      uphase ^= 1;
-      tc_fence_after();
-      for (int sp = 0; sp < s.n_split; ++sp) {
-        const uint4* src = reinterpret_cast<const uint4*>(s.feats + ((size_t)sp * s.u_pad + urow) * s.ld_feats);
-        for (int c = 0; c < s.D / 2; c += 8) {            // 8 columns = 16 features = one UMMA K step
-          uint32_t v[8];
-          uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
-          if (urow < s.U) { lo = __ldg(src + c / 4); hi = __ldg(src + c / 4 + 1); }
-          v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
-          tmem_st8(tA + lane_off + ub * a_cols + sp * (s.D / 2) + c, v);
-        }
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(afull);
-
-      float ts[TK]; int ti[TK];
-#pragma unroll
-      for (int r = 0; r < TK; ++r) { ts[r] = -INFINITY; ti[r] = -1; }
-      for (int t = t0; t < t1; ++t) {
-        mbar_wait(&tfull[as], aphase);
+      if (set == 0) {
+        // ---- stage this thread's user row into tensor memory (A operand, K-major, 2 bf16 per column) ----
+        mbar_wait(aempty, uphase ^ 1);                    // previous piece's MMAs no longer read the user tiles
+        uphase ^= 1;
         tc_fence_after();
-        const uint32_t taddr = tmem_base + lane_off + as * ACC_STRIDE + ub * NT;
-        const int col_row0 = s.row_lo + t * NT;                      // local table row of column 0
-        // all NT scores of this thread's row in flight at once (one TMEM round trip per tile)
-        uint32_t raw[NG][32];
-        if (s.debug == 2) {
-#pragma unroll
-          for (int g = 0; g < NG; ++g)
-#pragma unroll
-            for (int j = 0; j < 32; ++j) raw[g][j] = 0xff800000u;
-        } else {
-#pragma unroll
-          for (int g = 0; g < NG; ++g) tmem_ld32(taddr + g * 32, raw[g]);
-          tmem_ld_wait();
-        }
-        if (s.debug >= 1) {
-          uint32_t x = 0;
-#pragma unroll
-          for (int g = 0; g < NG; ++g) x |= raw[g][0] & raw[g][31];
-          if (x == 0x12345678u) ts[0] = 1.f;
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[as]);
-          if (++as == 2) { as = 0; aphase ^= 1; }
-          continue;
-        }
-        float gm[NG];
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-          // FMNMX3: two scores folded per ALU instruction
-          float m0 = fmax3(__uint_as_float(raw[g][0]), __uint_as_float(raw[g][1]), __uint_as_float(raw[g][2]));
-          float m1 = fmax3(__uint_as_float(raw[g][3]), __uint_as_float(raw[g][4]), __uint_as_float(raw[g][5]));
-#pragma unroll
-          for (int j = 6; j < 30; j += 4) {
-            m0 = fmax3(m0, __uint_as_float(raw[g][j]), __uint_as_float(raw[g][j + 1]));
-            m1 = fmax3(m1, __uint_as_float(raw[g][j + 2]), __uint_as_float(raw[g][j + 3]));
-          }
-          gm[g] = fmax3(fmaxf(m0, m1), __uint_as_float(raw[g][30]), __uint_as_float(raw[g][31]));
-        }
-        float tmax = gm[0];
-#pragma unroll
-        for (int g = 1; g < NG; ++g) tmax = fmaxf(tmax, gm[g]);
-        if (__any_sync(0xffffffffu, tmax > ts[TK - 1])) {
-#pragma unroll
-          for (int g = 0; g < NG; ++g) {
-            if (!__any_sync(0xffffffffu, gm[g] > ts[TK - 1])) continue;
-            uint32_t mask = 0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(raw[g][j]) > ts[TK - 1]) ? (1u << j) : 0u;
-            uint32_t wmask = __reduce_or_sync(0xffffffffu, mask);
-            const int base = col_row0 + g * 32;
-            while (wmask) {
-              const int j = __ffs(wmask) - 1;
-              wmask &= wmask - 1;
-              uint32_t one;
-              tmem_ld1(taddr + g * 32 + j, one);
-              tmem_ld_wait();
-              const float sc = __uint_as_float(one);
-              if (sc > ts[TK - 1] && base + j < s.row_hi) list_insert(ts, ti, sc, base + j);
-            }
+        for (int sp = 0; sp < s.n_split; ++sp) {
+          const uint4* src = reinterpret_cast<const uint4*>(s.feats + ((size_t)sp * s.u_pad + urow) * s.ld_feats);
+          for (int c = 0; c < s.D / 2; c += 8) {            // 8 columns = 16 features = one UMMA K step
+            uint32_t v[8];
+            uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+            if (urow < s.U) { lo = __ldg(src + c / 4); hi = __ldg(src + c / 4 + 1); }
+            v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+            tmem_st8(tA + lane_off + ub * a_cols + sp * (s.D / 2) + c, v);
           }
         }
+        tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[as]);
-        if (++as == 2) { as = 0; aphase ^= 1; }
+        if (lane == 0) mbar_arrive(afull);
+      }
+      float ts[TK]; int ti[TK];                       // this thread's TK best (tile maximum, tile index), sorted
+#pragma unroll
+      for (int r = 0; r < TK; ++r) { ts[r] = -INFINITY; ti[r] = -1; }
+      float thr = -INFINITY;
+      *thr_mine = -INFINITY;
+      // both threads of a row start the piece together: the partner's published threshold always belongs to THIS piece
+      named_bar_sync_t(1 + ub * 4 + quarter, 64);
+      for (int t = t0; t < t1; ++t, ++n) {
+        if ((n & 1) != set) continue;                     // the other set's tile
+        const int a = n % NACC;
+        uint32_t par = 0;
+#pragma unroll
+        for (int q = 0; q < NACC; ++q)
+          if (q == a) { par = cnt[q] & 1; cnt[q]++; }
+        const float thr_p = *thr_other;
+        mbar_wait(&tfull[a * 2 + set], par);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + lane_off + a * ACC_STRIDE + ub * NT;
+        uint32_t r0[32], r1[32];
+        tmem_ld32(taddr, r0);
+        if (NT > 32) tmem_ld32(taddr + 32, r1);
+        tmem_ld_wait();
+        tc_fence_before();                                // scores are in registers: hand the accumulator back now
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[a]);
+        if (t == s.tiles_total - 1) {                     // last tile of the table: columns past row_hi are not items
+          const int col_row0 = s.row_lo + t * NT;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (col_row0 + j >= s.row_hi) r0[j] = 0xff800000u;
+            if (NT > 32 && col_row0 + 32 + j >= s.row_hi) r1[j] = 0xff800000u;
+          }
+        }
+        // FMNMX3: two scores folded per ALU instruction
+        float m0 = fmax3(__uint_as_float(r0[0]), __uint_as_float(r0[1]), __uint_as_float(r0[2]));
+        float m1 = fmax3(__uint_as_float(r0[3]), __uint_as_float(r0[4]), __uint_as_float(r0[5]));
+#pragma unroll
+        for (int j = 6; j < 30; j += 4) {
+          m0 = fmax3(m0, __uint_as_float(r0[j]), __uint_as_float(r0[j + 1]));
+          m1 = fmax3(m1, __uint_as_float(r0[j + 2]), __uint_as_float(r0[j + 3]));
+        }
+        m0 = fmax3(m0, __uint_as_float(r0[30]), __uint_as_float(r0[31]));
+        if (NT > 32) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            m0 = fmax3(m0, __uint_as_float(r1[j]), __uint_as_float(r1[j + 1]));
+            m1 = fmax3(m1, __uint_as_float(r1[j + 2]), __uint_as_float(r1[j + 3]));
+          }
+        }
+        const float tmax = fmaxf(m0, m1);
+        thr = fmaxf(thr, thr_p);
+        if (tmax > thr && s.debug != 1) {                 // rare after warm-up, thread-divergent
+          ts[TK - 1] = tmax; ti[TK - 1] = t;
+#pragma unroll
+          for (int r = TK - 1; r > 0; --r) {              // strict: an equal maximum never overtakes an earlier tile
+            if (ts[r] > ts[r - 1]) {
+              const float fs = ts[r]; ts[r] = ts[r - 1]; ts[r - 1] = fs;
+              const int is = ti[r]; ti[r] = ti[r - 1]; ti[r - 1] = is;
+            }
+          }
+          thr = fmaxf(thr, ts[TK - 1]);
+          *thr_mine = thr;
+        }
       }
       if (urow < s.U) {
-        const size_t o = ((size_t)urow * s.chunks + ch) * TK;
+        const size_t o = ((size_t)urow * s.slots + piece * 2 + set) * TK;
 #pragma unroll
         for (int r = 0; r < TK; ++r) {
           s.out_scores[o + r] = ts[r];
-          s.out_ids[o + r] = ti[r] < 0 ? -1 : (int)(s.id_base + ti[r]);
+          s.out_ids[o + r] = ti[r];
         }
       }
+      lin += t1 - t0;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+  if (warp == NEPI + 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Phase 2: one warp per user row.  Merge the row's tile-maxima lists into the TK best tiles (max desc, tile asc),
+// re-score their TK x NT items with the same bf16 operands (fp32 accumulation), keep the exact top TK by
+// (score desc, id asc) and write it into slot 0 of the row's list buffer (global ids); the other slots are emptied
+// so that the merge kernel K9 sees one list per row and shard.
+__device__ __forceinline__ bool better(float sa, int ia, float sb, int ib) {       // (score desc, id asc); id < 0 = empty
+  if (ib < 0) return ia >= 0;
+  if (ia < 0) return false;
+  return sa > sb || (sa == sb && ia < ib);
+}
+
+__global__ void __launch_bounds__(256) catalogue_refine_kernel(TopkShape s) {
+  const int lane = threadIdx.x & 31;
+  const int64_t u = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (u >= s.U) return;
+  float* osc = s.out_scores + (size_t)u * s.slots * TK;
+  int* oid = s.out_ids + (size_t)u * s.slots * TK;
+  const int nent = s.slots * TK;
+  // ---- 1. the TK best tiles: TK rounds of warp arg-best over the (value, tile) pairs, each lane holding a strided share
+  int tiles[TK];
+  float last_v = INFINITY; int last_t = -1;             // everything chosen so far is better than (last_v, last_t)
+#pragma unroll 1
+  for (int r = 0; r < TK; ++r) {
+    float bv = -INFINITY; int bt = -1;
+    for (int e = lane; e < nent; e += 32) {
+      const float v = osc[e]; const int t = oid[e];
+      if (t < 0) continue;
+      const bool after_last = (last_t < 0) || v < last_v || (v == last_v && t > last_t);   // not chosen yet
+      if (after_last && better(v, t, bv, bt)) { bv = v; bt = t; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int ot = __shfl_xor_sync(0xffffffffu, bt, o);
+      if (better(ov, ot, bv, bt)) { bv = ov; bt = ot; }
+    }
+    tiles[r] = bt;
+    if (bt >= 0) { last_v = bv; last_t = bt; }
+  }
+  __syncwarp();
+  // ---- 2. exact scores of the candidate items; every lane keeps its own sorted top TK
+  float ts[TK]; int ti[TK];
+#pragma unroll
+  for (int r = 0; r < TK; ++r) { ts[r] = -INFINITY; ti[r] = -1; }
+#pragma unroll 1
+  for (int r = 0; r < TK; ++r) {
+    const int t = tiles[r];
+    if (t < 0) continue;
+    for (int j = lane; j < s.nt; j += 32) {
+      const int row = s.row_lo + t * s.nt + j;
+      if (row >= s.row_hi) continue;
+      const uint4* e = reinterpret_cast<const uint4*>(s.table + (size_t)row * s.ld_table);
+      float acc = 0.f;
+      for (int sp = 0; sp < s.n_split; ++sp) {
+        const uint4* f = reinterpret_cast<const uint4*>(s.feats + ((size_t)sp * s.u_pad + u) * s.ld_feats);
+        float a = 0.f;
+        for (int c = 0; c < s.D / 8; ++c) {
+          const uint4 fv = __ldg(f + c), ev = __ldg(e + c);
+          const uint32_t fw[4] = {fv.x, fv.y, fv.z, fv.w}, ew[4] = {ev.x, ev.y, ev.z, ev.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&fw[q]));
+            const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ew[q]));
+            a = fmaf(x.x, y.x, a);
+            a = fmaf(x.y, y.y, a);
+          }
+        }
+        acc += a;
+      }
+      if (better(acc, row, ts[TK - 1], ti[TK - 1])) {
+        ts[TK - 1] = acc; ti[TK - 1] = row;
+#pragma unroll
+        for (int k = TK - 1; k > 0; --k) {
+          if (better(ts[k], ti[k], ts[k - 1], ti[k - 1])) {
+            const float fs = ts[k]; ts[k] = ts[k - 1]; ts[k - 1] = fs;
+            const int is = ti[k]; ti[k] = ti[k - 1]; ti[k - 1] = is;
+          }
+        }
+      }
+    }
+  }
+  // ---- 3. warp merge: TK rounds; the lane whose head wins pops it
+  __syncwarp();
+  for (int e = lane; e < nent; e += 32) oid[e] = -1;    // empty every slot (phase-1 entries are consumed)
+  __syncwarp();
+#pragma unroll 1
+  for (int r = 0; r < TK; ++r) {
+    float bv = ts[0]; int bi = ti[0]; int bl = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; bl = ol; }
+    }
+    if (lane == 0) { osc[r] = bv; oid[r] = bi < 0 ? -1 : (int)(s.id_base + bi); }
+    if (lane == bl && bi >= 0) {                        // pop my head
+#pragma unroll
+      for (int k = 0; k < TK - 1; ++k) { ts[k] = ts[k + 1]; ti[k] = ti[k + 1]; }
+      ts[TK - 1] = -INFINITY; ti[TK - 1] = -1;
+    }
+  }
 }
 
 // K9: merge `nlists` candidate lists of length TK per user into the best k, order (score desc, id asc).
@@ -336,58 +489,61 @@ __global__ void merge_topk_kernel(const float* sc, const int* ids, int64_t U, in
 
 using namespace srfrd;
 
-// tile configuration: UBS user tiles x NT item columns; TMEM: 2 * UBS * NT accumulator + UBS * a_cols operand columns
-struct TopkCfg { int ubs, nt; };
+// tile configuration: UBS user tiles x NT item columns x NACC accumulator stages;
+// TMEM: NACC * UBS * NT accumulator + UBS * a_cols operand columns <= 512
+struct TopkCfg { int ubs, nt, nacc; };
 static TopkCfg pick_cfg(int D, int n_split) {
   const int a_cols = n_split * (D / 2);
-  const TopkCfg cands[] = {{2, 96}, {3, 64}, {2, 64}, {1, 128}, {1, 64}, {1, 32}};   // measured order at C3
-  const char* force = getenv("SRFRD_TOPK_CFG");       // e.g. "2x96" (experiments)
-  if (force) {
-    int u = 0, n = 0;
-    if (sscanf(force, "%dx%d", &u, &n) == 2)
-      for (const TopkCfg& c : cands)
-        if (c.ubs == u && c.nt == n && 2 * c.ubs * c.nt + c.ubs * a_cols <= 512) return c;
-  }
+  const TopkCfg cands[] = {{2, 64, 3}, {1, 64, 3}, {1, 64, 2}, {1, 32, 2}};
   for (const TopkCfg& c : cands)
-    if (2 * c.ubs * c.nt + c.ubs * a_cols <= 512) return c;
-  return TopkCfg{0, 0};
+    if (c.nacc * c.ubs * c.nt + c.ubs * a_cols <= 512) return c;
+  return TopkCfg{0, 0, 0};
 }
 
-static int plan_chunks(const TopkCfg& c, int64_t U, int64_t n_rows, int64_t row_lo) {
-  const int64_t tiles = (n_rows - row_lo + c.nt - 1) / c.nt;
-  const int64_t ugroups = (U + c.ubs * TILE_U - 1) / (c.ubs * TILE_U);
-  // One wave of work units: every unit restarts its top-10 lists cold (about 10 ln(n/10) insertions per row
-  // over n items), so item chunks are only used to occupy SMs that the user groups alone would leave idle.
-  int64_t chunks = ugroups > 0 ? num_sms() / ugroups : 1;
-  if (chunks > tiles / 8) chunks = tiles / 8;
-  if (chunks < 1) chunks = 1;
-  const int64_t per = (tiles + chunks - 1) / chunks;
-  chunks = per > 0 ? (tiles + per - 1) / per : 1;
-  return (int)(chunks < 1 ? 1 : chunks);
+struct TopkPlan { int ugroups, tiles_total, grid, slots; int64_t share; };
+static TopkPlan make_plan(const TopkCfg& c, int64_t U, int64_t n_rows, int64_t row_lo) {
+  TopkPlan p;
+  p.tiles_total = (int)((n_rows - row_lo + c.nt - 1) / c.nt);
+  p.ugroups = (int)((U + c.ubs * TILE_U - 1) / (c.ubs * TILE_U));
+  const int64_t total = (int64_t)p.ugroups * p.tiles_total;
+  int64_t grid = num_sms();
+  if (grid > total) grid = total;
+  // A piece restarts its lists cold (about 10 ln(n/10) insertions per row over n tiles): never cut a user group into
+  // pieces shorter than 64 tiles just to occupy more SMs.
+  const int64_t min_share = p.tiles_total < 64 ? p.tiles_total : 64;
+  p.share = (total + grid - 1) / grid;
+  if (p.share < min_share) p.share = min_share;
+  p.grid = (int)((total + p.share - 1) / p.share);
+  // a user group spans tiles_total consecutive indices; CTA boundaries fall on multiples of share
+  const int64_t max_pieces = (p.tiles_total + p.share - 1) / p.share + 1;
+  p.slots = (int)(2 * max_pieces);
+  return p;
 }
 
 extern "C" int srfrd_catalogue_topk_plan(int64_t U, int64_t n_rows, int64_t row_lo, int D, int n_split, int* chunks_out) {
   SRFRD_REQUIRE(chunks_out, "catalogue_topk_plan: null output");
   const TopkCfg c = pick_cfg(D, n_split);
   SRFRD_REQUIRE(c.ubs > 0, "catalogue_topk: D=%d with n_split=%d does not fit tensor memory", D, n_split);
-  *chunks_out = plan_chunks(c, U, n_rows, row_lo);
+  *chunks_out = make_plan(c, U, n_rows, row_lo).slots;
   return 0;
 }
 
-template <int UBS, int NT>
-static int launch_topk(const CUtensorMap& tmE, TopkShape& s, cudaStream_t stream) {
+template <int UBS, int NT, int NACC>
+static int launch_tilemax(const CUtensorMap& tmE, TopkShape& s, int grid, cudaStream_t stream) {
   const int b_tile = NT * KB * 2;
-  s.stages = (200 * 1024) / b_tile;
-  if (s.stages > 12) s.stages = 12;
-  const size_t smem = (size_t)s.stages * b_tile + 1024 + 512;
+  const int nepi = 8 * UBS;
+  const int list_bytes = (2 * TK + 1) * nepi * 32 * 4;
+  const int unit = NACC * s.kblocks;                    // ring length must be a multiple of this (see kernel comment)
+  s.stages = ((220 * 1024 - list_bytes) / b_tile) / unit * unit;
+  if (s.stages > 8 * unit) s.stages = 8 * unit;
+  SRFRD_REQUIRE(s.stages >= unit, "catalogue_topk: item tile ring does not fit shared memory");
+  const size_t smem = (size_t)s.stages * b_tile + list_bytes + 1024 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    SRFRD_CUDA(cudaFuncSetAttribute(catalogue_topk_kernel<UBS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SRFRD_CUDA(cudaFuncSetAttribute(catalogue_tilemax_kernel<UBS, NT, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  int grid = s.ugroups * s.chunks;
-  if (grid > num_sms()) grid = num_sms();
-  catalogue_topk_kernel<UBS, NT><<<grid, 96 + 128 * UBS, smem, stream>>>(tmE, s);
+  catalogue_tilemax_kernel<UBS, NT, NACC><<<grid, 32 * (nepi + 4), smem, stream>>>(tmE, s);
   SRFRD_LAUNCH_CHECK();
   return 0;
 }
@@ -399,32 +555,38 @@ extern "C" int srfrd_catalogue_topk(const void* feats_bf16, int64_t U, int64_t u
   SRFRD_REQUIRE(feats_bf16 && table_bf16 && part_scores && part_ids, "catalogue_topk: null pointer");
   SRFRD_REQUIRE(n_split >= 1 && n_split <= 3, "catalogue_topk: n_split must be 1..3");
   SRFRD_REQUIRE(D % 16 == 0 && ld_feats % 8 == 0 && ld_table % 8 == 0, "catalogue_topk: D %% 16 and ld %% 8 required (D=%d)", D);
-  SRFRD_REQUIRE(((uintptr_t)feats_bf16 & 15) == 0, "catalogue_topk: feats must be 16-byte aligned");
+  SRFRD_REQUIRE(((uintptr_t)feats_bf16 & 15) == 0 && ((uintptr_t)table_bf16 & 15) == 0, "catalogue_topk: operands must be 16-byte aligned");
   SRFRD_REQUIRE(U > 0 && n_rows > row_lo && row_lo >= 0, "catalogue_topk: empty problem");
   SRFRD_REQUIRE(n_rows < (1ll << 31) && id_base + n_rows < (1ll << 31), "catalogue_topk: ids must fit int32");
   const TopkCfg c = pick_cfg(D, n_split);
   SRFRD_REQUIRE(c.ubs > 0, "catalogue_topk: D=%d with n_split=%d does not fit tensor memory", D, n_split);
-  SRFRD_REQUIRE(chunks == plan_chunks(c, U, n_rows, row_lo), "catalogue_topk: chunks must come from srfrd_catalogue_topk_plan");
+  const TopkPlan pl = make_plan(c, U, n_rows, row_lo);
+  SRFRD_REQUIRE(chunks == pl.slots, "catalogue_topk: chunks must come from srfrd_catalogue_topk_plan");
   SRFRD_REQUIRE(u_pad >= U, "catalogue_topk: u_pad < U");
   TopkShape s;
   s.U = (int)U; s.D = D; s.n_split = n_split; s.u_pad = (int)u_pad;
   s.row_lo = (int)row_lo; s.row_hi = (int)n_rows; s.id_base = id_base;
   s.kblocks = (D + KB - 1) / KB;
-  s.tiles_total = (int)((n_rows - row_lo + c.nt - 1) / c.nt);
-  s.chunks = chunks;
-  s.tiles_per_chunk = (s.tiles_total + chunks - 1) / chunks;
-  s.ugroups = (int)((U + c.ubs * TILE_U - 1) / (c.ubs * TILE_U));
+  s.nt = c.nt;
+  s.tiles_total = pl.tiles_total; s.ugroups = pl.ugroups; s.share = pl.share; s.slots = pl.slots;
   s.feats = (const bf16*)feats_bf16; s.ld_feats = ld_feats;
+  s.table = (const bf16*)table_bf16; s.ld_table = ld_table;
   s.out_scores = part_scores; s.out_ids = part_ids;
   { const char* dbg = getenv("SRFRD_TOPK_DEBUG"); s.debug = dbg ? atoi(dbg) : 0; }
+  // list slots a user group does not use stay empty (index -1)
+  SRFRD_CUDA(cudaMemsetAsync(part_ids, 0xFF, (size_t)U * pl.slots * TK * sizeof(int), stream));
   CUtensorMap tmE;
   if (int rc = make_tmap_bf16_2d(&tmE, table_bf16, n_rows, D, ld_table, c.nt, KB)) return rc;
-  if (c.ubs == 3 && c.nt == 64) return launch_topk<3, 64>(tmE, s, stream);
-  if (c.ubs == 2 && c.nt == 96) return launch_topk<2, 96>(tmE, s, stream);
-  if (c.ubs == 2 && c.nt == 64) return launch_topk<2, 64>(tmE, s, stream);
-  if (c.ubs == 1 && c.nt == 128) return launch_topk<1, 128>(tmE, s, stream);
-  if (c.ubs == 1 && c.nt == 64) return launch_topk<1, 64>(tmE, s, stream);
-  return launch_topk<1, 32>(tmE, s, stream);
+  int rc;
+  if (c.ubs == 2 && c.nt == 64 && c.nacc == 3) rc = launch_tilemax<2, 64, 3>(tmE, s, pl.grid, stream);
+  else if (c.ubs == 1 && c.nt == 64 && c.nacc == 3) rc = launch_tilemax<1, 64, 3>(tmE, s, pl.grid, stream);
+  else if (c.ubs == 1 && c.nt == 64 && c.nacc == 2) rc = launch_tilemax<1, 64, 2>(tmE, s, pl.grid, stream);
+  else rc = launch_tilemax<1, 32, 2>(tmE, s, pl.grid, stream);
+  if (rc) return rc;
+  if (s.debug == 2) return 0;                           // profiling: phase 1 only
+  catalogue_refine_kernel<<<(unsigned)((U + 7) / 8), 256, 0, stream>>>(s);
+  SRFRD_LAUNCH_CHECK();
+  return 0;
 }
 
 extern "C" int srfrd_merge_topk(const float* scores, const int* ids, int64_t U, int nlists, int k, float* out_scores,

@@ -85,11 +85,13 @@ if what in ("ln", "all"):
     timeit("layernorm_bwd +add+rowmask", lambda i: ops.layernorm_bwd(res[i % NBUF], acts[i % NBUF], st, w, outs[i % NBUF], dw, dbb, add=acts[(i + 1) % NBUF], row_ids=ids), 4 * A + T * 16)
 
 if what in ("k1", "all"):
-    N = 12101
+    N = int(os.environ.get("KB_N", 12101))
     E, P, Fe = rnd(N + 1, 64, dtype=torch.float32), rnd(L, 64, dtype=torch.float32), rnd(3, H - 64, dtype=torch.float32)
     seq = torch.randint(0, N + 1, (B, L), device="cuda")
-    seq[:, : L // 2] = 0
+    valid = float(os.environ.get("KB_VALID", 0.5))
+    seq[:, : int(L * (1 - valid))] = 0
     rsq = torch.randint(0, 3, (B, L), device="cuda")
     w, b = rnd(H, dtype=torch.float32), rnd(H, dtype=torch.float32)
     st = torch.empty(T, 2, device="cuda")
-    timeit("embed_ln_fwd (K1) 50% valid", lambda i: ops.embed_ln_fwd(E, P, Fe, 1, seq, rsq, 1.0, w, b, 1e-8, x0_bf16=outs[i % NBUF], q_bf16=acts[i % NBUF], stats=st), 2 * A + T * 24 + T * 128)
+    nvalid = int((seq != 0).sum())
+    timeit(f"embed_ln_fwd (K1) N={N} valid={nvalid / T:.2f}", lambda i: ops.embed_ln_fwd(E, P, Fe, 1, seq, rsq, 1.0, w, b, 1e-8, x0_bf16=outs[i % NBUF], q_bf16=acts[i % NBUF], stats=st), 2 * A + T * 24 + nvalid * 256)
