@@ -125,6 +125,7 @@ typedef struct {
   void* dst; int dst_ld;          /* bf16 (rows, cols) or NULL */
   void* dst_t; int dst_t_ld;      /* bf16 (cols, rows) or NULL */
   int rows, cols;
+  int dst_is_f32;                 /* 1: dst is fp32 (zero-padded shadow of a bias / LayerNorm vector), dst_t unused */
 } srfrd_cast_desc_t;
 SRFRD_API int srfrd_cast_weights(const srfrd_cast_desc_t* descs_dev, int n, void* stream);
 /* hi[r] = bf16(src[row_index ? row_index[r] : r]); lo = bf16(src - hi) (lo, row_index may be NULL).

@@ -165,8 +165,23 @@ def main():
     np.savez_compressed(os.path.join(OUT, "SASRec_heads4.npz"), **fx)
     fx = legacy_sasrec_fixture(RM, 300)
     np.savez_compressed(os.path.join(OUT, "legacy_SASRec.npz"), **fx)
+    ragged_fixtures(SR)
     print("wrote", OUT)
 
 
+def ragged_fixtures(SR):
+    """Widths that are not multiples of 16: the author's own run (45 + 5, trainer.py:129-130) and the constructor
+    defaults (50 + 10, SRFR_model.py:54-63)."""
+    for name, kind, kw in (("SRFR_w50", "SRFR", dict(D=45, Fw=5)), ("SRFRN_w60", "SRFRN", dict(D=50, Fw=10)),
+                           ("SASRec_w50", "SASRec", dict(D=50)), ("SRFU_B_w50", "SRFU_B", dict(D=50))):
+        fx = one_fixture(kind, SR, 400 + len(name), N=70, L=14, nb=2, heads=1, B=5, **kw)
+        np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **fx)
+        print(name, "loss", fx["loss"], "steps", fx["loss_steps"])
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "ragged":      # only add the ragged-width fixtures
+        torch.set_num_threads(1)
+        ragged_fixtures(load_reference()[0])
+    else:
+        main()

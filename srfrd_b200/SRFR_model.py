@@ -59,7 +59,7 @@ class _EncodeAndScore(torch.autograd.Function):
                 nn_ = neg if neg is not None else pos
                 zp = torch.empty(B, L, dtype=torch.float32, device=seq.device)
                 zn = torch.empty(B, L, dtype=torch.float32, device=seq.device)
-                h2 = hidden.view(B * L, -1)
+                h2 = eng._ws["hfin"][:B * L]            # (T, Doutp) fp32, padding columns zero; score reads W true columns
                 ft = eng.fake_table()
                 ops.score_fwd(h2, eng.P.view(eng.spec.item_key), ft, pp.contiguous(), nn_.contiguous(),
                               None if ft is None else (prs if prs is not None else nrs).contiguous(),
@@ -93,7 +93,7 @@ class _EncodeAndScore(torch.autograd.Function):
         else:
             dh.zero_()
         if d_hidden is not None:
-            dh.add_(d_hidden.reshape(T, -1))
+            dh[:, :eng.spec.Dout].add_(d_hidden.reshape(T, -1))
         eng.backward(dh)
         grads = tuple(eng.P.view(n, grad=True).clone() for n in model._param_names)
         return (None,) * 7 + grads
@@ -201,14 +201,15 @@ def _split_gemm_logits(feats: torch.Tensor, table: torch.Tensor, label: torch.Te
     U, D = feats.shape
     I = label.numel()
     Ip = (I + 15) // 16 * 16
+    Dp = (D + 7) // 8 * 8                    # K-segments padded to 16 bytes (zero columns add nothing)
     dev = feats.device
-    A = torch.zeros(U, 3 * D, dtype=bf16, device=dev)
-    Bm = torch.zeros(Ip, 3 * D, dtype=bf16, device=dev)
+    A = torch.zeros(U, 3 * Dp, dtype=bf16, device=dev)
+    Bm = torch.zeros(Ip, 3 * Dp, dtype=bf16, device=dev)
     f = feats.contiguous()
-    ops.f32_to_bf16_split(f, A[:, :D], A[:, D:2 * D])
-    ops.f32_to_bf16_split(f, A[:, 2 * D:], None)
-    ops.f32_to_bf16_split(table, Bm[:I, :D], Bm[:I, 2 * D:], row_index=label)
-    ops.f32_to_bf16_split(table, Bm[:I, D:2 * D], None, row_index=label)
+    ops.f32_to_bf16_split(f, A[:, :D], A[:, Dp:Dp + D])
+    ops.f32_to_bf16_split(f, A[:, 2 * Dp:2 * Dp + D], None)
+    ops.f32_to_bf16_split(table, Bm[:I, :D], Bm[:I, 2 * Dp:2 * Dp + D], row_index=label)
+    ops.f32_to_bf16_split(table, Bm[:I, Dp:Dp + D], None, row_index=label)
     out = torch.empty(U, Ip, dtype=torch.float32, device=dev)
     ops.gemm_tn(A, Bm, out_f32=out)
     return out[:, :I]

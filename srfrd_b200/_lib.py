@@ -23,7 +23,7 @@ class GemmEpilogue(C.Structure):
 
 class CastDesc(C.Structure):
     _fields_ = [("src", vp), ("src_ld", i32), ("dst", vp), ("dst_ld", i32), ("dst_t", vp), ("dst_t_ld", i32),
-                ("rows", i32), ("cols", i32)]
+                ("rows", i32), ("cols", i32), ("dst_is_f32", i32)]
 
 
 # name -> argtypes, exactly the prototypes of include/srfrd_b200.h

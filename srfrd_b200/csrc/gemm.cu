@@ -574,7 +574,7 @@ extern "C" int srfrd_gemm_wgrad(const void* dY, int lda, const void* X, int ldb,
   cudaStream_t stream = (cudaStream_t)stream_;
   SRFRD_REQUIRE(dY && X && dW, "gemm_wgrad: null operand");
   SRFRD_REQUIRE(T > 0 && Mo > 0 && No > 0, "gemm_wgrad: empty shape");
-  SRFRD_REQUIRE(Mo % 8 == 0 && No % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, "gemm_wgrad: widths must be multiples of 8");
+  SRFRD_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && lda >= Mo && ldb >= No, "gemm_wgrad: leading dims must be multiples of 8 and cover the widths");
   SRFRD_REQUIRE(T < (1ll << 31), "gemm_wgrad: too many tokens");
   WgradShape s;
   s.T = (int)T; s.Mo = Mo; s.No = No;

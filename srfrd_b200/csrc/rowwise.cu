@@ -69,12 +69,15 @@ struct EmbedParams {
   uint64_t drop_seed; uint32_t drop_thresh, drop_stream; float drop_scale; const float* drop_step;
 };
 
-template <int LPR, int CH>
+// VEC: D (and F) multiples of 8 -> 16-byte vector loads; otherwise (the reference's own 45+5 / 50+10 widths) the same
+// arithmetic element by element.  Columns >= H (up to the padded leading dimension) are written as zeros.
+template <int LPR, int CH, bool VEC>
 __global__ void __launch_bounds__(256, 4) embed_ln_kernel(EmbedParams p) {
   if (p.drop_thresh) p.drop_seed = mix_seed(p.drop_seed, p.drop_step);
   constexpr int RPW = 32 / LPR;                         // rows per warp pass
   const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
   const int H = p.D + (p.mode == 1 ? p.F : 0);
+  const int Hc = (H + 7) & ~7;                          // chunked width (8 columns per lane chunk)
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t t0 = warp * RPW; t0 < p.T; t0 += nwarps * RPW) {
@@ -96,7 +99,26 @@ __global__ void __launch_bounds__(256, 4) embed_ln_kernel(EmbedParams p) {
       const int c = (ch * LPR + sub) * 8;
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[ch][j] = 0.f;
-      if (valid && c < H) {
+      if (!VEC) {
+        if (valid && c < Hc) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int col = c + j;
+            float x = 0.f;
+            if (col < p.D) {
+              x = __ldg(p.item_table + id * p.D + col);
+              if (p.item_scale != 1.f) x = __fmul_rn(x, p.item_scale);
+              x = __fadd_rn(x, __ldg(p.pos_table + (int64_t)l * p.D + col));
+              if (p.mode == 2) x = __fadd_rn(x, __ldg(p.aux_table + aid * p.D + col));
+            } else if (col < H) {
+              x = __ldg(p.aux_table + aid * p.F + (col - p.D));
+            }
+            if (p.drop_thresh && col < H)
+              x = dropout_keep(p.drop_seed, p.drop_stream, (uint64_t)t * H + col, p.drop_thresh) ? x * p.drop_scale : 0.f;
+            v[ch][j] = x;
+          }
+        }
+      } else if (valid && c < H) {
         if (c < p.D) {
           // __fmul_rn/__fadd_rn: no FMA contraction, so the pre-LN tensor is bit-identical to
           // torch's  E[id] (* sqrt(d)) + P[l] (+ Ul[label])   (SRFR_model.py:22-25, :622-624, :419-422)
@@ -135,9 +157,9 @@ __global__ void __launch_bounds__(256, 4) embed_ln_kernel(EmbedParams p) {
 #pragma unroll
       for (int ch = 0; ch < CH; ++ch) {
         const int c = (ch * LPR + sub) * 8;
-        if (c < H) {
+        if (c < Hc) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { const float d = v[ch][j] - mean; sq += d * d; }
+          for (int j = 0; j < 8; ++j) { const float d = v[ch][j] - mean; sq += (VEC || c + j < H) ? d * d : 0.f; }
         }
       }
       rstd = rsqrtf(group_sum<LPR>(sq) / H + p.eps);
@@ -146,15 +168,24 @@ __global__ void __launch_bounds__(256, 4) embed_ln_kernel(EmbedParams p) {
 #pragma unroll
     for (int ch = 0; ch < CH; ++ch) {
       const int c = (ch * LPR + sub) * 8;
-      if (c >= H) continue;
-      if (p.x0_f32) store8_f32(p.x0_f32 + t * H + c, v[ch]);
+      if (c >= Hc) continue;
+      if (p.x0_f32) {
+        if (VEC) store8_f32(p.x0_f32 + t * H + c, v[ch]);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) if (c + j < H) p.x0_f32[t * H + c + j] = v[ch][j];
+        }
+      }
       if (p.x0) *reinterpret_cast<uint4*>(p.x0 + t * p.ldx + c) = pack8(v[ch]);
       if (p.ln_w) {
         float w[8], b[8], y[8];
-        load8_f32(p.ln_w + c, w);
-        load8_f32(p.ln_b + c, b);
+        if (VEC) { load8_f32(p.ln_w + c, w); load8_f32(p.ln_b + c, b); }
+        else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = (v[ch][j] - mean) * rstd * w[j] + b[j];
+          for (int j = 0; j < 8; ++j) { w[j] = c + j < H ? __ldg(p.ln_w + c + j) : 0.f; b[j] = c + j < H ? __ldg(p.ln_b + c + j) : 0.f; }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = (VEC || c + j < H) ? (v[ch][j] - mean) * rstd * w[j] + b[j] : 0.f;
         *reinterpret_cast<uint4*>(p.q + t * p.ldx + c) = pack8(y);
       }
     }
@@ -173,10 +204,20 @@ struct LnFwdParams {
   int64_t row_offset;
 };
 
+// p.H is the number of VALID columns (LayerNorm width); rows are processed in 8-column chunks up to Hc = roundup(H, 8),
+// columns in [H, Hc) are read as zero-padding and written as zeros.
 template <int LPR, int CH>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(LnFwdParams p) {
+  __shared__ __align__(16) float swb[2][MAXW];
   constexpr int RPW = 32 / LPR, UN = 2;
   const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
+  const int Hc = (p.H + 7) & ~7;
+  const bool ragged = Hc != p.H;
+  for (int i = threadIdx.x; i < MAXW; i += blockDim.x) {
+    swb[0][i] = i < p.H ? __ldg(p.w + i) : 0.f;
+    swb[1][i] = i < p.H ? __ldg(p.b + i) : 0.f;
+  }
+  __syncthreads();
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t t0 = warp * RPW * UN; t0 < p.T; t0 += nwarps * RPW * UN) {
@@ -188,7 +229,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(LnFwdParams p) {
       for (int ch = 0; ch < CH; ++ch) {
         const int c = (ch * LPR + sub) * 8;
         raw[u][ch] = make_uint4(0, 0, 0, 0);
-        if (t < p.T && c < p.H)
+        if (t < p.T && c < Hc)
           raw[u][ch] = __ldg(reinterpret_cast<const uint4*>(p.x + (t * p.row_stride + p.row_offset) * p.ldx + c));
       }
     }
@@ -200,16 +241,21 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(LnFwdParams p) {
 #pragma unroll
       for (int ch = 0; ch < CH; ++ch) {
         unpack8(raw[u][ch], v[ch]);
+        const int c = (ch * LPR + sub) * 8;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sum += v[ch][j];
+        for (int j = 0; j < 8; ++j) {
+          if (ragged && c + j >= p.H) v[ch][j] = 0.f;
+          sum += v[ch][j];
+        }
       }
       const float mean = group_sum<LPR>(sum) / p.H;
       float sq = 0.f;
 #pragma unroll
       for (int ch = 0; ch < CH; ++ch) {
-        if ((ch * LPR + sub) * 8 < p.H) {
+        const int c = (ch * LPR + sub) * 8;
+        if (c < Hc) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { const float d = v[ch][j] - mean; sq += d * d; }
+          for (int j = 0; j < 8; ++j) { const float d = v[ch][j] - mean; sq += (!ragged || c + j < p.H) ? d * d : 0.f; }
         }
       }
       const float rstd = rsqrtf(group_sum<LPR>(sq) / p.H + p.eps);
@@ -217,12 +263,14 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(LnFwdParams p) {
 #pragma unroll
       for (int ch = 0; ch < CH; ++ch) {
         const int c = (ch * LPR + sub) * 8;
-        if (c >= p.H) continue;
-        float w[8], b[8], y[8];
-        load8_f32(p.w + c, w);
-        load8_f32(p.b + c, b);
+        if (c >= Hc) continue;
+        float y[8];
+        const float4 w0 = *reinterpret_cast<const float4*>(&swb[0][c]), w1 = *reinterpret_cast<const float4*>(&swb[0][c + 4]);
+        const float4 b0 = *reinterpret_cast<const float4*>(&swb[1][c]), b1 = *reinterpret_cast<const float4*>(&swb[1][c + 4]);
+        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = (v[ch][j] - mean) * rstd * w[j] + b[j];
+        for (int j = 0; j < 8; ++j) y[j] = (!ragged || c + j < p.H) ? (v[ch][j] - mean) * rstd * w[j] + b[j] : 0.f;
         if (p.y_bf16) *reinterpret_cast<uint4*>(p.y_bf16 + t * p.ldy + c) = pack8(y);
         if (p.y_f32) store8_f32(p.y_f32 + t * p.ldy + c, y);
       }
@@ -253,6 +301,8 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(LnBwdParams p) {
   __shared__ __align__(16) float sw[MAXW];
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
+  const int Hc = (p.H + 7) & ~7;                         // p.H = valid columns; [H, Hc) is zero padding
+  const bool ragged = Hc != p.H;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int i = threadIdx.x; i < MAXW; i += blockDim.x) { sdw[i] = sdb[i] = 0.f; sw[i] = i < p.H ? __ldg(p.w + i) : 0.f; }
@@ -278,7 +328,7 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(LnBwdParams p) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) df[ch][j] = 0.f;
       }
-      if (ok && c < p.H) {
+      if (ok && c < Hc) {
         if (F32DY) load8_f32(p.dy_f32 + t * p.lddy + c, df[ch]);
         else dr[ch] = __ldg(reinterpret_cast<const uint4*>(p.dy_bf16 + t * p.lddy + c));
         xr[ch] = __ldg(reinterpret_cast<const uint4*>(p.x + t * p.ldx + c));
@@ -290,7 +340,7 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(LnBwdParams p) {
 #pragma unroll
     for (int ch = 0; ch < CH; ++ch) {
       const int c = (ch * LPR + sub) * 8;
-      const bool cok = c < p.H && ok;
+      const bool cok = c < Hc && ok;
       float xv[8], dv[8];
       unpack8(xr[ch], xv);
       if (F32DY) {
@@ -303,7 +353,8 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(LnBwdParams p) {
       const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float xh = cok ? (xv[j] - mean) * rstd : 0.f;
+        const float xh = (cok && (!ragged || c + j < p.H)) ? (xv[j] - mean) * rstd : 0.f;
+        if (ragged && c + j >= p.H) dv[j] = 0.f;
         const float g = dv[j] * wv[j];
         adw[ch][j] = fmaf(dv[j], xh, adw[ch][j]);
         adb[ch][j] += dv[j];
@@ -317,7 +368,7 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(LnBwdParams p) {
 #pragma unroll
     for (int ch = 0; ch < CH; ++ch) {
       const int c = (ch * LPR + sub) * 8;
-      if (c >= p.H) continue;
+      if (c >= Hc) continue;
       float xv[8], dv[8], av[8], o[8];
       unpack8(xr[ch], xv);
       unpack8(ar[ch], av);
@@ -333,6 +384,7 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(LnBwdParams p) {
       for (int j = 0; j < 8; ++j) {
         const float xh = (xv[j] - mean) * rstd;
         o[j] = (rstd * (dv[j] * wv[j] - sg - xh * sgx) + av[j]) * msk;
+        if (ragged && c + j >= p.H) o[j] = 0.f;
       }
       *reinterpret_cast<uint4*>(p.dx + t * p.lddx + c) = pack8(o);
     }
@@ -350,7 +402,7 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(LnBwdParams p) {
       }
     }
     const int c = (ch * LPR + sub) * 8;
-    if (grp == 0 && c < p.H) {
+    if (grp == 0 && c < Hc) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) { atomicAdd(&sdw[c + j], adw[ch][j]); atomicAdd(&sdb[c + j], adb[ch][j]); }
     }
@@ -419,6 +471,10 @@ __global__ void cast_weights_kernel(const srfrd_cast_desc_t* descs, int n) {
   const int total = d.rows * d.cols;
   for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < total; i += gridDim.y * blockDim.x) {
     const int r = i / d.cols, c = i % d.cols;
+    if (d.dst_is_f32) {
+      reinterpret_cast<float*>(d.dst)[(size_t)r * d.dst_ld + c] = d.src[(size_t)r * d.src_ld + c];
+      continue;
+    }
     const bf16 v = f2bf(d.src[(size_t)r * d.src_ld + c]);
     if (d.dst) reinterpret_cast<bf16*>(d.dst)[(size_t)r * d.dst_ld + c] = v;
     if (d.dst_t) reinterpret_cast<bf16*>(d.dst_t)[(size_t)c * d.dst_t_ld + r] = v;
@@ -498,9 +554,9 @@ extern "C" int srfrd_embed_ln_fwd(const float* item_table, int64_t n_rows, int D
   SRFRD_REQUIRE(mode != 2 || aux_ids, "embed_ln_fwd: per-sequence labels required for mode 2");
   const int H = D + (mode == 1 ? F : 0);
   SRFRD_REQUIRE(H <= MAXW, "embed_ln_fwd: width %d > %d unsupported", H, MAXW);
-  SRFRD_REQUIRE(D % 8 == 0 && H % 8 == 0, "embed_ln_fwd: D and H must be multiples of 8 (D=%d H=%d)", D, H);
+  const bool vec = D % 8 == 0 && H % 8 == 0;
   SRFRD_REQUIRE(!ln_w || (ln_b && q_bf16), "embed_ln_fwd: LN needs weight, bias and an output");
-  SRFRD_REQUIRE((!x0_bf16 && !q_bf16) || (ldx >= H && ldx % 8 == 0), "embed_ln_fwd: bad ldx %d", ldx);
+  SRFRD_REQUIRE((!x0_bf16 && !q_bf16) || (ldx >= ((H + 7) & ~7) && ldx % 8 == 0), "embed_ln_fwd: bad ldx %d", ldx);
   (void)n_rows; (void)n_aux;
   if (B * L == 0) return 0;
   EmbedParams p;
@@ -511,7 +567,12 @@ extern "C" int srfrd_embed_ln_fwd(const float* item_table, int64_t n_rows, int D
   p.drop_seed = drop_seed; p.drop_stream = drop_stream; p.drop_step = drop_step;
   p.drop_thresh = drop_p > 0.f ? (uint32_t)((double)drop_p * 4294967296.0) : 0;
   p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-#define CALL(LPR, CH) embed_ln_kernel<LPR, CH><<<grid_for_rows(p.T, 8 * (32 / LPR), 8), 256, 0, (cudaStream_t)stream>>>(p)
+#define CALL(LPR, CH)                                                                                       \
+  do {                                                                                                      \
+    const int grid = grid_for_rows(p.T, 8 * (32 / LPR), 8);                                                 \
+    if (vec) embed_ln_kernel<LPR, CH, true><<<grid, 256, 0, (cudaStream_t)stream>>>(p);                     \
+    else embed_ln_kernel<LPR, CH, false><<<grid, 256, 0, (cudaStream_t)stream>>>(p);                        \
+  } while (0)
   SRFRD_ROW_DISPATCH(H, CALL);
 #undef CALL
   SRFRD_LAUNCH_CHECK();
@@ -522,7 +583,8 @@ extern "C" int srfrd_layernorm_fwd(const void* x, int ldx, const float* w, const
                                    float* y_f32, int ldy, float* stats, int64_t T, int H, int64_t row_stride,
                                    int64_t row_offset, void* stream) {
   SRFRD_REQUIRE(x && w && b && (y_bf16 || y_f32), "layernorm_fwd: null pointer");
-  SRFRD_REQUIRE(H <= MAXW && H % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "layernorm_fwd: width %d / ld unsupported", H);
+  SRFRD_REQUIRE(H <= MAXW && ldx % 8 == 0 && ldy % 8 == 0 && ldx >= ((H + 7) & ~7) && ldy >= ((H + 7) & ~7),
+                "layernorm_fwd: width %d / ld (%d, %d) unsupported (rows are padded to a multiple of 8 columns)", H, ldx, ldy);
   if (T == 0) return 0;
   LnFwdParams p;
   p.x = (const bf16*)x; p.ldx = ldx; p.w = w; p.b = b; p.eps = eps; p.y_bf16 = (bf16*)y_bf16; p.y_f32 = y_f32;
@@ -539,8 +601,10 @@ extern "C" int srfrd_layernorm_bwd(const void* dy_bf16, const float* dy_f32, int
                                    const int64_t* row_ids, void* dx, int lddx, float* dw, float* db, int64_t T, int H,
                                    void* stream) {
   SRFRD_REQUIRE((dy_bf16 || dy_f32) && x && stats && w && dx && dw && db, "layernorm_bwd: null pointer");
-  SRFRD_REQUIRE(H <= MAXW && H % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0 && lddy % 8 == 0 && (!add || ldadd % 8 == 0),
-                "layernorm_bwd: width %d / ld unsupported", H);
+  const int Hc8 = (H + 7) & ~7;
+  SRFRD_REQUIRE(H <= MAXW - 8 && ldx % 8 == 0 && lddx % 8 == 0 && lddy % 8 == 0 && (!add || ldadd % 8 == 0) &&
+                    ldx >= Hc8 && lddx >= Hc8 && lddy >= Hc8 && (!add || ldadd >= Hc8),
+                "layernorm_bwd: width %d / ld unsupported (rows are padded to a multiple of 8 columns)", H);
   if (T == 0) return 0;
   LnBwdParams p;
   p.dy_bf16 = (const bf16*)dy_bf16; p.dy_f32 = dy_f32; p.lddy = lddy; p.x = (const bf16*)x; p.ldx = ldx;

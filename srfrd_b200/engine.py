@@ -37,12 +37,10 @@ class ModelSpec:
     def __post_init__(self):
         if self.kind not in KINDS:
             raise ValueError(f"unknown model kind {self.kind}")
-        if self.H % 16 or self.D % 16:
-            raise ValueError(
-                f"srfrd_b200: encoder width H={self.H} and item width D={self.D} must be multiples of 16 "
-                "(tcgen05 N granularity / 16-byte TMA pitch); pad the embedding sizes")
         if self.H % self.num_heads:
             raise ValueError("hidden size must be divisible by num_heads")
+        if (self.H // self.num_heads) % 2:
+            raise ValueError(f"srfrd_b200: head width {self.H // self.num_heads} must be even (bf16 pairs)")
 
     @property
     def H(self) -> int:
@@ -51,6 +49,25 @@ class ModelSpec:
     @property
     def Dout(self) -> int:       # width of the hidden state the model returns
         return self.H if self.kind == "SRFRN" else self.D
+
+    # Activations and GEMM operands are laid out with their widths padded to a multiple of 16 (tcgen05 N granularity,
+    # 16-byte TMA pitch); the padding columns are zero everywhere, parameters and LayerNorm statistics keep their
+    # true widths.  The reference's own sizes (45 + 5, trainer.py:129-130; constructor defaults 50 + 10) need this.
+    @property
+    def Hp(self) -> int:
+        return (self.H + 15) // 16 * 16
+
+    @property
+    def Dp(self) -> int:
+        return (self.D + 15) // 16 * 16
+
+    @property
+    def Doutp(self) -> int:
+        return self.Hp if self.kind == "SRFRN" else self.Dp
+
+    @property
+    def padded(self) -> bool:
+        return self.Hp != self.H or self.Dp != self.D
 
     @property
     def mode(self) -> int:       # K1 mode
@@ -149,27 +166,61 @@ class HotPath:
     # ------------------------------------------------------------------ bf16 operand shadows
     def _build_shadows(self):
         s, P, dev = self.spec, self.P, self.device
-        H, D = s.H, s.D
+        H, D, Hp, Dp = s.H, s.D, s.Hp, s.Dp
         self.sh: Dict[str, torch.Tensor] = {}
+        self.vsh: Dict[str, torch.Tensor] = {}       # zero-padded fp32 shadows of biases (only when widths are padded)
         entries = []
+        zb = lambda r, c: torch.zeros(r, c, dtype=bf16, device=dev)
+
+        def vec(name, src, n_pad, dst_off=0, dst=None):
+            """bias vector `src` (true length) -> self.vsh[name][dst_off : dst_off + len]; identity when nothing is padded"""
+            if not s.padded:
+                return
+            if dst is None:
+                dst = self.vsh.setdefault(name, torch.zeros(n_pad, dtype=torch.float32, device=dev))
+            entries.append((src.view(1, -1), dst[dst_off:dst_off + src.numel()].view(1, -1), None))
+
         for i in range(s.num_blocks):
             win = P.mat(f"attention_layers.{i}.in_proj_weight")
-            self.sh[f"win{i}"] = torch.zeros(3 * H, H, dtype=bf16, device=dev)        # rows [0,H) = Wq, [H,3H) = Wkv
-            self.sh[f"wqT{i}"] = torch.zeros(H, H, dtype=bf16, device=dev)
-            self.sh[f"wkvT{i}"] = torch.zeros(H, 2 * H, dtype=bf16, device=dev)
-            entries.append((win[:H], self.sh[f"win{i}"][:H], self.sh[f"wqT{i}"]))
-            entries.append((win[H:], self.sh[f"win{i}"][H:], self.sh[f"wkvT{i}"]))
-            for tag, key in (("wo", f"attention_layers.{i}.out_proj.weight"), ("w1", f"forward_layers.{i}.conv1.weight"),
-                             ("w2", f"forward_layers.{i}.conv2.weight")):
-                self.sh[f"{tag}{i}"] = torch.zeros(H, H, dtype=bf16, device=dev)
-                self.sh[f"{tag}T{i}"] = torch.zeros(H, H, dtype=bf16, device=dev)
-                entries.append((P.mat(key), self.sh[f"{tag}{i}"], self.sh[f"{tag}T{i}"]))
+            bin_ = P.view(f"attention_layers.{i}.in_proj_bias")
+            self.sh[f"wq{i}"] = zb(Hp, Hp)                          # rows = output features (padded), K-major
+            self.sh[f"wkv{i}"] = zb(2 * Hp, Hp)                     # k rows at [0, H), v rows at [Hp, Hp + H)
+            self.sh[f"wqT{i}"] = zb(Hp, Hp)
+            self.sh[f"wkvT{i}"] = zb(Hp, 2 * Hp)
+            entries.append((win[:H], self.sh[f"wq{i}"][:H, :H], self.sh[f"wqT{i}"][:H, :H]))
+            entries.append((win[H:2 * H], self.sh[f"wkv{i}"][:H, :H], self.sh[f"wkvT{i}"][:H, :H]))
+            entries.append((win[2 * H:], self.sh[f"wkv{i}"][Hp:Hp + H, :H], self.sh[f"wkvT{i}"][:H, Hp:Hp + H]))
+            vec(f"bq{i}", bin_[:H], Hp)
+            vec(f"bkv{i}", bin_[H:2 * H], 2 * Hp)
+            vec(f"bkv{i}", bin_[2 * H:], 2 * Hp, dst_off=Hp)
+            for tag, key in (("wo", f"attention_layers.{i}.out_proj"), ("w1", f"forward_layers.{i}.conv1"),
+                             ("w2", f"forward_layers.{i}.conv2")):
+                self.sh[f"{tag}{i}"] = zb(Hp, Hp)
+                self.sh[f"{tag}T{i}"] = zb(Hp, Hp)
+                entries.append((P.mat(key + ".weight"), self.sh[f"{tag}{i}"][:H, :H], self.sh[f"{tag}T{i}"][:H, :H]))
+                vec(f"b{tag[1]}{i}", P.view(key + ".bias"), Hp)
         if s.kind == "SRFR":
-            self.sh["wc"] = torch.zeros(D, H, dtype=bf16, device=dev)
-            self.sh["wcT"] = torch.zeros(H, D, dtype=bf16, device=dev)
-            entries.append((P.mat("last_conv.weight"), self.sh["wc"], self.sh["wcT"]))
+            self.sh["wc"] = zb(Dp, Hp)
+            self.sh["wcT"] = zb(Hp, Dp)
+            entries.append((P.mat("last_conv.weight"), self.sh["wc"][:D, :H], self.sh["wcT"][:H, :D]))
+            vec("bc", P.view("last_conv.bias"), Dp)
         self._cast_table, self._cast_n = ops.make_cast_table(entries, dev)
         self.shadows_version = -1
+
+    def bias(self, tag: str, i: Optional[int] = None) -> torch.Tensor:
+        """Bias vector a GEMM epilogue reads (length = the GEMM's padded N)."""
+        s, P = self.spec, self.P
+        if s.padded:
+            return self.vsh[tag if i is None else f"{tag}{i}"]
+        if tag == "bq":
+            return P.view(f"attention_layers.{i}.in_proj_bias")[:s.H]
+        if tag == "bkv":
+            return P.view(f"attention_layers.{i}.in_proj_bias")[s.H:]
+        if tag == "bc":
+            return P.view("last_conv.bias")
+        key = {"bo": f"attention_layers.{i}.out_proj.bias", "b1": f"forward_layers.{i}.conv1.bias",
+               "b2": f"forward_layers.{i}.conv2.bias"}[tag]
+        return P.view(key)
 
     def refresh_shadows(self):
         """fp32 master weights -> bf16 GEMM operands (W and W^T); one launch."""
@@ -180,11 +231,11 @@ class HotPath:
         if T <= self._ws_tokens:
             return self._ws
         s, dev = self.spec, self.device
-        H, nb = s.H, s.num_blocks
-        ws: Dict[str, torch.Tensor] = {}
+        H, nb = s.Hp, s.num_blocks               # padded widths; padding columns stay zero (buffers start zeroed and
+        ws: Dict[str, torch.Tensor] = {}         # no kernel ever writes a non-zero value there)
 
         def act(name, w=H, dtype=bf16):
-            ws[name] = torch.empty(T, w, dtype=dtype, device=dev)
+            ws[name] = torch.zeros(T, w, dtype=dtype, device=dev)
 
         for i in range(nb + 1):
             act(f"x{i}")
@@ -195,15 +246,15 @@ class HotPath:
             act(f"st1_{i}", 2, torch.float32)
             act(f"st2_{i}", 2, torch.float32)
         if s.kind == "SRFR":
-            act("c", s.D)
+            act("c", s.Dp)
         act("stF", 2, torch.float32)
-        act("hfin", s.Dout, torch.float32)
-        act("dh", s.Dout, torch.float32)
+        act("hfin", s.Doutp, torch.float32)
+        act("dh", s.Doutp, torch.float32)
         for n in ("gA", "gB", "gC", "gD"):
             act(n)
         act("gKV", 2 * H)
         if s.kind == "SRFR":
-            act("gc", s.D)
+            act("gc", s.Dp)
         if s.dropout > 0:
             act("gE")
         ws["pos_tmp"] = torch.zeros(L * H, dtype=torch.float32, device=dev)
@@ -219,7 +270,7 @@ class HotPath:
         B, L = seq.shape
         if L > s.max_len:
             raise RuntimeError(f"sequence length {L} exceeds max_len {s.max_len} (pos_embed rows, SRFR_model.py:12)")
-        T, H, nb = B * L, s.H, s.num_blocks
+        T, H, Hp, nb = B * L, s.H, s.Hp, s.num_blocks
         ws = self._workspace(T, L)
         p_drop = s.dropout if training else 0.0
         step = self.step_state[0:1] if p_drop > 0 else None
@@ -242,33 +293,32 @@ class HotPath:
             Q, q, kv, o, r, y, h1 = (ws[f"{n}{i}"][:T] for n in ("Q", "q", "kv", "o", "r", "y", "h1"))
             if i > 0:
                 ops.layernorm_fwd(x[i], P.view(f"attention_layernorms.{i}.weight"), P.view(f"attention_layernorms.{i}.bias"),
-                                  LN_EPS, y_bf16=Q, stats=ws[f"st1_{i}"][:T])
-            bias_in = P.view(f"attention_layers.{i}.in_proj_bias")
-            ops.gemm_tn(Q, self.sh[f"win{i}"][:H], out_bf16=q, bias=bias_in[:H])
-            ops.gemm_tn(x[i], self.sh[f"win{i}"][H:], out_bf16=kv, bias=bias_in[H:])
-            ops.attention_fwd(q, kv[:, :H], kv[:, H:], o, B, L, H, s.num_heads, p_drop, seed, 10 + 4 * i, step)
-            ops.gemm_tn(o, self.sh[f"wo{i}"], out_bf16=r, bias=P.view(f"attention_layers.{i}.out_proj.bias"), residual=Q)
+                                  LN_EPS, y_bf16=Q, stats=ws[f"st1_{i}"][:T], H=H)
+            ops.gemm_tn(Q, self.sh[f"wq{i}"], out_bf16=q, bias=self.bias("bq", i))
+            ops.gemm_tn(x[i], self.sh[f"wkv{i}"], out_bf16=kv, bias=self.bias("bkv", i))
+            ops.attention_fwd(q, kv[:, :Hp], kv[:, Hp:], o, B, L, H, s.num_heads, p_drop, seed, 10 + 4 * i, step)
+            ops.gemm_tn(o, self.sh[f"wo{i}"], out_bf16=r, bias=self.bias("bo", i), residual=Q)
             ops.layernorm_fwd(r, P.view(f"forward_layernorms.{i}.weight"), P.view(f"forward_layernorms.{i}.bias"), LN_EPS,
-                              y_bf16=y, stats=ws[f"st2_{i}"][:T])
-            ops.gemm_tn(y, self.sh[f"w1{i}"], out_bf16=h1, bias=P.view(f"forward_layers.{i}.conv1.bias"), relu=True,
+                              y_bf16=y, stats=ws[f"st2_{i}"][:T], H=H)
+            ops.gemm_tn(y, self.sh[f"w1{i}"], out_bf16=h1, bias=self.bias("b1", i), relu=True,
                         drop_p=p_drop, drop_seed=seed, drop_stream=11 + 4 * i, drop_step=step)
-            ops.gemm_tn(h1, self.sh[f"w2{i}"], out_bf16=x[i + 1], bias=P.view(f"forward_layers.{i}.conv2.bias"),
+            ops.gemm_tn(h1, self.sh[f"w2{i}"], out_bf16=x[i + 1], bias=self.bias("b2", i),
                         residual=y, row_ids=seq_flat, drop_p=p_drop, drop_seed=seed, drop_stream=12 + 4 * i, drop_step=step)
         fin_in = x[nb]
         if s.kind == "SRFR":      # last_conv H -> D (SRFR_model.py:123)
-            ops.gemm_tn(x[nb], self.sh["wc"], out_bf16=ws["c"][:T], bias=P.view("last_conv.bias"))
+            ops.gemm_tn(x[nb], self.sh["wc"], out_bf16=ws["c"][:T], bias=self.bias("bc"))
             fin_in = ws["c"][:T]
         hfin = ws["hfin"][:T]
         if last_only:
             out = ws["hfin"][:B]
             ops.layernorm_fwd(fin_in, P.view("last_layernorm.weight"), P.view("last_layernorm.bias"), LN_EPS, y_f32=out,
                               T=B, H=s.Dout, row_stride=L, row_offset=L - 1)
-            return out
+            return out[:, :s.Dout]
         ops.layernorm_fwd(fin_in, P.view("last_layernorm.weight"), P.view("last_layernorm.bias"), LN_EPS, y_f32=hfin,
                           stats=ws["stF"][:T], H=s.Dout)
         if training if save is None else save:
             self.saved = dict(seq=seq, aux_ids=aux_ids, B=B, L=L, p_drop=p_drop, seed=seed, step=step)
-        return hfin.view(B, L, s.Dout)
+        return hfin.view(B, L, s.Doutp)[..., :s.Dout]
 
     # ------------------------------------------------------------------ backward
     def backward(self, dh: torch.Tensor) -> None:
@@ -278,7 +328,7 @@ class HotPath:
         if sv is None:
             raise RuntimeError("backward() without a training forward()")
         B, L = sv["B"], sv["L"]
-        T, H, nb = B * L, s.H, s.num_blocks
+        T, H, Hp, nb = B * L, s.H, s.Hp, s.num_blocks
         ws = self._ws
         seq_flat = sv["seq"].view(-1)
         p_drop, seed, step = sv["p_drop"], sv["seed"], sv["step"]
@@ -291,12 +341,12 @@ class HotPath:
         if s.kind == "SRFR":
             gc = ws["gc"][:T]
             ops.layernorm_bwd(dh, ws["c"][:T], ws["stF"][:T], P.view("last_layernorm.weight"), gc,
-                              G("last_layernorm.weight"), G("last_layernorm.bias"))
-            ops.gemm_wgrad(gc, x[nb], GM("last_conv.weight"), G("last_conv.bias"))
+                              G("last_layernorm.weight"), G("last_layernorm.bias"), H=s.D)
+            ops.gemm_wgrad(gc, x[nb], GM("last_conv.weight"), G("last_conv.bias"), Mo=s.D, No=H)
             ops.gemm_tn(gc, self.sh["wcT"], out_bf16=gA, row_ids=seq_flat)
         else:
             ops.layernorm_bwd(dh, x[nb], ws["stF"][:T], P.view("last_layernorm.weight"), gA,
-                              G("last_layernorm.weight"), G("last_layernorm.bias"), row_ids=seq_flat)
+                              G("last_layernorm.weight"), G("last_layernorm.bias"), row_ids=seq_flat, H=s.Dout)
 
         for i in reversed(range(nb)):
             Q, q, kv, o, r, y, h1 = (ws[f"{n}{i}"][:T] for n in ("Q", "q", "kv", "o", "r", "y", "h1"))
@@ -304,31 +354,36 @@ class HotPath:
             dz2 = dz
             if p_drop > 0:      # da2 = dz * mask2 (dropout2 sits between conv2 and the residual add)
                 dz2 = ws["gE"][:T]
-                ops.dropout_apply(dz, dz2, H, p_drop, seed, 12 + 4 * i, step)
+                ops.dropout_apply(dz, dz2, Hp, p_drop, seed, 12 + 4 * i, step)
             # FFN: z = drop2(h1 W2^T + b2) + y ; h1 = relu(drop1(y W1^T + b1))
-            ops.gemm_wgrad(dz2, h1, GM(f"forward_layers.{i}.conv2.weight"), G(f"forward_layers.{i}.conv2.bias"))
+            ops.gemm_wgrad(dz2, h1, GM(f"forward_layers.{i}.conv2.weight"), G(f"forward_layers.{i}.conv2.bias"), Mo=H, No=H)
             ops.gemm_tn(dz2, self.sh[f"w2T{i}"], out_bf16=gB, gate=h1, drop_p=p_drop, drop_seed=seed,
                         drop_stream=11 + 4 * i, drop_step=step)                                   # da1
-            ops.gemm_wgrad(gB, y, GM(f"forward_layers.{i}.conv1.weight"), G(f"forward_layers.{i}.conv1.bias"))
+            ops.gemm_wgrad(gB, y, GM(f"forward_layers.{i}.conv1.weight"), G(f"forward_layers.{i}.conv1.bias"), Mo=H, No=H)
             ops.gemm_tn(gB, self.sh[f"w1T{i}"], out_bf16=gC, residual=dz)                          # dy
             # LN2
             ops.layernorm_bwd(gC, r, ws[f"st2_{i}"][:T], P.view(f"forward_layernorms.{i}.weight"), gB,
-                              G(f"forward_layernorms.{i}.weight"), G(f"forward_layernorms.{i}.bias"))   # dr
+                              G(f"forward_layernorms.{i}.weight"), G(f"forward_layernorms.{i}.bias"), H=H)   # dr
             # r = Q + o Wo^T + bo
-            ops.gemm_wgrad(gB, o, GM(f"attention_layers.{i}.out_proj.weight"), G(f"attention_layers.{i}.out_proj.bias"))
+            ops.gemm_wgrad(gB, o, GM(f"attention_layers.{i}.out_proj.weight"), G(f"attention_layers.{i}.out_proj.bias"),
+                           Mo=H, No=H)
             ops.gemm_tn(gB, self.sh[f"woT{i}"], out_bf16=gC)                                       # do
-            ops.attention_bwd(gC, q, kv[:, :H], kv[:, H:], gD, gKV[:, :H], gKV[:, H:], B, L, H, s.num_heads, p_drop,
+            ops.attention_bwd(gC, q, kv[:, :Hp], kv[:, Hp:], gD, gKV[:, :Hp], gKV[:, Hp:], B, L, H, s.num_heads, p_drop,
                               seed, 10 + 4 * i, step)                                             # dq, dk|dv
             gin = GM(f"attention_layers.{i}.in_proj_weight")
             gbin = G(f"attention_layers.{i}.in_proj_bias")
-            ops.gemm_wgrad(gD, Q, gin[:H], gbin[:H])
+            ops.gemm_wgrad(gD, Q, gin[:H], gbin[:H], Mo=H, No=H)
             ops.gemm_tn(gD, self.sh[f"wqT{i}"], out_bf16=gC, residual=gB)                          # dQ = dr + dq Wq
-            ops.gemm_wgrad(gKV, x[i], gin[H:], gbin[H:])
+            if Hp == H:
+                ops.gemm_wgrad(gKV, x[i], gin[H:], gbin[H:], Mo=2 * H, No=H)
+            else:       # k and v gradients sit at column offsets 0 and Hp: two row blocks of in_proj_weight
+                ops.gemm_wgrad(gKV[:, :Hp], x[i], gin[H:2 * H], gbin[H:2 * H], Mo=H, No=H)
+                ops.gemm_wgrad(gKV[:, Hp:], x[i], gin[2 * H:], gbin[2 * H:], Mo=H, No=H)
             ops.gemm_tn(gKV, self.sh[f"wkvT{i}"], out_bf16=gD)                                     # dx via k, v
             # LN1 + the un-normalised k/v path; pad rows zeroed (x_i was masked, SRFR_model.py:99,121)
             ops.layernorm_bwd(gC, x[i], ws[f"st1_{i}"][:T], P.view(f"attention_layernorms.{i}.weight"), gA,
                               G(f"attention_layernorms.{i}.weight"), G(f"attention_layernorms.{i}.bias"),
-                              add=gD, row_ids=seq_flat)
+                              add=gD, row_ids=seq_flat, H=H)
 
         # embedding tables
         dx0 = gA
@@ -338,10 +393,10 @@ class HotPath:
         aux_grad = G(s.aux_key) if s.aux_key else None
         ops.embed_bwd(dx0, sv["seq"], sv["aux_ids"], s.D, s.F if s.mode == 1 else 0, s.mode, s.item_scale,
                       G(s.item_key), aux_grad)
-        pos_tmp = ws["pos_tmp"][:L * H]
+        pos_tmp = ws["pos_tmp"][:L * Hp]
         pos_tmp.zero_()
-        ops.colsum(dx0, pos_tmp, M=B, N=L * H, ld=L * H)
-        ops.add_segments(pos_tmp, L * H, H, s.D, G(s.pos_key))
+        ops.colsum(dx0, pos_tmp, M=B, N=L * Hp, ld=L * Hp)
+        ops.add_segments(pos_tmp, L * Hp, Hp, s.D, G(s.pos_key))
         self.saved = None
 
     # ------------------------------------------------------------------ scoring helpers

@@ -29,9 +29,10 @@ class CatalogueIndex:
     def __init__(self, table_f32: torch.Tensor, id_base: int = 0):
         self.id_base = int(id_base)
         self.n_rows, self.D = table_f32.shape
+        self.Dp = (self.D + 15) // 16 * 16          # zero-padded K (tcgen05 K step / 16-byte rows)
         self.row_lo = 1 if self.id_base == 0 else 0
-        self.table = torch.empty(self.n_rows, self.D, dtype=bf16, device=table_f32.device)
-        ops.f32_to_bf16_split(table_f32.contiguous(), self.table, None)
+        self.table = torch.zeros(self.n_rows, self.Dp, dtype=bf16, device=table_f32.device)
+        ops.f32_to_bf16_split(table_f32.contiguous(), self.table[:, :self.D], None)
 
     @staticmethod
     def shard_bounds(n_rows_total: int, rank: int, world: int) -> Tuple[int, int]:
@@ -44,22 +45,23 @@ def local_topk(feats_f32: torch.Tensor, index: CatalogueIndex, n_split: int = 1)
     """Per-user top-10 of feats (U, D) against the local shard -> (scores (U,10) fp32, ids (U,10) int64)."""
     U, D = feats_f32.shape
     dev = feats_f32.device
-    u_pad = (U + 383) // 384 * 384          # whole user groups (up to 3 tiles of 128) per split
-    fb = torch.zeros(n_split * u_pad, D, dtype=bf16, device=dev)
+    Dp = index.Dp
+    u_pad = (U + 255) // 256 * 256          # whole user groups (2 tiles of 128) per split
+    fb = torch.zeros(n_split * u_pad, Dp, dtype=bf16, device=dev)
     f = feats_f32.contiguous()
     if n_split == 1:
-        ops.f32_to_bf16_split(f, fb[:U], None)
+        ops.f32_to_bf16_split(f, fb[:U, :D], None)
     elif n_split == 2:
-        ops.f32_to_bf16_split(f, fb[:U], fb[u_pad:u_pad + U])
+        ops.f32_to_bf16_split(f, fb[:U, :D], fb[u_pad:u_pad + U, :D])
     else:
         # three-way split: hi, mid, lo  (f = hi + mid + lo to ~24 mantissa bits)
-        hi, mid = fb[:U], fb[u_pad:u_pad + U]
+        hi, mid = fb[:U, :D], fb[u_pad:u_pad + U, :D]
         ops.f32_to_bf16_split(f, hi, mid)
         rest = f - hi.float() - mid.float()
-        ops.f32_to_bf16_split(rest.contiguous(), fb[2 * u_pad:2 * u_pad + U], None)
+        ops.f32_to_bf16_split(rest.contiguous(), fb[2 * u_pad:2 * u_pad + U, :D], None)
     if index.n_rows <= index.row_lo:                      # empty shard
         return (torch.full((U, TK), float("-inf"), device=dev), torch.full((U, TK), -1, dtype=torch.int64, device=dev))
-    chunks = ops.catalogue_topk_plan(U, index.n_rows, index.row_lo, D, n_split)
+    chunks = ops.catalogue_topk_plan(U, index.n_rows, index.row_lo, Dp, n_split)
     ps = torch.empty(U, chunks, TK, dtype=torch.float32, device=dev)
     pi = torch.empty(U, chunks, TK, dtype=torch.int32, device=dev)
     ops.catalogue_topk(fb, U, u_pad, n_split, index.table, index.row_lo, index.id_base, chunks, ps, pi)

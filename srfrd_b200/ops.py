@@ -70,8 +70,9 @@ def layernorm_fwd(x, w, b, eps, y_bf16=None, y_f32=None, stats=None, T=None, H=N
          _p(stats), T, H, row_stride, row_offset, _stream())
 
 
-def layernorm_bwd(dy, x, stats, w, dx, dw, db, add=None, row_ids=None):
-    T, H = x.shape
+def layernorm_bwd(dy, x, stats, w, dx, dw, db, add=None, row_ids=None, H=None):
+    T = x.shape[0]
+    H = x.shape[1] if H is None else H          # valid (LayerNorm) width; the row pitch may be padded
     dyb = dy if dy.dtype == bf16 else None
     dyf = dy if dy.dtype == torch.float32 else None
     call("srfrd_layernorm_bwd", _p(dyb), _p(dyf), dy.stride(0), _p(x), x.stride(0), _p(stats), _p(w), _p(add),
@@ -92,10 +93,12 @@ def gemm_tn(A, B, out_bf16=None, out_f32=None, bias=None, residual=None, gate=No
     call("srfrd_gemm_tn", _p(A), A.stride(0), _p(B), B.stride(0), M, N, K, C.byref(ep), _stream())
 
 
-def gemm_wgrad(dY, X, dW, dbias=None):
-    """dW[Mo,No] += dY[T,Mo]^T @ X[T,No]  (dW fp32, atomically accumulated); dbias[Mo] += column sums of dY."""
-    T, Mo = dY.shape
-    No = X.shape[1]
+def gemm_wgrad(dY, X, dW, dbias=None, Mo=None, No=None):
+    """dW[Mo,No] += dY[T,Mo]^T @ X[T,No]  (dW fp32, atomically accumulated); dbias[Mo] += column sums of dY.
+    Mo / No default to the operand widths; pass the true widths when the operands carry zero padding columns."""
+    T = dY.shape[0]
+    Mo = dY.shape[1] if Mo is None else Mo
+    No = X.shape[1] if No is None else No
     call("srfrd_gemm_wgrad", _p(dY), dY.stride(0), _p(X), X.stride(0), T, Mo, No, _p(dW), dW.stride(0), _p(dbias),
          _stream())
 
@@ -129,11 +132,13 @@ def cast_weights(descs_dev, n):
 
 
 def make_cast_table(entries, device):
-    """entries: list of (src fp32 2-D view, dst bf16 or None, dst_t bf16 or None) -> uint8 device tensor."""
+    """entries: list of (src fp32 2-D view, dst bf16 or None, dst_t bf16 or None) -> uint8 device tensor.
+    A fp32 ``dst`` makes the entry a plain fp32 copy (zero-padded shadows of bias / LayerNorm vectors)."""
     arr = (CastDesc * len(entries))()
     for i, (src, dst, dst_t) in enumerate(entries):
+        is_f32 = int(dst is not None and dst.dtype == torch.float32)
         arr[i] = CastDesc(src.data_ptr(), src.stride(0), _p(dst), 0 if dst is None else dst.stride(0), _p(dst_t),
-                          0 if dst_t is None else dst_t.stride(0), src.shape[0], src.shape[1])
+                          0 if dst_t is None else dst_t.stride(0), src.shape[0], src.shape[1], is_f32)
     raw = bytes(arr)
     host = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
     return host.to(device), len(entries)

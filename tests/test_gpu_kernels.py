@@ -164,6 +164,60 @@ def test_layernorm_fwd_bwd(ops, T, H):
     torch.testing.assert_close(dx.float(), xr.grad, rtol=3e-2, atol=3e-2)
 
 
+def test_ragged_widths_gather_layernorm_wgrad(ops):
+    """Widths that are not multiples of 8 / 16 (the reference's own 45 + 5): operands carry zero padding columns up to
+    the padded leading dimension; gather stays bit-exact, LayerNorm statistics use the true width."""
+    from oracle import srfrd_oracle as O
+    from tests.conftest import load_golden
+    fx = load_golden("SRFR_w50")
+    N, L, D, Fw = (int(v) for v in fx["meta"][:4])
+    H, Hp = D + Fw, 64
+    sd, i = fx["param"], fx["in"]
+    ref = O.embed(sd, "SRFR", i["seq"], i["rsq"])
+    T = ref.shape[0] * L
+    x32 = torch.empty(T, H, device="cuda")
+    xb = torch.full((T, Hp), 7.0, dtype=bf16, device="cuda")
+    q = torch.full((T, Hp), 7.0, dtype=bf16, device="cuda")
+    st = torch.empty(T, 2, device="cuda")
+    w, b = sd["attention_layernorms.0.weight"].cuda(), sd["attention_layernorms.0.bias"].cuda()
+    ops.embed_ln_fwd(sd["embedding_layer.item_embed.weight"].cuda(), sd["embedding_layer.pos_embed.weight"].cuda(),
+                     sd["embedding_layer.fake_embed.weight"].cuda(), 1, i["seq"].cuda(), i["rsq"].cuda(), 1.0, w, b, 1e-8,
+                     x0_bf16=xb, x0_f32=x32, q_bf16=q, stats=st)
+    assert torch.equal(x32.cpu().view_as(ref), ref)                       # bit-exact gather + positional add
+    assert torch.equal(xb[:, :H].cpu(), ref.view(-1, H).to(bf16))
+    assert float(xb[:, H:56].abs().max()) == 0.0 and float(q[:, H:56].abs().max()) == 0.0   # chunk padding written as 0
+    qref = torch.nn.functional.layer_norm(ref, (H,), w.cpu(), b.cpu(), 1e-8)
+    torch.testing.assert_close(q[:, :H].float().cpu().view_as(qref), qref, rtol=1e-2, atol=1e-2)
+    # LayerNorm forward / backward on a zero-padded (T, 64) operand with true width 50
+    x = torch.zeros(300, Hp, dtype=bf16, device="cuda")
+    x[:, :H] = rnd((300, H), 25, dtype=bf16)
+    y = torch.full((300, Hp), 3.0, dtype=bf16, device="cuda")
+    st2 = torch.empty(300, 2, device="cuda")
+    ops.layernorm_fwd(x, w, b, 1e-8, y_bf16=y, stats=st2, H=H)
+    xr = x[:, :H].float().clone().requires_grad_(True)
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(xr, (H,), wr, br, 1e-8)
+    torch.testing.assert_close(y[:, :H].float(), yr.detach(), rtol=1e-2, atol=1e-2)
+    assert float(y[:, H:56].abs().max()) == 0.0
+    dy = torch.zeros(300, Hp, dtype=bf16, device="cuda")
+    dy[:, :H] = rnd((300, H), 26, dtype=bf16)
+    yr.backward(dy[:, :H].float())
+    dx = torch.full((300, Hp), 5.0, dtype=bf16, device="cuda")
+    dw, db = torch.zeros(H, device="cuda"), torch.zeros(H, device="cuda")
+    ops.layernorm_bwd(dy, x, st2, w, dx, dw, db, H=H)
+    torch.testing.assert_close(dx[:, :H].float(), xr.grad, rtol=3e-2, atol=3e-2)
+    assert float(dx[:, H:56].abs().max()) == 0.0
+    torch.testing.assert_close(dw, wr.grad, rtol=1e-3, atol=2e-2)
+    torch.testing.assert_close(db, br.grad, rtol=1e-3, atol=2e-2)
+    # weight gradient with true widths 50 x 45 inside padded operands
+    dY = torch.zeros(700, Hp, dtype=bf16, device="cuda"); dY[:, :H] = rnd((700, H), 27, dtype=bf16)
+    X = torch.zeros(700, 48, dtype=bf16, device="cuda"); X[:, :D] = rnd((700, D), 28, dtype=bf16)
+    dW, dbias = torch.zeros(H, D, device="cuda"), torch.zeros(H, device="cuda")
+    ops.gemm_wgrad(dY, X, dW, dbias, Mo=H, No=D)
+    torch.testing.assert_close(dW, dY[:, :H].float().T @ X[:, :D].float(), rtol=1e-3, atol=2e-3 * math.sqrt(700))
+    torch.testing.assert_close(dbias, dY[:, :H].float().sum(0), rtol=1e-3, atol=2e-3 * math.sqrt(700))
+
+
 # ------------------------------------------------------------------------------------------- attention
 def _attn_ref(q, k, v, heads):
     from oracle import srfrd_oracle as O

@@ -15,7 +15,9 @@ from tests.conftest import load_golden
 pytestmark = pytest.mark.gpu
 
 CASES = [("SRFR", "SRFR"), ("SRFRN", "SRFRN"), ("SRFU_B", "SRFU_B"), ("SRFU_F", "SRFU_F"), ("SRFU_R", "SRFU_R"),
-         ("SASRec", "SASRec"), ("SRFR_heads2", "SRFR"), ("SASRec_heads4", "SASRec")]
+         ("SASRec", "SASRec"), ("SRFR_heads2", "SRFR"), ("SASRec_heads4", "SASRec"),
+         # ragged widths (45 + 5 as in trainer.py:129-130, the constructor defaults 50 + 10): padded operand layout
+         ("SRFR_w50", "SRFR"), ("SRFRN_w60", "SRFRN"), ("SASRec_w50", "SASRec"), ("SRFU_B_w50", "SRFU_B")]
 
 
 def build_from_golden(name, kind, dropout=0.0):
@@ -120,7 +122,8 @@ def test_fused_trainer_matches_reference_golden(name, kind):
         assert float((got - ref).abs().max()) <= 6.5e-3, k
         u, v = (got - p0).flatten(), (ref - p0).flatten()
         nz = fx["grad"][k].flatten() != 0               # elements that never receive gradient (unused items) stay put
-        assert float(u[~nz].abs().max() if (~nz).any() else 0.0) == 0.0, k
+        if "emb" in k:                                  # (a dense weight can have exact zeros only through dead ReLU
+            assert float(u[~nz].abs().max() if (~nz).any() else 0.0) == 0.0, k   # units, which bf16 may revive)
         if int(nz.sum()) >= 64:
             cos = float(torch.dot(u[nz], v[nz]) / (u[nz].norm() * v[nz].norm() + 1e-30))
             assert cos > 0.9, f"{k}: update direction cosine {cos:.3f} after 3 Adam steps"
@@ -290,5 +293,6 @@ def test_state_dict_round_trip_and_device_errors():
     cpu_model = M.SRFR(10, 4, 16, 16, 0.0, 1, 1, "cpu")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         cpu_model(None, torch.ones(1, 4, dtype=torch.long), torch.ones(1, 4, dtype=torch.long))
-    with pytest.raises(ValueError, match="multiples of 16"):
-        M.SRFR(10, 4, 45, 5)
+    assert M.SRFR(10, 4, 45, 5).spec.Hp == 64            # the author's 45 + 5 widths run on a zero-padded layout
+    with pytest.raises(ValueError, match="even"):
+        M.SRFR(10, 4, 45, 4)
