@@ -165,7 +165,7 @@ def run_ours(args):
     m, data = make_model_and_data(dev)
     if world > 1:                               # identical replicas
         dist.broadcast(m.flat_parameters().data, 0)
-    tr = FusedTrainer(m, lr=1e-3, betas=(0.9, 0.98), process_group=pg, use_graph=(world == 1))
+    tr = FusedTrainer(m, lr=1e-3, betas=(0.9, 0.98), process_group=pg, use_graph=True)
     smp = synth.BatchSampler(data, L, seed=100 + rank)
     npool = 8
     host, dev_batches = [], []
@@ -245,6 +245,11 @@ def run_ours(args):
     if not args.no_catalogue:
         cat = bench_catalogue(dev, rank, world, pg, args, pk, timed)
 
+    # ---- gather: K1 on the C3 item table (1 M rows x 64 fp32 = 256 MB > L2), 4 M tokens, every slot valid ----
+    gat = None
+    if not args.no_catalogue and rank == 0:
+        gat = bench_gather(dev, pk)
+
     # ---- CPU baseline (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -263,11 +268,55 @@ def run_ours(args):
                     gpu_launches=int(calls_per_step * args.steps), clocks=clocks, roofline=roofline)
         if cat is not None:
             line["catalogue"] = cat
+        if gat is not None:
+            line["gather"] = gat
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tear down without dist.destroy_process_group(): with the NCCL all-reduce captured inside live CUDA graphs the
+        # communicator teardown can block for minutes.  All ranks meet, drop the graphs, and leave.
+        torch.cuda.synchronize()
+        dist.barrier()
+        tr._graph = None
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
+def bench_gather(dev, pk):
+    """K1 (gather + positional add + fake concat + pad mask + LayerNorm) at a size where the table cannot sit in L2:
+    algorithmic bytes per token = 16 (ids) + 256 (fp32 row) + 2 x 160 (x0, LN out, bf16) + 8 (stats) = 600."""
+    from srfrd_b200 import ops
+    N, D, F, L, B = 1_000_000, 64, 16, 50, 81920
+    T, H = B * L, D + F
+    g = torch.Generator(device="cpu").manual_seed(1238)
+    E = torch.randn(N + 1, D, generator=g).to(dev)
+    P, Fe = torch.randn(L, D, generator=g).to(dev), torch.randn(3, F, generator=g).to(dev)
+    w, b = torch.ones(H, device=dev), torch.zeros(H, device=dev)
+    seq = torch.randint(1, N + 1, (B, L), generator=g).to(dev)
+    rsq = torch.randint(1, 3, (B, L), generator=g).to(dev)
+    x0 = [torch.empty(T, H, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+    q = [torch.empty(T, H, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+    st = torch.empty(T, 2, device=dev)
+    run = lambda i: ops.embed_ln_fwd(E, P, Fe, 1, seq, rsq, 1.0, w, b, 1e-8, x0_bf16=x0[i % 2], q_bf16=q[i % 2], stats=st)
+    for i in range(3):
+        run(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(10):
+        run(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    by = T * 600.0
+    gbs = by / (ms * 1e-3) / 1e9
+    return dict(kernel="srfrd_embed_ln_fwd", tokens=T, table_rows=N + 1, table_bytes=(N + 1) * D * 4, ms=round(ms, 4),
+                roofline=dict(bound="hbm", achieved=round(gbs, 1), peak=pk["hbm"], unit="GB/s", frac=round(gbs / pk["hbm"], 4),
+                              traffic=None, bytes_per_token=600, peak_source=pk["src"]),
+                config="C3 table (1M x 64 fp32, 256 MB > L2), 81920 x 50 tokens, all slots valid, SRFR D=64 F=16")
 
 
 def bench_catalogue(dev, rank, world, pg, args, pk, timed):

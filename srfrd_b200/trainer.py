@@ -134,8 +134,9 @@ class FusedTrainer:
         key = (tuple(self._static["seq"].shape), self._has_w)
         if self.use_graph and self._graph is not None and self._graph_key == key:
             self._graph.replay()
-        elif self.use_graph and self.steps >= 1 and self.pg is None:
-            # capture after one eager step has sized the workspaces and set kernel attributes
+        elif self.use_graph and self.steps >= 1:
+            # capture after one eager step has sized the workspaces, set kernel attributes and (data parallel) warmed
+            # up the NCCL communicator; the gradient all-reduce is captured into the same graph
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
             with torch.cuda.graph(g):

@@ -246,6 +246,31 @@ def test_gradients_match_oracle_at_scale(kind):
         assert rel <= 0.08 and cos >= 0.996, f"{k}: rel L2 err {rel:.4f}, cos {cos:.5f}"
 
 
+def test_long_sequence_c4_shape_trains_like_the_oracle():
+    """C4 shape (maxlen 200, D = 256, F = 16 -> H = 272, 4 blocks): two 96-column GEMM tiles per row, SIMT attention
+    with packed-triangle scores (maxlen > 128).  Three fused steps vs the CPU oracle on the same batches."""
+    from oracle import srfrd_oracle as O
+    from srfrd_b200 import SRFR_model as M, synth
+    from srfrd_b200.trainer import FusedTrainer
+    data = synth.make_interactions(31, 300, 800, 20, 60.0, 200)
+    torch.manual_seed(5)
+    m = M.SRFR(data.itemnum, 200, 256, 16, 0.0, 4, 1, "cuda")
+    for _, p in m.named_parameters():
+        if p.dim() >= 2:
+            torch.nn.init.xavier_normal_(p.data)
+    m = m.to("cuda")
+    sd0 = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    orc = O.OracleTrainer(sd0, "SRFR", 1)
+    tr = FusedTrainer(m, use_graph=True)
+    smp = synth.BatchSampler(data, 200, 9)
+    for step in range(3):
+        nb = smp.next_batch(12)
+        tb = {k: torch.from_numpy(v) for k, v in nb.items()}
+        ref_loss = orc.step(tb, None)
+        loss = float(tr.step({k: v.cuda() for k, v in tb.items()}))
+        assert abs(loss - ref_loss) < 5e-3, f"step {step}: {loss} vs oracle {ref_loss}"
+
+
 def test_full_catalogue_metrics_match_oracle():
     """HR@10 / NDCG@10 over the full catalogue: GPU top-10 vs the oracle's exact ranking, |delta| <= 1e-3."""
     from oracle import srfrd_oracle as O
