@@ -184,6 +184,18 @@ SRFRD_API int srfrd_catalogue_topk(const void* feats_bf16, int64_t U, int64_t u_
 SRFRD_API int srfrd_merge_topk(const float* scores, const int* ids, int64_t U, int nlists, int k, float* out_scores,
                      int64_t* out_ids, void* stream);
 
+/* ---- on-device batch sampler (next row 8f #1) ----
+ * replaces: WarpSampler_fr / sample_function_fr (utils.py:14-90) and the seven LongTensor.to(device) copies per
+ * step (trainer.py:29).  CSR training interactions (offsets int64 (usernum+1), items int32, labels int8 {1 fake,
+ * 2 real}, p_fake fp32 or NULL), `eligible` = 0-based rows of users with > 1 train item (utils.py:25).  Writes the
+ * reference's batch layout: right-aligned, left-padded int64 (B, L) arrays seq / rsq / pos / prs / neg / nrs, the
+ * chosen 1-based user ids (B) and, if w_pos != NULL, the discriminator weights of row L (policy 0 none, 1 mask,
+ * 2 soft).  `step` (device fp32 counter, may be NULL) is mixed into the seed so graph replays draw new batches. */
+SRFRD_API int srfrd_sample_batch(const int64_t* offsets, const int* items, const int8_t* labels, const float* p_fake,
+                       const int* eligible, int n_eligible, int itemnum, int B, int L, int policy, uint64_t seed,
+                       const float* step, int64_t* users, int64_t* seq, int64_t* rsq, int64_t* pos, int64_t* prs,
+                       int64_t* neg, int64_t* nrs, float* w_pos, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,6 +58,7 @@ SIGNATURES = {
     "srfrd_catalogue_topk_plan": [i64, i64, i64, i32, i32, C.POINTER(i32)],
     "srfrd_catalogue_topk": [vp, i64, i64, i32, vp, i64, i64, i64, i32, i32, i32, i32, vp, vp, vp],
     "srfrd_merge_topk": [vp, vp, i64, i32, i32, vp, vp, vp],
+    "srfrd_sample_batch": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
 }
 
 _lib = None

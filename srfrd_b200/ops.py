@@ -226,3 +226,11 @@ def catalogue_topk(feats, U, u_pad, n_split, table, row_lo, id_base, chunks, par
 def merge_topk(scores, ids, U, nlists, k, out_scores, out_ids):
     _lib.require_device()
     call("srfrd_merge_topk", _p(scores), _p(ids), U, nlists, k, _p(out_scores), _p(out_ids), _stream())
+
+
+def sample_batch(offsets, items, labels, p_fake, eligible, itemnum, B, L, policy, seed, step, out, w_pos=None):
+    """out: dict with int64 (B, L) tensors seq, rsq, pos, prs, neg, nrs and int64 (B,) users."""
+    _lib.require_device()
+    call("srfrd_sample_batch", _p(offsets), _p(items), _p(labels), _p(p_fake), _p(eligible), eligible.numel(), int(itemnum),
+         B, L, int(policy), int(seed), _p(step), _p(out.get("users")), _p(out["seq"]), _p(out["rsq"]), _p(out["pos"]),
+         _p(out["prs"]), _p(out["neg"]), _p(out["nrs"]), _p(w_pos), _stream())

@@ -19,7 +19,50 @@ import torch
 from . import ops
 from .engine import HotPath
 
-__all__ = ["simulate", "FusedTrainer", "discriminator_weights"]
+__all__ = ["simulate", "FusedTrainer", "DeviceSampler", "discriminator_weights"]
+
+POLICIES = {"none": 0, "mask": 1, "soft": 2}
+
+
+class DeviceSampler:
+    """The training interactions resident on the device in CSR form plus the batch-building kernel
+    (srfrd_sample_batch): the B200-side replacement of WarpSampler_fr (utils.py:67-90).  ``next_batch`` keeps the
+    reference's 7-tuple order (u, seq, rsq, pos, prs, neg, nrs) as int64 device tensors; ``FusedTrainer.step_sampled``
+    draws inside the captured CUDA graph so no batch ever crosses PCIe."""
+
+    def __init__(self, data, maxlen: int, device, seed: int = 0):
+        """data: srfrd_b200.synth.Interactions (or any object with offsets / items / labels / p_fake / itemnum)."""
+        dev = torch.device(device)
+        self.L, self.itemnum, self.seed = maxlen, int(data.itemnum), int(seed)
+        self.offsets = torch.as_tensor(np.asarray(data.offsets, np.int64)).to(dev)
+        self.items = torch.as_tensor(np.asarray(data.items, np.int32)).to(dev)
+        self.labels = torch.as_tensor(np.asarray(data.labels, np.int8)).to(dev)
+        pf = getattr(data, "p_fake", None)
+        self.p_fake = None if pf is None else torch.as_tensor(np.asarray(pf, np.float32)).to(dev)
+        lens = np.diff(np.asarray(data.offsets, np.int64))
+        self.eligible = torch.as_tensor(np.nonzero(lens > 1)[0].astype(np.int32)).to(dev)      # utils.py:25
+        if self.eligible.numel() == 0:
+            raise ValueError("no user has more than one training interaction")
+        self.device = dev
+        self.draws = 0
+
+    def alloc(self, B: int):
+        z = lambda: torch.zeros(B, self.L, dtype=torch.int64, device=self.device)
+        return dict(users=torch.zeros(B, dtype=torch.int64, device=self.device), seq=z(), rsq=z(), pos=z(), prs=z(),
+                    neg=z(), nrs=z())
+
+    def sample_into(self, out, w_pos=None, policy: str = "none", step=None):
+        """Fill pre-allocated tensors; ``step`` = device fp32 counter mixed into the seed (graph replays)."""
+        B = out["seq"].shape[0]
+        ops.sample_batch(self.offsets, self.items, self.labels, self.p_fake, self.eligible, self.itemnum, B, self.L,
+                         POLICIES[policy], self.seed + (0 if step is not None else self.draws), step, out, w_pos)
+        self.draws += 1
+
+    def next_batch(self, batch_size: int):
+        out = self.alloc(batch_size)
+        self.sample_into(out)
+        return out["users"], out["seq"], out["rsq"], out["pos"], out["prs"], out["neg"], out["nrs"]
+
 
 
 def discriminator_weights(pos: torch.Tensor, p_fake: Optional[torch.Tensor], policy: str = "none") -> torch.Tensor:
@@ -89,6 +132,9 @@ class FusedTrainer:
         w_pos = st["w_pos"].view(-1) if has_wp else None
         w_neg = st["w_neg"].view(-1) if has_wn else None
         norm, acc, loss = self.scal[0:2], self.scal[2:4], self.scal[4:5]
+        smp = getattr(self, "_sampler", None)
+        if smp is not None:
+            smp.sample_into(st, st["w_pos"] if has_wp else None, self._sampler_policy, step=eng.step_state[0:1])
         ops.weight_sums(pos, w_pos, w_neg, norm)
         acc.zero_()
         if self.pg is not None:
@@ -131,7 +177,7 @@ class FusedTrainer:
 
     def run_step(self) -> torch.Tensor:
         """Run one step on the loaded batch; returns the device scalar holding the loss (no sync)."""
-        key = (tuple(self._static["seq"].shape), self._has_w)
+        key = (tuple(self._static["seq"].shape), self._has_w, id(getattr(self, "_sampler", None)))
         if self.use_graph and self._graph is not None and self._graph_key == key:
             self._graph.replay()
         elif self.use_graph and self.steps >= 1:
@@ -151,6 +197,17 @@ class FusedTrainer:
     def step(self, batch, w_pos=None, w_neg=None) -> torch.Tensor:
         self.load_batch(batch, w_pos, w_neg)
         return self.run_step()
+
+    def step_sampled(self, sampler: "DeviceSampler", batch_size: int, policy: str = "none") -> torch.Tensor:
+        """One step on a batch drawn ON THE DEVICE by ``sampler`` (no host batch, no H2D copies): the sampling kernel
+        is the first node of the captured graph and re-seeds itself from the device-resident step counter."""
+        if self._static is None or self._static["seq"].shape != (batch_size, sampler.L):
+            self._alloc_static(batch_size, sampler.L)
+        self._sampler, self._sampler_policy = sampler, policy
+        self._has_w = (policy != "none", False)
+        out = self.run_step()
+        self._sampler = None
+        return out
 
     def state_dict(self):
         return {k: v.detach().clone() for k, v in self.model.state_dict().items()}

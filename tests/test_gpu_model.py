@@ -293,6 +293,49 @@ def test_full_catalogue_metrics_match_oracle():
     assert abs(hr - hr_ref) <= 1e-3 and abs(ndcg - ndcg_ref) <= 1e-3, (hr, hr_ref, ndcg, ndcg_ref)
 
 
+def test_device_sampler_reproduces_the_reference_batch_layout():
+    """srfrd_sample_batch vs the sampler semantics of utils.py:21-65: for the users it drew, seq / pos / rsq / prs are
+    bit-identical to the host construction; negatives are uniform ids outside the user's own item set wherever
+    pos != 0 and 0 elsewhere; nrs == 1[pos != 0]; only users with > 1 train item are drawn."""
+    from srfrd_b200 import synth
+    from srfrd_b200.trainer import DeviceSampler, FusedTrainer
+    from srfrd_b200 import SRFR_model as M
+    L = 50
+    data = synth.make_interactions(41, 3000, 2000, 1, 6.0, L)
+    smp = DeviceSampler(data, L, "cuda", seed=17)
+    u, seq, rsq, pos, prs, neg, nrs = (t.cpu().numpy() for t in smp.next_batch(777))
+    u0 = u - 1
+    a, n = data.offsets[u0], np.diff(data.offsets)[u0]
+    assert (n > 1).all()
+    t = np.arange(L)[None, :]
+    src = (n[:, None] - 1) - (L - t)
+    valid = src >= 0
+    gi = np.where(valid, a[:, None] + src, 0)
+    assert np.array_equal(seq, np.where(valid, data.items[gi], 0))
+    assert np.array_equal(rsq, np.where(valid, data.labels[gi], 0))
+    assert np.array_equal(pos, np.where(valid, data.items[np.where(valid, gi + 1, 0)], 0))
+    assert np.array_equal(prs, np.where(valid, data.labels[np.where(valid, gi + 1, 0)], 0))
+    assert np.array_equal(nrs, valid.astype(np.int64))
+    assert ((neg >= 1) & (neg <= data.itemnum))[valid].all() and (neg[~valid] == 0).all()
+    for b in range(len(u0)):                        # negatives never come from the user's own train items
+        own = set(data.items[data.offsets[u0[b]]:data.offsets[u0[b] + 1]].tolist())
+        assert not (set(neg[b][valid[b]].tolist()) & own)
+    assert len(np.unique(u)) > 400                  # users are spread, negatives roughly uniform
+    assert abs(neg[valid].mean() / data.itemnum - 0.5) < 0.05
+    # in the fused, graph-captured step every replay draws a new batch (seeded by the device-resident step counter)
+    torch.manual_seed(4)
+    m = M.SRFR(data.itemnum, L, 64, 16, 0.0, 2, 1, "cuda").to("cuda")
+    tr = FusedTrainer(m, use_graph=True)
+    seen, losses = [], []
+    for _ in range(6):
+        losses.append(float(tr.step_sampled(smp, 256, policy="soft")))
+        seen.append(tr._static["seq"].clone())
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+    assert not any(torch.equal(seen[i], seen[i + 1]) for i in range(5))
+    w = tr._static["w_pos"]
+    assert float(w.min()) >= 0.0 and float(w.max()) <= 1.0 and torch.equal(w != 0, (tr._static["pos"] != 0) & (w != 0))
+
+
 def test_dropout_training_step_runs_and_is_stochastic():
     from srfrd_b200 import SRFR_model as M
     from srfrd_b200.trainer import FusedTrainer
