@@ -1,5 +1,6 @@
 // C-ABI plumbing: error reporting, device check, TMA descriptor construction.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -14,6 +15,14 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  // measured at C2: no gain (1.83 vs 1.81 ms / step) -- the persistent kernels fill every SM's shared memory, so a
+  // dependent CTA cannot become resident before its predecessor's CTAs exit.  Off unless SRFRD_PDL=1.
+  if (v < 0) { const char* e = getenv("SRFRD_PDL"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
 }
 
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {

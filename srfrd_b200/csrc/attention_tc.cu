@@ -175,7 +175,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = p.n_tiles * p.heads;
-  if (DROP) p.drop_seed = mix_seed(p.drop_seed, p.drop_step);
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmO);
@@ -189,6 +188,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tO = tmem_base + 128;
+  pdl_prologue_done();
+  if (DROP) p.drop_seed = mix_seed(p.drop_seed, p.drop_step);
 
   if (warp == 8) {
     uint32_t ph = 0;
@@ -396,7 +397,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = p.n_tiles * p.heads;
-  if (DROP) p.drop_seed = mix_seed(p.drop_seed, p.drop_step);
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
@@ -409,6 +409,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_prologue_done();
+  if (DROP) p.drop_seed = mix_seed(p.drop_seed, p.drop_step);
   // S and dP live in columns [0,128) and [128,256); once the softmax backward has consumed them the same
   // columns receive dK and dV, and dQ goes to [256, 256+hd).
   const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDK = tmem_base, tDV = tmem_base + 128, tDQ = tmem_base + 256;
@@ -699,8 +701,10 @@ extern "C" int srfrd_attention_fwd(const void* q, int ldq, const void* k, const 
   }
   int grid = p.n_tiles * heads;
   if (grid > 2 * num_sms()) grid = 2 * num_sms();
-  if (p.drop_thresh) attn_fwd_tc_kernel<true><<<grid, AF_THREADS, smem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, tmO, p);
-  else attn_fwd_tc_kernel<false><<<grid, AF_THREADS, smem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, tmO, p);
+  if (p.drop_thresh)
+    SRFRD_CUDA(launch_pdl(attn_fwd_tc_kernel<true>, dim3(grid), dim3(AF_THREADS), smem, (cudaStream_t)stream, tmQ, tmK, tmV, tmO, p));
+  else
+    SRFRD_CUDA(launch_pdl(attn_fwd_tc_kernel<false>, dim3(grid), dim3(AF_THREADS), smem, (cudaStream_t)stream, tmQ, tmK, tmV, tmO, p));
   SRFRD_LAUNCH_CHECK();
   return 0;
 }
@@ -739,9 +743,11 @@ extern "C" int srfrd_attention_bwd(const void* dout, int lddo, const void* q, in
   int grid = p.n_tiles * heads;
   if (grid > num_sms()) grid = num_sms();
   if (p.drop_thresh)
-    attn_bwd_tc_kernel<true><<<grid, AF_THREADS, smem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, tmDO, tmDQ, tmDK, tmDV, p);
+    SRFRD_CUDA(launch_pdl(attn_bwd_tc_kernel<true>, dim3(grid), dim3(AF_THREADS), smem, (cudaStream_t)stream, tmQ, tmK, tmV,
+                          tmDO, tmDQ, tmDK, tmDV, p));
   else
-    attn_bwd_tc_kernel<false><<<grid, AF_THREADS, smem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, tmDO, tmDQ, tmDK, tmDV, p);
+    SRFRD_CUDA(launch_pdl(attn_bwd_tc_kernel<false>, dim3(grid), dim3(AF_THREADS), smem, (cudaStream_t)stream, tmQ, tmK, tmV,
+                          tmDO, tmDQ, tmDK, tmDV, p));
   SRFRD_LAUNCH_CHECK();
   return 0;
 }

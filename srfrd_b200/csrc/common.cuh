@@ -36,6 +36,23 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 #define SRFRD_LAUNCH_CHECK() SRFRD_CUDA(cudaGetLastError())
 
+// Programmatic dependent launch: a kernel launched through launch_pdl may begin (prologue: barrier init, TMEM
+// allocation, descriptor prefetch) while the previous kernel of the stream / graph is still draining; it must call
+// pdl_prologue_done() before it touches anything an earlier kernel wrote.  Opt-in: SRFRD_PDL=1 (see api.cu).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int num_sms() {
   static int n = 0;
   if (!n) {
@@ -52,6 +69,11 @@ static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b)
 // ---------------------------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------------------------
+// wait until every earlier grid has completed and its writes are visible, then allow the next grid to start launching
+__device__ __forceinline__ void pdl_prologue_done() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

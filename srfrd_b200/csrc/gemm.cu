@@ -132,6 +132,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (blockIdx.x < 160) g_gemm_cta[2 * blockIdx.x] = (long long)gt;
   }
   if (warp == 17) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+  pdl_prologue_done();                                   // everything below may read what earlier kernels wrote
   for (int i = threadIdx.x; i < MAX_BIAS; i += blockDim.x) sbias[i] = (e.bias && i < s.N) ? __ldg(e.bias + i) : 0.f;
   tc_fence_before();
   __syncthreads();
@@ -377,6 +378,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_prologue_done();
 
   if (nkb > 0) {
     if (warp == 0) {
@@ -551,7 +553,8 @@ extern "C" int srfrd_gemm_tn(const void* A, int lda, const void* B, int ldb, int
                                       227 * 1024));                                                                   \
       attr_set = true;                                                                                                \
     }                                                                                                                 \
-    gemm_tn_kernel<AUXM, DROPF><<<grid, TN_THREADS, smem, stream>>>(tmA, tmB, tmAux, tmOut, s, e);                    \
+    SRFRD_CUDA(launch_pdl(gemm_tn_kernel<AUXM, DROPF>, dim3(grid), dim3(TN_THREADS), smem, stream, tmA, tmB, tmAux,    \
+                          tmOut, s, e));                                                                              \
   } while (0)
   const bool drop = e.drop_thresh != 0;
   if (aux_mode == 0) { if (drop) SRFRD_TN_LAUNCH(0, true); else SRFRD_TN_LAUNCH(0, false); }
@@ -603,7 +606,7 @@ extern "C" int srfrd_gemm_wgrad(const void* dY, int lda, const void* X, int ldb,
     attr_set = true;
   }
   dim3 grid(s.k_splits, m_tiles, n_tiles);
-  gemm_wgrad_kernel<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, s);
+  SRFRD_CUDA(launch_pdl(gemm_wgrad_kernel, grid, dim3(GEMM_THREADS), smem, stream, tmA, tmB, s));
   SRFRD_LAUNCH_CHECK();
   return 0;
 }

@@ -30,6 +30,7 @@ __device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + __expf(
 
 __global__ void __launch_bounds__(256) score_kernel(ScoreParams p) {
   __shared__ float red[2][8];
+  pdl_prologue_done();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int64_t warp0 = (int64_t)blockIdx.x * nw + warp, nwarps = (int64_t)gridDim.x * nw;
   const int W = p.D + (p.fake_table ? p.F : 0);
@@ -144,6 +145,7 @@ __global__ void __launch_bounds__(256) weight_sums_kernel(const int64_t* pos, co
 }
 
 __global__ void loss_finalize_kernel(const float* acc, const float* norm, float* loss) {
+  pdl_prologue_done();
   const float a = norm[0] > 0.f ? acc[0] / norm[0] : 0.f;
   const float b = norm[1] > 0.f ? acc[1] / norm[1] : 0.f;
   loss[0] = a + b;
@@ -163,6 +165,7 @@ struct EmbedBwdParams {
 
 __global__ void embed_bwd_kernel(EmbedBwdParams p) {
   extern __shared__ int64_t ids[];   // [L] seq ids, [L] fake ids
+  pdl_prologue_done();
   const int64_t b = blockIdx.x;
   const int c = threadIdx.x;
   const int H = p.D + (p.mode == 1 ? p.F : 0);
@@ -196,6 +199,7 @@ __global__ void embed_bwd_kernel(EmbedBwdParams p) {
 
 // out[(n / seg_in) * seg_out + n % seg_in] += in[n] where n % seg_in < seg_out
 __global__ void add_segments_kernel(const float* in, int64_t n, int seg_in, int seg_out, float* out) {
+  pdl_prologue_done();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int c = (int)(i % seg_in);
@@ -206,6 +210,7 @@ __global__ void add_segments_kernel(const float* in, int64_t n, int seg_in, int 
 // K7: Adam.  state = {step, 1 - beta1^step, 1 - beta2^step}; kept on device so a captured CUDA
 // graph can replay the whole training step.
 __global__ void adam_tick_kernel(float* state, float beta1, float beta2) {
+  pdl_prologue_done();
   const float step = state[0] + 1.f;
   state[0] = step;
   state[1] = (float)(1.0 - pow((double)beta1, (double)step));
@@ -215,6 +220,7 @@ __global__ void adam_tick_kernel(float* state, float beta1, float beta2) {
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, int64_t n, float lr, float beta1, float beta2,
                                                    float eps, const float* __restrict__ state, int zero_grad) {
+  pdl_prologue_done();
   // torch.optim.Adam (trainer.py:390): step_size = lr / bc1; denom = sqrt(v) / sqrt(bc2) + eps
   const float step_size = lr / state[1];
   const float inv_sqrt_bc2 = rsqrtf(state[2]);
@@ -254,7 +260,7 @@ static int score_launch(ScoreParams& p, void* stream) {
   int64_t blocks = (p.T + 7) / 8;
   const int64_t cap = (int64_t)num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  score_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  SRFRD_CUDA(launch_pdl(score_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, p));
   SRFRD_LAUNCH_CHECK();
   return 0;
 }
@@ -312,7 +318,7 @@ extern "C" int srfrd_weight_sums(const int64_t* pos, const float* w_pos, const f
 
 extern "C" int srfrd_loss_finalize(const float* acc2, const float* norm2, float* loss, void* stream) {
   SRFRD_REQUIRE(acc2 && norm2 && loss, "loss_finalize: null pointer");
-  loss_finalize_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(acc2, norm2, loss);
+  SRFRD_CUDA(launch_pdl(loss_finalize_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, acc2, norm2, loss));
   SRFRD_LAUNCH_CHECK();
   return 0;
 }
@@ -329,7 +335,7 @@ extern "C" int srfrd_embed_bwd(const void* dx0, int ldx, const int64_t* seq, con
   p.dx0 = (const bf16*)dx0; p.ldx = ldx; p.seq = seq; p.aux_ids = aux_ids; p.L = L; p.D = D; p.F = F; p.mode = mode;
   p.item_scale = item_scale; p.d_item = d_item; p.d_aux = d_aux;
   const int threads = (H + 31) & ~31;
-  embed_bwd_kernel<<<(unsigned)B, threads, 2 * L * sizeof(int64_t), (cudaStream_t)stream>>>(p);
+  SRFRD_CUDA(launch_pdl(embed_bwd_kernel, dim3((unsigned)B), dim3(threads), 2 * L * sizeof(int64_t), (cudaStream_t)stream, p));
   SRFRD_LAUNCH_CHECK();
   return 0;
 }
@@ -337,14 +343,15 @@ extern "C" int srfrd_embed_bwd(const void* dx0, int ldx, const int64_t* seq, con
 extern "C" int srfrd_add_segments(const float* in, int64_t n, int seg_in, int seg_out, float* out, void* stream) {
   SRFRD_REQUIRE(in && out && seg_in > 0 && seg_out <= seg_in, "add_segments: bad arguments");
   if (n == 0) return 0;
-  add_segments_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, n, seg_in, seg_out, out);
+  SRFRD_CUDA(launch_pdl(add_segments_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, in, n, seg_in,
+                        seg_out, out));
   SRFRD_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int srfrd_adam_tick(float* state3, float beta1, float beta2, void* stream) {
   SRFRD_REQUIRE(state3, "adam_tick: null state");
-  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state3, beta1, beta2);
+  SRFRD_CUDA(launch_pdl(adam_tick_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, state3, beta1, beta2));
   SRFRD_LAUNCH_CHECK();
   return 0;
 }
@@ -357,7 +364,8 @@ extern "C" int srfrd_adam_step(float* p, float* g, float* m, float* v, int64_t n
   int64_t blocks = (n / 4 + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-  adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, state3, zero_grad);
+  SRFRD_CUDA(launch_pdl(adam_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, n, lr, beta1, beta2,
+                        eps, state3, zero_grad));
   SRFRD_LAUNCH_CHECK();
   return 0;
 }

@@ -73,6 +73,7 @@ struct EmbedParams {
 // arithmetic element by element.  Columns >= H (up to the padded leading dimension) are written as zeros.
 template <int LPR, int CH, bool VEC>
 __global__ void __launch_bounds__(256, 4) embed_ln_kernel(EmbedParams p) {
+  pdl_prologue_done();
   if (p.drop_thresh) p.drop_seed = mix_seed(p.drop_seed, p.drop_step);
   constexpr int RPW = 32 / LPR;                         // rows per warp pass
   const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
@@ -206,18 +207,13 @@ struct LnFwdParams {
 
 // p.H is the number of VALID columns (LayerNorm width); rows are processed in 8-column chunks up to Hc = roundup(H, 8),
 // columns in [H, Hc) are read as zero-padding and written as zeros.
-template <int LPR, int CH>
+template <int LPR, int CH, bool RAGGED>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(LnFwdParams p) {
-  __shared__ __align__(16) float swb[2][MAXW];
   constexpr int RPW = 32 / LPR, UN = 2;
   const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
   const int Hc = (p.H + 7) & ~7;
-  const bool ragged = Hc != p.H;
-  for (int i = threadIdx.x; i < MAXW; i += blockDim.x) {
-    swb[0][i] = i < p.H ? __ldg(p.w + i) : 0.f;
-    swb[1][i] = i < p.H ? __ldg(p.b + i) : 0.f;
-  }
-  __syncthreads();
+  constexpr bool ragged = RAGGED;
+  pdl_prologue_done();
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t t0 = warp * RPW * UN; t0 < p.T; t0 += nwarps * RPW * UN) {
@@ -264,11 +260,12 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(LnFwdParams p) {
       for (int ch = 0; ch < CH; ++ch) {
         const int c = (ch * LPR + sub) * 8;
         if (c >= Hc) continue;
-        float y[8];
-        const float4 w0 = *reinterpret_cast<const float4*>(&swb[0][c]), w1 = *reinterpret_cast<const float4*>(&swb[0][c + 4]);
-        const float4 b0 = *reinterpret_cast<const float4*>(&swb[1][c]), b1 = *reinterpret_cast<const float4*>(&swb[1][c + 4]);
-        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float y[8], w[8], b[8];
+        if (!ragged) { load8_f32(p.w + c, w); load8_f32(p.b + c, b); }
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { w[j] = c + j < p.H ? __ldg(p.w + c + j) : 0.f; b[j] = c + j < p.H ? __ldg(p.b + c + j) : 0.f; }
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) y[j] = (!ragged || c + j < p.H) ? (v[ch][j] - mean) * rstd * w[j] + b[j] : 0.f;
         if (p.y_bf16) *reinterpret_cast<uint4*>(p.y_bf16 + t * p.ldy + c) = pack8(y);
@@ -295,16 +292,17 @@ struct LnBwdParams {
 // Lean register layout: the per-lane column accumulators (dw, db: 2 x CH x 8) are the only persistent state; the LN
 // weight is re-read from shared memory, dy / x / add stay packed (bf16) until used, and g = dy * w and
 // xh = (x - mean) * rstd are recomputed in the output pass instead of being kept.
-template <int LPR, int CH, bool F32DY>
+template <int LPR, int CH, bool F32DY, bool RAGGED>
 __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(LnBwdParams p) {
   __shared__ float sdw[MAXW], sdb[MAXW];
   __shared__ __align__(16) float sw[MAXW];
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
   const int Hc = (p.H + 7) & ~7;                         // p.H = valid columns; [H, Hc) is zero padding
-  const bool ragged = Hc != p.H;
+  constexpr bool ragged = RAGGED;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  pdl_prologue_done();
   for (int i = threadIdx.x; i < MAXW; i += blockDim.x) { sdw[i] = sdb[i] = 0.f; sw[i] = i < p.H ? __ldg(p.w + i) : 0.f; }
   __syncthreads();
   float adw[CH][8], adb[CH][8];
@@ -440,6 +438,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* X, int64_t M, i
                                                      int rows_per_block) {
   // blockDim = (TX, TY): thread x handles column pairs, y strides rows
   extern __shared__ float sm[];
+  pdl_prologue_done();
   const int TX = blockDim.x, TY = blockDim.y;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t r1 = min(M, r0 + rows_per_block);
@@ -467,6 +466,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* X, int64_t M, i
 
 // dst[r, c] = bf16(src[r, c]), dstT[c, r] = bf16(src[r, c]) for a table of small weight matrices
 __global__ void cast_weights_kernel(const srfrd_cast_desc_t* descs, int n) {
+  pdl_prologue_done();
   const srfrd_cast_desc_t d = descs[blockIdx.x];
   const int total = d.rows * d.cols;
   for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < total; i += gridDim.y * blockDim.x) {
@@ -520,6 +520,7 @@ __global__ void f32_to_bf16_rows_kernel(const float* src, int64_t src_ld, const 
 
 __global__ void dropout_apply_kernel(const bf16* x, int ldx, bf16* out, int ldo, int64_t M, int N, uint64_t seed,
                                      uint32_t thresh, uint32_t stream_id, float scale, const float* step) {
+  pdl_prologue_done();
   seed = mix_seed(seed, step);
   const int64_t n2 = M * (N / 2);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
@@ -570,8 +571,8 @@ extern "C" int srfrd_embed_ln_fwd(const float* item_table, int64_t n_rows, int D
 #define CALL(LPR, CH)                                                                                       \
   do {                                                                                                      \
     const int grid = grid_for_rows(p.T, 8 * (32 / LPR), 8);                                                 \
-    if (vec) embed_ln_kernel<LPR, CH, true><<<grid, 256, 0, (cudaStream_t)stream>>>(p);                     \
-    else embed_ln_kernel<LPR, CH, false><<<grid, 256, 0, (cudaStream_t)stream>>>(p);                        \
+    if (vec) SRFRD_CUDA(launch_pdl(embed_ln_kernel<LPR, CH, true>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, p)); \
+    else SRFRD_CUDA(launch_pdl(embed_ln_kernel<LPR, CH, false>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, p));    \
   } while (0)
   SRFRD_ROW_DISPATCH(H, CALL);
 #undef CALL
@@ -589,7 +590,12 @@ extern "C" int srfrd_layernorm_fwd(const void* x, int ldx, const float* w, const
   LnFwdParams p;
   p.x = (const bf16*)x; p.ldx = ldx; p.w = w; p.b = b; p.eps = eps; p.y_bf16 = (bf16*)y_bf16; p.y_f32 = y_f32;
   p.ldy = ldy; p.stats = stats; p.T = T; p.H = H; p.row_stride = row_stride; p.row_offset = row_offset;
-#define CALL(LPR, CH) ln_fwd_kernel<LPR, CH><<<grid_for_rows(T, 16 * (32 / LPR), 8), 256, 0, (cudaStream_t)stream>>>(p)
+#define CALL(LPR, CH)                                                                                                   \
+  do {                                                                                                                  \
+    const dim3 grid(grid_for_rows(T, 16 * (32 / LPR), 8));                                                              \
+    if (H % 8) SRFRD_CUDA(launch_pdl(ln_fwd_kernel<LPR, CH, true>, grid, dim3(256), 0, (cudaStream_t)stream, p));       \
+    else SRFRD_CUDA(launch_pdl(ln_fwd_kernel<LPR, CH, false>, grid, dim3(256), 0, (cudaStream_t)stream, p));            \
+  } while (0)
   SRFRD_ROW_DISPATCH(H, CALL);
 #undef CALL
   SRFRD_LAUNCH_CHECK();
@@ -613,8 +619,10 @@ extern "C" int srfrd_layernorm_bwd(const void* dy_bf16, const float* dy_f32, int
 #define CALL(LPR, CH)                                                                                             \
   do {                                                                                                            \
     const int grid = grid_for_rows(T, 8 * (32 / LPR) * 8, 2);                                                     \
-    if (dy_f32) ln_bwd_kernel<LPR, CH, true><<<grid, 256, 0, (cudaStream_t)stream>>>(p);                          \
-    else ln_bwd_kernel<LPR, CH, false><<<grid, 256, 0, (cudaStream_t)stream>>>(p);                                \
+    if (dy_f32 && (H % 8)) SRFRD_CUDA(launch_pdl(ln_bwd_kernel<LPR, CH, true, true>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, p));        \
+    else if (dy_f32) SRFRD_CUDA(launch_pdl(ln_bwd_kernel<LPR, CH, true, false>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, p));       \
+    else if (H % 8) SRFRD_CUDA(launch_pdl(ln_bwd_kernel<LPR, CH, false, true>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, p));        \
+    else SRFRD_CUDA(launch_pdl(ln_bwd_kernel<LPR, CH, false, false>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, p));                  \
   } while (0)
   SRFRD_ROW_DISPATCH(H, CALL);
 #undef CALL
@@ -636,8 +644,8 @@ extern "C" int srfrd_colsum(const void* X, int64_t M, int N, int64_t ld, float* 
   if (rows_per_block < ty * 4) rows_per_block = ty * 4;
   gx = (M + rows_per_block - 1) / rows_per_block;
   dim3 grid((unsigned)gx, (unsigned)gy), block(tx, ty);
-  colsum_kernel<<<grid, block, 256 * 2 * sizeof(float), (cudaStream_t)stream>>>((const bf16*)X, M, N, ld, out,
-                                                                               (int)rows_per_block);
+  SRFRD_CUDA(launch_pdl(colsum_kernel, grid, block, 256 * 2 * sizeof(float), (cudaStream_t)stream, (const bf16*)X, M, N, ld, out,
+                        (int)rows_per_block));
   SRFRD_LAUNCH_CHECK();
   return 0;
 }
@@ -645,7 +653,7 @@ extern "C" int srfrd_colsum(const void* X, int64_t M, int N, int64_t ld, float* 
 extern "C" int srfrd_cast_weights(const srfrd_cast_desc_t* descs_dev, int n, void* stream) {
   SRFRD_REQUIRE(descs_dev || n == 0, "cast_weights: null table");
   if (n == 0) return 0;
-  cast_weights_kernel<<<dim3(n, 8), 256, 0, (cudaStream_t)stream>>>(descs_dev, n);
+  SRFRD_CUDA(launch_pdl(cast_weights_kernel, dim3(n, 8), dim3(256), 0, (cudaStream_t)stream, descs_dev, n));
   SRFRD_LAUNCH_CHECK();
   return 0;
 }
@@ -678,9 +686,9 @@ extern "C" int srfrd_dropout_apply(const void* x, int ldx, void* out, int ldo, i
   if (M == 0) return 0;
   int64_t blocks = (M * (N / 2) + 255) / 256;
   if (blocks > num_sms() * 16) blocks = num_sms() * 16;
-  dropout_apply_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)x, ldx, (bf16*)out, ldo, M, N, seed, (uint32_t)((double)drop_p * 4294967296.0), stream_id,
-      1.f / (1.f - drop_p), drop_step);
+  SRFRD_CUDA(launch_pdl(dropout_apply_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, ldx,
+                        (bf16*)out, ldo, M, N, seed, (uint32_t)((double)drop_p * 4294967296.0), stream_id,
+                        1.f / (1.f - drop_p), drop_step));
   SRFRD_LAUNCH_CHECK();
   return 0;
 }
