@@ -9,6 +9,8 @@ The block wiring reproduces the reference's non-standard encoder (SRFR_model.py:
 from __future__ import annotations
 
 import math
+import os
+from contextlib import contextmanager
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
@@ -160,6 +162,11 @@ class HotPath:
         self._ws: Dict[str, torch.Tensor] = {}
         self._build_shadows()
         self.step_state = torch.zeros(4, dtype=torch.float32, device=self.device)   # Adam {step, bc1, bc2}
+        # Independent branches of the step (the k/v projection next to LN1 + the q projection; every weight-gradient
+        # GEMM next to the data-gradient chain) are enqueued on a second stream: captured into the CUDA graph they
+        # become parallel branches, so one kernel's launch latency, tail and CTA skew are filled by the other's CTAs.
+        self.side = torch.cuda.Stream(device=self.device)
+        self.overlap = os.environ.get("SRFRD_OVERLAP", "1") != "0"
         self.drop_seed = 0x5EED5EED
         self.saved: Optional[dict] = None
 
@@ -226,6 +233,21 @@ class HotPath:
         """fp32 master weights -> bf16 GEMM operands (W and W^T); one launch."""
         ops.cast_weights(self._cast_table, self._cast_n)
 
+    @contextmanager
+    def _branch(self):
+        """Run the enclosed launches on the side stream, ordered after everything enqueued so far on the main one."""
+        if not self.overlap:
+            yield
+            return
+        main = torch.cuda.current_stream()
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            yield
+
+    def _join(self):
+        if self.overlap:
+            torch.cuda.current_stream().wait_stream(self.side)
+
     # ------------------------------------------------------------------ workspaces
     def _workspace(self, T: int, L: int) -> Dict[str, torch.Tensor]:
         if T <= self._ws_tokens:
@@ -250,13 +272,18 @@ class HotPath:
         act("stF", 2, torch.float32)
         act("hfin", s.Doutp, torch.float32)
         act("dh", s.Doutp, torch.float32)
-        for n in ("gA", "gB", "gC", "gD"):
+        for n in ("gA", "gC", "gD", "gX"):          # data-gradient chain only (never read by a side-stream GEMM)
             act(n)
-        act("gKV", 2 * H)
+        for i in range(nb):                         # operands of weight-gradient GEMMs: one buffer each, so a later
+            for n in ("gda1_", "gdr_", "gdq_"):     # kernel of the main chain never overwrites what a side-stream
+                act(f"{n}{i}")                      # wgrad is still reading
+            act(f"gdz_{i}")
+            act(f"gdkv_{i}", 2 * H)
         if s.kind == "SRFR":
             act("gc", s.Dp)
         if s.dropout > 0:
-            act("gE")
+            for i in range(nb):
+                act(f"gE_{i}")
         ws["pos_tmp"] = torch.zeros(L * H, dtype=torch.float32, device=dev)
         self._ws, self._ws_tokens = ws, T
         return ws
@@ -291,11 +318,13 @@ class HotPath:
         seq_flat = seq.view(-1)
         for i in range(nb):
             Q, q, kv, o, r, y, h1 = (ws[f"{n}{i}"][:T] for n in ("Q", "q", "kv", "o", "r", "y", "h1"))
+            with self._branch():                                   # k | v need the un-normalised x only
+                ops.gemm_tn(x[i], self.sh[f"wkv{i}"], out_bf16=kv, bias=self.bias("bkv", i))
             if i > 0:
                 ops.layernorm_fwd(x[i], P.view(f"attention_layernorms.{i}.weight"), P.view(f"attention_layernorms.{i}.bias"),
                                   LN_EPS, y_bf16=Q, stats=ws[f"st1_{i}"][:T], H=H)
             ops.gemm_tn(Q, self.sh[f"wq{i}"], out_bf16=q, bias=self.bias("bq", i))
-            ops.gemm_tn(x[i], self.sh[f"wkv{i}"], out_bf16=kv, bias=self.bias("bkv", i))
+            self._join()                                           # k | v (side stream) are ready
             ops.attention_fwd(q, kv[:, :Hp], kv[:, Hp:], o, B, L, H, s.num_heads, p_drop, seed, 10 + 4 * i, step)
             ops.gemm_tn(o, self.sh[f"wo{i}"], out_bf16=r, bias=self.bias("bo", i), residual=Q)
             ops.layernorm_fwd(r, P.view(f"forward_layernorms.{i}.weight"), P.view(f"forward_layernorms.{i}.bias"), LN_EPS,
@@ -332,64 +361,71 @@ class HotPath:
         ws = self._ws
         seq_flat = sv["seq"].view(-1)
         p_drop, seed, step = sv["p_drop"], sv["seed"], sv["step"]
-        gA, gB, gC, gD, gKV = (ws[n][:T] for n in ("gA", "gB", "gC", "gD", "gKV"))
+        gA, gC, gD, gX = (ws[n][:T] for n in ("gA", "gC", "gD", "gX"))
         G = lambda name: P.view(name, grad=True)
         GM = lambda name: P.mat(name, grad=True)
         x = [ws[f"x{i}"][:T] for i in range(nb + 1)]
+        dz_top = ws[f"gdz_{nb - 1}"][:T]
 
         # final LayerNorm (+ last_conv) -> dz = dL/dx[nb], pad rows zeroed
         if s.kind == "SRFR":
             gc = ws["gc"][:T]
             ops.layernorm_bwd(dh, ws["c"][:T], ws["stF"][:T], P.view("last_layernorm.weight"), gc,
                               G("last_layernorm.weight"), G("last_layernorm.bias"), H=s.D)
-            ops.gemm_wgrad(gc, x[nb], GM("last_conv.weight"), G("last_conv.bias"), Mo=s.D, No=H)
-            ops.gemm_tn(gc, self.sh["wcT"], out_bf16=gA, row_ids=seq_flat)
+            with self._branch():
+                ops.gemm_wgrad(gc, x[nb], GM("last_conv.weight"), G("last_conv.bias"), Mo=s.D, No=H)
+            ops.gemm_tn(gc, self.sh["wcT"], out_bf16=dz_top, row_ids=seq_flat)
         else:
-            ops.layernorm_bwd(dh, x[nb], ws["stF"][:T], P.view("last_layernorm.weight"), gA,
+            ops.layernorm_bwd(dh, x[nb], ws["stF"][:T], P.view("last_layernorm.weight"), dz_top,
                               G("last_layernorm.weight"), G("last_layernorm.bias"), row_ids=seq_flat, H=s.Dout)
 
         for i in reversed(range(nb)):
             Q, q, kv, o, r, y, h1 = (ws[f"{n}{i}"][:T] for n in ("Q", "q", "kv", "o", "r", "y", "h1"))
-            dz = gA
+            dz, da1, dr, dq, dkv = (ws[f"{n}{i}"][:T] for n in ("gdz_", "gda1_", "gdr_", "gdq_", "gdkv_"))
+            dx_out = ws[f"gdz_{i - 1}"][:T] if i > 0 else gA          # dL/dx[i]: the next (earlier) block's dz
             dz2 = dz
             if p_drop > 0:      # da2 = dz * mask2 (dropout2 sits between conv2 and the residual add)
-                dz2 = ws["gE"][:T]
+                dz2 = ws[f"gE_{i}"][:T]
                 ops.dropout_apply(dz, dz2, Hp, p_drop, seed, 12 + 4 * i, step)
             # FFN: z = drop2(h1 W2^T + b2) + y ; h1 = relu(drop1(y W1^T + b1))
-            ops.gemm_wgrad(dz2, h1, GM(f"forward_layers.{i}.conv2.weight"), G(f"forward_layers.{i}.conv2.bias"), Mo=H, No=H)
-            ops.gemm_tn(dz2, self.sh[f"w2T{i}"], out_bf16=gB, gate=h1, drop_p=p_drop, drop_seed=seed,
+            with self._branch():
+                ops.gemm_wgrad(dz2, h1, GM(f"forward_layers.{i}.conv2.weight"), G(f"forward_layers.{i}.conv2.bias"), Mo=H, No=H)
+            ops.gemm_tn(dz2, self.sh[f"w2T{i}"], out_bf16=da1, gate=h1, drop_p=p_drop, drop_seed=seed,
                         drop_stream=11 + 4 * i, drop_step=step)                                   # da1
-            ops.gemm_wgrad(gB, y, GM(f"forward_layers.{i}.conv1.weight"), G(f"forward_layers.{i}.conv1.bias"), Mo=H, No=H)
-            ops.gemm_tn(gB, self.sh[f"w1T{i}"], out_bf16=gC, residual=dz)                          # dy
+            with self._branch():
+                ops.gemm_wgrad(da1, y, GM(f"forward_layers.{i}.conv1.weight"), G(f"forward_layers.{i}.conv1.bias"), Mo=H, No=H)
+            ops.gemm_tn(da1, self.sh[f"w1T{i}"], out_bf16=gC, residual=dz)                         # dy
             # LN2
-            ops.layernorm_bwd(gC, r, ws[f"st2_{i}"][:T], P.view(f"forward_layernorms.{i}.weight"), gB,
+            ops.layernorm_bwd(gC, r, ws[f"st2_{i}"][:T], P.view(f"forward_layernorms.{i}.weight"), dr,
                               G(f"forward_layernorms.{i}.weight"), G(f"forward_layernorms.{i}.bias"), H=H)   # dr
             # r = Q + o Wo^T + bo
-            ops.gemm_wgrad(gB, o, GM(f"attention_layers.{i}.out_proj.weight"), G(f"attention_layers.{i}.out_proj.bias"),
-                           Mo=H, No=H)
-            ops.gemm_tn(gB, self.sh[f"woT{i}"], out_bf16=gC)                                       # do
-            ops.attention_bwd(gC, q, kv[:, :Hp], kv[:, Hp:], gD, gKV[:, :Hp], gKV[:, Hp:], B, L, H, s.num_heads, p_drop,
+            with self._branch():
+                ops.gemm_wgrad(dr, o, GM(f"attention_layers.{i}.out_proj.weight"), G(f"attention_layers.{i}.out_proj.bias"),
+                               Mo=H, No=H)
+            ops.gemm_tn(dr, self.sh[f"woT{i}"], out_bf16=gC)                                       # do
+            ops.attention_bwd(gC, q, kv[:, :Hp], kv[:, Hp:], dq, dkv[:, :Hp], dkv[:, Hp:], B, L, H, s.num_heads, p_drop,
                               seed, 10 + 4 * i, step)                                             # dq, dk|dv
             gin = GM(f"attention_layers.{i}.in_proj_weight")
             gbin = G(f"attention_layers.{i}.in_proj_bias")
-            ops.gemm_wgrad(gD, Q, gin[:H], gbin[:H], Mo=H, No=H)
-            ops.gemm_tn(gD, self.sh[f"wqT{i}"], out_bf16=gC, residual=gB)                          # dQ = dr + dq Wq
-            if Hp == H:
-                ops.gemm_wgrad(gKV, x[i], gin[H:], gbin[H:], Mo=2 * H, No=H)
-            else:       # k and v gradients sit at column offsets 0 and Hp: two row blocks of in_proj_weight
-                ops.gemm_wgrad(gKV[:, :Hp], x[i], gin[H:2 * H], gbin[H:2 * H], Mo=H, No=H)
-                ops.gemm_wgrad(gKV[:, Hp:], x[i], gin[2 * H:], gbin[2 * H:], Mo=H, No=H)
-            ops.gemm_tn(gKV, self.sh[f"wkvT{i}"], out_bf16=gD)                                     # dx via k, v
+            with self._branch():
+                ops.gemm_wgrad(dq, Q, gin[:H], gbin[:H], Mo=H, No=H)
+                if Hp == H:
+                    ops.gemm_wgrad(dkv, x[i], gin[H:], gbin[H:], Mo=2 * H, No=H)
+                else:   # k and v gradients sit at column offsets 0 and Hp: two row blocks of in_proj_weight
+                    ops.gemm_wgrad(dkv[:, :Hp], x[i], gin[H:2 * H], gbin[H:2 * H], Mo=H, No=H)
+                    ops.gemm_wgrad(dkv[:, Hp:], x[i], gin[2 * H:], gbin[2 * H:], Mo=H, No=H)
+            ops.gemm_tn(dq, self.sh[f"wqT{i}"], out_bf16=gD, residual=dr)                          # dQ = dr + dq Wq
+            ops.gemm_tn(dkv, self.sh[f"wkvT{i}"], out_bf16=gX)                                     # dx via k, v
             # LN1 + the un-normalised k/v path; pad rows zeroed (x_i was masked, SRFR_model.py:99,121)
-            ops.layernorm_bwd(gC, x[i], ws[f"st1_{i}"][:T], P.view(f"attention_layernorms.{i}.weight"), gA,
+            ops.layernorm_bwd(gD, x[i], ws[f"st1_{i}"][:T], P.view(f"attention_layernorms.{i}.weight"), dx_out,
                               G(f"attention_layernorms.{i}.weight"), G(f"attention_layernorms.{i}.bias"),
-                              add=gD, row_ids=seq_flat, H=H)
+                              add=gX, row_ids=seq_flat, H=H)
 
         # embedding tables
         dx0 = gA
         if s.kind == "SASRec" and p_drop > 0:
-            ops.dropout_apply(gA, gB, H, p_drop, seed, 1, step)
-            dx0 = gB
+            ops.dropout_apply(gA, gC, H, p_drop, seed, 1, step)
+            dx0 = gC
         aux_grad = G(s.aux_key) if s.aux_key else None
         ops.embed_bwd(dx0, sv["seq"], sv["aux_ids"], s.D, s.F if s.mode == 1 else 0, s.mode, s.item_scale,
                       G(s.item_key), aux_grad)
@@ -397,6 +433,7 @@ class HotPath:
         pos_tmp.zero_()
         ops.colsum(dx0, pos_tmp, M=B, N=L * Hp, ld=L * Hp)
         ops.add_segments(pos_tmp, L * Hp, Hp, s.D, G(s.pos_key))
+        self._join()                                # every weight gradient has landed in P.grad
         self.saved = None
 
     # ------------------------------------------------------------------ scoring helpers
