@@ -85,10 +85,10 @@ def algorithmic_bytes(name, a, valid_frac):
         T, Mo, No = a[4], a[5], a[6]
         return T * (Mo + No) * 2 + Mo * No * 4, 2.0 * T * Mo * No
     if name == "srfrd_attention_fwd":
-        B, L, H = a[7], a[8], a[9]
+        B, L, H = a[8], a[9], a[10]
         return 4 * B * L * H * 2, 2.0 * B * L * L * H           # causal half of 2 x (2 L^2 H)
     if name == "srfrd_attention_bwd":
-        B, L, H = a[12], a[13], a[14]
+        B, L, H = a[15], a[16], a[17]
         return 7 * B * L * H * 2, 5.0 * B * L * L * H
     if name == "srfrd_layernorm_fwd":
         T, H = a[9], a[10]

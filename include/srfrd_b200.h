@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SRFRD_ABI_VERSION 1
+#define SRFRD_ABI_VERSION 2
 #if defined(__GNUC__)
 #define SRFRD_API __attribute__((visibility("default")))
 #else
@@ -133,15 +133,20 @@ SRFRD_API int srfrd_cast_weights(const srfrd_cast_desc_t* descs_dev, int n, void
 SRFRD_API int srfrd_f32_to_bf16_split(const float* src, int64_t src_ld, const int64_t* row_index, void* hi, void* lo,
                             int64_t rows, int cols, int dst_ld, void* stream);
 
-/* ---- causal self-attention, one (sequence, head) per CTA ----
+/* ---- causal self-attention ----
  * replaces: F.multi_head_attention_forward need_weights branch reached from SRFR_model.py:112
- * (q scaling, baddbmm, softmax, dropout, bmm) and its backward.  k and v share ldkv. */
+ * (q scaling, baddbmm, softmax, dropout, bmm) and its backward.  k and v share ldkv.
+ * tcgen05 kernels for maxlen <= 128 (one 128-token window of whole sequences per tile) and for 128 < maxlen <= 256
+ * (two query tiles per sequence); SIMT otherwise.  `stats` (fp32, 4 per (token, head): max * scale * log2e, 1 / sum,
+ * delta, -) is written by the forward when non-NULL; the backward of maxlen > 128 needs it together with the forward
+ * output `o` (FlashAttention-2 style independent tile pairs); both may be NULL for maxlen <= 128. */
 SRFRD_API int srfrd_attention_fwd(const void* q, int ldq, const void* k, const void* v, int ldkv, void* o, int ldo,
-                        int64_t B, int L, int H, int heads, float drop_p, uint64_t seed, uint32_t stream_id,
+                        float* stats, int64_t B, int L, int H, int heads, float drop_p, uint64_t seed, uint32_t stream_id,
                         const float* drop_step, void* stream);
 SRFRD_API int srfrd_attention_bwd(const void* dout, int lddo, const void* q, int ldq, const void* k, const void* v, int ldkv,
-                        void* dq, int lddq, void* dk, void* dv, int lddkv, int64_t B, int L, int H, int heads,
-                        float drop_p, uint64_t seed, uint32_t stream_id, const float* drop_step, void* stream);
+                        const void* o, int ldo, float* stats, void* dq, int lddq, void* dk, void* dv, int lddkv, int64_t B,
+                        int L, int H, int heads, float drop_p, uint64_t seed, uint32_t stream_id, const float* drop_step,
+                        void* stream);
 
 /* ---- K4: pos/neg scoring + (discriminator-weighted) BCE ----
  * replaces: SRFR_model.py:129-136 (SRFRN :225-233, SASRec :657-661) and trainer.py:31-38.

@@ -46,8 +46,9 @@ SIGNATURES = {
     "srfrd_dropout_apply": [vp, i32, vp, i32, i64, i32, f32, u64, u32, vp, vp],
     "srfrd_cast_weights": [vp, i32, vp],
     "srfrd_f32_to_bf16_split": [vp, i64, vp, vp, vp, i64, i32, i32, vp],
-    "srfrd_attention_fwd": [vp, i32, vp, vp, i32, vp, i32, i64, i32, i32, i32, f32, u64, u32, vp, vp],
-    "srfrd_attention_bwd": [vp, i32, vp, i32, vp, vp, i32, vp, i32, vp, vp, i32, i64, i32, i32, i32, f32, u64, u32, vp, vp],
+    "srfrd_attention_fwd": [vp, i32, vp, vp, i32, vp, i32, vp, i64, i32, i32, i32, f32, u64, u32, vp, vp],
+    "srfrd_attention_bwd": [vp, i32, vp, i32, vp, vp, i32, vp, i32, vp, vp, i32, vp, vp, i32, i64, i32, i32, i32, f32, u64,
+                            u32, vp, vp],
     "srfrd_score_fwd": [vp, i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp, vp, vp],
     "srfrd_score_bwd": [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp, i32, vp, vp, vp],
     "srfrd_score_loss_fused": [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp],
@@ -82,7 +83,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)            # AttributeError if the symbol is not exported
         fn.argtypes = argtypes
         fn.restype = C.c_int
-    if lib.srfrd_abi_version() != 1:
+    if lib.srfrd_abi_version() != 2:
         raise RuntimeError("srfrd_b200: ABI version mismatch between _lib.py and the built library")
     _lib = lib
     return lib

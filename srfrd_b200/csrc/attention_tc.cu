@@ -23,6 +23,14 @@ int attn_bwd_simt(const void* dout, int lddo, const void* q, int ldq, const void
                   int lddq, void* dk, void* dv, int lddkv, int64_t B, int L, int H, int heads, float drop_p,
                   uint64_t seed, uint32_t stream_id, const float* drop_step, void* stream);
 
+bool attn_long_supported(int64_t B, int L, int H, int heads, int ldq, int ldkv);
+int attn_long_fwd(const void* q, int ldq, const void* k, const void* v, int ldkv, void* o, int ldo, float* stats, int64_t B,
+                  int L, int H, int heads, float drop_p, uint64_t seed, uint32_t stream_id, const float* drop_step,
+                  void* stream);
+int attn_long_bwd(const void* dout, int lddo, const void* q, int ldq, const void* k, const void* v, int ldkv, const void* o,
+                  int ldo, float* stats, void* dq, int lddq, void* dk, void* dv, int lddkv, int64_t B, int L, int H, int heads,
+                  float drop_p, uint64_t seed, uint32_t stream_id, const float* drop_step, void* stream);
+
 static constexpr int TILE = 128;
 static constexpr int OPB = TILE * 64 * 2;     // operand block: 128 rows x 64 bf16 = 16 KB
 static constexpr int ATC_THREADS = 192;
@@ -675,10 +683,12 @@ extern "C" int srfrd_attn_debug_read(long long* host_dst) {
 }
 
 extern "C" int srfrd_attention_fwd(const void* q, int ldq, const void* k, const void* v, int ldkv, void* o, int ldo,
-                                   int64_t B, int L, int H, int heads, float drop_p, uint64_t seed,
+                                   float* stats, int64_t B, int L, int H, int heads, float drop_p, uint64_t seed,
                                    uint32_t stream_id, const float* drop_step, void* stream) {
   SRFRD_REQUIRE(q && k && v && o, "attention_fwd: null pointer");
   if (B == 0 || L == 0) return 0;
+  if (attn_long_supported(B, L, H, heads, ldq, ldkv) && ldo % 8 == 0 && ((uintptr_t)o & 15) == 0 && !getenv("SRFRD_ATTN_SIMT"))
+    return attn_long_fwd(q, ldq, k, v, ldkv, o, ldo, stats, B, L, H, heads, drop_p, seed, stream_id, drop_step, stream);
   if (!tc_supported(L, H, heads, ldq, ldkv) || ldo % 8 || ((uintptr_t)o & 15))
     return attn_fwd_simt(q, ldq, k, v, ldkv, o, ldo, B, L, H, heads, drop_p, seed, stream_id, drop_step, stream);
   AttnTc p = {};
@@ -710,11 +720,14 @@ extern "C" int srfrd_attention_fwd(const void* q, int ldq, const void* k, const 
 }
 
 extern "C" int srfrd_attention_bwd(const void* dout, int lddo, const void* q, int ldq, const void* k, const void* v,
-                                   int ldkv, void* dq, int lddq, void* dk, void* dv, int lddkv, int64_t B, int L,
-                                   int H, int heads, float drop_p, uint64_t seed, uint32_t stream_id,
-                                   const float* drop_step, void* stream) {
+                                   int ldkv, const void* o, int ldo, float* stats, void* dq, int lddq, void* dk, void* dv,
+                                   int lddkv, int64_t B, int L, int H, int heads, float drop_p, uint64_t seed,
+                                   uint32_t stream_id, const float* drop_step, void* stream) {
   SRFRD_REQUIRE(dout && q && k && v && dq && dk && dv, "attention_bwd: null pointer");
   if (B == 0 || L == 0) return 0;
+  if (attn_long_supported(B, L, H, heads, ldq, ldkv) && o && stats && !getenv("SRFRD_ATTN_SIMT"))
+    return attn_long_bwd(dout, lddo, q, ldq, k, v, ldkv, o, ldo, stats, dq, lddq, dk, dv, lddkv, B, L, H, heads, drop_p, seed,
+                         stream_id, drop_step, stream);
   if (!tc_supported(L, H, heads, ldq, ldkv) || lddo % 8 || lddq % 8 || lddkv % 8)
     return attn_bwd_simt(dout, lddo, q, ldq, k, v, ldkv, dq, lddq, dk, dv, lddkv, B, L, H, heads, drop_p, seed,
                          stream_id, drop_step, stream);

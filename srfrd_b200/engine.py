@@ -267,6 +267,8 @@ class HotPath:
             act(f"kv{i}", 2 * H)
             act(f"st1_{i}", 2, torch.float32)
             act(f"st2_{i}", 2, torch.float32)
+            if L > 128:                              # softmax row statistics for the tile-pair backward (maxlen > 128)
+                ws[f"ast{i}"] = torch.zeros(T * s.num_heads, 4, dtype=torch.float32, device=dev)
         if s.kind == "SRFR":
             act("c", s.Dp)
         act("stF", 2, torch.float32)
@@ -325,7 +327,8 @@ class HotPath:
                                   LN_EPS, y_bf16=Q, stats=ws[f"st1_{i}"][:T], H=H)
             ops.gemm_tn(Q, self.sh[f"wq{i}"], out_bf16=q, bias=self.bias("bq", i))
             self._join()                                           # k | v (side stream) are ready
-            ops.attention_fwd(q, kv[:, :Hp], kv[:, Hp:], o, B, L, H, s.num_heads, p_drop, seed, 10 + 4 * i, step)
+            ops.attention_fwd(q, kv[:, :Hp], kv[:, Hp:], o, B, L, H, s.num_heads, p_drop, seed, 10 + 4 * i, step,
+                              stats=ws.get(f"ast{i}"))
             ops.gemm_tn(o, self.sh[f"wo{i}"], out_bf16=r, bias=self.bias("bo", i), residual=Q)
             ops.layernorm_fwd(r, P.view(f"forward_layernorms.{i}.weight"), P.view(f"forward_layernorms.{i}.bias"), LN_EPS,
                               y_bf16=y, stats=ws[f"st2_{i}"][:T], H=H)
@@ -404,7 +407,7 @@ class HotPath:
                                Mo=H, No=H)
             ops.gemm_tn(dr, self.sh[f"woT{i}"], out_bf16=gC)                                       # do
             ops.attention_bwd(gC, q, kv[:, :Hp], kv[:, Hp:], dq, dkv[:, :Hp], dkv[:, Hp:], B, L, H, s.num_heads, p_drop,
-                              seed, 10 + 4 * i, step)                                             # dq, dk|dv
+                              seed, 10 + 4 * i, step, o=o, stats=ws.get(f"ast{i}"))               # dq, dk|dv
             gin = GM(f"attention_layers.{i}.in_proj_weight")
             gbin = G(f"attention_layers.{i}.in_proj_bias")
             with self._branch():

@@ -152,16 +152,18 @@ def f32_to_bf16_split(src, hi, lo=None, row_index=None):
          _stream())
 
 
-def attention_fwd(q, k, v, o, B, L, H, heads, drop_p=0.0, seed=0, stream_id=0, drop_step=None):
+def attention_fwd(q, k, v, o, B, L, H, heads, drop_p=0.0, seed=0, stream_id=0, drop_step=None, stats=None):
+    """stats: optional fp32 (B*L*heads, 4) row statistics, required later by attention_bwd when L > 128."""
     _lib.require_device()
-    call("srfrd_attention_fwd", _p(q), q.stride(0), _p(k), _p(v), k.stride(0), _p(o), o.stride(0), B, L, H, heads,
+    call("srfrd_attention_fwd", _p(q), q.stride(0), _p(k), _p(v), k.stride(0), _p(o), o.stride(0), _p(stats), B, L, H, heads,
          float(drop_p), int(seed), int(stream_id), _p(drop_step), _stream())
 
 
-def attention_bwd(dout, q, k, v, dq, dk, dv, B, L, H, heads, drop_p=0.0, seed=0, stream_id=0, drop_step=None):
-    call("srfrd_attention_bwd", _p(dout), dout.stride(0), _p(q), q.stride(0), _p(k), _p(v), k.stride(0), _p(dq),
-         dq.stride(0), _p(dk), _p(dv), dk.stride(0), B, L, H, heads, float(drop_p), int(seed), int(stream_id),
-         _p(drop_step), _stream())
+def attention_bwd(dout, q, k, v, dq, dk, dv, B, L, H, heads, drop_p=0.0, seed=0, stream_id=0, drop_step=None, o=None,
+                  stats=None):
+    call("srfrd_attention_bwd", _p(dout), dout.stride(0), _p(q), q.stride(0), _p(k), _p(v), k.stride(0), _p(o),
+         0 if o is None else o.stride(0), _p(stats), _p(dq), dq.stride(0), _p(dk), _p(dv), dk.stride(0), B, L, H, heads,
+         float(drop_p), int(seed), int(stream_id), _p(drop_step), _stream())
 
 
 def score_fwd(h, item_table, fake_table, pos, neg, prs, nrs, zp, zn):

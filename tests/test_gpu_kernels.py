@@ -226,27 +226,29 @@ def _attn_ref(q, k, v, heads):
 
 @pytest.mark.parametrize("B,L,H,heads", [(3, 12, 32, 1), (5, 50, 80, 1), (2, 50, 80, 2), (2, 200, 272, 1), (4, 7, 16, 4),
                                          (64, 50, 64, 1), (7, 50, 64, 2), (3, 128, 64, 1), (5, 100, 128, 1),
-                                         (300, 50, 80, 1), (9, 33, 96, 3), (2, 240, 32, 1)])
+                                         (300, 50, 80, 1), (9, 33, 96, 3), (2, 240, 32, 1),
+                                         # 128 < maxlen <= 256: two query tiles per sequence, FlashAttention-2 style backward
+                                         (3, 129, 64, 1), (2, 256, 128, 2), (5, 200, 80, 1), (160, 200, 272, 1), (3, 150, 96, 2)])
 def test_attention_fwd_bwd(ops, B, L, H, heads):
     T = B * L
     q, kv = rnd((T, H), 30, 0.7, bf16), rnd((T, 2 * H), 31, 0.7, bf16)
     o = torch.empty(T, H, dtype=bf16, device="cuda")
-    ops.attention_fwd(q, kv[:, :H], kv[:, H:], o, B, L, H, heads)
+    stats = torch.zeros(T * heads, 4, device="cuda") if L > 128 else None
+    ops.attention_fwd(q, kv[:, :H], kv[:, H:], o, B, L, H, heads, stats=stats)
     qr = q.float().cpu().view(B, L, H).requires_grad_(True)
     kr = kv[:, :H].float().cpu().view(B, L, H).requires_grad_(True)
     vr = kv[:, H:].float().cpu().view(B, L, H).requires_grad_(True)
     ref = _attn_ref(qr, kr, vr, heads)
     torch.testing.assert_close(o.float().cpu().view(B, L, H), ref.detach(), rtol=2e-2, atol=1e-2)   # bf16 output
-    ntri = (L * (L + 1) // 2 + 3) // 4 * 4      # SIMT path (L > 128): packed causal triangles of P and dS in smem
+    ntri = (L * (L + 1) // 2 + 3) // 4 * 4      # SIMT path (no stats given): packed causal triangles of P and dS in smem
     if L > 128 and 2 * ntri * 4 + 4 * L * 34 > 227 * 1024:
         with pytest.raises(RuntimeError, match="shared memory"):
             ops.attention_bwd(o, q, kv[:, :H], kv[:, H:], o, kv[:, :H], kv[:, H:], B, L, H, heads)
-        return
     do = rnd((T, H), 32, dtype=bf16)
     ref.backward(do.float().cpu().view(B, L, H))
     dq = torch.empty(T, H, dtype=bf16, device="cuda")
     dkv = torch.empty(T, 2 * H, dtype=bf16, device="cuda")
-    ops.attention_bwd(do, q, kv[:, :H], kv[:, H:], dq, dkv[:, :H], dkv[:, H:], B, L, H, heads)
+    ops.attention_bwd(do, q, kv[:, :H], kv[:, H:], dq, dkv[:, :H], dkv[:, H:], B, L, H, heads, o=o, stats=stats)
     for got, want in ((dq, qr.grad), (dkv[:, :H], kr.grad), (dkv[:, H:], vr.grad)):
         w = want.view(T, H)
         torch.testing.assert_close(got.float().cpu(), w, rtol=3e-2, atol=2e-2 * float(w.abs().max()))
