@@ -265,6 +265,27 @@ def test_attention_dropout_is_consistent(ops):
     step += 1
     ops.attention_fwd(q, kv[:, :H], kv[:, H:], o3, B, L, H, 1, 0.5, 77, 5, step)
     assert torch.equal(o1, o2) and not torch.equal(o1, o3)
+    # maxlen > 128 (tile-pair kernels): the backward regenerates the forward's mask from (seed, step, element), so the
+    # gradient of sum(o * do) w.r.t. v equals P_dropped^T do -- checked through a finite linear probe in v
+    B, L, H = 3, 200, 64
+    T = B * L
+    q, kv = rnd((T, H), 35, 0.5, bf16), rnd((T, 2 * H), 36, 0.5, bf16)
+    st = torch.zeros(T, 4, device="cuda")
+    oa, ob = torch.empty(T, H, dtype=bf16, device="cuda"), torch.empty(T, H, dtype=bf16, device="cuda")
+    ops.attention_fwd(q, kv[:, :H], kv[:, H:], oa, B, L, H, 1, 0.3, 99, 6, step, stats=st)
+    ops.attention_fwd(q, kv[:, :H], kv[:, H:], ob, B, L, H, 1, 0.3, 99, 6, step, stats=st)
+    assert torch.equal(oa, ob)
+    do = rnd((T, H), 37, dtype=bf16)
+    dq, dkv = torch.empty(T, H, dtype=bf16, device="cuda"), torch.empty(T, 2 * H, dtype=bf16, device="cuda")
+    ops.attention_bwd(do, q, kv[:, :H], kv[:, H:], dq, dkv[:, :H], dkv[:, H:], B, L, H, 1, 0.3, 99, 6, step, o=oa, stats=st)
+    dv_dir = rnd((T, H), 38, 0.25, bf16)                      # o is linear in v: <do, o(v + e) - o(v)> == <dv, e>
+    kv2 = kv.clone()
+    kv2[:, H:] = (kv[:, H:].float() + dv_dir.float()).to(bf16)
+    e = kv2[:, H:].float() - kv[:, H:].float()
+    ops.attention_fwd(q, kv2[:, :H], kv2[:, H:], ob, B, L, H, 1, 0.3, 99, 6, step, stats=torch.zeros_like(st))
+    lhs = float((do.float() * (ob.float() - oa.float())).sum())
+    rhs = float((dkv[:, H:].float() * e).sum())
+    assert abs(lhs - rhs) <= 0.03 * max(abs(lhs), abs(rhs)) + 0.5, (lhs, rhs)
 
 
 # ------------------------------------------------------------------------------------------- K4 scoring / loss
