@@ -116,11 +116,22 @@ class FusedTrainer:
         self.steps = 0
 
     # ------------------------------------------------------------------
+    _KEYS = ("seq", "rsq", "pos", "prs", "neg", "nrs")
+
+    @staticmethod
+    def _carve(flat: torch.Tensor, B: int, L: int):
+        """views of one flat int64 buffer: six (B, L) int64 id arrays followed by two (B, L) fp32 weight arrays"""
+        n = B * L
+        out = {k: flat[i * n:(i + 1) * n].view(B, L) for i, k in enumerate(FusedTrainer._KEYS)}
+        w = flat[6 * n:7 * n].view(torch.float32)            # n int64 words = 2 n fp32 words
+        out["w_pos"], out["w_neg"] = w[:n].view(B, L), w[n:].view(B, L)
+        return out
+
     def _alloc_static(self, B: int, L: int):
         dev = self.eng.device
-        z = lambda dt=torch.int64: torch.zeros(B, L, dtype=dt, device=dev)
-        self._static = dict(seq=z(), rsq=z(), pos=z(), prs=z(), neg=z(), nrs=z(), w_pos=z(torch.float32),
-                            w_neg=z(torch.float32))
+        self._static_flat = torch.zeros(7 * B * L, dtype=torch.int64, device=dev)   # ONE buffer: one D2D copy fills it
+        self._static = self._carve(self._static_flat, B, L)
+        self._stage_flat = None
         self._graph = None
 
     def _step_body(self, has_wp: bool, has_wn: bool):
@@ -174,6 +185,45 @@ class FusedTrainer:
         if w_neg is not None:
             st["w_neg"].copy_(torch.as_tensor(w_neg), non_blocking=non_blocking)
         self._has_w = (w_pos is not None, w_neg is not None)
+
+    # ---- host batches pipelined across steps: H2D of batch n+1 (copy stream) overlaps the compute of batch n ----------
+    def prefetch(self, batch: Dict[str, torch.Tensor], w_pos=None, w_neg=None):
+        """Start copying a (pinned) host batch into a device staging buffer on a separate copy stream.  The next
+        ``step_prefetched()`` waits for it, moves it into the step's static buffers with ONE device-to-device copy and
+        runs the step, so the PCIe transfer of the next batch hides behind the current step."""
+        B, L = batch["seq"].shape
+        if self._static is None or self._static["seq"].shape != (B, L):
+            self._alloc_static(B, L)
+        if self._stage_flat is None:
+            self._stage_flat = torch.zeros_like(self._static_flat)
+            self._stage = self._carve(self._stage_flat, B, L)
+            self._copy_stream = torch.cuda.Stream(device=self.eng.device)
+            self._stage_free = torch.cuda.Event()
+            self._stage_full = torch.cuda.Event()
+            self._stage_free.record()                             # (after the zero fill above, on the current stream)
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._stage_free)        # the previous staged batch has been consumed
+            for k in self._KEYS:
+                src = batch.get(k)
+                if src is None:
+                    self._stage[k].zero_()
+                else:
+                    self._stage[k].copy_(torch.as_tensor(src), non_blocking=True)
+            if w_pos is not None:
+                self._stage["w_pos"].copy_(torch.as_tensor(w_pos), non_blocking=True)
+            if w_neg is not None:
+                self._stage["w_neg"].copy_(torch.as_tensor(w_neg), non_blocking=True)
+            self._stage_full.record()
+        self._stage_w = (w_pos is not None, w_neg is not None)
+
+    def step_prefetched(self) -> torch.Tensor:
+        """Run one step on the batch handed to ``prefetch``; returns the device loss scalar (no sync)."""
+        main = torch.cuda.current_stream()
+        main.wait_event(self._stage_full)
+        self._static_flat.copy_(self._stage_flat)                 # one D2D copy (10 MB at C2: a few microseconds)
+        self._stage_free.record(main)
+        self._has_w = self._stage_w
+        return self.run_step()
 
     def run_step(self) -> torch.Tensor:
         """Run one step on the loaded batch; returns the device scalar holding the loss (no sync)."""
