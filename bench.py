@@ -372,18 +372,13 @@ def cpu_baseline(sample_steps=2, batch=None):
     """The reference's CPU path (oracle port: same arithmetic as SRFR_model.py + trainer.py:27-41 through torch's
     CPU kernels) on this box's host cores, on a bounded sample of the SAME workload (C2 batches of 4096)."""
     from oracle import srfrd_oracle as O
-    from srfrd_b200 import SRFR_model as M, synth
+    from srfrd_b200 import synth                 # synthetic data generator only: no product kernel or model on this path
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     c = CFG
     B = batch or c["batch"]
     data = synth.make_interactions(1236, c["usernum"], c["itemnum"], 5, 4.0, c["L"])
-    torch.manual_seed(1236)
-    m = M.SRFR(c["itemnum"], c["L"], c["D"], c["F"], 0.0, c["blocks"], c["heads"], "cpu")
-    for _, p in m.named_parameters():
-        if p.dim() >= 2:
-            torch.nn.init.xavier_normal_(p.data)
-    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    sd = O.init_state_dict("SRFR", c["itemnum"], c["L"], c["D"], c["F"], 0, c["blocks"], seed=1236)
     orc = O.OracleTrainer(sd, "SRFR", 1)
     smp = synth.BatchSampler(data, c["L"], seed=100)
     batches = [{k: torch.from_numpy(v) for k, v in smp.next_batch(B).items()} for _ in range(sample_steps + 1)]

@@ -49,6 +49,44 @@ def _emb_keys(kind: str) -> Tuple[str, str]:
     return "embedding_layer.item_embed.weight", "embedding_layer.pos_embed.weight"
 
 
+def init_state_dict(kind: str, item_number: int, max_len: int, D: int, F: int = 0, n_labels: int = 0, num_blocks: int = 2,
+                    seed: int = 0) -> Dict[str, Tensor]:
+    """A state_dict with the reference's parameter names and shapes (dumped from the live modules) and the
+    trainer's initialisation: xavier_normal_ on every >= 2-D parameter (trainer.py:364-369, which also overwrites the
+    padding rows), LayerNorm weight 1 / bias 0, other biases 0.  Lets the CPU baseline run without the product package."""
+    g = torch.Generator().manual_seed(seed)
+    H = D + F if kind in ("SRFR", "SRFRN") else D
+    shapes = []
+    if kind == "SASRec":
+        shapes += [("item_emb.weight", (item_number + 1, D)), ("pos_emb.weight", (max_len, D))]
+    elif kind in ("SRFR", "SRFRN"):
+        shapes += [("embedding_layer.item_embed.weight", (item_number + 1, D)), ("embedding_layer.fake_embed.weight", (3, F)),
+                   ("embedding_layer.pos_embed.weight", (max_len, D))]
+    else:
+        shapes += [("embedding_layer.item_embed.weight", (item_number + 1, D)),
+                   ("embedding_layer.user_label_embed.weight", (n_labels, D)), ("embedding_layer.pos_embed.weight", (max_len, D))]
+    for i in range(num_blocks):
+        shapes += [(f"attention_layernorms.{i}.weight", (H,)), (f"attention_layernorms.{i}.bias", (H,)),
+                   (f"attention_layers.{i}.in_proj_weight", (3 * H, H)), (f"attention_layers.{i}.in_proj_bias", (3 * H,)),
+                   (f"attention_layers.{i}.out_proj.weight", (H, H)), (f"attention_layers.{i}.out_proj.bias", (H,)),
+                   (f"forward_layernorms.{i}.weight", (H,)), (f"forward_layernorms.{i}.bias", (H,)),
+                   (f"forward_layers.{i}.conv1.weight", (H, H, 1)), (f"forward_layers.{i}.conv1.bias", (H,)),
+                   (f"forward_layers.{i}.conv2.weight", (H, H, 1)), (f"forward_layers.{i}.conv2.bias", (H,))]
+    if kind == "SRFR":
+        shapes += [("last_conv.weight", (D, H, 1)), ("last_conv.bias", (D,))]
+    dout = H if kind == "SRFRN" else D
+    shapes += [("last_layernorm.weight", (dout,)), ("last_layernorm.bias", (dout,))]
+    sd = {}
+    for name, shape in shapes:
+        t = torch.zeros(shape)
+        if len(shape) >= 2:
+            torch.nn.init.xavier_normal_(t, generator=g)
+        elif "layernorm" in name and name.endswith("weight"):
+            t.fill_(1.0)
+        sd[name] = t
+    return sd
+
+
 def num_blocks_of(sd: Dict[str, Tensor]) -> int:
     n = 0
     while f"attention_layers.{n}.in_proj_weight" in sd:
