@@ -373,12 +373,13 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     mbar_init(tfull, 1);
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_prologue_done();
+  constexpr int BIAS_COL = 496;                          // accumulator columns [496, 512): sum_t dY[t, row]
 
   if (nkb > 0) {
     if (warp == 0) {
@@ -400,7 +401,10 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else if (warp == 1) {
       int bn = min(s.block_n, s.No - n0);
       bn = (bn + 15) & ~15;
-      const uint32_t idesc = umma_idesc_bf16(BLOCK_M, bn, 1, 1);
+      // a column tile wider than 256 (H = 272) takes two MMAs per K step: columns [0, 256) and [256, bn)
+      const int bn1 = min(bn, 256), bn2 = bn - bn1;
+      const uint32_t idesc = umma_idesc_bf16(BLOCK_M, bn1, 1, 1);
+      const uint32_t idesc2 = umma_idesc_bf16(BLOCK_M, bn2 > 0 ? bn2 : 16, 1, 1);
       // MN-major SW128: 64-wide MN atoms are ATOM_BYTES apart (LBO); 8 k-rows = 1024 B (SBO);
       // one UMMA_K = 16 k-rows = 2048 B (= 128 in descriptor units)
       const uint64_t adesc0 = umma_smem_desc(smem_u32(smA), ATOM_BYTES, 1024);
@@ -416,10 +420,16 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k)
             umma_bf16(tmem_base, ad + 128 * k, bd + 128 * k, idesc, (kb > kb_begin) || (k > 0));
+          if (bn2 > 0) {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / 16; ++k)       // B atoms 4.. (columns 256..): 4 atoms further in the stage
+              umma_bf16(tmem_base + 256, ad + 128 * k, bd + (uint64_t)(4 * (ATOM_BYTES >> 4)) + 128 * k, idesc2,
+                        (kb > kb_begin) || (k > 0));
+          }
           if (do_bias) {
 #pragma unroll
             for (int k = 0; k < BLOCK_K / 16; ++k)
-              umma_bf16(tmem_base + 240, ad + 128 * k, onesdesc + 128 * k, idesc_ones, (kb > kb_begin) || (k > 0));
+              umma_bf16(tmem_base + BIAS_COL, ad + 128 * k, onesdesc + 128 * k, idesc_ones, (kb > kb_begin) || (k > 0));
           }
           umma_commit(&empty[stage]);
           if (kb == kb_end - 1) umma_commit(tfull);
@@ -447,7 +457,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       if (do_bias) {                       // columns [240, 256) all hold sum_t dY[t, row]
         uint32_t raw[16];
-        tmem_ld16(taddr + 240, raw);
+        tmem_ld16(taddr + BIAS_COL, raw);
         tmem_ld_wait();
         if (row < s.Mo) red_add_f32(s.dbias + row, __uint_as_float(raw[0]));
       }
@@ -455,7 +465,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -581,7 +591,9 @@ extern "C" int srfrd_gemm_wgrad(const void* dY, int lda, const void* X, int ldb,
   SRFRD_REQUIRE(T < (1ll << 31), "gemm_wgrad: too many tokens");
   WgradShape s;
   s.T = (int)T; s.Mo = Mo; s.No = No;
-  s.block_n = pick_block_n((No + 15) & ~15);
+  // one column tile up to 480 columns (H = 272: X is then read once per 128-row tile of dY instead of once per
+  // (row tile, column tile) pair); wider outputs are split evenly
+  s.block_n = No <= 480 ? ((No + 15) & ~15) : pick_block_n((No + 15) & ~15);
   const int n_tiles = (No + s.block_n - 1) / s.block_n, m_tiles = (Mo + BLOCK_M - 1) / BLOCK_M;
   s.a_atoms = 2;
   s.b_atoms = (s.block_n + 63) / 64;
@@ -594,7 +606,7 @@ extern "C" int srfrd_gemm_wgrad(const void* dY, int lda, const void* X, int ldb,
   if (splits > kblocks) splits = kblocks;
   s.k_splits = splits;
   s.out = dW; s.ldw = ldw; s.dbias = dbias;
-  SRFRD_REQUIRE(!dbias || s.block_n <= 240, "gemm_wgrad: fused bias gradient needs a column tile <= 240");
+  SRFRD_REQUIRE(s.block_n <= 480, "gemm_wgrad: column tile %d too wide", s.block_n);
   const size_t smem = (size_t)s.stages * stage_bytes + 1024 + 1024 + BLOCK_K * 128;
   CUtensorMap tmA, tmB;
   // MN-major: the TMA box is [64 tokens (rows), 64 features (cols)]
