@@ -444,15 +444,26 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(tfull, 0);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      const bool vec_red = (s.ldw % 4 == 0) && ((reinterpret_cast<uintptr_t>(s.out) & 15) == 0);
       for (int c = 0; c < bn; c += 16) {
         uint32_t raw[16];
         tmem_ld16(taddr + c, raw);
         tmem_ld_wait();
         if (row < s.Mo) {
           float* o = s.out + (size_t)row * s.ldw + n0 + c;
+          // 148 CTAs add into the same Mo x No block at the same moment: 16-byte vector reductions cut the number of
+          // L2 atomic operations by four (ncu: the scalar version spent a third of the CTA's lifetime here)
+          if (vec_red && n0 + c + 16 <= s.No) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (n0 + c + j < s.No) red_add_f32(o + j, __uint_as_float(raw[j]));
+            for (int j = 0; j < 16; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(__uint_as_float(raw[j])),
+                           "f"(__uint_as_float(raw[j + 1])), "f"(__uint_as_float(raw[j + 2])), "f"(__uint_as_float(raw[j + 3]))
+                           : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (n0 + c + j < s.No) red_add_f32(o + j, __uint_as_float(raw[j]));
+          }
         }
       }
       if (do_bias) {                       // columns [240, 256) all hold sum_t dY[t, row]
