@@ -1,5 +1,6 @@
 // Shared device/host helpers for the srfrd_b200 kernels (sm_100a only).
 #pragma once
+#include <stdlib.h>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>

@@ -28,6 +28,12 @@ struct ScoreParams {
 __device__ __forceinline__ float softplus(float x) { return fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x))); }
 __device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + __expf(-x)); }
 
+// A warp takes 32 consecutive tokens at a time: their ids / weights arrive in one coalesced load each, the hidden-state
+// gradient rows of the inactive tokens (pad slots: 88 % of a C2 batch) are zeroed with 16-byte stores, and only the active
+// tokens go through the gather-dot-scatter path below (one token per pass, lane c owns columns c, c+32, ...).
+// Gradients of the 3-row fake table are kept in registers and flushed once per warp: every active token hits the same two
+// rows, which made them the most contended addresses of the step.
+template <int NC>
 __global__ void __launch_bounds__(256) score_kernel(ScoreParams p) {
   __shared__ float red[2][8];
   pdl_prologue_done();
@@ -41,72 +47,108 @@ __global__ void __launch_bounds__(256) score_kernel(ScoreParams p) {
     inv_np = a > 0.f ? 1.f / a : 0.f;
     inv_nn = b > 0.f ? 1.f / b : 0.f;
   }
-  for (int64_t t = warp0; t < p.T; t += nwarps) {
-    const int64_t pid = __ldg(p.pos + t), nid = __ldg(p.neg + t);
-    float wp = 0.f, wn = 0.f, dzp = 0.f, dzn = 0.f;
-    bool active = true;
-    if (p.mode == 1) {
-      wp = p.w_pos ? __ldg(p.w_pos + t) : (pid != 0 ? 1.f : 0.f);
-      wn = p.w_neg ? __ldg(p.w_neg + t) : wp;
-      active = (wp != 0.f) || (wn != 0.f) || p.zp;
-    } else if (p.mode == 2) {
-      dzp = __ldg(p.dzp_in + t);
-      dzn = __ldg(p.dzn_in + t);
-      active = (dzp != 0.f) || (dzn != 0.f);
-    }
-    if (!active) {
-      if (p.dh) {
+  float fk1[NC], fk2[NC];                    // d_fake rows 1 and 2, columns owned by this lane
 #pragma unroll
-        for (int i = 0; i < MAXC; ++i) {
-          const int c = lane + 32 * i;
-          if (c < W) p.dh[t * p.lddh + c] = 0.f;
+  for (int i = 0; i < NC; ++i) fk1[i] = fk2[i] = 0.f;
+  const bool dh_vec = p.dh && (p.lddh == W) && (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.dh) & 15) == 0);
+  for (int64_t t0 = warp0 * 32; t0 < p.T; t0 += nwarps * 32) {
+    const int64_t tl = t0 + lane;
+    const bool in = tl < p.T;
+    int64_t my_pid = 0, my_nid = 0, my_pf = 0, my_nf = 0;
+    float my_a = 0.f, my_b = 0.f;             // mode 1: (w_pos, w_neg); mode 2: (dz+, dz-)
+    bool my_active = false;
+    if (in) {
+      my_pid = __ldg(p.pos + tl);
+      my_nid = __ldg(p.neg + tl);
+      if (p.mode == 1) {
+        my_a = p.w_pos ? __ldg(p.w_pos + tl) : (my_pid != 0 ? 1.f : 0.f);
+        my_b = p.w_neg ? __ldg(p.w_neg + tl) : my_a;
+        my_active = (my_a != 0.f) || (my_b != 0.f) || p.zp;
+      } else if (p.mode == 2) {
+        my_a = __ldg(p.dzp_in + tl);
+        my_b = __ldg(p.dzn_in + tl);
+        my_active = (my_a != 0.f) || (my_b != 0.f);
+      } else {
+        my_active = true;
+      }
+      if (p.fake_table && my_active) { my_pf = __ldg(p.prs + tl); my_nf = __ldg(p.nrs + tl); }
+    }
+    unsigned mask = __ballot_sync(0xffffffffu, my_active);
+    if (p.dh) {                               // zero rows of the inactive tokens
+      const int nrow = (int)min((int64_t)32, p.T - t0);
+      if (dh_vec) {
+        const int per_row = W >> 2, total = nrow * per_row;
+        float4* base = reinterpret_cast<float4*>(p.dh + t0 * p.lddh);
+        for (int i = lane; i < total; i += 32)
+          if (!((mask >> (i / per_row)) & 1u)) base[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        for (int r = 0; r < nrow; ++r) {
+          if ((mask >> r) & 1u) continue;
+          for (int c = lane; c < W; c += 32) p.dh[(t0 + r) * p.lddh + c] = 0.f;
         }
       }
-      continue;
     }
-    int64_t pf = 0, nf = 0;
-    if (p.fake_table) { pf = __ldg(p.prs + t); nf = __ldg(p.nrs + t); }
-    float hv[MAXC], ep[MAXC], en[MAXC];
-    float sp = 0.f, sn = 0.f;
+    while (mask) {
+      const int r = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const int64_t t = t0 + r;
+      const int64_t pid = __shfl_sync(0xffffffffu, my_pid, r), nid = __shfl_sync(0xffffffffu, my_nid, r);
+      const int pf = (int)__shfl_sync(0xffffffffu, (int)my_pf, r), nf = (int)__shfl_sync(0xffffffffu, (int)my_nf, r);
+      const float ta = __shfl_sync(0xffffffffu, my_a, r), tb = __shfl_sync(0xffffffffu, my_b, r);
+      float hv[NC], ep[NC], en[NC];
+      float sp = 0.f, sn = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXC; ++i) {
-      const int c = lane + 32 * i;
-      hv[i] = ep[i] = en[i] = 0.f;
-      if (c < W) {
-        hv[i] = p.h[t * p.ldh + c];
-        if (c < p.D) {
-          ep[i] = __ldg(p.item_table + pid * p.D + c);
-          en[i] = __ldg(p.item_table + nid * p.D + c);
-        } else {
-          ep[i] = __ldg(p.fake_table + pf * p.F + (c - p.D));
-          en[i] = __ldg(p.fake_table + nf * p.F + (c - p.D));
+      for (int i = 0; i < NC; ++i) {
+        const int c = lane + 32 * i;
+        hv[i] = ep[i] = en[i] = 0.f;
+        if (c < W) {
+          hv[i] = p.h[t * p.ldh + c];
+          if (c < p.D) {
+            ep[i] = __ldg(p.item_table + pid * p.D + c);
+            en[i] = __ldg(p.item_table + nid * p.D + c);
+          } else {
+            ep[i] = __ldg(p.fake_table + (int64_t)pf * p.F + (c - p.D));
+            en[i] = __ldg(p.fake_table + (int64_t)nf * p.F + (c - p.D));
+          }
+          sp = fmaf(hv[i], ep[i], sp);
+          sn = fmaf(hv[i], en[i], sn);
         }
-        sp = fmaf(hv[i], ep[i], sp);
-        sn = fmaf(hv[i], en[i], sn);
+      }
+      const float zp = warp_sum(sp), zn = warp_sum(sn);
+      if (p.zp && lane == 0) { p.zp[t] = zp; p.zn[t] = zn; }
+      if (p.mode == 0) continue;
+      float dzp = ta, dzn = tb;
+      if (p.mode == 1) {
+        lp_acc += ta * softplus(-zp);
+        ln_acc += tb * softplus(zn);
+        dzp = ta * (sigmoidf(zp) - 1.f) * inv_np;
+        dzn = tb * sigmoidf(zn) * inv_nn;
+      }
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        const int c = lane + 32 * i;
+        if (c < W) {
+          if (p.dh) p.dh[t * p.lddh + c] = dzp * ep[i] + dzn * en[i];
+          if (c < p.D) {
+            // padding_idx = 0: the pad row never receives gradient (SRFR_model.py:10)
+            if (p.d_item && pid != 0 && dzp != 0.f) red_add_f32(p.d_item + pid * p.D + c, dzp * hv[i]);
+            if (p.d_item && nid != 0 && dzn != 0.f) red_add_f32(p.d_item + nid * p.D + c, dzn * hv[i]);
+          } else {
+            const float gp = dzp * hv[i], gn = dzn * hv[i];
+            fk1[i] += (pf == 1 ? gp : 0.f) + (nf == 1 ? gn : 0.f);
+            fk2[i] += (pf == 2 ? gp : 0.f) + (nf == 2 ? gn : 0.f);
+          }
+        }
       }
     }
-    const float zp = warp_sum(sp), zn = warp_sum(sn);
-    if (p.zp && lane == 0) { p.zp[t] = zp; p.zn[t] = zn; }
-    if (p.mode == 0) continue;
-    if (p.mode == 1) {
-      lp_acc += wp * softplus(-zp);
-      ln_acc += wn * softplus(zn);
-      dzp = wp * (sigmoidf(zp) - 1.f) * inv_np;
-      dzn = wn * sigmoidf(zn) * inv_nn;
-    }
+  }
+  if (p.d_fake) {
 #pragma unroll
-    for (int i = 0; i < MAXC; ++i) {
+    for (int i = 0; i < NC; ++i) {
       const int c = lane + 32 * i;
-      if (c < W) {
-        if (p.dh) p.dh[t * p.lddh + c] = dzp * ep[i] + dzn * en[i];
-        if (c < p.D) {
-          // padding_idx = 0: the pad row never receives gradient (SRFR_model.py:10)
-          if (p.d_item && pid != 0 && dzp != 0.f) red_add_f32(p.d_item + pid * p.D + c, dzp * hv[i]);
-          if (p.d_item && nid != 0 && dzn != 0.f) red_add_f32(p.d_item + nid * p.D + c, dzn * hv[i]);
-        } else if (p.d_fake) {
-          if (pf != 0 && dzp != 0.f) red_add_f32(p.d_fake + pf * p.F + (c - p.D), dzp * hv[i]);
-          if (nf != 0 && dzn != 0.f) red_add_f32(p.d_fake + nf * p.F + (c - p.D), dzn * hv[i]);
-        }
+      if (c >= p.D && c < W) {
+        if (fk1[i] != 0.f) red_add_f32(p.d_fake + 1 * p.F + (c - p.D), fk1[i]);
+        if (fk2[i] != 0.f) red_add_f32(p.d_fake + 2 * p.F + (c - p.D), fk2[i]);
       }
     }
   }
@@ -257,10 +299,19 @@ static int score_launch(ScoreParams& p, void* stream) {
   const int W = p.D + (p.fake_table ? p.F : 0);
   SRFRD_REQUIRE(W <= 32 * MAXC, "score: width %d unsupported", W);
   if (p.T == 0) return 0;
-  int64_t blocks = (p.T + 7) / 8;
+  int64_t blocks = (p.T + 255) / 256;              // a warp takes 32 tokens per pass
   const int64_t cap = (int64_t)num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  SRFRD_CUDA(launch_pdl(score_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, p));
+  const int nc = (W + 31) / 32;
+#define SCORE_CALL(NC) SRFRD_CUDA(launch_pdl(score_kernel<NC>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, p))
+  if (nc <= 1) SCORE_CALL(1);
+  else if (nc <= 2) SCORE_CALL(2);
+  else if (nc <= 3) SCORE_CALL(3);
+  else if (nc <= 4) SCORE_CALL(4);
+  else if (nc <= 6) SCORE_CALL(6);
+  else if (nc <= 9) SCORE_CALL(9);
+  else SCORE_CALL(MAXC);
+#undef SCORE_CALL
   SRFRD_LAUNCH_CHECK();
   return 0;
 }
