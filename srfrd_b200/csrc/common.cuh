@@ -170,6 +170,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Several barriers at once: an mbarrier test costs ~250 cycles even when the phase completed long ago (measured), so the
+// tests are issued back to back and only then examined -- their latencies overlap instead of adding up.
+__device__ __forceinline__ void mbar_wait2(uint64_t* a, uint32_t pa, uint64_t* b, uint32_t pb) {
+  const bool oa = mbar_try_wait(a, pa), ob = mbar_try_wait(b, pb);
+  if (!oa) mbar_wait(a, pa);
+  if (!ob) mbar_wait(b, pb);
+}
+__device__ __forceinline__ void mbar_wait3(uint64_t* a, uint32_t pa, uint64_t* b, uint32_t pb, uint64_t* c, uint32_t pc) {
+  const bool oa = mbar_try_wait(a, pa), ob = mbar_try_wait(b, pb), oc = mbar_try_wait(c, pc);
+  if (!oa) mbar_wait(a, pa);
+  if (!ob) mbar_wait(b, pb);
+  if (!oc) mbar_wait(c, pc);
+}
+
 #define SRFRD_EVICT_NORMAL 0x1000000000000000ull
 #define SRFRD_EVICT_FIRST 0x12F0000000000000ull
 #define SRFRD_EVICT_LAST 0x14F0000000000000ull

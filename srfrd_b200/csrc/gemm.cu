@@ -42,7 +42,7 @@ struct GemmEpilogue {
 
 // profiling experiments only (SRFRD_GEMM_DEBUG=5): clock64 timeline of CTA 0, [event][tile], read by srfrd_gemm_debug_read
 __device__ long long g_gemm_dbg[32 * 16];
-__device__ long long g_gemm_cta[2 * 160];     // per-CTA start / end globaltimer (SRFRD_GEMM_DEBUG=5)
+__device__ long long g_gemm_cta[2 * 160];     // per-CTA start / end globaltimer (SRFRD_GEMM_DEBUG=5); end stamp | smid << 48
 #define TN_STAMP(ev, tile) do { if (s.debug == 5 && blockIdx.x == 0 && (tile) < 16) { if (elect_one()) g_gemm_dbg[(ev) * 16 + (tile)] = clock64(); } } while (0)
 
 struct GemmShape {
@@ -52,7 +52,19 @@ struct GemmShape {
   int tma_out;              // bf16 output written IN PLACE over the aux block(s) and stored with TMA
   int buf_blocks;           // 64-column blocks per set's tile buffer (0 if neither aux nor TMA output)
   int debug;                // SRFRD_GEMM_DEBUG (profiling experiments only): 1 = no TMA store, 2 = no epilogue math, 5 = timeline
+  int b_resident;           // the whole B operand (one column tile, all K blocks) is loaded once and stays in shared memory
+  int sched_slot;           // which {next tile, CTAs done} pair of g_tn_sched this launch uses
+  int kgroup;               // K blocks per pipeline stage / barrier (resident B, K <= 192: the whole K in one stage)
+  int nacc;                 // TMEM accumulator stages: 4 x 128 columns when the tile is <= 128 wide, else 2 x 256
+  int dynamic;              // draw tile ids from the atomic counter (experiment switch, see the producer warp)
 };
+
+// Dynamic tile scheduler state (SRFRD_GEMM_DYNAMIC=1, off by default: no measured gain).  Per-CTA durations on identical
+// work spread by up to 40 % (per-SM globaltimer stamps; whole GPCs are slower than others).  The last CTA to exit resets
+// its pair; launches rotate through the pairs so that kernels running concurrently on two streams never share one.
+static constexpr int TN_SCHED_SLOTS = 64;
+__device__ int g_tn_sched[TN_SCHED_SLOTS * 2];
+static constexpr int TN_RING = 16;                       // tile-id ring between the producer and the other warps
 
 // byte offset of the 16-byte chunk j (8 bf16 columns) of row r inside a 128-byte-swizzled [128 x 64] bf16 block
 __device__ __forceinline__ uint32_t sw128_chunk(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
@@ -99,31 +111,42 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_stage_bytes = ((s.block_n * BLOCK_K * 2) + 1023) & ~1023;
   uint8_t* smA = smem;
-  uint8_t* smB = smA + s.stages * A_STAGE_BYTES;
-  uint8_t* smBuf = smB + s.stages * b_stage_bytes;       // [set][buf_blocks][16 KB]
+  const int kblocks = (s.K + BLOCK_K - 1) / BLOCK_K;
+  const int a_stage_bytes = s.kgroup * A_STAGE_BYTES;
+  uint8_t* smB = smA + s.stages * a_stage_bytes;         // [stages] or, resident, [kblocks]
+  uint8_t* smBuf = smB + (s.b_resident ? kblocks : s.stages) * b_stage_bytes;   // [set][buf_blocks][16 KB]
   float* sbias = reinterpret_cast<float*>(smBuf + 2 * s.buf_blocks * EPI_BLK_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + MAX_BIAS);
   uint64_t* full = bars;
   uint64_t* empty = bars + s.stages;
   uint64_t* tfull = bars + 2 * s.stages;
-  uint64_t* tempty = tfull + 2;
-  uint64_t* xfull = tempty + 2;                          // [set] aux tile landed
+  uint64_t* tempty = tfull + 4;                          // [nacc <= 4] accumulator stages (tile tl uses stage tl % nacc)
+  uint64_t* xfull = tempty + 4;                          // [set] aux tile landed
   uint64_t* bfree = xfull + 2;                           // [set] tile buffer free again (TMA store has read it)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfree + 2);
+  uint64_t* sfull = bfree + 2;                           // [TN_RING] tile id published
+  uint64_t* bres = sfull + TN_RING;                      // resident B landed
+  int* ring = reinterpret_cast<int*>(bres + 1);          // [TN_RING] tile ids, -1 = no more tiles
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ring + TN_RING);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = s.m_tiles * s.n_tiles;
-  const int kblocks = (s.K + BLOCK_K - 1) / BLOCK_K;
+  int* sched = g_tn_sched + 2 * s.sched_slot;
 
-  if (warp == 16 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    if (s.has_aux) tma_prefetch_desc(&tmAux);
-    if (s.tma_out) tma_prefetch_desc(&tmOut);
-    for (int i = 0; i < s.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); mbar_init(&xfull[i], 1); mbar_init(&bfree[i], 1);
+  if (warp == 16) {                                      // barrier initialisation spread over the lanes
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      if (s.has_aux) tma_prefetch_desc(&tmAux);
+      if (s.tma_out) tma_prefetch_desc(&tmOut);
     }
+    if (lane < s.stages) { mbar_init(&full[lane], 1); mbar_init(&empty[lane], 1); }
+    if (lane >= 8 && lane < 10) {
+      const int i = lane - 8;
+      mbar_init(&xfull[i], 1); mbar_init(&bfree[i], 1);
+    }
+    if (lane >= 12 && lane < 16) { mbar_init(&tfull[lane - 12], 1); mbar_init(&tempty[lane - 12], 8); }
+    if (lane >= 16) mbar_init(&sfull[lane - 16], 1);
+    if (lane == 10) mbar_init(bres, 1);
     fence_barrier_init();
   }
   if (s.debug == 5 && threadIdx.x == 0) {
@@ -143,61 +166,128 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // addresses and descriptors live in uniform registers (see topk.cu for the measurement behind this).
   if (warp == 16) {
     int stage = 0; uint32_t phase = 0;
-    int tl = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+    if (s.b_resident) {
+      if (elect_one()) {
+        mbar_expect_tx(bres, kblocks * s.block_n * BLOCK_K * 2);
+        for (int kb = 0; kb < kblocks; ++kb)
+          tma_load_2d(smB + kb * b_stage_bytes, &tmB, bres, kb * BLOCK_K, 0, SRFRD_EVICT_LAST);
+      }
+      __syncwarp();
+    }
+    // Tile ids travel to the other warps through a small ring (one mbarrier per entry, -1 = end).  The producer fills it
+    // with the static round-robin order; SRFRD_GEMM_DYNAMIC=1 draws the ids from an atomic counter instead (first two
+    // tiles static).  Measured at C2 the dynamic order gains nothing: a tile has to be claimed when its loads are issued,
+    // 4-6 tiles before it completes, which is as long as the imbalance it could correct.
+    int t = blockIdx.x, t1 = blockIdx.x + (int)gridDim.x;
+    if (t1 >= total_tiles) t1 = -1;
+    for (int tl = 0;; ++tl) {
+      int fetched = -1;
+      if (lane == 0) {
+        if (t >= 0 && t1 >= 0) fetched = s.dynamic ? atomicAdd(sched, 1) + 2 * (int)gridDim.x : t1 + (int)gridDim.x;
+        ring[tl & (TN_RING - 1)] = t;
+        mbar_arrive(&sfull[tl & (TN_RING - 1)]);
+        if (t < 0) {                                     // end marker twice: each epilogue set reads every other entry
+          ring[(tl + 1) & (TN_RING - 1)] = -1;
+          mbar_arrive(&sfull[(tl + 1) & (TN_RING - 1)]);
+        }
+      }
+      __syncwarp();
+      if (t < 0) break;
       const int m0 = (t / s.n_tiles) * BLOCK_M, n0 = (t % s.n_tiles) * s.block_n;
-      for (int kb = 0; kb < kblocks; ++kb) {
+      for (int kb = 0; kb < kblocks; kb += s.kgroup) {
         mbar_wait(&empty[stage], phase ^ 1);
         if (kb == 0) TN_STAMP(0, tl);
         if (elect_one()) {
-          mbar_expect_tx(&full[stage], A_STAGE_BYTES + s.block_n * BLOCK_K * 2);
-          tma_load_2d(smA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BLOCK_K, m0, SRFRD_EVICT_FIRST);
-          tma_load_2d(smB + stage * b_stage_bytes, &tmB, &full[stage], kb * BLOCK_K, n0, SRFRD_EVICT_LAST);
+          if (s.b_resident) {
+            const int ng = min(s.kgroup, kblocks - kb);
+            mbar_expect_tx(&full[stage], ng * A_STAGE_BYTES);
+            for (int j = 0; j < ng; ++j)
+              tma_load_2d(smA + stage * a_stage_bytes + j * A_STAGE_BYTES, &tmA, &full[stage], (kb + j) * BLOCK_K, m0,
+                          SRFRD_EVICT_FIRST);
+          } else {
+            mbar_expect_tx(&full[stage], A_STAGE_BYTES + s.block_n * BLOCK_K * 2);
+            tma_load_2d(smA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BLOCK_K, m0, SRFRD_EVICT_FIRST);
+            tma_load_2d(smB + stage * b_stage_bytes, &tmB, &full[stage], kb * BLOCK_K, n0, SRFRD_EVICT_LAST);
+          }
         }
         __syncwarp();
         if (++stage == s.stages) { stage = 0; phase ^= 1; }
       }
+      t = t1;
+      t1 = __shfl_sync(0xffffffffu, fetched, 0);
+      if (t1 >= total_tiles) t1 = -1;
     }
-  } else if (warp == 17) {
-    int stage = 0; uint32_t phase = 0;
-    int as = 0; uint32_t aphase = 0;
-    const uint64_t adesc0 = umma_smem_desc(smem_u32(smA), 0, 1024), bdesc0 = umma_smem_desc(smem_u32(smB), 0, 1024);
-    int tl = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
-      const int n0 = (t % s.n_tiles) * s.block_n;
-      int bn = min(s.block_n, s.N - n0);
-      bn = (bn + 15) & ~15;
-      const uint32_t idesc = umma_idesc_bf16(BLOCK_M, bn, 0, 0);
-      mbar_wait(&tempty[as], aphase ^ 1);
-      tc_fence_after();
-      TN_STAMP(1, tl);
-      const uint32_t tacc = tmem_base + as * 256;
-      for (int kb = 0; kb < kblocks; ++kb) {
-        mbar_wait(&full[stage], phase);
-        tc_fence_after();
-        if (kb == 0) TN_STAMP(2, tl);
-        if (kb == kblocks - 1) TN_STAMP(3, tl);
-        // K-major SW128: 8-row groups are 1024 B apart (SBO); +32 B (= 2 in descriptor units) per UMMA_K = 16
-        const uint64_t ad = adesc0 + (uint64_t)(stage * (A_STAGE_BYTES >> 4));
-        const uint64_t bd = bdesc0 + (uint64_t)(stage * (b_stage_bytes >> 4));
-        const int ksteps = min(BLOCK_K / 16, (s.K - kb * BLOCK_K + 15) / 16);
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k)
-            if (k < ksteps) umma_bf16(tacc, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
-          umma_commit(&empty[stage]);
-          if (kb == kblocks - 1) umma_commit(&tfull[as]);
+  } else if (warp == 17 || warp == 19) {
+    // MMA issuers.  The per-tile issue chain (barrier tests, five MMAs, two commits: ~1 650 cycles, clock64 timeline) was
+    // the CTA's critical path, so with one stage per tile and an even number of stages two warps take alternate tiles:
+    // issuer p owns accumulator stage p and the stages of equal parity, so every barrier still has a single waiter.
+    const bool two = (s.kgroup * 1 >= kblocks) && (s.stages % 2 == 0);
+    const int p = warp == 19 ? 1 : 0, step = two ? 2 : 1;
+    if (two || p == 0) {
+      const uint64_t adesc0 = umma_smem_desc(smem_u32(smA), 0, 1024), bdesc0 = umma_smem_desc(smem_u32(smB), 0, 1024);
+      if (s.b_resident) { mbar_wait(bres, 0); tc_fence_after(); }
+      mbar_wait(&sfull[p], 0);
+      int t = ring[p];
+      int stage = two ? p : 0; uint32_t phase = 0;
+      const int acc_cols = 512 / s.nacc;
+      for (int tl = p; t >= 0; tl += step) {
+        const int as = tl % s.nacc;                      // accumulator stage: up to nacc - 1 tiles ahead of the epilogues
+        const uint32_t aphase = (tl / s.nacc) & 1;
+        const int n0 = (t % s.n_tiles) * s.block_n;
+        int bn = min(s.block_n, s.N - n0);
+        bn = (bn + 15) & ~15;
+        const uint32_t idesc = umma_idesc_bf16(BLOCK_M, bn, 0, 0);
+        // this issuer's next ring entry is published once the loads of the tile before it are issued, which never waits
+        // on this tile: one overlapped test for the ring entry, the accumulator stage and the operands
+        // (only with one stage per tile: otherwise the producer may need this tile's stages back before it can finish
+        // issuing the tile, and the next entry is read after the last K block instead)
+        const int nx = tl + step;
+        const bool merged = s.kgroup >= kblocks;
+        if (merged) {
+          mbar_wait3(&sfull[nx & (TN_RING - 1)], (nx / TN_RING) & 1, &tempty[as], aphase ^ 1, &full[stage], phase);
+          t = ring[nx & (TN_RING - 1)];
+        } else {
+          mbar_wait2(&tempty[as], aphase ^ 1, &full[stage], phase);
         }
-        __syncwarp();
-        if (++stage == s.stages) { stage = 0; phase ^= 1; }
+        tc_fence_after();
+        TN_STAMP(1, tl);
+        const uint32_t tacc = tmem_base + as * acc_cols;
+        for (int kb = 0; kb < kblocks; kb += s.kgroup) {
+          if (kb) mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          if (kb == 0) TN_STAMP(2, tl);
+          const bool last = kb + s.kgroup >= kblocks;
+          if (last) TN_STAMP(3, tl);
+          if (elect_one()) {
+            for (int j = 0; j < s.kgroup && kb + j < kblocks; ++j) {
+              // K-major SW128: 8-row groups are 1024 B apart (SBO); +32 B (= 2 in descriptor units) per UMMA_K = 16
+              const uint64_t ad = adesc0 + (uint64_t)((stage * a_stage_bytes + j * A_STAGE_BYTES) >> 4);
+              const uint64_t bd = bdesc0 + (uint64_t)((s.b_resident ? kb + j : stage) * (b_stage_bytes >> 4));
+              const int ksteps = min(BLOCK_K / 16, (s.K - (kb + j) * BLOCK_K + 15) / 16);
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / 16; ++k)
+                if (k < ksteps) umma_bf16(tacc, ad + 2 * k, bd + 2 * k, idesc, ((kb + j) | k) != 0);
+            }
+            umma_commit(&empty[stage]);
+            if (last) umma_commit(&tfull[as]);
+          }
+          __syncwarp();
+          if (two) { stage += 2; if (stage >= s.stages) { stage -= s.stages; phase ^= 1; } }
+          else if (++stage == s.stages) { stage = 0; phase ^= 1; }
+        }
+        if (!merged) {
+          mbar_wait(&sfull[nx & (TN_RING - 1)], (nx / TN_RING) & 1);
+          t = ring[nx & (TN_RING - 1)];
+        }
       }
-      if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else if (warp == 18) {
     if (AUX) {
       uint32_t bph0 = 0, bph1 = 0;                       // parity of the bfree phase each set's NEXT load waits for
-      int n_local = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++n_local) {
+      for (int n_local = 0;; ++n_local) {
+        mbar_wait(&sfull[n_local & (TN_RING - 1)], (n_local / TN_RING) & 1);
+        const int t = ring[n_local & (TN_RING - 1)];
+        if (t < 0) break;
         const int m0 = (t / s.n_tiles) * BLOCK_M, n0 = (t % s.n_tiles) * s.block_n;
         const int nblk = (min(s.block_n, s.N - n0) + 63) >> 6;
         const int set = n_local & 1;
@@ -220,12 +310,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool stamp = (quarter == 0) && (half == 0);
     uint8_t* buf = smBuf + set * s.buf_blocks * EPI_BLK_BYTES;
     const bool use_buf = AUX || s.tma_out;
-    uint32_t tph = 0;                                    // parity for this set's tfull / xfull / bfree
+    uint32_t tph = 0;                                    // parity for this set's xfull / bfree
     if (DROP) e.drop_seed = mix_seed(e.drop_seed, e.drop_step);
     const float relu_floor = e.relu ? 0.f : -INFINITY;
-    int n_local = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++n_local) {
-      if ((n_local & 1) != set) continue;                // the other set's tile
+    for (int n_local = set;; n_local += 2) {             // tiles alternate between the sets
+      mbar_wait(&sfull[n_local & (TN_RING - 1)], (n_local / TN_RING) & 1);
+      const int t = ring[n_local & (TN_RING - 1)];
+      if (t < 0) break;
       const int m0 = (t / s.n_tiles) * BLOCK_M, n0 = (t % s.n_tiles) * s.block_n;
       const int bn = min(s.block_n, s.N - n0);           // multiple of 16
       const int nblk = (bn + 63) >> 6;
@@ -233,13 +324,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool row_ok = row < s.M;
       float rowm = 1.f;
       if (e.row_ids && row_ok) rowm = (__ldg(e.row_ids + row) != 0) ? 1.f : 0.f;
-      mbar_wait(&tfull[set], tph);
-      tc_fence_after();
       if (stamp) TN_STAMP(4, n_local);
-      if (AUX) mbar_wait(&xfull[set], tph);              // aux tile landed (implies the buffer was free)
-      else if (s.tma_out) mbar_wait(&bfree[set], tph ^ 1);   // previous store of this set has read the buffer
+      // accumulator ready AND (aux tile landed, which implies the buffer was free | previous store has read the buffer)
+      const int as = n_local % s.nacc;
+      const uint32_t aph = (n_local / s.nacc) & 1;
+      if (AUX) mbar_wait2(&tfull[as], aph, &xfull[set], tph);
+      else if (s.tma_out) mbar_wait2(&tfull[as], aph, &bfree[set], tph ^ 1);
+      else mbar_wait(&tfull[as], aph);
+      tc_fence_after();
       if (stamp) TN_STAMP(5, n_local);
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + set * 256;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * (512 / s.nacc);
       if (s.debug != 2) {
 #pragma unroll 1
         for (int c = half * 32; c < bn; c += 64) {       // this warp's 32-column chunks of the tile
@@ -295,7 +389,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (stamp) TN_STAMP(6, n_local);
       tc_fence_before();                                 // accumulator fully read: hand the TMEM stage back
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[set]);
+      if (lane == 0) mbar_arrive(&tempty[as]);
       if (use_buf) {
         if (s.tma_out) fence_proxy_async();              // generic-proxy smem writes -> visible to the TMA store
         if (stamp) TN_STAMP(7, n_local);
@@ -320,9 +414,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (s.debug == 5 && threadIdx.x == 0) {
     unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
     if (blockIdx.x == 0) { g_gemm_dbg[11 * 16] = (long long)gt; g_gemm_dbg[11 * 16 + 1] = clock64(); }
-    if (blockIdx.x < 160) g_gemm_cta[2 * blockIdx.x + 1] = (long long)gt;
+    unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (blockIdx.x < 160) g_gemm_cta[2 * blockIdx.x + 1] = (long long)((gt & 0xffffffffffffull) | ((unsigned long long)smid << 48));
   }
   if (warp == 17) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+  if (s.dynamic && threadIdx.x == 0) {                   // last CTA out rearms the scheduler pair for its next user
+    __threadfence();
+    if (atomicAdd(sched + 1, 1) == (int)gridDim.x - 1) { sched[0] = 0; sched[1] = 0; __threadfence(); }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -541,11 +640,30 @@ extern "C" int srfrd_gemm_tn(const void* A, int lda, const void* B, int ldb, int
   const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
   { const char* dbg = getenv("SRFRD_GEMM_DEBUG"); s.debug = dbg ? atoi(dbg) : 0; }
   s.buf_blocks = (s.has_aux || s.tma_out) ? (s.block_n + 63) / 64 : 0;
-  const int fixed = 1024 + 2 * s.buf_blocks * EPI_BLK_BYTES + MAX_BIAS * 4 + 512;
-  s.stages = (227 * 1024 - fixed) / stage_bytes;
+  int fixed = 1024 + 2 * s.buf_blocks * EPI_BLK_BYTES + MAX_BIAS * 4 + 1024;
+  // B (the weight matrix) is identical for every row tile: with one column tile and few K blocks it is loaded once
+  const int kblocks_h = (K + BLOCK_K - 1) / BLOCK_K;
+  s.b_resident = (s.n_tiles == 1 && kblocks_h * b_stage_bytes <= 48 * 1024) ? 1 : 0;
+  { const char* r = getenv("SRFRD_GEMM_BRES"); if (r) s.b_resident = s.b_resident && atoi(r); }
+  s.kgroup = 1;
+  if (s.b_resident) {
+    fixed += kblocks_h * b_stage_bytes;
+    // the whole K of a tile in one stage (one barrier round trip per tile instead of one per K block) while >= 3 fit
+    if ((227 * 1024 - fixed) / (kblocks_h * A_STAGE_BYTES) >= 3) s.kgroup = kblocks_h;
+    { const char* g = getenv("SRFRD_GEMM_KGROUP"); if (g && atoi(g) == 0) s.kgroup = 1; }
+    s.stages = (227 * 1024 - fixed) / (s.kgroup * A_STAGE_BYTES);
+  } else {
+    s.stages = (227 * 1024 - fixed) / stage_bytes;
+  }
   if (s.stages > 6) s.stages = 6;
   SRFRD_REQUIRE(s.stages >= 2, "gemm_tn: tile does not fit shared memory");
-  const size_t smem = (size_t)s.stages * stage_bytes + fixed;
+  const size_t smem = (size_t)s.stages * (s.b_resident ? s.kgroup * A_STAGE_BYTES : stage_bytes) + fixed;
+  { const char* d = getenv("SRFRD_GEMM_DYNAMIC"); s.dynamic = d ? atoi(d) : 0; }
+  s.nacc = s.block_n <= 128 ? 4 : 2;
+  { const char* a = getenv("SRFRD_GEMM_NACC"); if (a && atoi(a) == 2) s.nacc = 2; }
+  static int next_slot = 0;
+  s.sched_slot = next_slot;
+  next_slot = (next_slot + 1) % TN_SCHED_SLOTS;
   CUtensorMap tmA, tmB, tmAux, tmOut;
   if (int rc = make_tmap_bf16_2d(&tmA, A, M, K, lda, BLOCK_M, BLOCK_K)) return rc;
   if (int rc = make_tmap_bf16_2d(&tmB, B, N, K, ldb, s.block_n, BLOCK_K)) return rc;

@@ -25,7 +25,9 @@ def rnd(shape, seed, scale=1.0, dtype=torch.float32):
 
 # ------------------------------------------------------------------------------------------- GEMMs
 @pytest.mark.parametrize("M,N,K", [(128, 16, 16), (300, 80, 80), (1000, 160, 80), (257, 240, 96), (200, 272, 272),
-                                   (64, 64, 80), (4096, 80, 80), (130, 544, 272), (50000, 80, 80)])
+                                   (64, 64, 80), (4096, 80, 80), (130, 544, 272), (50000, 80, 80),
+                                   # several tiles per CTA with more K blocks than pipeline stages / with 3 merged K blocks
+                                   (40000, 272, 272), (30000, 80, 160), (30000, 160, 80)])
 def test_gemm_tn_plain(ops, M, N, K):
     A, B = rnd((M, K), 1, dtype=bf16), rnd((N, K), 2, 0.2, bf16)
     out = torch.full((M, N), float("nan"), device="cuda")
