@@ -38,16 +38,58 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback (B200_PROFILING.md)")
 
 
+def measured_traffic(key):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of a kernel from the committed `ncu --set full`
+    capture (profiles/traffic.json, written by tools/profile_round.py); None if the capture is missing."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")) as f:
+            return json.load(f).get(key)
+    except Exception:
+        return None
+
+
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples SM clocks / throttle reasons DURING the timed region: NVML in a thread every 2 ms (the timed region of a
+    default run is a few hundred ms, shorter than `nvidia-smi -lms` needs to start); nvidia-smi as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.h, self.nv = index, [], None, None, None
+        self.sm, self.reason_bits, self.mx, self._stop = [], 0, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber devices: look the handle up by the CUDA device's PCI bus id
+            bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(h).bus == bus:
+                        self.h = h
+            self.nv = pynvml
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self._stop:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self.nv is not None:
+            self._stop = False
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -61,6 +103,15 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nv is not None:
+            self._stop = True
+            self.thread.join(timeout=1.0)
+            nv, bits = self.nv, self.reason_bits
+            table = [("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", 0x8), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", 0x20), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", 0x4)]
+            reasons = sorted(name for name, attr, dflt in table if bits & int(getattr(nv, attr, dflt)))
+            return dict(sm_mhz=float(np.median(self.sm)) if self.sm else None, sm_max_mhz=self.mx, reasons=reasons,
+                        samples=len(self.sm), source="nvml")
         if self.proc is not None:
             self.proc.terminate()
         sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
@@ -68,7 +119,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
-                    samples=len(sm))
+                    samples=len(sm), source="nvidia-smi")
 
 
 # ---------------------------------------------------------------------------------------------
@@ -242,7 +293,8 @@ def run_ours(args):
     else:
         bound, ach, peak, unit = "hbm", td["bytes"] / td["n"] / (per_ms * 1e-3) / 1e9, pk["hbm"], "GB/s"
     roofline = dict(bound=bound, kernel=tname, achieved=round(ach, 1), peak=peak, unit=unit, frac=round(ach / peak, 4),
-                    traffic=None, peak_source=pk["src"] + ", sustained figure not needed for HBM", avg_launch_ms=round(per_ms, 4),
+                    traffic=measured_traffic(tname), algorithmic_bytes_per_launch=round(td["bytes"] / td["n"]),
+                    peak_source=pk["src"] + ", sustained figure not needed for HBM", avg_launch_ms=round(per_ms, 4),
                     share_of_step=round(td["ms"] / tot, 3),
                     how="event-bracketed pass of 3 eager steps right after the timed region (which replays a CUDA graph); the "
                         "GPU is parked behind a spin kernel while the host enqueues each step, so the deltas are GPU time",
@@ -326,7 +378,7 @@ def bench_gather(dev, pk):
     gbs = by / (ms * 1e-3) / 1e9
     return dict(kernel="srfrd_embed_ln_fwd", tokens=T, table_rows=N + 1, table_bytes=(N + 1) * D * 4, ms=round(ms, 4),
                 roofline=dict(bound="hbm", achieved=round(gbs, 1), peak=pk["hbm"], unit="GB/s", frac=round(gbs / pk["hbm"], 4),
-                              traffic=None, bytes_per_token=600, peak_source=pk["src"]),
+                              traffic=measured_traffic("srfrd_embed_ln_fwd@C3"), bytes_per_token=600, peak_source=pk["src"]),
                 config="C3 table (1M x 64 fp32, 256 MB > L2), 81920 x 50 tokens, all slots valid, SRFR D=64 F=16")
 
 
@@ -364,7 +416,7 @@ def bench_catalogue(dev, rank, world, pg, args, pk, timed):
                 config="C3: 1M items x D=64 bf16 table row-sharded, 16384 users, top-10, all-gather merge",
                 roofline=dict(bound="tensor", kernel="srfrd_catalogue_topk", achieved=round(tf, 1), peak=pk["tf_burst"],
                               unit="TFLOP/s", frac=round(tf / pk["tf_burst"], 4), avg_launch_ms=round(float(kms), 4),
-                              traffic=None, peak_source=pk["src"] + ", burst figure (kernel timed alone)"))
+                              traffic=measured_traffic("srfrd_catalogue_topk"), peak_source=pk["src"] + ", burst figure (kernel timed alone)"))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -416,8 +468,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-catalogue", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -202,8 +202,7 @@ catalogue_tilemax_kernel(const __grid_constant__ CUtensorMap tmE, TopkShape s) {
         }
         // the item tile usually landed long ago: take that (cheap) wait first so that nothing but the MMA issue sits
         // between the accumulator coming back (tempty) and the tensor pipe starting on it
-        mbar_wait(&full[stage], phase);
-        mbar_wait(&tempty[w], aphase ^ 1);
+        mbar_wait2(&tempty[w], aphase ^ 1, &full[stage], phase);   // both tests in flight together (~250 cycles each)
         aphase ^= 1;
         tc_fence_after();
         for (int kb = 0; kb < s.kblocks; ++kb) {
