@@ -4,7 +4,9 @@ import csv, json, os, subprocess, sys
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "r1c"
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-out, prof = os.path.join(root, "gpurun_out"), os.path.join(root, "profiles")
+out = os.path.join(root, "gpurun_out")
+prof = os.path.join(root, sys.argv[2]) if len(sys.argv) > 2 else os.path.join(root, "profiles")
+os.makedirs(prof, exist_ok=True)
 
 
 def raw(rep):
