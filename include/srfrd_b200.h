@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SRFRD_ABI_VERSION 2
+#define SRFRD_ABI_VERSION 3
 #if defined(__GNUC__)
 #define SRFRD_API __attribute__((visibility("default")))
 #else
@@ -91,6 +91,15 @@ typedef struct {
   uint64_t drop_seed;
   const float* drop_step;  /* device scalar mixed into the seed (the Adam step counter) or NULL: lets a
                               captured CUDA graph draw a fresh mask on every replay */
+  /* Optional fused LayerNorm of the result row (the LayerNorm that follows the residual add in the reference,
+   * SRFR_model.py:113-118 / :100-104): ln_out[m, :] = LN(bf16(out[m, :])) * ln_w + ln_b, ln_stats[m] = (mean, rstd).
+   * Needs residual, out_bf16, N <= 128 and N a multiple of 16; NULL ln_out = off. */
+  void* ln_out_bf16;       /* [M, ld_ln] or NULL */
+  const float* ln_w;       /* [N] */
+  const float* ln_b;       /* [N] */
+  float* ln_stats;         /* [M, 2] or NULL */
+  int ld_ln;
+  float ln_eps;
 } srfrd_gemm_epilogue_t;
 
 /* C[M,N] = epilogue(A[M,K] . B[N,K]^T), A and B bf16 K-major. */

@@ -18,7 +18,8 @@ vp, i32, i64, f32, u32, u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uin
 class GemmEpilogue(C.Structure):
     _fields_ = [("bias", vp), ("residual", vp), ("gate", vp), ("row_ids", vp), ("out_bf16", vp), ("out_f32", vp),
                 ("ldr", i32), ("ldg", i32), ("ldc", i32), ("relu", i32), ("drop_p", f32), ("drop_stream", u32),
-                ("drop_seed", u64), ("drop_step", vp)]
+                ("drop_seed", u64), ("drop_step", vp),
+                ("ln_out_bf16", vp), ("ln_w", vp), ("ln_b", vp), ("ln_stats", vp), ("ld_ln", i32), ("ln_eps", f32)]
 
 
 class CastDesc(C.Structure):
@@ -83,7 +84,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)            # AttributeError if the symbol is not exported
         fn.argtypes = argtypes
         fn.restype = C.c_int
-    if lib.srfrd_abi_version() != 2:
+    if lib.srfrd_abi_version() != 3:
         raise RuntimeError("srfrd_b200: ABI version mismatch between _lib.py and the built library")
     _lib = lib
     return lib

@@ -24,6 +24,7 @@ static constexpr int TMEM_COLS = 512;
 static constexpr int EPI_BLK_BYTES = BLOCK_M * 64 * 2;   // one [128 rows x 64 cols] bf16 epilogue block, 16 KB
 static constexpr int TN_MAX_BLOCK_N = 192;               // <= 3 epilogue blocks per tile and per set
 static constexpr int MAX_BIAS = 1024;
+static constexpr int MAX_LN = 128;                       // widest row of the fused LayerNorm epilogue (two staging blocks x 2)
 
 struct GemmEpilogue {
   const float* bias;        // [N] or null
@@ -38,6 +39,10 @@ struct GemmEpilogue {
   uint32_t drop_thresh, drop_stream;
   float drop_scale;
   const float* drop_step;
+  const float* ln_w;        // fused LayerNorm of the result row (LNF kernels): weight / bias [N], stats [M, 2] or null
+  const float* ln_b;
+  float* ln_stats;
+  float ln_eps;
 };
 
 // profiling experiments only (SRFRD_GEMM_DEBUG=5): clock64 timeline of CTA 0, [event][tile], read by srfrd_gemm_debug_read
@@ -102,11 +107,15 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 //     The control warps have the HIGHEST warp ids: the scheduler favours high ids, and with low ids the MMA issuer
 //     took ~700 cycles to issue five MMAs while the epilogue warps of its scheduler were busy (clock64 timeline).
 // AUX: 0 none, 1 residual (v += aux), 2 gate (v = aux > 0 ? v : 0).  bias / ReLU / row mask are branch-free.
-template <int AUX, bool DROP>
+// LNF: the LayerNorm that follows the residual add is computed in the epilogue.  After the set's named barrier the whole
+// row (one column tile) sits in the set's staging buffer as bf16 -- exactly what the separate LayerNorm kernel would read
+// back from HBM -- so every thread re-reads its row from shared memory for the statistics (both warps of a row compute
+// them redundantly: no exchange), normalises its own chunks into a second staging buffer and a second TMA store writes it.
+template <int AUX, bool DROP, bool LNF>
 __global__ void __launch_bounds__(TN_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmAux, const __grid_constant__ CUtensorMap tmOut, GemmShape s,
-               GemmEpilogue e) {
+               const __grid_constant__ CUtensorMap tmAux, const __grid_constant__ CUtensorMap tmOut,
+               const __grid_constant__ CUtensorMap tmLn, GemmShape s, GemmEpilogue e) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_stage_bytes = ((s.block_n * BLOCK_K * 2) + 1023) & ~1023;
@@ -115,8 +124,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int a_stage_bytes = s.kgroup * A_STAGE_BYTES;
   uint8_t* smB = smA + s.stages * a_stage_bytes;         // [stages] or, resident, [kblocks]
   uint8_t* smBuf = smB + (s.b_resident ? kblocks : s.stages) * b_stage_bytes;   // [set][buf_blocks][16 KB]
-  float* sbias = reinterpret_cast<float*>(smBuf + 2 * s.buf_blocks * EPI_BLK_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + MAX_BIAS);
+  uint8_t* smY = smBuf + 2 * s.buf_blocks * EPI_BLK_BYTES;   // LNF: [set][buf_blocks][16 KB] LayerNorm output staging
+  float* sbias = reinterpret_cast<float*>(smY + (LNF ? 2 * s.buf_blocks * EPI_BLK_BYTES : 0));
+  float* sln = sbias + MAX_BIAS;                             // LNF: weight [MAX_LN], bias [MAX_LN]
+  float* sxch = sln + (LNF ? 2 * MAX_LN : 0);                // LNF: [set][half][128 rows] (sum, sum of squares)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sxch + (LNF ? 2 * 2 * BLOCK_M * 2 : 0));
   uint64_t* full = bars;
   uint64_t* empty = bars + s.stages;
   uint64_t* tfull = bars + 2 * s.stages;
@@ -138,6 +150,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tma_prefetch_desc(&tmB);
       if (s.has_aux) tma_prefetch_desc(&tmAux);
       if (s.tma_out) tma_prefetch_desc(&tmOut);
+      if (LNF) tma_prefetch_desc(&tmLn);
     }
     if (lane < s.stages) { mbar_init(&full[lane], 1); mbar_init(&empty[lane], 1); }
     if (lane >= 8 && lane < 10) {
@@ -157,6 +170,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 17) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
   pdl_prologue_done();                                   // everything below may read what earlier kernels wrote
   for (int i = threadIdx.x; i < MAX_BIAS; i += blockDim.x) sbias[i] = (e.bias && i < s.N) ? __ldg(e.bias + i) : 0.f;
+  if (LNF) {
+    for (int i = threadIdx.x; i < MAX_LN; i += blockDim.x) {
+      sln[i] = i < s.N ? __ldg(e.ln_w + i) : 0.f;
+      sln[MAX_LN + i] = i < s.N ? __ldg(e.ln_b + i) : 0.f;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -334,6 +353,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       if (stamp) TN_STAMP(5, n_local);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * (512 / s.nacc);
+      float ln_sum = 0.f, ln_sq = 0.f;
       if (s.debug != 2) {
 #pragma unroll 1
         for (int c = half * 32; c < bn; c += 64) {       // this warp's 32-column chunks of the tile
@@ -370,8 +390,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               v[i] = x * rowm;
             }
             if (s.tma_out) {
-              *reinterpret_cast<uint4*>(blkp + sw128_chunk(r, cj + j)) =
-                  make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+              const uint4 pk = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+              *reinterpret_cast<uint4*>(blkp + sw128_chunk(r, cj + j)) = pk;
+              if (LNF) {                                 // row statistics of the ROUNDED values (what a LayerNorm kernel would read)
+                const uint32_t pw[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float lo = __uint_as_float(pw[i] << 16), hi = __uint_as_float(pw[i] & 0xffff0000u);
+                  ln_sum += lo + hi;
+                  ln_sq = fmaf(lo, lo, fmaf(hi, hi, ln_sq));
+                }
+              }
             } else if (row_ok) {
               const int n = nc + 8 * j;
               if (e.out_bf16)
@@ -392,9 +421,52 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) mbar_arrive(&tempty[as]);
       if (use_buf) {
         if (s.tma_out) fence_proxy_async();              // generic-proxy smem writes -> visible to the TMA store
+        if (LNF) *reinterpret_cast<float2*>(sxch + ((set * 2 + half) * BLOCK_M + r) * 2) = make_float2(ln_sum, ln_sq);
         if (stamp) TN_STAMP(7, n_local);
         named_bar_sync(1 + set, 256);                    // every warp of the set is done with the tile buffer
         if (stamp) TN_STAMP(8, n_local);
+        if (LNF) {
+          if (issuer && s.debug != 1) {                  // x leaves while the row statistics are computed
+            for (int blk = 0; blk < nblk; ++blk) tma_store_2d(&tmOut, buf + blk * EPI_BLK_BYTES, n0 + blk * 64, m0);
+            bulk_commit();
+          }
+          uint8_t* ybuf = smY + set * s.buf_blocks * EPI_BLK_BYTES;
+          // one-pass statistics: the two warps of a row exchange (sum, sum of squares) of their columns
+          const float2 other = *reinterpret_cast<const float2*>(sxch + ((set * 2 + (half ^ 1)) * BLOCK_M + r) * 2);
+          const float invn = 1.f / (float)bn;
+          const float mean = (ln_sum + other.x) * invn;
+          const float var = fmaxf((ln_sq + other.y) * invn - mean * mean, 0.f);
+          const float rstd = rsqrtf(var + e.ln_eps), nb = -mean * rstd;
+#pragma unroll 1
+          for (int c = half * 32; c < bn; c += 64) {
+            const int cj = (c & 63) >> 3;
+            const uint32_t boff = (uint32_t)((c >> 6) * EPI_BLK_BYTES);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (c + 8 * j >= bn) break;
+              float f[8], y[8];
+              const uint32_t off = boff + sw128_chunk(r, cj + j);
+              unpack_bf16x8(*reinterpret_cast<const uint4*>(buf + off), f);
+              const float* w = sln + c + 8 * j;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) y[i] = fmaf(fmaf(f[i], rstd, nb), w[i], w[MAX_LN + i]);
+              *reinterpret_cast<uint4*>(ybuf + off) =
+                  make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+            }
+          }
+          if (half == 0 && row_ok && e.ln_stats) *reinterpret_cast<float2*>(e.ln_stats + 2 * (size_t)row) = make_float2(mean, rstd);
+          fence_proxy_async();
+          named_bar_sync(1 + set, 256);                  // LayerNorm rows complete in the second staging buffer
+          if (issuer) {
+            if (s.debug != 1) {
+              for (int blk = 0; blk < nblk; ++blk) tma_store_2d(&tmLn, ybuf + blk * EPI_BLK_BYTES, n0 + blk * 64, m0);
+              bulk_commit();
+              bulk_wait_read<0>();                       // both stores have read their buffers
+            }
+            mbar_arrive(&bfree[set]);
+          }
+          __syncwarp();
+        } else {
         if (issuer) {
           if (s.tma_out && s.debug != 1) {
             for (int blk = 0; blk < nblk; ++blk) tma_store_2d(&tmOut, buf + blk * EPI_BLK_BYTES, n0 + blk * 64, m0);
@@ -404,6 +476,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_arrive(&bfree[set]);
         }
         __syncwarp();
+        }
       }
       if (stamp) TN_STAMP(9, n_local);
       tph ^= 1;
@@ -640,7 +713,13 @@ extern "C" int srfrd_gemm_tn(const void* A, int lda, const void* B, int ldb, int
   const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
   { const char* dbg = getenv("SRFRD_GEMM_DEBUG"); s.debug = dbg ? atoi(dbg) : 0; }
   s.buf_blocks = (s.has_aux || s.tma_out) ? (s.block_n + 63) / 64 : 0;
-  int fixed = 1024 + 2 * s.buf_blocks * EPI_BLK_BYTES + MAX_BIAS * 4 + 1024;
+  const bool lnf = ep->ln_out_bf16 != nullptr;
+  if (lnf) {
+    SRFRD_REQUIRE(ep->residual && s.tma_out && s.n_tiles == 1 && N <= MAX_LN && ep->ln_w && ep->ln_b,
+                  "gemm_tn: fused LayerNorm needs a residual, a bf16 output, one column tile (N=%d) and ln_w / ln_b", N);
+    SRFRD_REQUIRE(ep->ld_ln % 8 == 0 && ep->ld_ln >= N && (((uintptr_t)ep->ln_out_bf16 & 15) == 0), "gemm_tn: bad ln_out");
+  }
+  int fixed = 1024 + (lnf ? 4 : 2) * s.buf_blocks * EPI_BLK_BYTES + MAX_BIAS * 4 + (lnf ? 2 * MAX_LN * 4 + 2 * 2 * BLOCK_M * 2 * 4 : 0) + 1024;
   // B (the weight matrix) is identical for every row tile: with one column tile and few K blocks it is loaded once
   const int kblocks_h = (K + BLOCK_K - 1) / BLOCK_K;
   s.b_resident = (s.n_tiles == 1 && kblocks_h * b_stage_bytes <= 48 * 1024) ? 1 : 0;
@@ -649,7 +728,7 @@ extern "C" int srfrd_gemm_tn(const void* A, int lda, const void* B, int ldb, int
   if (s.b_resident) {
     fixed += kblocks_h * b_stage_bytes;
     // the whole K of a tile in one stage (one barrier round trip per tile instead of one per K block) while >= 3 fit
-    if ((227 * 1024 - fixed) / (kblocks_h * A_STAGE_BYTES) >= 3) s.kgroup = kblocks_h;
+    if ((227 * 1024 - fixed) / (kblocks_h * A_STAGE_BYTES) >= (lnf ? 2 : 3)) s.kgroup = kblocks_h;
     { const char* g = getenv("SRFRD_GEMM_KGROUP"); if (g && atoi(g) == 0) s.kgroup = 1; }
     s.stages = (227 * 1024 - fixed) / (s.kgroup * A_STAGE_BYTES);
   } else {
@@ -664,18 +743,21 @@ extern "C" int srfrd_gemm_tn(const void* A, int lda, const void* B, int ldb, int
   static int next_slot = 0;
   s.sched_slot = next_slot;
   next_slot = (next_slot + 1) % TN_SCHED_SLOTS;
-  CUtensorMap tmA, tmB, tmAux, tmOut;
+  CUtensorMap tmA, tmB, tmAux, tmOut, tmLn;
   if (int rc = make_tmap_bf16_2d(&tmA, A, M, K, lda, BLOCK_M, BLOCK_K)) return rc;
   if (int rc = make_tmap_bf16_2d(&tmB, B, N, K, ldb, s.block_n, BLOCK_K)) return rc;
   tmAux = tmA; tmOut = tmA;
   if (s.has_aux) if (int rc = make_tmap_bf16_2d(&tmAux, aux, M, N, ldaux, BLOCK_M, 64)) return rc;
   if (s.tma_out) if (int rc = make_tmap_bf16_2d(&tmOut, ep->out_bf16, M, N, ep->ldc, BLOCK_M, 64)) return rc;
+  tmLn = tmA;
+  if (lnf) if (int rc = make_tmap_bf16_2d(&tmLn, ep->ln_out_bf16, M, N, ep->ld_ln, BLOCK_M, 64)) return rc;
   GemmEpilogue e;
   e.bias = ep->bias; e.residual = (const bf16*)ep->residual; e.gate = (const bf16*)ep->gate;
   e.row_ids = ep->row_ids; e.out_bf16 = (bf16*)ep->out_bf16; e.out_f32 = ep->out_f32;
   e.ldr = ep->ldr; e.ldg = ep->ldg; e.ldc = ep->ldc; e.relu = ep->relu;
   e.drop_seed = ep->drop_seed; e.drop_stream = ep->drop_stream; e.drop_step = ep->drop_step;
   e.drop_thresh = 0; e.drop_scale = 1.f;
+  e.ln_w = ep->ln_w; e.ln_b = ep->ln_b; e.ln_stats = ep->ln_stats; e.ln_eps = ep->ln_eps;
   if (ep->drop_p > 0.f) {
     SRFRD_REQUIRE(ep->drop_p < 1.f, "gemm_tn: dropout p must be < 1");
     e.drop_thresh = (uint32_t)((double)ep->drop_p * 4294967296.0);
@@ -684,21 +766,22 @@ extern "C" int srfrd_gemm_tn(const void* A, int lda, const void* B, int ldb, int
   int grid = s.m_tiles * s.n_tiles;
   if (grid > num_sms()) grid = num_sms();
   const int aux_mode = ep->residual ? 1 : (ep->gate ? 2 : 0);
-#define SRFRD_TN_LAUNCH(AUXM, DROPF)                                                                                  \
+#define SRFRD_TN_LAUNCH(AUXM, DROPF, LNFF)                                                                            \
   do {                                                                                                                \
     static bool attr_set = false;                                                                                     \
     if (!attr_set) {                                                                                                  \
-      SRFRD_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<AUXM, DROPF>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+      SRFRD_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<AUXM, DROPF, LNFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                       227 * 1024));                                                                   \
       attr_set = true;                                                                                                \
     }                                                                                                                 \
-    SRFRD_CUDA(launch_pdl(gemm_tn_kernel<AUXM, DROPF>, dim3(grid), dim3(TN_THREADS), smem, stream, tmA, tmB, tmAux,    \
-                          tmOut, s, e));                                                                              \
+    SRFRD_CUDA(launch_pdl(gemm_tn_kernel<AUXM, DROPF, LNFF>, dim3(grid), dim3(TN_THREADS), smem, stream, tmA, tmB,    \
+                          tmAux, tmOut, tmLn, s, e));                                                                 \
   } while (0)
   const bool drop = e.drop_thresh != 0;
-  if (aux_mode == 0) { if (drop) SRFRD_TN_LAUNCH(0, true); else SRFRD_TN_LAUNCH(0, false); }
-  else if (aux_mode == 1) { if (drop) SRFRD_TN_LAUNCH(1, true); else SRFRD_TN_LAUNCH(1, false); }
-  else { if (drop) SRFRD_TN_LAUNCH(2, true); else SRFRD_TN_LAUNCH(2, false); }
+  if (lnf) { if (drop) SRFRD_TN_LAUNCH(1, true, true); else SRFRD_TN_LAUNCH(1, false, true); }
+  else if (aux_mode == 0) { if (drop) SRFRD_TN_LAUNCH(0, true, false); else SRFRD_TN_LAUNCH(0, false, false); }
+  else if (aux_mode == 1) { if (drop) SRFRD_TN_LAUNCH(1, true, false); else SRFRD_TN_LAUNCH(1, false, false); }
+  else { if (drop) SRFRD_TN_LAUNCH(2, true, false); else SRFRD_TN_LAUNCH(2, false, false); }
 #undef SRFRD_TN_LAUNCH
   SRFRD_LAUNCH_CHECK();
   return 0;

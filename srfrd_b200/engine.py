@@ -318,24 +318,36 @@ class HotPath:
                          x0_bf16=x[0], q_bf16=ws["Q0"][:T], stats=ws["st1_0"][:T],
                          drop_p=p_drop if s.kind == "SASRec" else 0.0, drop_seed=seed, drop_stream=1, drop_step=step)
         seq_flat = seq.view(-1)
+        # rows wider than the true width (ragged H, zero padded) keep the separate LayerNorm with true-width statistics
+        fuse_ln = (H == Hp) and Hp <= 128 and os.environ.get("SRFRD_FUSE_LN", "1") != "0"
         for i in range(nb):
             Q, q, kv, o, r, y, h1 = (ws[f"{n}{i}"][:T] for n in ("Q", "q", "kv", "o", "r", "y", "h1"))
             with self._branch():                                   # k | v need the un-normalised x only
                 ops.gemm_tn(x[i], self.sh[f"wkv{i}"], out_bf16=kv, bias=self.bias("bkv", i))
-            if i > 0:
+            if i > 0 and not fuse_ln:
                 ops.layernorm_fwd(x[i], P.view(f"attention_layernorms.{i}.weight"), P.view(f"attention_layernorms.{i}.bias"),
                                   LN_EPS, y_bf16=Q, stats=ws[f"st1_{i}"][:T], H=H)
             ops.gemm_tn(Q, self.sh[f"wq{i}"], out_bf16=q, bias=self.bias("bq", i))
             self._join()                                           # k | v (side stream) are ready
             ops.attention_fwd(q, kv[:, :Hp], kv[:, Hp:], o, B, L, H, s.num_heads, p_drop, seed, 10 + 4 * i, step,
                               stats=ws.get(f"ast{i}"))
-            ops.gemm_tn(o, self.sh[f"wo{i}"], out_bf16=r, bias=self.bias("bo", i), residual=Q)
-            ops.layernorm_fwd(r, P.view(f"forward_layernorms.{i}.weight"), P.view(f"forward_layernorms.{i}.bias"), LN_EPS,
-                              y_bf16=y, stats=ws[f"st2_{i}"][:T], H=H)
+            if fuse_ln:                                            # LayerNorm computed in the GEMM's epilogue
+                ops.gemm_tn(o, self.sh[f"wo{i}"], out_bf16=r, bias=self.bias("bo", i), residual=Q, ln_out=y,
+                            ln_w=P.view(f"forward_layernorms.{i}.weight"), ln_b=P.view(f"forward_layernorms.{i}.bias"),
+                            ln_eps=LN_EPS, ln_stats=ws[f"st2_{i}"][:T])
+            else:
+                ops.gemm_tn(o, self.sh[f"wo{i}"], out_bf16=r, bias=self.bias("bo", i), residual=Q)
+                ops.layernorm_fwd(r, P.view(f"forward_layernorms.{i}.weight"), P.view(f"forward_layernorms.{i}.bias"), LN_EPS,
+                                  y_bf16=y, stats=ws[f"st2_{i}"][:T], H=H)
             ops.gemm_tn(y, self.sh[f"w1{i}"], out_bf16=h1, bias=self.bias("b1", i), relu=True,
                         drop_p=p_drop, drop_seed=seed, drop_stream=11 + 4 * i, drop_step=step)
+            nxt = {}
+            if fuse_ln and i + 1 < nb:                             # the next block's attention LayerNorm rides along
+                nxt = dict(ln_out=ws[f"Q{i + 1}"][:T], ln_w=P.view(f"attention_layernorms.{i + 1}.weight"),
+                           ln_b=P.view(f"attention_layernorms.{i + 1}.bias"), ln_eps=LN_EPS, ln_stats=ws[f"st1_{i + 1}"][:T])
             ops.gemm_tn(h1, self.sh[f"w2{i}"], out_bf16=x[i + 1], bias=self.bias("b2", i),
-                        residual=y, row_ids=seq_flat, drop_p=p_drop, drop_seed=seed, drop_stream=12 + 4 * i, drop_step=step)
+                        residual=y, row_ids=seq_flat, drop_p=p_drop, drop_seed=seed, drop_stream=12 + 4 * i, drop_step=step,
+                        **nxt)
         fin_in = x[nb]
         if s.kind == "SRFR":      # last_conv H -> D (SRFR_model.py:123)
             ops.gemm_tn(x[nb], self.sh["wc"], out_bf16=ws["c"][:T], bias=self.bias("bc"))

@@ -80,8 +80,9 @@ def layernorm_bwd(dy, x, stats, w, dx, dw, db, add=None, row_ids=None, H=None):
 
 
 def gemm_tn(A, B, out_bf16=None, out_f32=None, bias=None, residual=None, gate=None, row_ids=None, relu=False,
-            drop_p=0.0, drop_seed=0, drop_stream=0, drop_step=None, M=None):
-    """out[M,N] = epilogue(A[M,K] @ B[N,K]^T)."""
+            drop_p=0.0, drop_seed=0, drop_stream=0, drop_step=None, M=None, ln_out=None, ln_w=None, ln_b=None, ln_eps=0.0,
+            ln_stats=None):
+    """out[M,N] = epilogue(A[M,K] @ B[N,K]^T); with ln_out also ln_out = LayerNorm(out) * ln_w + ln_b (+ ln_stats)."""
     _lib.require_device()
     M = A.shape[0] if M is None else M
     K = A.shape[1]
@@ -89,7 +90,8 @@ def gemm_tn(A, B, out_bf16=None, out_f32=None, bias=None, residual=None, gate=No
     out = out_bf16 if out_bf16 is not None else out_f32
     ep = GemmEpilogue(_p(bias), _p(residual), _p(gate), _p(row_ids), _p(out_bf16), _p(out_f32),
                       0 if residual is None else residual.stride(0), 0 if gate is None else gate.stride(0),
-                      out.stride(0), int(relu), float(drop_p), int(drop_stream), int(drop_seed), _p(drop_step))
+                      out.stride(0), int(relu), float(drop_p), int(drop_stream), int(drop_seed), _p(drop_step),
+                      _p(ln_out), _p(ln_w), _p(ln_b), _p(ln_stats), 0 if ln_out is None else ln_out.stride(0), float(ln_eps))
     call("srfrd_gemm_tn", _p(A), A.stride(0), _p(B), B.stride(0), M, N, K, C.byref(ep), _stream())
 
 

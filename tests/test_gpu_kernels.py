@@ -81,6 +81,30 @@ def test_gemm_wgrad(ops, T, Mo, No):
     torch.testing.assert_close(db, dY.float().sum(0), rtol=1e-3, atol=2e-3 * math.sqrt(T))
 
 
+@pytest.mark.parametrize("M,N,K,drop", [(300, 80, 80, 0.0), (20000, 80, 80, 0.0), (5000, 64, 64, 0.0), (3000, 96, 160, 0.0),
+                                        (4100, 80, 80, 0.3), (777, 128, 128, 0.0)])
+def test_gemm_tn_fused_layernorm(ops, M, N, K, drop):
+    """The LayerNorm folded into the residual GEMM's epilogue equals GEMM followed by the LayerNorm kernel."""
+    A, B = rnd((M, K), 50, dtype=bf16), rnd((N, K), 51, 0.2, bf16)
+    bias, res = rnd((N,), 52), rnd((M, N), 53, dtype=bf16)
+    w, b = rnd((N,), 54) * 0.3 + 1.0, rnd((N,), 55) * 0.1
+    ids = (torch.arange(M, device="cuda") % 7 != 0).long()
+    kw = dict(bias=bias, residual=res, row_ids=ids, drop_p=drop, drop_seed=99, drop_stream=3)
+    x_ref = torch.empty(M, N, dtype=bf16, device="cuda")
+    y_ref = torch.empty_like(x_ref)
+    st_ref = torch.empty(M, 2, device="cuda")
+    ops.gemm_tn(A, B, out_bf16=x_ref, **kw)
+    ops.layernorm_fwd(x_ref, w, b, 1e-8, y_bf16=y_ref, stats=st_ref)
+    x, y, st = torch.empty_like(x_ref), torch.empty_like(x_ref), torch.empty_like(st_ref)
+    ops.gemm_tn(A, B, out_bf16=x, ln_out=y, ln_w=w, ln_b=b, ln_eps=1e-8, ln_stats=st, **kw)
+    assert torch.equal(x, x_ref)
+    torch.testing.assert_close(st[:, 0], st_ref[:, 0], rtol=1e-4, atol=1e-5)
+    live = ids.bool()                                     # masked rows are all-zero: rstd = eps^-1/2 amplifies rounding noise
+    torch.testing.assert_close(st[live, 1], st_ref[live, 1], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(y.float(), y_ref.float(), rtol=1.6e-2, atol=1e-2)
+    assert float((y.float() - y_ref.float()).abs().mean()) < 1e-3
+
+
 # ------------------------------------------------------------------------------------------- K1
 @pytest.mark.parametrize("kind", ["SRFR", "SRFRN", "SRFU_B", "SRFU_F", "SRFU_R", "SASRec"])
 def test_embed_gather_bit_exact(ops, kind):
