@@ -21,6 +21,10 @@ def to_bytes(v, unit):
 
 
 traffic = {}
+try:                                     # keep entries of captures that are not being refreshed
+    traffic = json.load(open(os.path.join(root, "profiles", "traffic.json")))
+except Exception:
+    pass
 for name, key, match in [("gemm_tn", "srfrd_gemm_tn", "gemm_tn"), ("topk", "srfrd_catalogue_topk", "catalogue_"),
                          ("k1", "srfrd_embed_ln_fwd@C3", "embed_ln"), ("misc", None, "")]:
     rep = os.path.join(out, f"{tag}_{name}.ncu-rep")
