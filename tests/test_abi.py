@@ -45,10 +45,27 @@ def test_python_bindings_match_header_arity(lib):
     lib.load()
 
 
-def test_struct_layouts_match_header(lib):
-    # sizes a C compiler gives the two structs in the header (LP64)
-    assert ctypes.sizeof(lib.GemmEpilogue) == 6 * 8 + 4 * 4 + 4 + 4 + 8 + 8
-    assert ctypes.sizeof(lib.CastDesc) == 56
+def test_struct_layouts_match_header(lib, tmp_path):
+    """sizeof / field offsets the C compiler gives the header's structs == the ctypes mirrors in _lib.py."""
+    import shutil
+    import subprocess
+    assert ctypes.sizeof(lib.GemmEpilogue) == 128 and ctypes.sizeof(lib.CastDesc) == 56      # LP64
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "layout.c"
+    src.write_text(
+        '#include <stddef.h>\n#include <stdio.h>\n#include "srfrd_b200.h"\n'
+        "int main(void) {\n"
+        '  printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(srfrd_gemm_epilogue_t), offsetof(srfrd_gemm_epilogue_t, ldc),\n'
+        "         offsetof(srfrd_gemm_epilogue_t, drop_seed), offsetof(srfrd_gemm_epilogue_t, ln_out_bf16),\n"
+        "         offsetof(srfrd_gemm_epilogue_t, ln_eps), sizeof(srfrd_cast_desc_t));\n  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run(["gcc", "-I", inc, str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    G = lib.GemmEpilogue
+    assert got == [ctypes.sizeof(G), G.ldc.offset, G.drop_seed.offset, G.ln_out_bf16.offset, G.ln_eps.offset,
+                   ctypes.sizeof(lib.CastDesc)]
 
 
 def test_no_cpu_fallback_without_device(lib):
