@@ -216,6 +216,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_expect_tx(v_full, opbytes);
         for (int kb = 0; kb < p.kblocks; ++kb)
           tma_load_2d(Vs + kb * OPB, &tmV, v_full, col0 + kb * 64, row0, SRFRD_EVICT_FIRST);
+        // (no L2 prefetch of the next item here: two CTAs per SM already overlap one item's loads with the other's
+        //  compute, and the extra live values spill at the 96-register cap that two CTAs per SM impose)
       }
       __syncwarp();
     }
@@ -436,6 +438,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           tma_load_2d(Ks + kb * OPB, &tmK, in_full, col0 + kb * 64, row0, SRFRD_EVICT_FIRST);
           tma_load_2d(Vs + kb * OPB, &tmV, in_full, col0 + kb * 64, row0, SRFRD_EVICT_FIRST);
           tma_load_2d(Ds + kb * OPB, &tmDO, in_full, col0 + kb * 64, row0, SRFRD_EVICT_FIRST);
+        }
+        if (!(p.debug & 256) && it + (int)gridDim.x < n_items) {        // next item's operands: HBM -> L2 while this one computes
+          const int itn = it + gridDim.x;
+          const int rown = (itn / p.heads) * p.spt * p.L, coln = (itn % p.heads) * p.hd;
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            tma_prefetch_l2_2d(&tmQ, coln + kb * 64, rown);
+            tma_prefetch_l2_2d(&tmK, coln + kb * 64, rown);
+            tma_prefetch_l2_2d(&tmV, coln + kb * 64, rown);
+            tma_prefetch_l2_2d(&tmDO, coln + kb * 64, rown);
+          }
         }
       }
       __syncwarp();
@@ -696,6 +708,7 @@ extern "C" int srfrd_attention_fwd(const void* q, int ldq, const void* k, const 
   p.o = (bf16*)o; p.ldo = ldo;
   p.tma_o = (heads == 1 || p.hd % 64 == 0) ? 1 : 0;
   { const char* dbg = getenv("SRFRD_ATTN_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+  { const char* l2 = getenv("SRFRD_L2_PREFETCH"); if (l2 && atoi(l2) == 0) p.debug |= 256; }   // bit 8: no L2 prefetch (backward)
   CUtensorMap tmQ, tmK, tmV, tmO;
   if (int rc = make_tmap_bf16_2d(&tmQ, q, p.T, H, ldq, TILE, 64)) return rc;
   if (int rc = make_tmap_bf16_2d(&tmK, k, p.T, H, ldkv, TILE, 64)) return rc;

@@ -188,6 +188,11 @@ __device__ __forceinline__ void mbar_wait3(uint64_t* a, uint32_t pa, uint64_t* b
 #define SRFRD_EVICT_FIRST 0x12F0000000000000ull
 #define SRFRD_EVICT_LAST 0x14F0000000000000ull
 
+// Ask the TMA unit to pull a box into L2 only (no shared memory, no barrier).  Issued one or more tiles ahead of the real
+// load, whose latency then is the L2 -> SM leg instead of an HBM round trip under load (~3 700 cycles measured).
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1,
                                             uint64_t hint) {
   asm volatile(

@@ -62,6 +62,7 @@ struct GemmShape {
   int kgroup;               // K blocks per pipeline stage / barrier (resident B, K <= 192: the whole K in one stage)
   int nacc;                 // TMEM accumulator stages: 4 x 128 columns when the tile is <= 128 wide, else 2 x 256
   int dynamic;              // draw tile ids from the atomic counter (experiment switch, see the producer warp)
+  int l2_prefetch;          // TMA-prefetch the residual / gate tile (and the next A tile) into L2 ahead of the real load
 };
 
 // Dynamic tile scheduler state (SRFRD_GEMM_DYNAMIC=1, off by default: no measured gain).  Per-CTA durations on identical
@@ -232,6 +233,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         if (++stage == s.stages) { stage = 0; phase ^= 1; }
       }
+      if (s.l2_prefetch && s.stages * s.kgroup < 2 * kblocks + 2 && t1 >= 0 && elect_one()) {   // shallow A pipeline (fused LN)
+        const int m1 = (t1 / s.n_tiles) * BLOCK_M;
+        for (int kb = 0; kb < kblocks; ++kb) tma_prefetch_l2_2d(&tmA, kb * BLOCK_K, m1);
+      }
+      __syncwarp();
       t = t1;
       t1 = __shfl_sync(0xffffffffu, fetched, 0);
       if (t1 >= total_tiles) t1 = -1;
@@ -311,6 +317,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int nblk = (min(s.block_n, s.N - n0) + 63) >> 6;
         const int set = n_local & 1;
         const uint32_t bph = set ? bph1 : bph0;
+        // The tile id is known several tiles before the set's buffer is free again: pull the tile into L2 now, so that the
+        // load issued once the buffer is free costs an L2 hit instead of an HBM round trip in the epilogue's chain.
+        if (s.l2_prefetch && elect_one())
+          for (int blk = 0; blk < nblk; ++blk) tma_prefetch_l2_2d(&tmAux, n0 + blk * 64, m0);
+        __syncwarp();
         mbar_wait(&bfree[set], bph ^ 1);                 // first tile of a set: passes at once (fresh barrier)
         if (elect_one()) {
           mbar_expect_tx(&xfull[set], nblk * EPI_BLK_BYTES);
@@ -738,6 +749,7 @@ extern "C" int srfrd_gemm_tn(const void* A, int lda, const void* B, int ldb, int
   SRFRD_REQUIRE(s.stages >= 2, "gemm_tn: tile does not fit shared memory");
   const size_t smem = (size_t)s.stages * (s.b_resident ? s.kgroup * A_STAGE_BYTES : stage_bytes) + fixed;
   { const char* d = getenv("SRFRD_GEMM_DYNAMIC"); s.dynamic = d ? atoi(d) : 0; }
+  { const char* l = getenv("SRFRD_L2_PREFETCH"); s.l2_prefetch = l ? atoi(l) : 1; }
   s.nacc = s.block_n <= 128 ? 4 : 2;
   { const char* a = getenv("SRFRD_GEMM_NACC"); if (a && atoi(a) == 2) s.nacc = 2; }
   static int next_slot = 0;
