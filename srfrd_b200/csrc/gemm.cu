@@ -63,6 +63,8 @@ struct GemmShape {
   int nacc;                 // TMEM accumulator stages: 4 x 128 columns when the tile is <= 128 wide, else 2 x 256
   int dynamic;              // draw tile ids from the atomic counter (experiment switch, see the producer warp)
   int l2_prefetch;          // TMA-prefetch the residual / gate tile (and the next A tile) into L2 ahead of the real load
+  int nbuf;                 // tile buffers: 2 (one per epilogue set) or 4 (two per set: residual prefetch and the TMA store's
+                            // read latency leave the epilogue's chain); tile n uses buffer n % nbuf
 };
 
 // Dynamic tile scheduler state (SRFRD_GEMM_DYNAMIC=1, off by default: no measured gain).  Per-CTA durations on identical
@@ -125,7 +127,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int a_stage_bytes = s.kgroup * A_STAGE_BYTES;
   uint8_t* smB = smA + s.stages * a_stage_bytes;         // [stages] or, resident, [kblocks]
   uint8_t* smBuf = smB + (s.b_resident ? kblocks : s.stages) * b_stage_bytes;   // [set][buf_blocks][16 KB]
-  uint8_t* smY = smBuf + 2 * s.buf_blocks * EPI_BLK_BYTES;   // LNF: [set][buf_blocks][16 KB] LayerNorm output staging
+  uint8_t* smY = smBuf + s.nbuf * s.buf_blocks * EPI_BLK_BYTES;   // LNF: [set][buf_blocks][16 KB] LayerNorm output staging
   float* sbias = reinterpret_cast<float*>(smY + (LNF ? 2 * s.buf_blocks * EPI_BLK_BYTES : 0));
   float* sln = sbias + MAX_BIAS;                             // LNF: weight [MAX_LN], bias [MAX_LN]
   float* sxch = sln + (LNF ? 2 * MAX_LN : 0);                // LNF: [set][half][128 rows] (sum, sum of squares)
@@ -134,9 +136,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty = bars + s.stages;
   uint64_t* tfull = bars + 2 * s.stages;
   uint64_t* tempty = tfull + 4;                          // [nacc <= 4] accumulator stages (tile tl uses stage tl % nacc)
-  uint64_t* xfull = tempty + 4;                          // [set] aux tile landed
-  uint64_t* bfree = xfull + 2;                           // [set] tile buffer free again (TMA store has read it)
-  uint64_t* sfull = bfree + 2;                           // [TN_RING] tile id published
+  uint64_t* xfull = tempty + 4;                          // [nbuf <= 4] aux tile landed
+  uint64_t* bfree = xfull + 4;                           // [nbuf] tile buffer free again (TMA store has read it)
+  uint64_t* sfull = bfree + 4;                           // [TN_RING] tile id published
   uint64_t* bres = sfull + TN_RING;                      // resident B landed
   int* ring = reinterpret_cast<int*>(bres + 1);          // [TN_RING] tile ids, -1 = no more tiles
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ring + TN_RING);
@@ -154,7 +156,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (LNF) tma_prefetch_desc(&tmLn);
     }
     if (lane < s.stages) { mbar_init(&full[lane], 1); mbar_init(&empty[lane], 1); }
-    if (lane >= 8 && lane < 10) {
+    if (lane >= 8 && lane < 12) {
       const int i = lane - 8;
       mbar_init(&xfull[i], 1); mbar_init(&bfree[i], 1);
     }
@@ -308,29 +310,27 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 18) {
     if (AUX) {
-      uint32_t bph0 = 0, bph1 = 0;                       // parity of the bfree phase each set's NEXT load waits for
       for (int n_local = 0;; ++n_local) {
         mbar_wait(&sfull[n_local & (TN_RING - 1)], (n_local / TN_RING) & 1);
         const int t = ring[n_local & (TN_RING - 1)];
         if (t < 0) break;
         const int m0 = (t / s.n_tiles) * BLOCK_M, n0 = (t % s.n_tiles) * s.block_n;
         const int nblk = (min(s.block_n, s.N - n0) + 63) >> 6;
-        const int set = n_local & 1;
-        const uint32_t bph = set ? bph1 : bph0;
-        // The tile id is known several tiles before the set's buffer is free again: pull the tile into L2 now, so that the
+        const int b = n_local % s.nbuf;
+        const uint32_t bph = (n_local / s.nbuf) & 1;       // use count of buffer b -> parity
+        // The tile id is known several tiles before the buffer is free again: pull the tile into L2 now, so that the
         // load issued once the buffer is free costs an L2 hit instead of an HBM round trip in the epilogue's chain.
         if (s.l2_prefetch && elect_one())
           for (int blk = 0; blk < nblk; ++blk) tma_prefetch_l2_2d(&tmAux, n0 + blk * 64, m0);
         __syncwarp();
-        mbar_wait(&bfree[set], bph ^ 1);                 // first tile of a set: passes at once (fresh barrier)
+        mbar_wait(&bfree[b], bph ^ 1);                   // first use of a buffer: passes at once (fresh barrier)
         if (elect_one()) {
-          mbar_expect_tx(&xfull[set], nblk * EPI_BLK_BYTES);
+          mbar_expect_tx(&xfull[b], nblk * EPI_BLK_BYTES);
           for (int blk = 0; blk < nblk; ++blk)
-            tma_load_2d(smBuf + (set * s.buf_blocks + blk) * EPI_BLK_BYTES, &tmAux, &xfull[set], n0 + blk * 64, m0,
+            tma_load_2d(smBuf + (b * s.buf_blocks + blk) * EPI_BLK_BYTES, &tmAux, &xfull[b], n0 + blk * 64, m0,
                         SRFRD_EVICT_FIRST);
         }
         __syncwarp();
-        if (set) bph1 ^= 1; else bph0 ^= 1;
       }
     }
   } else if (warp < 16) {
@@ -338,9 +338,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int r = quarter * 32 + lane;                   // row inside the tile == TMEM lane
     const bool issuer = (quarter == 0) && (half == 0) && (lane == 0);
     const bool stamp = (quarter == 0) && (half == 0);
-    uint8_t* buf = smBuf + set * s.buf_blocks * EPI_BLK_BYTES;
     const bool use_buf = AUX || s.tma_out;
-    uint32_t tph = 0;                                    // parity for this set's xfull / bfree
+    int pending_b = -1;                                  // issuer, nbuf == 4: buffer whose TMA store may still be reading
     if (DROP) e.drop_seed = mix_seed(e.drop_seed, e.drop_step);
     const float relu_floor = e.relu ? 0.f : -INFINITY;
     for (int n_local = set;; n_local += 2) {             // tiles alternate between the sets
@@ -358,8 +357,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // accumulator ready AND (aux tile landed, which implies the buffer was free | previous store has read the buffer)
       const int as = n_local % s.nacc;
       const uint32_t aph = (n_local / s.nacc) & 1;
-      if (AUX) mbar_wait2(&tfull[as], aph, &xfull[set], tph);
-      else if (s.tma_out) mbar_wait2(&tfull[as], aph, &bfree[set], tph ^ 1);
+      const int b = n_local % s.nbuf;                    // tile buffer (nbuf even: a buffer always belongs to one set)
+      const uint32_t tph = (n_local / s.nbuf) & 1;       // its use count -> parity
+      uint8_t* buf = smBuf + b * s.buf_blocks * EPI_BLK_BYTES;
+      if (AUX) mbar_wait2(&tfull[as], aph, &xfull[b], tph);
+      else if (s.tma_out) mbar_wait2(&tfull[as], aph, &bfree[b], tph ^ 1);
       else mbar_wait(&tfull[as], aph);
       tc_fence_after();
       if (stamp) TN_STAMP(5, n_local);
@@ -474,23 +476,39 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               bulk_commit();
               bulk_wait_read<0>();                       // both stores have read their buffers
             }
-            mbar_arrive(&bfree[set]);
+            mbar_arrive(&bfree[b]);
           }
           __syncwarp();
         } else {
         if (issuer) {
-          if (s.tma_out && s.debug != 1) {
-            for (int blk = 0; blk < nblk; ++blk) tma_store_2d(&tmOut, buf + blk * EPI_BLK_BYTES, n0 + blk * 64, m0);
-            bulk_commit();
-            bulk_wait_read<0>();                         // smem has been read: the buffer may be refilled
+          if (s.nbuf == 4 && s.tma_out) {
+            // two buffers per set: do not wait for THIS store to read its buffer (1 300 - 1 800 cycles, during which the
+            // whole set would stand at its next named barrier); the set's previous store has long finished -- release
+            // that buffer now.  It is next needed four tiles after its use, i.e. by the set's tile after next.
+            if (s.debug != 1) {
+              for (int blk = 0; blk < nblk; ++blk) tma_store_2d(&tmOut, buf + blk * EPI_BLK_BYTES, n0 + blk * 64, m0);
+              bulk_commit();
+              if (pending_b >= 0) bulk_wait_read<1>();   // all but the newest group have read their source
+            }
+            if (pending_b >= 0) mbar_arrive(&bfree[pending_b]);
+            pending_b = b;
+          } else {
+            if (s.tma_out && s.debug != 1) {
+              for (int blk = 0; blk < nblk; ++blk) tma_store_2d(&tmOut, buf + blk * EPI_BLK_BYTES, n0 + blk * 64, m0);
+              bulk_commit();
+              bulk_wait_read<0>();                       // smem has been read: the buffer may be refilled
+            }
+            mbar_arrive(&bfree[b]);
           }
-          mbar_arrive(&bfree[set]);
         }
         __syncwarp();
         }
       }
       if (stamp) TN_STAMP(9, n_local);
-      tph ^= 1;
+    }
+    if (issuer && pending_b >= 0) {                      // smem must outlive the last store's read
+      bulk_wait_read<0>();
+      mbar_arrive(&bfree[pending_b]);
     }
   }
   tc_fence_before();
@@ -730,7 +748,15 @@ extern "C" int srfrd_gemm_tn(const void* A, int lda, const void* B, int ldb, int
                   "gemm_tn: fused LayerNorm needs a residual, a bf16 output, one column tile (N=%d) and ln_w / ln_b", N);
     SRFRD_REQUIRE(ep->ld_ln % 8 == 0 && ep->ld_ln >= N && (((uintptr_t)ep->ln_out_bf16 & 15) == 0), "gemm_tn: bad ln_out");
   }
-  int fixed = 1024 + (lnf ? 4 : 2) * s.buf_blocks * EPI_BLK_BYTES + MAX_BIAS * 4 + (lnf ? 2 * MAX_LN * 4 + 2 * 2 * BLOCK_M * 2 * 4 : 0) + 1024;
+  // residual / gate tiles without the LayerNorm fusion: two tile buffers per set when a two-stage A pipeline still fits
+  s.nbuf = 2;
+  if (s.has_aux && s.tma_out && !lnf && s.n_tiles == 1) {
+    const int kb_h = (K + BLOCK_K - 1) / BLOCK_K;
+    const int need = 1024 + 4 * s.buf_blocks * EPI_BLK_BYTES + MAX_BIAS * 4 + 1024 + kb_h * b_stage_bytes + 2 * kb_h * A_STAGE_BYTES;
+    if (need <= 227 * 1024 && kb_h * b_stage_bytes <= 48 * 1024) s.nbuf = 4;
+    { const char* nb = getenv("SRFRD_GEMM_NBUF"); if (nb && atoi(nb) == 2) s.nbuf = 2; }
+  }
+  int fixed = 1024 + (lnf ? 4 : s.nbuf) * s.buf_blocks * EPI_BLK_BYTES + MAX_BIAS * 4 + (lnf ? 2 * MAX_LN * 4 + 2 * 2 * BLOCK_M * 2 * 4 : 0) + 1024;
   // B (the weight matrix) is identical for every row tile: with one column tile and few K blocks it is loaded once
   const int kblocks_h = (K + BLOCK_K - 1) / BLOCK_K;
   s.b_resident = (s.n_tiles == 1 && kblocks_h * b_stage_bytes <= 48 * 1024) ? 1 : 0;
@@ -739,7 +765,7 @@ extern "C" int srfrd_gemm_tn(const void* A, int lda, const void* B, int ldb, int
   if (s.b_resident) {
     fixed += kblocks_h * b_stage_bytes;
     // the whole K of a tile in one stage (one barrier round trip per tile instead of one per K block) while >= 3 fit
-    if ((227 * 1024 - fixed) / (kblocks_h * A_STAGE_BYTES) >= (lnf ? 2 : 3)) s.kgroup = kblocks_h;
+    if ((227 * 1024 - fixed) / (kblocks_h * A_STAGE_BYTES) >= ((lnf || s.nbuf == 4) ? 2 : 3)) s.kgroup = kblocks_h;
     { const char* g = getenv("SRFRD_GEMM_KGROUP"); if (g && atoi(g) == 0) s.kgroup = 1; }
     s.stages = (227 * 1024 - fixed) / (s.kgroup * A_STAGE_BYTES);
   } else {
