@@ -131,6 +131,8 @@ def algorithmic_bytes(name, a, valid_frac):
         ep = a[7]._obj
         b = M * K * 2 + N * K * 2 + M * N * (2 if ep.out_bf16 else 4)
         b += (M * N * 2 if ep.residual else 0) + (M * N * 2 if ep.gate else 0) + (M * 8 if ep.row_ids else 0)
+        if ep.ln_out_bf16:                       # fused LayerNorm: its output and (mean, rstd) are extra stores
+            b += M * N * 2 + (M * 8 if ep.ln_stats else 0)
         return b, 2.0 * M * N * K
     if name == "srfrd_gemm_wgrad":
         T, Mo, No = a[4], a[5], a[6]
