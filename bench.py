@@ -319,6 +319,12 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(sample_steps=10)          # ~10 s of host work
+    eager = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            eager = gpu_eager_baseline(dev)          # the same arithmetic as stock PyTorch eager on this GPU (informative)
+        except Exception as ex:                      # a baseline must never take the product's line down
+            eager = dict(unavailable=str(ex)[:200])
 
     if rank == 0:
         line = dict(metric=METRIC, value=round(value, 1), unit="seqs/s", n_gpus=world, steps=args.steps, warmup=W,
@@ -337,6 +343,8 @@ def run_ours(args):
             line["gather"] = gat
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if eager is not None:
+            line["gpu_eager_baseline"] = eager
         print(json.dumps(line), flush=True)
     if world > 1:
         # Tear down without dist.destroy_process_group(): with the NCCL all-reduce captured inside live CUDA graphs the
@@ -445,6 +453,32 @@ def cpu_baseline(sample_steps=2, batch=None):
     return dict(value=round(B * sample_steps / dt, 1), unit="seqs/s", cores=cores, kind="port",
                 sample=f"{sample_steps} steps of batch {B} (C2 workload, fp32, dropout 0.0, soft discriminator weights), "
                        f"torch {torch.__version__} CPU with {cores} threads", seconds=round(dt, 2))
+
+
+def gpu_eager_baseline(dev, sample_steps=10):
+    """SURVEY 8(d) / BASELINE.md 3.4 'the honest bar': the reference's arithmetic (oracle port) as stock PyTorch eager fp32
+    on the SAME B200 (cuBLAS / cuDNN / ATen kernels; the reference ships no GPU kernel of its own), C2 batches resident on
+    the device.  A reported baseline like cpu_baseline: nothing of the product runs here."""
+    from oracle import srfrd_oracle as O
+    from srfrd_b200 import synth
+    c = CFG
+    B = c["batch"]
+    data = synth.make_interactions(1236, c["usernum"], c["itemnum"], 5, 4.0, c["L"])
+    sd = {k: v.to(dev) for k, v in O.init_state_dict("SRFR", c["itemnum"], c["L"], c["D"], c["F"], 0, c["blocks"], seed=1236).items()}
+    orc = O.OracleTrainer(sd, "SRFR", 1)
+    smp = synth.BatchSampler(data, c["L"], seed=100)
+    batches = [{k: torch.from_numpy(v).to(dev) for k, v in smp.next_batch(B).items()} for _ in range(4)]
+    ws = [O.discriminator_weights(b["pos"], b["p_fake"], "soft") for b in batches]
+    for i in range(3):
+        orc.step(batches[i % 4], ws[i % 4])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(sample_steps):
+        orc.step(batches[i % 4], ws[i % 4])      # float(loss) inside: one D2H sync per step, as trainer.py:39 does
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return dict(value=round(B * sample_steps / dt, 1), unit="seqs/s", kind="oracle port, PyTorch eager fp32 on this GPU",
+                sample=f"{sample_steps} steps of batch {B}, batches resident on the device", ms_per_step=round(dt / sample_steps * 1e3, 3))
 
 
 def run_reference(args):

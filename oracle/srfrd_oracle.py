@@ -120,15 +120,15 @@ def embed(sd: Dict[str, Tensor], kind: str, input_ids: Tensor, fake_ids: Optiona
     ik, pk = _emb_keys(kind)
     E, P = sd[ik], sd[pk]
     B, L = input_ids.shape
-    x = E[input_ids.long()]
+    x = F.embedding(input_ids.long(), E, padding_idx=0)      # nn.Embedding(..., padding_idx=0), SRFR_model.py:10
     if kind == "SASRec":
         x = x * (E.shape[1] ** 0.5)
-    x = x + P[torch.arange(L)].unsqueeze(0)
+    x = x + P[torch.arange(L, device=P.device)].unsqueeze(0)
     if kind in ("SRFR", "SRFRN"):
         Fe = sd["embedding_layer.fake_embed.weight"]
         if fake_ids is None:
-            fake_ids = torch.zeros(B, L, dtype=torch.long)
-        x = torch.cat([x, Fe[fake_ids.long()]], dim=2)
+            fake_ids = torch.zeros(B, L, dtype=torch.long, device=E.device)
+        x = torch.cat([x, F.embedding(fake_ids.long(), Fe, padding_idx=0)], dim=2)       # SRFR_model.py:11
     elif kind.startswith("SRFU"):
         Ul = sd["embedding_layer.user_label_embed.weight"]
         lab = srfu_labels(kind, fake_ids).long().view(B, 1)
@@ -154,7 +154,7 @@ def attention(q: Tensor, k: Tensor, v: Tensor, num_heads: int) -> Tensor:
     kh = k.view(B, L, num_heads, hd).transpose(1, 2)
     vh = v.view(B, L, num_heads, hd).transpose(1, 2)
     s = qh @ kh.transpose(-1, -2)
-    causal = torch.ones(L, L, dtype=torch.bool).tril()
+    causal = torch.ones(L, L, dtype=torch.bool, device=s.device).tril()
     s = s.masked_fill(~causal, float("-inf"))
     a = torch.softmax(s, dim=-1)
     o = a @ vh
@@ -211,9 +211,9 @@ def target_rows(sd: Dict[str, Tensor], kind: str, ids: Tensor, fake_ids: Optiona
     """Rows the hidden state is dotted with: E[id] (SRFR :129-136, SRFU :516-525, SASRec :657-658)
     or E[id] || Fe[fake_id] for SRFRN (:225,:231)."""
     E = sd[_emb_keys(kind)[0]]
-    rows = E[ids.long()]
+    rows = F.embedding(ids.long(), E, padding_idx=0)         # the same nn.Embedding module is called (SRFR_model.py:129)
     if kind == "SRFRN":
-        rows = torch.cat([rows, sd["embedding_layer.fake_embed.weight"][fake_ids.long()]], dim=-1)
+        rows = torch.cat([rows, F.embedding(fake_ids.long(), sd["embedding_layer.fake_embed.weight"], padding_idx=0)], dim=-1)
     return rows
 
 
