@@ -2,12 +2,12 @@
 //
 //  gemm_tn   : C[M,N] = epilogue(A[M,K] * B[N,K]^T)   both operands K-major (row-major, K contiguous)
 //              forward linears (A = activations, B = weight (out,in)) and data-gradients
-//              (A = dY, B = W^T shadow).  Persistent CTAs, 128-row tiles, TMEM double buffering.
+//              (A = dY, B = W^T shadow).  Persistent CTAs, 128-row tiles, 640 threads (roles at the kernel), optional
+//              LayerNorm of the result row folded into the epilogue.
 //  gemm_wgrad: dW[Mo,No] += sum_t A[t,Mo] * B[t,No]   both operands MN-major (token index = K)
-//              weight gradients, split-K over tokens, fp32 red.add into the flat gradient buffer.
-//
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..5 = epilogue (TMEM lane quarter = warp_idx & 3).
+//              weight gradients, split-K over tokens, 16-byte vector red.add into the flat fp32 gradient buffer.
+//              192 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
+//              (TMEM lane quarter = warp_idx & 3).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -103,17 +103,22 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 // A / B tiles and the residual-or-gate ("aux") tile arrive by TMA, the bf16 result is written IN PLACE over the
 // aux tile (same thread, same 16-byte chunk) and leaves by TMA stores, so the epilogue threads only touch TMEM
 // and shared memory and nothing in the per-tile critical path waits on an HBM round trip.
-//   warps 0..7 / 8..15: epilogue set 0 / 1.  Set s owns accumulator stage s and tile buffer s (tiles alternate between
-//     the sets); warp (quarter q, half h) owns TMEM lanes [32q, 32q+32) and the 32-column chunks with chunk % 2 == h.
-//     Four epilogue warps per scheduler: measured, the epilogue is a chain of TMEM / barrier latencies, not bandwidth.
-//   warp 16: TMA producer for A/B   warp 17: TMEM allocator + MMA issuer   warp 18: TMA producer for aux
+//   warps 0..7 / 8..15: epilogue set 0 / 1 (tiles alternate between the sets).  Tile n uses accumulator stage n % nacc
+//     (4 x 128 TMEM columns for tiles <= 128 wide, else 2 x 256) and tile buffer n % nbuf (2, or 4 for residual / gate
+//     tiles: the store of a tile is then only waited for when the set issues its NEXT store).  Warp (quarter q, half h)
+//     owns TMEM lanes [32q, 32q+32) and the 32-column chunks with chunk % 2 == h.  Four epilogue warps per scheduler:
+//     measured, the epilogue is a chain of TMEM / barrier latencies, not bandwidth.
+//   warp 16: TMA producer for A (and B: loaded once and kept when there is one column tile and K <= 192, else per stage);
+//            publishes the tile ids in a small ring (static round-robin order; an atomic counter behind a switch)
+//   warp 17: TMEM allocator + MMA issuer   warp 19: second MMA issuer (alternate tiles) when a stage holds a tile's whole K
+//   warp 18: TMA producer for the aux tile, L2-prefetched as soon as the tile id is known
 //     The control warps have the HIGHEST warp ids: the scheduler favours high ids, and with low ids the MMA issuer
 //     took ~700 cycles to issue five MMAs while the epilogue warps of its scheduler were busy (clock64 timeline).
 // AUX: 0 none, 1 residual (v += aux), 2 gate (v = aux > 0 ? v : 0).  bias / ReLU / row mask are branch-free.
-// LNF: the LayerNorm that follows the residual add is computed in the epilogue.  After the set's named barrier the whole
-// row (one column tile) sits in the set's staging buffer as bf16 -- exactly what the separate LayerNorm kernel would read
-// back from HBM -- so every thread re-reads its row from shared memory for the statistics (both warps of a row compute
-// them redundantly: no exchange), normalises its own chunks into a second staging buffer and a second TMA store writes it.
+// LNF: the LayerNorm that follows the residual add is computed in the epilogue.  While packing its columns to bf16 a
+// thread accumulates sum and sum of squares of the ROUNDED values (what a separate LayerNorm kernel would read back);
+// the two warps of a row exchange them through shared memory at the set's named barrier; each thread then re-reads its
+// own chunks from the staging buffer, normalises them into a second staging buffer and a second TMA store writes it.
 template <int AUX, bool DROP, bool LNF>
 __global__ void __launch_bounds__(TN_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
