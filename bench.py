@@ -9,7 +9,12 @@ Adam) of the reference SRFR model on Beauty-shaped synthetic data, config C2 of 
 22 363 users, 12 101 items, maxlen 50, D=64, F=16, 2 blocks, batch 4096 per GPU (weak scaling).
 `value` = global sequences / second with the batch already resident in HBM; `e2e` = the same step driven
 through FusedTrainer.step() from pinned HOST batches (H2D copies + a D2H read of the loss every step).
-A second object, "catalogue", reports full-catalogue top-10 users/s (C3: 1 M items, row-sharded).
+A second object, "catalogue", reports full-catalogue top-10 users/s (C3: 1 M items, row-sharded); "gather" reports K1
+at catalogue scale against the HBM roofline.  `roofline` = the dominant kernel's algorithmic bytes per launch / its
+event-timed launch duration, `roofline.traffic` = its DRAM bytes per launch from the committed ncu capture
+(profiles/traffic.json); `clocks` = NVML samples taken every 2 ms DURING the timed region.  Baselines on rank 0 at N = 1
+only: `cpu_baseline` (the reference's arithmetic, oracle port, on the host cores) and `gpu_eager_baseline` (the same as
+stock PyTorch eager fp32 on this GPU).  Nothing of the product runs in either baseline.
 """
 import argparse
 import json
