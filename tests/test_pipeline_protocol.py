@@ -1,0 +1,366 @@
+"""CPU model check of gemm_tn's intra-CTA pipeline protocol (srfrd_b200/csrc/gemm.cu, gemm_tn_kernel).
+
+The kernel's warps talk through mbarriers whose waits are PARITY waits: a wait for "the phase with parity p" passes as soon
+as the barrier's most recently completed phase has parity p -- also when that is the phase BEFORE the one the waiter meant
+(two phases behind) or two phases after it.  DESIGN.md section 5 states the rule the kernel is built on ("no waiter ever
+skips a phase"); this test transcribes every warp role's loop (producer + tile-id ring, one or two MMA issuers, aux
+producer, two epilogue sets with 2 or 4 tile buffers and the deferred store-read wait) into coroutines over simulated
+barriers and runs them under random interleavings and random completion delays of the asynchronous operations
+(TMA loads, tcgen05.commit arrivals, TMA store reads).  It asserts
+  * every wait passes on exactly the phase it was written for (no aliasing, no skipped phase),
+  * a tile-id ring entry is never overwritten before every reader has consumed it,
+  * a tile buffer is never reloaded / rewritten while a TMA store may still read it,
+  * all roles terminate (no deadlock) and every tile is processed exactly once, in order, by each role.
+No GPU, no product code is executed: this is a model of the protocol, kept next to the kernel it mirrors.
+"""
+import random
+
+import pytest
+
+RING = 16
+
+
+class MBar:
+    """mbarrier with an arrival count and a transaction count; `phase` = number of completed phases."""
+
+    def __init__(self, count):
+        self.count, self.arrived, self.tx, self.phase = count, 0, 0, 0
+
+    def _maybe_complete(self):
+        if self.arrived == self.count and self.tx == 0:
+            self.arrived = 0
+            self.phase += 1
+
+    def arrive(self, n=1):
+        self.arrived += n
+        assert self.arrived <= self.count, "more arrivals than the barrier expects"
+        self._maybe_complete()
+
+    def arrive_expect_tx(self, ntx):
+        self.tx += ntx
+        self.arrive()
+
+    def complete_tx(self):
+        self.tx -= 1
+        self._maybe_complete()
+
+    def passes(self, parity):
+        # try_wait.parity: true iff the most recently completed phase has this parity (fresh barrier: parity 1 passes)
+        return ((self.phase - 1) & 1) == parity
+
+
+class Sim:
+    def __init__(self, seed, T, kblocks, stages, kgroup, nacc, nbuf, aux, lnf, max_delay=6):
+        self.rng = random.Random(seed)
+        self.T, self.kblocks, self.stages, self.kgroup, self.nacc, self.nbuf = T, kblocks, stages, kgroup, nacc, nbuf
+        self.aux, self.lnf, self.max_delay = aux, lnf, max_delay
+        self.merged = kgroup >= kblocks
+        self.two = self.merged and stages % 2 == 0
+        self.full = [MBar(1) for _ in range(stages)]
+        self.empty = [MBar(1) for _ in range(stages)]
+        self.tfull = [MBar(1) for _ in range(4)]
+        self.tempty = [MBar(8) for _ in range(4)]
+        self.xfull = [MBar(1) for _ in range(4)]
+        self.bfree = [MBar(1) for _ in range(4)]
+        self.sfull = [MBar(1) for _ in range(RING)]
+        self.ring = [None] * RING
+        self.events = []            # (due_step, seq, fn)
+        self.step_no = 0
+        self.seq = 0
+        self.progress = {}          # reader name -> number of ring entries consumed
+        self.buf_busy = [0] * 4     # outstanding TMA store reads per tile buffer
+        self.done_tiles = {"mma": [], "epi": [], "aux": []}
+
+    # ---- asynchronous completions ------------------------------------------------------------------
+    def later(self, fn, after=None):
+        due = self.step_no + (after if after is not None else self.rng.randint(1, self.max_delay))
+        self.seq += 1
+        self.events.append((due, self.seq, fn))
+
+    def wait(self, bar, parity, intended):
+        """generator: spin until the parity wait passes, then check it passed on the intended phase"""
+        while not bar.passes(parity):
+            yield
+        assert bar.phase == intended + 1, f"wait meant phase {intended}, barrier has completed {bar.phase} phases"
+
+    def read_ring(self, who, idx):
+        yield from self.wait(self.sfull[idx % RING], (idx // RING) & 1, idx // RING)
+        t = self.ring[idx % RING]
+        self.progress[who] = idx + 1
+        return t
+
+    # ---- warp 16: producer + tile ids ----------------------------------------------------------------
+    def producer(self):
+        stage, phase, uses = 0, 0, [0] * self.stages
+        for tl in range(self.T + 1):
+            t = tl if tl < self.T else -1
+            for j in ([tl, tl + 1] if t < 0 else [tl]):
+                if j >= RING:                     # about to overwrite entry j - RING: every reader must be past it
+                    for who, n in self.progress.items():
+                        if who in self.readers_of(j - RING):
+                            assert n > j - RING, f"ring entry {j - RING} overwritten before {who} read it"
+                self.ring[j % RING] = t
+                self.sfull[j % RING].arrive()
+            if t < 0:
+                return
+            for kb in range(0, self.kblocks, self.kgroup):
+                yield from self.wait(self.empty[stage], phase ^ 1, uses[stage] - 1)
+                n = min(self.kgroup, self.kblocks - kb)
+                bar = self.full[stage]
+                bar.arrive_expect_tx(n)
+                for _ in range(n):
+                    self.later(bar.complete_tx)
+                uses[stage] += 1
+                stage += 1
+                if stage == self.stages:
+                    stage, phase = 0, phase ^ 1
+            yield
+
+    def readers_of(self, idx):
+        r = {"mma%d" % (idx & 1 if self.two else 0), "epi%d" % (idx & 1)}
+        if self.aux:
+            r.add("aux")
+        return r
+
+    # ---- warps 17 / 19: MMA issuers -------------------------------------------------------------------
+    def issuer(self, p):
+        who = "mma%d" % p
+        step = 2 if self.two else 1
+        commits = []                              # in-order completion of this thread's commits
+
+        def commit(bar):
+            commits.append(bar)
+            delay = self.rng.randint(1, self.max_delay)
+
+            def fire():
+                # commits of one thread complete in issue order
+                while commits and commits[0] is not bar:
+                    return self.later(fire, 1)
+                commits.pop(0)
+                bar.arrive()
+            self.later(fire, delay)
+
+        t = yield from self.read_ring(who, p)
+        stage, phase = (p if self.two else 0), 0
+        uses = [0] * self.stages
+        tl = p
+        while t >= 0:
+            a, aph = tl % self.nacc, (tl // self.nacc) & 1
+            nx = tl + step
+            if self.merged:
+                t_next = yield from self.read_ring(who, nx)
+            yield from self.wait(self.tempty[a], aph ^ 1, tl // self.nacc - 1)
+            for kb in range(0, self.kblocks, self.kgroup):
+                yield from self.wait(self.full[stage], phase, uses[stage])
+                uses[stage] += 1
+                yield                                 # MMA issue
+                commit(self.empty[stage])
+                if kb + self.kgroup >= self.kblocks:
+                    commit(self.tfull[a])
+                if self.two:
+                    stage += 2
+                    if stage >= self.stages:
+                        stage, phase = stage - self.stages, phase ^ 1
+                else:
+                    stage += 1
+                    if stage == self.stages:
+                        stage, phase = 0, phase ^ 1
+            self.done_tiles["mma"].append(t)
+            if not self.merged:
+                t_next = yield from self.read_ring(who, nx)
+            t = t_next
+            tl += step
+
+    # ---- warp 18: aux producer ------------------------------------------------------------------------
+    def aux_warp(self):
+        n = 0
+        while True:
+            t = yield from self.read_ring("aux", n)
+            if t < 0:
+                return
+            b = n % self.nbuf
+            yield from self.wait(self.bfree[b], ((n // self.nbuf) & 1) ^ 1, n // self.nbuf - 1)
+            assert self.buf_busy[b] == 0, "aux tile loaded into a buffer a TMA store may still be reading"
+            bar = self.xfull[b]
+            bar.arrive_expect_tx(2)
+            self.later(bar.complete_tx)
+            self.later(bar.complete_tx)
+            self.done_tiles["aux"].append(t)
+            n += 1
+            yield
+
+    # ---- warps 0..15: one coroutine per epilogue set ----------------------------------------------------
+    def epilogue(self, s):
+        who = "epi%d" % s
+        reads = []                                # this issuer thread's outstanding bulk groups, oldest first: (buffers)
+        pending_b = -1
+
+        def store(bufs):
+            grp = {"bufs": bufs, "done": False}
+            reads.append(grp)
+            for b in bufs:
+                self.buf_busy[b] += 1
+
+            def fire():
+                if reads and reads[0] is not grp and not reads[0]["done"] and grp in reads and reads.index(grp) > 0 \
+                        and not all(g["done"] for g in reads[:reads.index(grp)]):
+                    return self.later(fire, 1)    # bulk groups complete in order
+                grp["done"] = True
+                for b in grp["bufs"]:
+                    self.buf_busy[b] -= 1
+            self.later(fire)
+            return grp
+
+        def wait_read(keep):
+            """cp.async.bulk.wait_group.read keep: all but the `keep` newest groups have been read"""
+            while True:
+                while reads and reads[0]["done"]:
+                    reads.pop(0)
+                if len(reads) <= keep:
+                    return
+                yield
+
+        n = s
+        while True:
+            t = yield from self.read_ring(who, n)
+            if t < 0:
+                break
+            a, aph = n % self.nacc, (n // self.nacc) & 1
+            b, tph = n % self.nbuf, (n // self.nbuf) & 1
+            yield from self.wait(self.tfull[a], aph, n // self.nacc)
+            if self.aux:
+                yield from self.wait(self.xfull[b], tph, n // self.nbuf)
+            else:
+                yield from self.wait(self.bfree[b], tph ^ 1, n // self.nbuf - 1)
+            assert self.buf_busy[b] == 0, "epilogue writes a tile buffer a TMA store may still be reading"
+            yield                                     # TMEM -> registers -> smem
+            self.tempty[a].arrive(8)
+            yield                                     # named barrier of the set
+            if self.lnf:
+                store([b])                            # x
+                yield                                 # LayerNorm into the second staging buffer, second named barrier
+                store([])                             # y (its own buffer, not modelled)
+                yield from wait_read(0)
+                self.bfree[b].arrive()
+            elif self.nbuf == 4:
+                store([b])
+                if pending_b >= 0:
+                    yield from wait_read(1)
+                    self.bfree[pending_b].arrive()
+                pending_b = b
+            else:
+                store([b])
+                yield from wait_read(0)
+                self.bfree[b].arrive()
+            self.done_tiles["epi"].append(t)
+            n += 2
+        if pending_b >= 0:
+            yield from wait_read(0)
+            self.bfree[pending_b].arrive()
+
+    # ---- scheduler --------------------------------------------------------------------------------------
+    def run(self, max_steps=200000):
+        procs = {"producer": self.producer(), "mma0": self.issuer(0), "epi0": self.epilogue(0), "epi1": self.epilogue(1)}
+        if self.two:
+            procs["mma1"] = self.issuer(1)
+        if self.aux:
+            procs["aux"] = self.aux_warp()
+        for k in procs:
+            if k != "producer":
+                self.progress[k] = 0
+        while procs:
+            self.step_no += 1
+            assert self.step_no < max_steps, f"deadlock / livelock: {sorted(procs)} still running"
+            due = [e for e in self.events if e[0] <= self.step_no]
+            self.events = [e for e in self.events if e[0] > self.step_no]
+            for _, _, fn in sorted(due, key=lambda e: (e[0], e[1])):
+                fn()
+            name = self.rng.choice(sorted(procs))
+            try:
+                next(procs[name])
+            except StopIteration:
+                del procs[name]
+        # drain outstanding asynchronous work
+        while self.events:
+            self.step_no += 1
+            due = [e for e in self.events if e[0] <= self.step_no]
+            self.events = [e for e in self.events if e[0] > self.step_no]
+            for _, _, fn in sorted(due, key=lambda e: (e[0], e[1])):
+                fn()
+        tiles = list(range(self.T))
+        assert sorted(self.done_tiles["mma"]) == tiles and sorted(self.done_tiles["epi"]) == tiles
+        if self.aux:
+            assert self.done_tiles["aux"] == tiles
+        assert all(v == 0 for v in self.buf_busy)
+
+
+def host_config(kblocks, aux, lnf, narrow=True):
+    """the combinations srfrd_gemm_tn's host code can produce (gemm.cu, srfrd_gemm_tn)"""
+    out = []
+    for stages in (2, 3, 4, 5, 6):
+        for kgroup in {1, kblocks}:
+            for nacc in ((4,) if narrow else (2,)):
+                for nbuf in ((2, 4) if (aux and not lnf) else (2,)):
+                    out.append(dict(stages=stages, kgroup=kgroup, nacc=nacc, nbuf=nbuf))
+    return out
+
+
+@pytest.mark.parametrize("kblocks", [1, 2, 3, 5])
+@pytest.mark.parametrize("aux,lnf", [(False, False), (True, False), (True, True)])
+def test_gemm_tn_pipeline_protocol(kblocks, aux, lnf):
+    n = 0
+    for narrow in (True, False):
+        for cfg in host_config(kblocks, aux, lnf, narrow):
+            for T in (1, 2, 3, 5, 11, 23, 40):
+                for seed in range(3):
+                    Sim(seed * 7919 + T, T, kblocks, aux=aux, lnf=lnf, max_delay=(2 if seed == 0 else 9), **cfg).run()
+                    n += 1
+    assert n > 100
+
+
+def test_model_detects_a_skipped_phase():
+    """the checker itself: a consumer that falls two phases behind a count-1 barrier is reported"""
+    sim = Sim(0, 1, 1, 2, 1, 4, 2, False, False)
+    bar = MBar(1)
+    bar.arrive()
+    bar.arrive()
+    bar.arrive()                                   # three phases completed; the waiter meant phase 0 (parity 0)
+    g = sim.wait(bar, 0, 0)
+    with pytest.raises(AssertionError, match="meant phase 0"):
+        next(g)
+
+
+def _flags(make, runs=8):
+    n = 0
+    for seed in range(runs):
+        try:
+            make(seed).run(max_steps=20000)
+        except AssertionError:
+            n += 1
+    return n
+
+
+def test_model_flags_a_ring_that_is_too_small(monkeypatch):
+    """producer up to `stages` tiles ahead of the MMAs + `nacc` accumulators ahead of the epilogues needs > 4 entries"""
+    import sys
+    monkeypatch.setattr(sys.modules[__name__], "RING", 4)
+    assert _flags(lambda seed: Sim(seed, 23, 1, stages=6, kgroup=1, nacc=4, nbuf=2, aux=False, lnf=False)) == 8
+
+
+def test_model_flags_two_issuers_on_an_odd_stage_count():
+    """the kernel only enables the second issuer when stages % 2 == 0: with 3 stages the issuers would share barriers"""
+    def make(seed):
+        sim = Sim(seed, 23, 2, stages=3, kgroup=2, nacc=4, nbuf=2, aux=True, lnf=False)
+        sim.two = True
+        return sim
+    assert _flags(make) == 8
+
+
+def test_model_flags_the_lookahead_deadlock():
+    """the bug found on the GPU this round: reading the NEXT ring entry before issuing a tile whose K blocks outnumber the
+    pipeline stages deadlocks (the producer needs the tile's first stages back before it can publish the next id)"""
+    def make(seed):
+        sim = Sim(seed, 5, 5, stages=3, kgroup=1, nacc=2, nbuf=2, aux=False, lnf=False)
+        sim.merged = True                          # forces the early ring read of the merged path
+        return sim
+    assert _flags(make) == 8
