@@ -105,6 +105,11 @@ typedef struct {
 /* C[M,N] = epilogue(A[M,K] . B[N,K]^T), A and B bf16 K-major. */
 SRFRD_API int srfrd_gemm_tn(const void* A_bf16, int lda, const void* B_bf16, int ldb, int M, int N, int K,
                   const srfrd_gemm_epilogue_t* ep, void* stream);
+/* The tile / pipeline plan srfrd_gemm_tn would use for a shape, without launching anything (no device needed): out[11] =
+ * {block_n, n_tiles, stages, kgroup (K blocks per stage), b_resident, nacc (TMEM accumulator stages), nbuf (tile buffers),
+ *  buf_blocks, dynamic shared memory bytes, second MMA issuer active, K blocks}.  Used by the CPU tests to check the host
+ * logic for every shape and to feed the pipeline-protocol model check with the real configurations. */
+SRFRD_API int srfrd_gemm_tn_plan(int M, int N, int K, int has_aux, int bf16_out, int fused_ln, int* out);
 /* dW[Mo,No] += sum_t dY[t,Mo] * X[t,No]  (fp32 atomics into dW; split over tokens).
  * dbias (nullable): dbias[Mo] += sum_t dY[t,Mo], from one extra N=16 MMA per K step against an all-ones operand. */
 /* profiling experiments only: with SRFRD_GEMM_DEBUG=5 gemm_tn records a clock64 timeline of CTA 0 (32 x 16 int64). */

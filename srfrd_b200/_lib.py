@@ -38,6 +38,7 @@ SIGNATURES = {
     "srfrd_layernorm_fwd": [vp, i32, vp, vp, f32, vp, vp, i32, vp, i64, i32, i64, i64, vp],
     "srfrd_layernorm_bwd": [vp, vp, i32, vp, i32, vp, vp, vp, i32, vp, vp, i32, vp, vp, i64, i32, vp],
     "srfrd_gemm_tn": [vp, i32, vp, i32, i32, i32, i32, C.POINTER(GemmEpilogue), vp],
+    "srfrd_gemm_tn_plan": [i32, i32, i32, i32, i32, i32, vp],
     "srfrd_gemm_debug_read": [vp],
     "srfrd_attn_debug_read": [vp],
     "srfrd_gemm_wgrad": [vp, i32, vp, i32, i64, i32, i32, vp, i32, vp, vp],

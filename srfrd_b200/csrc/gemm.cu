@@ -719,40 +719,20 @@ static int pick_block_n_tn(int N) {
 
 using namespace srfrd;
 
-extern "C" int srfrd_gemm_tn(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
-                             const srfrd_gemm_epilogue_t* ep, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  SRFRD_REQUIRE(A && B && ep, "gemm_tn: null operand");
-  SRFRD_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_tn: empty shape M=%d N=%d K=%d", M, N, K);
-  SRFRD_REQUIRE(N % 16 == 0 && K % 8 == 0, "gemm_tn: need N %% 16 == 0 and K %% 8 == 0 (got N=%d K=%d)", N, K);
-  SRFRD_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && lda >= K && ldb >= K, "gemm_tn: bad leading dims lda=%d ldb=%d", lda, ldb);
-  SRFRD_REQUIRE(ep->out_bf16 || ep->out_f32, "gemm_tn: no output");
-  SRFRD_REQUIRE(ep->ldc % 8 == 0 && ep->ldc >= N, "gemm_tn: bad ldc=%d", ep->ldc);
-  SRFRD_REQUIRE(!ep->residual || ep->ldr % 8 == 0, "gemm_tn: bad ldr");
-  SRFRD_REQUIRE(!ep->gate || ep->ldg % 8 == 0, "gemm_tn: bad ldg");
-  SRFRD_REQUIRE(!(ep->residual && ep->gate), "gemm_tn: residual and gate cannot be combined (one aux operand)");
-  SRFRD_REQUIRE(!ep->bias || N <= MAX_BIAS, "gemm_tn: bias with N=%d > %d unsupported", N, MAX_BIAS);
-  GemmShape s;
+// Tile / pipeline plan of one gemm_tn launch: pure host arithmetic (no CUDA call), shared by the launcher and by
+// srfrd_gemm_tn_plan(), through which the CPU tests check every shape's plan (shared memory, stage counts, issuer rule).
+static int plan_gemm_tn(int M, int N, int K, bool has_aux, bool tma_out, bool lnf, GemmShape& s, size_t& smem_out) {
   s.M = M; s.N = N; s.K = K;
   s.block_n = pick_block_n_tn(N);
   s.n_tiles = (N + s.block_n - 1) / s.block_n;
   s.m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
-  const void* aux = ep->residual ? ep->residual : ep->gate;
-  const int ldaux = ep->residual ? ep->ldr : ep->ldg;
-  s.has_aux = aux != nullptr;
-  // TMA store needs a 16-byte aligned bf16 output; the fp32 output (predict logits, tests) is stored directly
-  s.tma_out = ep->out_bf16 && !ep->out_f32 && (((uintptr_t)ep->out_bf16 & 15) == 0);
-  SRFRD_REQUIRE(!aux || (((uintptr_t)aux & 15) == 0), "gemm_tn: residual / gate must be 16-byte aligned");
+  s.has_aux = has_aux;
+  s.tma_out = tma_out;
   const int b_stage_bytes = ((s.block_n * BLOCK_K * 2) + 1023) & ~1023;
   const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
   { const char* dbg = getenv("SRFRD_GEMM_DEBUG"); s.debug = dbg ? atoi(dbg) : 0; }
   s.buf_blocks = (s.has_aux || s.tma_out) ? (s.block_n + 63) / 64 : 0;
-  const bool lnf = ep->ln_out_bf16 != nullptr;
-  if (lnf) {
-    SRFRD_REQUIRE(ep->residual && s.tma_out && s.n_tiles == 1 && N <= MAX_LN && ep->ln_w && ep->ln_b,
-                  "gemm_tn: fused LayerNorm needs a residual, a bf16 output, one column tile (N=%d) and ln_w / ln_b", N);
-    SRFRD_REQUIRE(ep->ld_ln % 8 == 0 && ep->ld_ln >= N && (((uintptr_t)ep->ln_out_bf16 & 15) == 0), "gemm_tn: bad ln_out");
-  }
+  SRFRD_REQUIRE(!lnf || s.n_tiles == 1, "gemm_tn: fused LayerNorm needs one column tile (N=%d)", N);
   // residual / gate tiles without the LayerNorm fusion: two tile buffers per set when a two-stage A pipeline still fits
   s.nbuf = 2;
   if (s.has_aux && s.tma_out && !lnf && s.n_tiles == 1) {
@@ -778,11 +758,57 @@ extern "C" int srfrd_gemm_tn(const void* A, int lda, const void* B, int ldb, int
   }
   if (s.stages > 6) s.stages = 6;
   SRFRD_REQUIRE(s.stages >= 2, "gemm_tn: tile does not fit shared memory");
-  const size_t smem = (size_t)s.stages * (s.b_resident ? s.kgroup * A_STAGE_BYTES : stage_bytes) + fixed;
+  smem_out = (size_t)s.stages * (s.b_resident ? s.kgroup * A_STAGE_BYTES : stage_bytes) + fixed;
   { const char* d = getenv("SRFRD_GEMM_DYNAMIC"); s.dynamic = d ? atoi(d) : 0; }
   { const char* l = getenv("SRFRD_L2_PREFETCH"); s.l2_prefetch = l ? atoi(l) : 1; }
   s.nacc = s.block_n <= 128 ? 4 : 2;
   { const char* a = getenv("SRFRD_GEMM_NACC"); if (a && atoi(a) == 2) s.nacc = 2; }
+  s.sched_slot = 0;
+  return 0;
+}
+
+extern "C" int srfrd_gemm_tn_plan(int M, int N, int K, int has_aux, int bf16_out, int fused_ln, int* out) {
+  SRFRD_REQUIRE(out && M > 0 && N > 0 && K > 0 && N % 16 == 0 && K % 8 == 0, "gemm_tn_plan: bad arguments");
+  GemmShape s;
+  size_t smem = 0;
+  if (int rc = plan_gemm_tn(M, N, K, has_aux != 0, bf16_out != 0, fused_ln != 0, s, smem)) return rc;
+  const int kblocks = (K + BLOCK_K - 1) / BLOCK_K;
+  out[0] = s.block_n; out[1] = s.n_tiles; out[2] = s.stages; out[3] = s.kgroup; out[4] = s.b_resident;
+  out[5] = s.nacc; out[6] = s.nbuf; out[7] = s.buf_blocks; out[8] = (int)smem;
+  out[9] = (s.kgroup >= kblocks && s.stages % 2 == 0) ? 1 : 0;      // second MMA issuer active (same rule as the kernel)
+  out[10] = kblocks;
+  return 0;
+}
+
+extern "C" int srfrd_gemm_tn(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
+                             const srfrd_gemm_epilogue_t* ep, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SRFRD_REQUIRE(A && B && ep, "gemm_tn: null operand");
+  SRFRD_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_tn: empty shape M=%d N=%d K=%d", M, N, K);
+  SRFRD_REQUIRE(N % 16 == 0 && K % 8 == 0, "gemm_tn: need N %% 16 == 0 and K %% 8 == 0 (got N=%d K=%d)", N, K);
+  SRFRD_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && lda >= K && ldb >= K, "gemm_tn: bad leading dims lda=%d ldb=%d", lda, ldb);
+  SRFRD_REQUIRE(ep->out_bf16 || ep->out_f32, "gemm_tn: no output");
+  SRFRD_REQUIRE(ep->ldc % 8 == 0 && ep->ldc >= N, "gemm_tn: bad ldc=%d", ep->ldc);
+  SRFRD_REQUIRE(!ep->residual || ep->ldr % 8 == 0, "gemm_tn: bad ldr");
+  SRFRD_REQUIRE(!ep->gate || ep->ldg % 8 == 0, "gemm_tn: bad ldg");
+  SRFRD_REQUIRE(!(ep->residual && ep->gate), "gemm_tn: residual and gate cannot be combined (one aux operand)");
+  SRFRD_REQUIRE(!ep->bias || N <= MAX_BIAS, "gemm_tn: bias with N=%d > %d unsupported", N, MAX_BIAS);
+  GemmShape s;
+  const void* aux = ep->residual ? ep->residual : ep->gate;
+  const int ldaux = ep->residual ? ep->ldr : ep->ldg;
+  // TMA store needs a 16-byte aligned bf16 output; the fp32 output (predict logits, tests) is stored directly
+  const bool tma_out = ep->out_bf16 && !ep->out_f32 && (((uintptr_t)ep->out_bf16 & 15) == 0);
+  SRFRD_REQUIRE(!aux || (((uintptr_t)aux & 15) == 0), "gemm_tn: residual / gate must be 16-byte aligned");
+  const bool lnf = ep->ln_out_bf16 != nullptr;
+  if (lnf) {
+    SRFRD_REQUIRE(ep->residual && tma_out && N <= MAX_LN && ep->ln_w && ep->ln_b,
+                  "gemm_tn: fused LayerNorm needs a residual, a bf16 output, N <= %d (N=%d) and ln_w / ln_b", MAX_LN, N);
+    SRFRD_REQUIRE(ep->ld_ln % 8 == 0 && ep->ld_ln >= N && (((uintptr_t)ep->ln_out_bf16 & 15) == 0), "gemm_tn: bad ln_out");
+  }
+  size_t smem = 0;
+  if (int rc = plan_gemm_tn(M, N, K, aux != nullptr, tma_out, lnf, s, smem)) return rc;
+  const int b_stage_bytes = ((s.block_n * BLOCK_K * 2) + 1023) & ~1023;
+  (void)b_stage_bytes;
   static int next_slot = 0;
   s.sched_slot = next_slot;
   next_slot = (next_slot + 1) % TN_SCHED_SLOTS;
