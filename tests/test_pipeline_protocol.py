@@ -364,3 +364,154 @@ def test_model_flags_the_lookahead_deadlock():
         sim.merged = True                          # forces the early ring read of the merged path
         return sim
     assert _flags(make) == 8
+
+
+# =========================================================================================================
+# catalogue_tilemax_kernel (srfrd_b200/csrc/topk.cu): NACC issuer warps, two epilogue sets, pieces of item tiles
+# =========================================================================================================
+class TopkSim(Sim):
+    """Same machinery for the catalogue kernel's protocol.  The item-tile ring is consumed by issuer (tile % NACC); an
+    issuer SKIPS the other issuers' stages without touching their barriers, which is only sound when the ring length is
+    a multiple of NACC * kblocks (host: make_plan).  tfull is indexed [accumulator][set], tempty[accumulator] collects the
+    arrivals of whichever set read it, afull / aempty hand the user tiles in TMEM from set 0 to the issuers per piece."""
+
+    def __init__(self, seed, pieces, kblocks, stages, nacc, max_delay=6):
+        Sim.__init__(self, seed, sum(pieces), kblocks, stages, 1, nacc, 2, False, False, max_delay)
+        self.pieces = pieces
+        self.tfull2 = [MBar(1) for _ in range(2 * nacc)]
+        self.tempty = [MBar(1) for _ in range(nacc)]       # (4 * UBS warp arrivals modelled as one)
+        self.afull, self.aempty = MBar(1), MBar(nacc)
+        self.meet = [0, 0]                                  # per-piece rendezvous of the two sets (named barrier)
+        self.seen = {"mma": [], "epi": []}
+
+    def t_producer(self):
+        stage, phase, uses = 0, 0, [0] * self.stages
+        for ntiles in self.pieces:
+            for _ in range(ntiles):
+                for _ in range(self.kblocks):
+                    yield from self.wait(self.empty[stage], phase ^ 1, uses[stage] - 1)
+                    bar = self.full[stage]
+                    bar.arrive_expect_tx(1)
+                    self.later(bar.complete_tx)
+                    uses[stage] += 1
+                    stage += 1
+                    if stage == self.stages:
+                        stage, phase = 0, phase ^ 1
+                yield
+
+    def t_issuer(self, w):
+        commits = []
+
+        def commit(bar):
+            commits.append(bar)
+
+            def fire():
+                if commits[0] is not bar:
+                    return self.later(fire, 1)
+                commits.pop(0)
+                bar.arrive()
+            self.later(fire)
+
+        stage, phase, uphase, aphase = 0, 0, 0, 0
+        n, own, passes = 0, 0, 0
+        for pi, ntiles in enumerate(self.pieces):
+            yield from self.wait(self.afull, uphase, pi)
+            uphase ^= 1
+            for _ in range(ntiles):
+                if n % self.nacc != w:
+                    stage += self.kblocks
+                    if stage >= self.stages:
+                        stage, phase, passes = stage - self.stages, phase ^ 1, passes + 1
+                    n += 1
+                    continue
+                yield from self.wait(self.tempty[w], aphase ^ 1, own - 1)
+                aphase ^= 1
+                for kb in range(self.kblocks):
+                    yield from self.wait(self.full[stage], phase, passes)
+                    yield
+                    if kb == self.kblocks - 1:
+                        commit(self.tfull2[w * 2 + (n & 1)])
+                    commit(self.empty[stage])
+                    stage += 1
+                    if stage == self.stages:
+                        stage, phase, passes = 0, phase ^ 1, passes + 1
+                self.seen["mma"].append(n)
+                own += 1
+                n += 1
+            commit(self.aempty)
+
+    def t_epilogue(self, s):
+        uphase, cnt, n = 0, [0] * self.nacc, 0
+        for pi, ntiles in enumerate(self.pieces):
+            if s == 0:
+                yield from self.wait(self.aempty, uphase ^ 1, pi - 1)
+                uphase ^= 1
+                yield                                     # stage the user tiles into TMEM
+                self.afull.arrive()
+            self.meet[s] += 1                             # named barrier: both threads of a row start the piece together
+            while self.meet[1 - s] < self.meet[s]:
+                yield
+            for _ in range(ntiles):
+                if (n & 1) != s:
+                    n += 1
+                    continue
+                a = n % self.nacc
+                par, use = cnt[a] & 1, cnt[a]
+                cnt[a] += 1
+                yield from self.wait(self.tfull2[a * 2 + s], par, use)
+                yield                                     # tcgen05.ld
+                self.tempty[a].arrive()
+                self.seen["epi"].append(n)
+                n += 1
+
+    def run(self, max_steps=400000):
+        procs = {"producer": self.t_producer(), "epi0": self.t_epilogue(0), "epi1": self.t_epilogue(1)}
+        for w in range(self.nacc):
+            procs["mma%d" % w] = self.t_issuer(w)
+        while procs:
+            self.step_no += 1
+            assert self.step_no < max_steps, f"deadlock / livelock: {sorted(procs)} still running"
+            due = [e for e in self.events if e[0] <= self.step_no]
+            self.events = [e for e in self.events if e[0] > self.step_no]
+            for _, _, fn in sorted(due, key=lambda e: (e[0], e[1])):
+                fn()
+            name = self.rng.choice(sorted(procs))
+            try:
+                next(procs[name])
+            except StopIteration:
+                del procs[name]
+        tiles = list(range(sum(self.pieces)))
+        assert sorted(self.seen["mma"]) == tiles and sorted(self.seen["epi"]) == tiles
+
+
+@pytest.mark.parametrize("nacc", [2, 3])
+@pytest.mark.parametrize("kblocks", [1, 2, 4])
+def test_catalogue_kernel_protocol(nacc, kblocks):
+    unit = nacc * kblocks
+    for mult in (1, 2, 5):
+        for pieces in ([1], [2], [7], [3, 1, 4], [1, 1, 1, 1], [11, 6], [40]):
+            for seed in range(3):
+                TopkSim(seed + 13 * mult, pieces, kblocks, stages=unit * mult, nacc=nacc, max_delay=(2 if seed == 0 else 9)).run()
+
+
+def test_catalogue_model_flags_a_ring_that_is_not_a_multiple_of_the_issuer_count():
+    """make_plan rounds the ring down to a multiple of NACC * kblocks; without that a stage is waited for by different
+    issuers in turn, and when TMA completions arrive far out of order one of them passes on the PREVIOUS phase"""
+    flagged = 0
+    for seed in range(16):
+        try:
+            TopkSim(seed, [23], 1, stages=4, nacc=3, max_delay=1000).run(max_steps=400000)
+        except AssertionError as e:
+            assert "wait meant phase" in str(e)
+            flagged += 1
+    assert flagged >= 4
+
+
+def test_protocols_hold_under_extreme_reordering():
+    """completion delays two orders of magnitude longer than a tile's issue time (loads, commits, store reads far out of order)"""
+    for seed in range(4):
+        for nacc, kb, mult in ((3, 1, 2), (2, 2, 1), (3, 2, 3)):
+            TopkSim(seed, [11, 6, 9], kb, stages=nacc * kb * mult, nacc=nacc, max_delay=400).run(max_steps=2000000)
+        Sim(seed, 23, 2, stages=4, kgroup=2, nacc=4, nbuf=4, aux=True, lnf=False, max_delay=400).run(max_steps=2000000)
+        Sim(seed, 23, 2, stages=2, kgroup=2, nacc=4, nbuf=2, aux=True, lnf=True, max_delay=400).run(max_steps=2000000)
+        Sim(seed, 23, 5, stages=3, kgroup=1, nacc=2, nbuf=2, aux=True, lnf=False, max_delay=400).run(max_steps=2000000)
