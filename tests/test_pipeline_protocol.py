@@ -515,3 +515,147 @@ def test_protocols_hold_under_extreme_reordering():
         Sim(seed, 23, 2, stages=4, kgroup=2, nacc=4, nbuf=4, aux=True, lnf=False, max_delay=400).run(max_steps=2000000)
         Sim(seed, 23, 2, stages=2, kgroup=2, nacc=4, nbuf=2, aux=True, lnf=True, max_delay=400).run(max_steps=2000000)
         Sim(seed, 23, 5, stages=3, kgroup=1, nacc=2, nbuf=2, aux=True, lnf=False, max_delay=400).run(max_steps=2000000)
+
+
+# =========================================================================================================
+# attn_long_fwd_kernel (srfrd_b200/csrc/attention_long.cu): one ring of [128 x 64] tiles feeds S = Q K^T and O = P V
+# =========================================================================================================
+class LongFwdSim(Sim):
+    """Producer and MMA issuer walk the same tile sequence (per K block: Q tile, K tiles 0..i; then per 64-column output
+    block: V tiles 0..i) through one ring; the Q slot is only released with the LAST key tile of its K block, so the ring
+    must hold i + 2 tiles at least.  Output blocks go through 4 accumulator slots (o_full / o_empty, use count -> parity),
+    softmax warps of `part` p read the slots with slot == p; s_full / p_full / pv_done are per-item barriers."""
+
+    def __init__(self, seed, items, kblocks, ring, max_delay=6):
+        Sim.__init__(self, seed, len(items), kblocks, ring, 1, 2, 2, False, False, max_delay)
+        self.items = items                                  # query-tile index i of every item this CTA handles
+        self.s_full, self.p_full, self.pv_done = MBar(1), MBar(4), MBar(1)     # p_full: 16 warps = 4 per modelled part
+        self.o_full = [MBar(1) for _ in range(4)]
+        self.o_empty = [MBar(4) for _ in range(4)]          # the four lane quarters of one part
+        self.items_done = {"mma": 0, "sm": [0, 0, 0, 0]}
+
+    def l_producer(self):
+        slot, ph, uses = 0, 0, [0] * self.stages
+
+        def push():
+            nonlocal slot, ph
+            yield from self.wait(self.empty[slot], ph ^ 1, uses[slot] - 1)
+            bar = self.full[slot]
+            bar.arrive_expect_tx(1)
+            self.later(bar.complete_tx)
+            uses[slot] += 1
+            slot += 1
+            if slot == self.stages:
+                slot, ph = 0, ph ^ 1
+        for i in self.items:
+            for _ in range(self.kblocks):
+                yield from push()                           # Q
+                for _ in range(i + 1):
+                    yield from push()                       # K_j
+            for _ in range(self.kblocks):
+                for _ in range(i + 1):
+                    yield from push()                       # V_j
+            yield
+
+    def l_mma(self):
+        commits = []
+
+        def commit(bar):
+            commits.append(bar)
+
+            def fire():
+                if commits[0] is not bar:
+                    return self.later(fire, 1)
+                commits.pop(0)
+                bar.arrive()
+            self.later(fire)
+
+        slot, ph, iph, ocnt = 0, 0, 0, 0
+        uses = [0] * self.stages
+
+        def take():
+            nonlocal slot, ph
+            yield from self.wait(self.full[slot], ph, uses[slot])
+            uses[slot] += 1
+            s = slot
+            slot += 1
+            if slot == self.stages:
+                slot, ph = 0, ph ^ 1
+            return s
+        for n, i in enumerate(self.items):
+            for _ in range(self.kblocks):
+                q = yield from take()
+                for j in range(i + 1):
+                    k = yield from take()
+                    yield
+                    commit(self.empty[k])
+                    if j == i:
+                        commit(self.empty[q])
+            commit(self.s_full)
+            yield from self.wait(self.p_full, iph, n)
+            for cb in range(self.kblocks):
+                o = ocnt & 3
+                yield from self.wait(self.o_empty[o], ((ocnt >> 2) & 1) ^ 1, (ocnt >> 2) - 1)
+                for _ in range(i + 1):
+                    v = yield from take()
+                    yield
+                    commit(self.empty[v])
+                commit(self.o_full[o])
+                if cb == self.kblocks - 1:
+                    commit(self.pv_done)
+                ocnt += 1
+            iph ^= 1
+            self.items_done["mma"] += 1
+
+    def l_softmax(self, part):
+        """the four warps (lane quarters) of one `part`"""
+        iph, ocnt = 0, 0
+        for n, _ in enumerate(self.items):
+            yield from self.wait(self.s_full, iph, n)
+            yield                                           # S -> registers, exponentials
+            if n:
+                yield from self.wait(self.pv_done, iph ^ 1, n - 1)
+            yield                                           # P -> shared memory
+            self.p_full.arrive()
+            for cb in range(self.kblocks):
+                oc = ocnt + cb
+                if (oc & 3) != part:
+                    continue
+                yield from self.wait(self.o_full[oc & 3], (oc >> 2) & 1, oc >> 2)
+                yield
+                self.o_empty[oc & 3].arrive(4)
+            ocnt += self.kblocks
+            iph ^= 1
+            self.items_done["sm"][part] += 1
+
+    def run(self, max_steps=400000):
+        procs = {"producer": self.l_producer(), "mma": self.l_mma()}
+        for p in range(4):
+            procs["sm%d" % p] = self.l_softmax(p)
+        while procs:
+            self.step_no += 1
+            assert self.step_no < max_steps, f"deadlock / livelock: {sorted(procs)} still running"
+            due = [e for e in self.events if e[0] <= self.step_no]
+            self.events = [e for e in self.events if e[0] > self.step_no]
+            for _, _, fn in sorted(due, key=lambda e: (e[0], e[1])):
+                fn()
+            name = self.rng.choice(sorted(procs))
+            try:
+                next(procs[name])
+            except StopIteration:
+                del procs[name]
+        assert self.items_done["mma"] == len(self.items) and self.items_done["sm"] == [len(self.items)] * 4
+
+
+@pytest.mark.parametrize("kblocks", [1, 2, 5, 8])            # head widths 64 ... 512
+def test_long_attention_forward_protocol(kblocks):
+    for items in ([0], [1], [0, 1], [1, 1, 0, 1, 0, 0, 1], [0] * 9, [1] * 9):
+        for seed in range(3):
+            LongFwdSim(seed, items, kblocks, ring=9, max_delay=(2 if seed == 0 else 12)).run()
+    LongFwdSim(5, [1, 0, 1, 1, 0], kblocks, ring=9, max_delay=300).run(max_steps=3000000)
+
+
+def test_long_attention_model_flags_a_ring_shorter_than_a_query_tiles_keys():
+    """the Q slot is held until its last key tile has been multiplied: with i = 1 a ring of 2 tiles can never advance"""
+    with pytest.raises(AssertionError, match="deadlock"):
+        LongFwdSim(0, [1, 1], 2, ring=2).run(max_steps=20000)
