@@ -659,3 +659,148 @@ def test_long_attention_model_flags_a_ring_shorter_than_a_query_tiles_keys():
     """the Q slot is held until its last key tile has been multiplied: with i = 1 a ring of 2 tiles can never advance"""
     with pytest.raises(AssertionError, match="deadlock"):
         LongFwdSim(0, [1, 1], 2, ring=2).run(max_steps=20000)
+
+
+# =========================================================================================================
+# attn_long_bwd_kernel<MODE> (attention_long.cu): FlashAttention-2 style passes over (query tile, key tile) pairs
+# =========================================================================================================
+class LongBwdSim(Sim):
+    """Per pair: S (and, except in the dV pass, dP into the SAME 128 TMEM columns once S is in registers), then one output
+    MMA batch per 64-column block from the P / dS tile the workers wrote to shared memory.  Barriers: s_full, s_read(8),
+    dp_full, sd_free(8), x_full(8), x_done per pair; acc_full, acc_free(8) per item.  The eight worker warps are modelled as
+    two processes (the two `part`s) arriving with four each, so that they may drift apart."""
+
+    def __init__(self, seed, items, kblocks, ring, dv, max_delay=6):
+        Sim.__init__(self, seed, len(items), kblocks, ring, 1, 2, 2, False, False, max_delay)
+        self.items, self.dv = items, dv                       # pairs per item
+        self.s_full, self.dp_full, self.x_done, self.acc_full = MBar(1), MBar(1), MBar(1), MBar(1)
+        self.s_read, self.sd_free, self.x_full, self.acc_free = MBar(8), MBar(8), MBar(8), MBar(8)
+        self.done = {"mma": 0, "w": [0, 0]}
+
+    def b_producer(self):
+        slot, ph, uses = 0, 0, [0] * self.stages
+
+        def push():
+            nonlocal slot, ph
+            yield from self.wait(self.empty[slot], ph ^ 1, uses[slot] - 1)
+            bar = self.full[slot]
+            bar.arrive_expect_tx(1)
+            self.later(bar.complete_tx)
+            uses[slot] += 1
+            slot += 1
+            if slot == self.stages:
+                slot, ph = 0, ph ^ 1
+        for npairs in self.items:
+            for _ in range(npairs):
+                for _ in range(self.kblocks * (2 if self.dv else 4)):
+                    yield from push()
+                for _ in range(self.kblocks):
+                    yield from push()
+            yield
+
+    def b_mma(self):
+        commits = []
+
+        def commit(bar):
+            commits.append(bar)
+
+            def fire():
+                if commits[0] is not bar:
+                    return self.later(fire, 1)
+                commits.pop(0)
+                bar.arrive()
+            self.later(fire)
+
+        slot, ph, np_, uses = 0, 0, 0, [0] * self.stages
+
+        def take():
+            nonlocal slot, ph
+            yield from self.wait(self.full[slot], ph, uses[slot])
+            uses[slot] += 1
+            s = slot
+            slot += 1
+            if slot == self.stages:
+                slot, ph = 0, ph ^ 1
+            return s
+        for ni, npairs in enumerate(self.items):
+            for pr in range(npairs):
+                pp = np_ & 1
+                yield from self.wait(self.sd_free, pp ^ 1, np_ - 1)
+                for ph2 in range(1 if self.dv else 2):
+                    if ph2 == 1:
+                        yield from self.wait(self.s_read, pp, np_)
+                    for _ in range(self.kblocks):
+                        a = yield from take()
+                        b = yield from take()
+                        yield
+                        commit(self.empty[a])
+                        commit(self.empty[b])
+                    commit(self.s_full if ph2 == 0 else self.dp_full)
+                yield from self.wait(self.x_full, pp, np_)
+                if pr == 0:
+                    yield from self.wait(self.acc_free, (ni & 1) ^ 1, ni - 1)
+                for cb in range(self.kblocks):
+                    c = yield from take()
+                    yield
+                    commit(self.empty[c])
+                    if cb == self.kblocks - 1:
+                        commit(self.x_done)
+                        if pr == npairs - 1:
+                            commit(self.acc_full)
+                np_ += 1
+            self.done["mma"] += 1
+
+    def b_worker(self, part):
+        np_ = 0
+        for ni, npairs in enumerate(self.items):
+            for _ in range(npairs):
+                pp = np_ & 1
+                yield from self.wait(self.s_full, pp, np_)
+                yield                                         # S -> registers
+                (self.sd_free if self.dv else self.s_read).arrive(4)
+                if not self.dv:
+                    yield from self.wait(self.dp_full, pp, np_)
+                    yield                                     # dP -> registers
+                    self.sd_free.arrive(4)
+                yield from self.wait(self.x_done, pp ^ 1, np_ - 1)
+                yield                                         # P / dS -> shared memory
+                self.x_full.arrive(4)
+                np_ += 1
+            yield from self.wait(self.acc_full, ni & 1, ni)
+            yield                                             # output rows
+            self.acc_free.arrive(4)
+            self.done["w"][part] += 1
+
+    def run(self, max_steps=600000):
+        procs = {"producer": self.b_producer(), "mma": self.b_mma(), "w0": self.b_worker(0), "w1": self.b_worker(1)}
+        while procs:
+            self.step_no += 1
+            assert self.step_no < max_steps, f"deadlock / livelock: {sorted(procs)} still running"
+            due = [e for e in self.events if e[0] <= self.step_no]
+            self.events = [e for e in self.events if e[0] > self.step_no]
+            for _, _, fn in sorted(due, key=lambda e: (e[0], e[1])):
+                fn()
+            name = self.rng.choice(sorted(procs))
+            try:
+                next(procs[name])
+            except StopIteration:
+                del procs[name]
+        assert self.done["mma"] == len(self.items) and self.done["w"] == [len(self.items)] * 2
+
+
+@pytest.mark.parametrize("dv", [False, True])
+@pytest.mark.parametrize("kblocks", [1, 2, 5, 8])
+def test_long_attention_backward_protocol(kblocks, dv):
+    for items in ([1], [2], [1, 2], [2, 1, 2, 2, 1, 1], [1] * 7, [2] * 7):
+        for seed in range(3):
+            LongBwdSim(seed, items, kblocks, ring=11, dv=dv, max_delay=(2 if seed == 0 else 12)).run()
+    LongBwdSim(9, [2, 1, 2, 1], kblocks, ring=11, dv=dv, max_delay=300).run(max_steps=4000000)
+
+
+def test_long_backward_model_flags_a_miscounted_barrier():
+    """s_read must collect all eight worker warps before dP may overwrite S in the shared TMEM columns: initialised with a
+    count of 4 it completes a phase per `part`, and its single waiter (the MMA issuer) is found off by a phase"""
+    sim = LongBwdSim(0, [2, 2, 2], 1, ring=11, dv=False)
+    sim.s_read = MBar(4)
+    with pytest.raises(AssertionError):
+        sim.run(max_steps=50000)
