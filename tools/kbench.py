@@ -94,4 +94,5 @@ if what in ("k1", "all"):
     w, b = rnd(H, dtype=torch.float32), rnd(H, dtype=torch.float32)
     st = torch.empty(T, 2, device="cuda")
     nvalid = int((seq != 0).sum())
-    timeit(f"embed_ln_fwd (K1) N={N} valid={nvalid / T:.2f}", lambda i: ops.embed_ln_fwd(E, P, Fe, 1, seq, rsq, 1.0, w, b, 1e-8, x0_bf16=outs[i % NBUF], q_bf16=acts[i % NBUF], stats=st), 2 * A + T * 24 + nvalid * 256)
+    mode = 1 if H > 64 else 0                       # KB_H=64: no fake-review columns (SASRec / SRFU shaped)
+    timeit(f"embed_ln_fwd (K1) N={N} valid={nvalid / T:.2f}", lambda i: ops.embed_ln_fwd(E, P, Fe if mode else None, mode, seq, rsq if mode else None, 1.0, w, b, 1e-8, x0_bf16=outs[i % NBUF], q_bf16=acts[i % NBUF], stats=st), 2 * A + T * 24 + nvalid * 256)
