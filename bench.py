@@ -9,8 +9,13 @@ Adam) of the reference SRFR model on Beauty-shaped synthetic data, config C2 of 
 22 363 users, 12 101 items, maxlen 50, D=64, F=16, 2 blocks, batch 4096 per GPU (weak scaling).
 `value` = global sequences / second with the batch already resident in HBM; `e2e` = the same step driven
 through FusedTrainer.step() from pinned HOST batches (H2D copies + a D2H read of the loss every step).
-A second object, "catalogue", reports full-catalogue top-10 users/s (C3: 1 M items, row-sharded); "gather" reports K1
-at catalogue scale against the HBM roofline.  `roofline` = the dominant kernel's algorithmic bytes per launch / its
+Further objects in the same line (every BASELINE.json config is driver-measured at every N): "catalogue" = full-catalogue
+top-10 users/s (C3: 1 M items, row-sharded; score + top-k + all-gather + merge, and `with_encode` = the same plus the
+sequence encoder), "c4" = the long-sequence variant (maxlen 200, D=256, 4 blocks, batch 1024/GPU, DP), "c5" = the
+Yelp-shaped setting (~10 M interactions, 30 % fake, batches drawn ON THE DEVICE inside the step graph, soft and mask
+discriminator policies, batch 4096/GPU), "dropout" = C2 at the reference's default dropout 0.5 (trainer.py:128),
+"dp_parity" (N > 1) = first-step DP loss vs one rank on the concatenated batch + sharded vs unsharded top-10, "gather" =
+K1 at catalogue scale against the HBM roofline.  `roofline` = the dominant kernel's algorithmic bytes per launch / its
 event-timed launch duration, `roofline.traffic` = its DRAM bytes per launch from the committed ncu capture
 (profiles/traffic.json); `clocks` = NVML samples taken every 2 ms DURING the timed region.  Baselines on rank 0 at N = 1
 only: `cpu_baseline` (the reference's arithmetic, oracle port, on the host cores) and `gpu_eager_baseline` (the same as
@@ -198,16 +203,155 @@ def kernel_breakdown(tr, steps, valid_frac):
 
 
 # ---------------------------------------------------------------------------------------------
-def make_model_and_data(device, seed=1236):
-    from srfrd_b200 import SRFR_model as M, synth
-    c = CFG
-    data = synth.make_interactions(seed, c["usernum"], c["itemnum"], 5, 4.0, c["L"])
+def make_model(device, itemnum, L, D, F, blocks, heads=1, dropout=0.0, seed=1236):
+    from srfrd_b200 import SRFR_model as M
     torch.manual_seed(seed)
-    m = M.SRFR(c["itemnum"], c["L"], c["D"], c["F"], 0.0, c["blocks"], c["heads"], device)
+    m = M.SRFR(itemnum, L, D, F, dropout, blocks, heads, device)
     for _, p in m.named_parameters():          # trainer.py:364-369
         if p.dim() >= 2:
             torch.nn.init.xavier_normal_(p.data)
-    return m.to(device), data
+    return m.to(device)
+
+
+def make_model_and_data(device, seed=1236, dropout=0.0):
+    from srfrd_b200 import synth
+    c = CFG
+    data = synth.make_interactions(seed, c["usernum"], c["itemnum"], 5, 4.0, c["L"])
+    return make_model(device, c["itemnum"], c["L"], c["D"], c["F"], c["blocks"], c["heads"], dropout, seed), data
+
+
+class Timer:
+    """barrier + synchronize on both sides, CUDA events on the launching stream, MAX over ranks."""
+
+    def __init__(self, dev, world):
+        self.dev, self.world = dev, world
+
+    def sync_all(self):
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def __call__(self, fn, steps, warm):
+        import torch.distributed as dist
+        for i in range(warm):
+            fn(i)
+        self.sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warm + i)
+        e1.record()
+        self.sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+
+def top_kernel_roofline(agg, nsteps, pk, traffic_key=None):
+    tot = sum(d["ms"] for d in agg.values())
+    tname, td = max(agg.items(), key=lambda kv: kv[1]["ms"])
+    per_ms = td["ms"] / td["n"]
+    ach = td["bytes"] / td["n"] / (per_ms * 1e-3) / 1e9
+    return dict(bound="hbm", kernel=tname, achieved=round(ach, 1), peak=pk["hbm"], unit="GB/s", frac=round(ach / pk["hbm"], 4),
+                traffic=measured_traffic(traffic_key or tname), algorithmic_bytes_per_launch=round(td["bytes"] / td["n"]),
+                peak_source=pk["src"] + ", sustained figure not needed for HBM", avg_launch_ms=round(per_ms, 4),
+                share_of_step=round(td["ms"] / tot, 3),
+                kernels={k: dict(ms_per_step=round(v["ms"] / nsteps, 4), launches_per_step=v["n"] // nsteps,
+                                 gbs=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None,
+                                 tflops=round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["flops"] else None)
+                         for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])})
+
+
+def bench_train_config(name, dev, rank, world, pg, timed, pk, steps, model_kw, data_kw, B, L, dropout=0.0, policy="soft",
+                       sampler="host", breakdown=True):
+    """One training configuration: device-resident batches (or batches drawn on the device inside the step graph),
+    CUDA-graph replay, max-over-ranks CUDA-event time.  Returns ms/step, global seqs/s and the dominant kernel's roofline."""
+    import torch.distributed as dist
+    from srfrd_b200 import synth
+    from srfrd_b200.trainer import DeviceSampler, FusedTrainer, discriminator_weights
+    data = synth.make_interactions(**data_kw)
+    m = make_model(dev, data.itemnum, L, dropout=dropout, seed=data_kw["seed"], **model_kw)
+    if world > 1:
+        dist.broadcast(m.flat_parameters().data, 0)
+    tr = FusedTrainer(m, lr=1e-3, betas=(0.9, 0.98), process_group=pg, use_graph=True)
+    if sampler == "device":
+        smp = DeviceSampler(data, L, dev, seed=1000 + rank)
+        fn = lambda i: tr.step_sampled(smp, B, policy)
+        valid_frac = float(np.minimum(np.maximum(data.train_len() - 1, 0), L)[data.train_len() > 1].mean() / L)
+    else:
+        hs = synth.BatchSampler(data, L, seed=200 + rank)
+        packs, vf = [], []
+        for _ in range(4):
+            nb = hs.next_batch(B)
+            b = {k: torch.from_numpy(nb[k]).to(dev) for k in ("seq", "rsq", "pos", "prs", "neg", "nrs", "p_fake")}
+            vf.append(float((b["pos"] != 0).float().mean()))
+            packs.append(tr.pack_batch(b, w_pos=discriminator_weights(b["pos"], b["p_fake"], policy)))
+        valid_frac = float(np.mean(vf))
+        fn = lambda i: tr.step_packed(packs[i % 4])
+    W = 4
+    timed(fn, 2, W)
+    ms = timed(fn, steps, W)
+    out = dict(value=round(world * B * steps / (ms / 1e3), 1), unit="seqs/s", ms_per_step=round(ms / steps, 4), steps=steps,
+               warmup=W, batch_per_gpu=B, n_gpus=world, valid_slot_fraction=round(valid_frac, 4), policy=policy,
+               dropout=dropout, loss=round(float(tr.scal[4]), 5))
+    if breakdown and rank == 0:
+        if sampler == "device":                      # the eager pass needs the sampler attached for its step body
+            tr._sampler, tr._sampler_policy = smp, policy
+        agg, calls = kernel_breakdown(tr, 2, valid_frac)
+        out["roofline"] = top_kernel_roofline(agg, 2, pk)
+        out["gpu_launches_per_step"] = calls
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        tr._graph = None                             # drop the captured NCCL work before the trainer goes away
+        torch.cuda.synchronize()
+    del tr, m
+    torch.cuda.empty_cache()
+    return out
+
+
+def dp_parity_check(dev, rank, world, pg):
+    """N > 1, before any timing: (1) the first DP step (batch rows sharded over the ranks, loss normalised by the
+    all-reduced weight sums, gradients SUM-all-reduced) against ONE rank stepping the concatenated batch: loss and
+    parameters after the step; (2) row-sharded catalogue top-10 (all-gather + merge) torch.equal the unsharded one on
+    dyadic data, where every accumulation order is exact."""
+    import torch.distributed as dist
+    from srfrd_b200 import evaluation as EV, parallel as PL, synth
+    from srfrd_b200.trainer import FusedTrainer, discriminator_weights
+    c = CFG
+    Bg, L = 512 * world, c["L"]
+    data = synth.make_interactions(4321, 6000, 3000, 5, 4.0, L)
+    nb = synth.BatchSampler(data, L, seed=9).next_batch(Bg)               # same global batch on every rank
+    full = {k: torch.from_numpy(v).to(dev) for k, v in nb.items()}
+    w = discriminator_weights(full["pos"], full["p_fake"], "soft")
+    m_dp = make_model(dev, 3000, L, c["D"], c["F"], c["blocks"], seed=77)
+    m_one = make_model(dev, 3000, L, c["D"], c["F"], c["blocks"], seed=77)
+    dist.broadcast(m_dp.flat_parameters().data, 0)
+    tr_dp = FusedTrainer(m_dp, process_group=pg, use_graph=False)
+    sh = PL.shard_batch({**full, "w": w}, rank, world)
+    l_dp = float(tr_dp.step(sh, w_pos=sh["w"]))
+    tr_one = FusedTrainer(m_one, use_graph=False)
+    l_one = float(tr_one.step(full, w_pos=w))
+    a, b = m_one.flat_parameters().data, m_dp.flat_parameters().data
+    drift = torch.tensor([float((a - b).abs().max())], device=dev)
+    dist.all_reduce(drift, op=dist.ReduceOp.MAX)
+    g = torch.Generator().manual_seed(3)
+    feats = (torch.randint(-16, 17, (1000, 64), generator=g).float() / 8).to(dev)
+    table = (torch.randint(-16, 17, (50001, 64), generator=g).float() / 8).to(dev)
+    _, ref = EV.local_topk(feats, EV.CatalogueIndex(table, 0), 1)
+    lo, hi = EV.CatalogueIndex.shard_bounds(table.shape[0], rank, world)
+    _, ids = EV.sharded_topk(feats, EV.CatalogueIndex(table[lo:hi], lo), pg, 1)
+    same = torch.tensor([1.0 if torch.equal(ids, ref) else 0.0], device=dev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    torch.cuda.synchronize()
+    del tr_dp, tr_one
+    return dict(loss_dp=round(l_dp, 6), loss_single_rank_on_concatenated_batch=round(l_one, 6),
+                loss_abs_diff=round(abs(l_dp - l_one), 7), param_max_abs_diff_after_step=float(drift),
+                sharded_top10_equals_unsharded=bool(same.item() == 1.0), global_batch=Bg,
+                ok=bool(abs(l_dp - l_one) < 2e-3 and float(drift) < 2e-3 and same.item() == 1.0))
 
 
 def run_ours(args):
@@ -224,47 +368,40 @@ def run_ours(args):
         pg = dist.group.WORLD
     c = CFG
     B, L = c["batch"], c["L"]
+    timed = Timer(dev, world)
+    pk = peaks()
+
+    def guarded(fn, *a, **kw):
+        """Secondary objects must never take the headline line down: an exception becomes {"error": ...} (all ranks
+        run the same code, so a deterministic failure fails everywhere and no rank is left waiting in a collective)."""
+        try:
+            return fn(*a, **kw)
+        except Exception as ex:  # noqa: BLE001
+            return dict(error=f"{type(ex).__name__}: {str(ex)[:300]}")
+
+    # ---- N > 1: DP == single rank on the concatenated batch, sharded top-10 == unsharded, BEFORE any timing ----
+    dp_parity = guarded(dp_parity_check, dev, rank, world, pg) if world > 1 else None
+
     m, data = make_model_and_data(dev)
     if world > 1:                               # identical replicas
         dist.broadcast(m.flat_parameters().data, 0)
     tr = FusedTrainer(m, lr=1e-3, betas=(0.9, 0.98), process_group=pg, use_graph=True)
     smp = synth.BatchSampler(data, L, seed=100 + rank)
     npool = 8
-    host, dev_batches = [], []
+    host, packs = [], []
     for _ in range(npool):
         nb = smp.next_batch(B)
         hb = {k: torch.from_numpy(nb[k]).pin_memory() for k in ("seq", "rsq", "pos", "prs", "neg", "nrs", "p_fake")}
         host.append(hb)
-        dev_batches.append({k: v.to(dev) for k, v in hb.items()})
+        db = {k: v.to(dev) for k, v in hb.items()}
+        # inputs resident in HBM, already in the layout of the step's static buffers: ONE device-to-device copy per step
+        packs.append(tr.pack_batch(db, w_pos=discriminator_weights(db["pos"], db["p_fake"], "soft")))
     valid_frac = float(np.mean([float((hb["pos"] != 0).float().mean()) for hb in host]))
     h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in ("seq", "rsq", "pos", "prs", "neg", "nrs")) + B * L * 4
 
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def timed(fn, steps, warm):
-        for i in range(warm):
-            fn(i)
-        sync_all()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            fn(warm + i)
-        e1.record()
-        sync_all()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms)
-
-    # ---- value: batch resident in HBM (device->device copy into the step's static buffers; weights 'soft') ----
-    dev_w = [discriminator_weights(b["pos"], b["p_fake"], "soft") for b in dev_batches]     # inputs, resident like the ids
-
+    # ---- value: batch resident in HBM (weights 'soft') ----
     def dev_step(i):
-        tr.step(dev_batches[i % npool], w_pos=dev_w[i % npool])
+        tr.step_packed(packs[i % npool])
 
     # ---- e2e: pinned host batch -> H2D -> step -> D2H loss ----
     wbuf = [discriminator_weights(hb["pos"], hb["p_fake"], "soft").pin_memory() for hb in host]
@@ -289,36 +426,57 @@ def run_ours(args):
     e2e = world * B * args.steps / (ms_e2e / 1e3)
 
     # ---- per-kernel breakdown + roofline of the dominant kernel (rank 0) ----
-    pk = peaks()
     agg, calls_per_step = kernel_breakdown(tr, 3, valid_frac)
-    tot = sum(d["ms"] for d in agg.values())
-    top = max(agg.items(), key=lambda kv: kv[1]["ms"])
-    tname, td = top
-    per_ms = td["ms"] / td["n"]
-    if td["flops"] > 0 and tname in ("srfrd_attention_fwd", "srfrd_attention_bwd"):
-        bound, ach, peak, unit = "hbm", td["bytes"] / td["n"] / (per_ms * 1e-3) / 1e9, pk["hbm"], "GB/s"
-    else:
-        bound, ach, peak, unit = "hbm", td["bytes"] / td["n"] / (per_ms * 1e-3) / 1e9, pk["hbm"], "GB/s"
-    roofline = dict(bound=bound, kernel=tname, achieved=round(ach, 1), peak=peak, unit=unit, frac=round(ach / peak, 4),
-                    traffic=measured_traffic(tname), algorithmic_bytes_per_launch=round(td["bytes"] / td["n"]),
-                    peak_source=pk["src"] + ", sustained figure not needed for HBM", avg_launch_ms=round(per_ms, 4),
-                    share_of_step=round(td["ms"] / tot, 3),
-                    how="event-bracketed pass of 3 eager steps right after the timed region (which replays a CUDA graph); the "
-                        "GPU is parked behind a spin kernel while the host enqueues each step, so the deltas are GPU time",
-                    kernels={k: dict(ms_per_step=round(v["ms"] / 3, 4), launches_per_step=v["n"] // 3,
-                                     gbs=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None,
-                                     tflops=round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["flops"] else None)
-                             for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])})
+    roofline = top_kernel_roofline(agg, 3, pk)
+    roofline["how"] = ("event-bracketed pass of 3 eager steps right after the timed region (which replays a CUDA graph); the "
+                       "GPU is parked behind a spin kernel while the host enqueues each step, so the deltas are GPU time")
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        tr._graph = None
+        torch.cuda.synchronize()
+    del tr, m, packs
+    torch.cuda.empty_cache()
+
+    extras = {}
+    if not args.no_extras:
+        ex_steps = max(5, min(args.steps, 40))
+        c2_model = dict(D=c["D"], F=c["F"], blocks=c["blocks"])
+        c2_data = dict(seed=1236, usernum=c["usernum"], itemnum=c["itemnum"], min_len=5, mean_extra=4.0, max_len=L)
+        # C2 at the reference's default dropout 0.5 (trainer.py:128): in-kernel dropout in attention and twice in the FFN
+        extras["dropout"] = guarded(bench_train_config, "C2-dropout0.5", dev, rank, world, pg, timed, pk, ex_steps, c2_model,
+                                    c2_data, B, L, dropout=0.5)
+        # C4: maxlen 200, D = 256, F = 16, 4 blocks, batch 1024 per GPU, data parallel at N
+        c4 = synth.CONFIGS["C4"]
+        extras["c4"] = guarded(bench_train_config, "C4", dev, rank, world, pg, timed, pk, max(4, ex_steps // 2),
+                               dict(D=c4["D"], F=c4["F"], blocks=c4["blocks"]),
+                               dict(seed=c4["seed"], usernum=c4["usernum"], itemnum=c4["itemnum"], min_len=c4["min_len"],
+                                    mean_extra=c4["mean_extra"], max_len=c4["max_len"]), c4["batch"], c4["L"])
+        if isinstance(extras["c4"], dict) and "value" in extras["c4"]:
+            extras["c4"]["config"] = "C4: SRFR maxlen 200, D=256 F=16 (H=272), 4 blocks, 12101 items, batch 1024/GPU, soft weights, DP"
+        # C5: Yelp-shaped, ~10 M interactions, 500 k users, 150 k items, 30 % fake; batches drawn on the device INSIDE the
+        # step graph (no host batch at all), discriminator-in-the-loop weights under both policies
+        c5 = synth.CONFIGS["C5"]
+        c5_data = dict(seed=c5["seed"], usernum=c5["usernum"], itemnum=c5["itemnum"], min_len=c5["min_len"],
+                       mean_extra=c5["mean_extra"], max_len=c5["max_len"], fake_rate=c5["fake_rate"], lognormal=True)
+        c5_model = dict(D=c5["D"], F=c5["F"], blocks=c5["blocks"])
+        c5o = {}
+        for pol in ("soft", "mask"):
+            c5o[pol] = guarded(bench_train_config, "C5-" + pol, dev, rank, world, pg, timed, pk, ex_steps, c5_model, c5_data,
+                               c5["batch"], c5["L"], policy=pol, sampler="device", breakdown=(pol == "soft"))
+        c5o["config"] = ("C5: Yelp-shaped synthetic, ~10.05 M interactions, 500 k users, 150 k items, 30 % fake-labelled, SRFR D=64 F=16 "
+                         "L=50 2 blocks, batch 4096/GPU drawn by the on-device sampler inside the CUDA graph, weights per batch")
+        extras["c5"] = c5o
 
     # ---- catalogue: C3, 1 M items row-sharded, U = 16384 users ----
     cat = None
     if not args.no_catalogue:
-        cat = bench_catalogue(dev, rank, world, pg, args, pk, timed)
+        cat = guarded(bench_catalogue, dev, rank, world, pg, args, pk, timed)
 
     # ---- gather: K1 on the C3 item table (1 M rows x 64 fp32 = 256 MB > L2), 4 M tokens, every slot valid ----
     gat = None
     if not args.no_catalogue and rank == 0:
-        gat = bench_gather(dev, pk)
+        gat = guarded(bench_gather, dev, pk)
 
     # ---- CPU baseline (rank 0, N = 1 only) ----
     cpu = None
@@ -326,10 +484,7 @@ def run_ours(args):
         cpu = cpu_baseline(sample_steps=10)          # ~10 s of host work
     eager = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        try:
-            eager = gpu_eager_baseline(dev)          # the same arithmetic as stock PyTorch eager on this GPU (informative)
-        except Exception as ex:                      # a baseline must never take the product's line down
-            eager = dict(unavailable=str(ex)[:200])
+        eager = guarded(gpu_eager_baseline, dev)     # the same arithmetic as stock PyTorch eager on this GPU (informative)
 
     if rank == 0:
         line = dict(metric=METRIC, value=round(value, 1), unit="seqs/s", n_gpus=world, steps=args.steps, warmup=W,
@@ -342,6 +497,9 @@ def run_ours(args):
                     e2e=dict(value=round(e2e, 1), unit="seqs/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4,
                              ms_per_step=round(ms_e2e / args.steps, 4)),
                     gpu_launches=int(calls_per_step * args.steps), clocks=clocks, roofline=roofline)
+        if dp_parity is not None:
+            line["dp_parity"] = dp_parity
+        line.update(extras)
         if cat is not None:
             line["catalogue"] = cat
         if gat is not None:
@@ -353,10 +511,9 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         # Tear down without dist.destroy_process_group(): with the NCCL all-reduce captured inside live CUDA graphs the
-        # communicator teardown can block for minutes.  All ranks meet, drop the graphs, and leave.
+        # communicator teardown can block for minutes.  All ranks meet and leave.
         torch.cuda.synchronize()
         dist.barrier()
-        tr._graph = None
         torch.cuda.synchronize()
         sys.stdout.flush()
         sys.stderr.flush()
@@ -398,26 +555,36 @@ def bench_gather(dev, pk):
 
 
 def bench_catalogue(dev, rank, world, pg, args, pk, timed):
-    from srfrd_b200 import evaluation as EV
+    """C3: (a) score + top-k + all-gather + merge on given user representations (the roofline-graded part), (b) the same
+    preceded by the sequence encoder on 16 384 Beauty-shaped sequences over the 1 M-item catalogue (SURVEY 8d metric 2:
+    encode + score + top-k + all-gather + merge).  Every rank encodes all users (no exchange), the table is row-sharded."""
+    from srfrd_b200 import evaluation as EV, synth, _lib
     N, D, U = 1_000_000, 64, 16384
     lo, hi = EV.CatalogueIndex.shard_bounds(N + 1, rank, world)
+    m = make_model(dev, N, 50, D, 16, 2, seed=1237)             # xavier_normal_ on the (N+1, D) table (trainer.py:364-369)
+    table = m.flat_parameters().view(m.spec.item_key)
+    table.copy_(table.to(torch.bfloat16).float())              # bf16-representable rows (SURVEY 8d C3)
+    index = EV.CatalogueIndex(table[lo:hi], lo)
     g = torch.Generator(device="cpu").manual_seed(1237)
-    std = (2.0 / (N + 1 + D)) ** 0.5            # xavier_normal_ on an (N+1, D) weight
-    table = torch.randn(N + 1, D, generator=g)[lo:hi].mul_(std).to(torch.bfloat16).float().to(dev)
-    index = EV.CatalogueIndex(table, lo)
-    del table
     feats = torch.randn(U, D, generator=g).to(dev)
+    data = synth.make_interactions(1237, U, N, 5, 4.0, 50)
+    seq, rsq, _ = synth.eval_sequences(data, 50, np.arange(U))
+    seq, rsq = torch.from_numpy(seq).to(dev), torch.from_numpy(rsq).to(dev)
     out = {}
 
     def step(i):
         out["r"] = EV.sharded_topk(feats, index, pg, 1)
 
+    def step_enc(i):
+        f = m.encode_last(seq, rsq)
+        out["e"] = EV.sharded_topk(f[:, :D], index, pg, 1)
+
     steps = max(3, min(args.steps, 10))
     ms = timed(step, steps, 3)
+    ms_enc = timed(step_enc, steps, 3)
     users_s = U * steps / (ms / 1e3)
     flops = 2.0 * U * (hi - lo) * D
     # kernel-only time of the scoring kernel on this rank
-    from srfrd_b200 import _lib
     recs = []
     _lib.set_profile(recs)
     for i in range(3):
@@ -427,18 +594,26 @@ def bench_catalogue(dev, rank, world, pg, args, pk, timed):
     _lib.set_profile(None)
     kms = np.mean([e0.elapsed_time(e1) for n, a, e0, e1 in recs if n == "srfrd_catalogue_topk"])
     tf = flops / (kms * 1e-3) / 1e12
-    return dict(value=round(users_s, 1), unit="users/s", users=U, items=N, D=D, shards=world, ms_per_pass=round(ms / steps, 4),
-                config="C3: 1M items x D=64 bf16 table row-sharded, 16384 users, top-10, all-gather merge",
-                roofline=dict(bound="tensor", kernel="srfrd_catalogue_topk", achieved=round(tf, 1), peak=pk["tf_burst"],
-                              unit="TFLOP/s", frac=round(tf / pk["tf_burst"], 4), avg_launch_ms=round(float(kms), 4),
-                              traffic=measured_traffic("srfrd_catalogue_topk"), peak_source=pk["src"] + ", burst figure (kernel timed alone)"))
+    res = dict(value=round(users_s, 1), unit="users/s", users=U, items=N, D=D, shards=world, ms_per_pass=round(ms / steps, 4),
+               config="C3: 1M items x D=64 bf16 table row-sharded, 16384 users, top-10, all-gather merge",
+               with_encode=dict(value=round(U * steps / (ms_enc / 1e3), 1), unit="users/s", ms_per_pass=round(ms_enc / steps, 4),
+                                what="SRFR encoder (D=64 F=16 L=50 2 blocks) on 16384 sequences + score + top-10 + all-gather + merge"),
+               roofline=dict(bound="tensor", kernel="srfrd_catalogue_topk", achieved=round(tf, 1), peak=pk["tf_burst"],
+                             unit="TFLOP/s", frac=round(tf / pk["tf_burst"], 4), avg_launch_ms=round(float(kms), 4),
+                             traffic=measured_traffic("srfrd_catalogue_topk"), peak_source=pk["src"] + ", burst figure (kernel timed alone)"))
+    del m, index
+    torch.cuda.empty_cache()
+    return res
 
 
 # ---------------------------------------------------------------------------------------------
 def cpu_baseline(sample_steps=2, batch=None):
-    """The reference's CPU path (oracle port: same arithmetic as SRFR_model.py + trainer.py:27-41 through torch's
-    CPU kernels) on this box's host cores, on a bounded sample of the SAME workload (C2 batches of 4096)."""
-    from oracle import srfrd_oracle as O
+    """The reference's CPU path on this box's host cores, on a bounded sample of the SAME workload (C2 batches of 4096,
+    soft discriminator weights, dropout 0.0).  kind "reference": the UNMODIFIED reference module SRFR_model.SRFR staged
+    under oracle/_ref/ by oracle/build_ref.py (the upstream checkout itself does not exist on the GPU box) driven by the
+    step of trainer.py:27-41 (forward, BCE over pos != 0 -- here with the discriminator weights of row L --, backward,
+    Adam(1e-3, (0.9, 0.98))); kind "port": the oracle restatement of the same arithmetic when oracle/_ref is absent."""
+    from oracle import build_ref, srfrd_oracle as O
     from srfrd_b200 import synth                 # synthetic data generator only: no product kernel or model on this path
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -446,18 +621,38 @@ def cpu_baseline(sample_steps=2, batch=None):
     B = batch or c["batch"]
     data = synth.make_interactions(1236, c["usernum"], c["itemnum"], 5, 4.0, c["L"])
     sd = O.init_state_dict("SRFR", c["itemnum"], c["L"], c["D"], c["F"], 0, c["blocks"], seed=1236)
-    orc = O.OracleTrainer(sd, "SRFR", 1)
     smp = synth.BatchSampler(data, c["L"], seed=100)
     batches = [{k: torch.from_numpy(v) for k, v in smp.next_batch(B).items()} for _ in range(sample_steps + 1)]
     ws = [O.discriminator_weights(b["pos"], b["p_fake"], "soft") for b in batches]
-    orc.step(batches[0], ws[0])                 # warm-up
+    SR = build_ref.load_ref()
+    if SR is not None:
+        model = SR.SRFR(c["itemnum"], c["L"], c["D"], c["F"], 0.0, c["blocks"], c["heads"], "cpu")
+        model.load_state_dict(sd)
+        model.train()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.98))      # trainer.py:390
+
+        def step(b, w):
+            _, zp, zn = model(None, b["seq"], b["rsq"], b["pos"], b["prs"], b["neg"], b["nrs"])   # trainer.py:30
+            opt.zero_grad()
+            loss = O.weighted_loss(zp, zn, w)                                                     # trainer.py:36-38 + row L
+            loss.backward()                                                                       # trainer.py:40
+            opt.step()                                                                            # trainer.py:41
+            return float(loss.item())                                                             # trainer.py:42
+        kind = "reference"
+    else:
+        orc = O.OracleTrainer(sd, "SRFR", 1)
+        step = lambda b, w: orc.step(b, w)
+        kind = "port"
+    step(batches[0], ws[0])                     # warm-up
     t0 = time.perf_counter()
     for b, w in zip(batches[1:], ws[1:]):
-        orc.step(b, w)
+        step(b, w)
     dt = time.perf_counter() - t0
-    return dict(value=round(B * sample_steps / dt, 1), unit="seqs/s", cores=cores, kind="port",
+    return dict(value=round(B * sample_steps / dt, 1), unit="seqs/s", cores=cores, kind=kind,
                 sample=f"{sample_steps} steps of batch {B} (C2 workload, fp32, dropout 0.0, soft discriminator weights), "
-                       f"torch {torch.__version__} CPU with {cores} threads", seconds=round(dt, 2))
+                       f"torch {torch.__version__} CPU with {cores} threads"
+                       + (", unmodified reference SRFR_model.SRFR (oracle/_ref)" if kind == "reference" else ", oracle port"),
+                seconds=round(dt, 2))
 
 
 def gpu_eager_baseline(dev, sample_steps=10):
@@ -499,8 +694,7 @@ def run_reference(args):
                 warmup=W, ms_per_step=round(1e3 * CFG["batch"] / cpu["value"], 2), higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f32", data="synthetic",
                 config=dict(workload="C2: SRFR D=64 F=16 L=50 2 blocks 1 head, 12101 items, batch 4096, soft discriminator "
-                                     "weights, dropout 0.0, Adam(1e-3,(0.9,0.98)) -- reference CPU path (oracle port: the "
-                                     "upstream checkout is Python and does not exist on the GPU box)"),
+                                     "weights, dropout 0.0, Adam(1e-3,(0.9,0.98)) -- reference CPU path (" + cpu["kind"] + ")"),
                 cpu_baseline=cpu, e2e=dict(value=cpu["value"], unit="seqs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 wall_s=round(time.perf_counter() - t0, 1))
     print(json.dumps(line))
@@ -514,6 +708,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-catalogue", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C4 / C5 / dropout objects")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SRFRD_ABI_VERSION 3
+#define SRFRD_ABI_VERSION 4
 #if defined(__GNUC__)
 #define SRFRD_API __attribute__((visibility("default")))
 #else
@@ -125,8 +125,8 @@ SRFRD_API int srfrd_gemm_ref(const void* A, int lda, const void* B, int ldb, flo
 
 /* out[n] += sum_m X[m, n]   (bias gradients; positional-table gradient through the (B, L*ld) view) */
 SRFRD_API int srfrd_colsum(const void* X_bf16, int64_t M, int N, int64_t ld, float* out, void* stream);
-/* out[(n / seg_in) * seg_out + n % seg_in] += in[n] for n % seg_in < seg_out */
-SRFRD_API int srfrd_add_segments(const float* in, int64_t n, int seg_in, int seg_out, float* out, void* stream);
+/* out[(n / seg_in) * seg_out + n % seg_in] += in[n] for n % seg_in < seg_out; `in` is consumed (zeroed) */
+SRFRD_API int srfrd_add_segments(float* in, int64_t n, int seg_in, int seg_out, float* out, void* stream);
 
 /* out = keep(seed ^ step, stream_id, m*N+n) ? x / (1-p) : 0  -- re-applies a forward dropout mask to a
  * gradient (same hash as the forward kernels, nothing is stored). */
@@ -182,7 +182,8 @@ SRFRD_API int srfrd_score_loss_fused(const float* h, int ldh, const float* item_
                            void* stream);
 SRFRD_API int srfrd_weight_sums(const int64_t* pos, const float* w_pos, const float* w_neg, int64_t T, float* out2,
                       void* stream);
-SRFRD_API int srfrd_loss_finalize(const float* acc2, const float* norm2, float* loss, void* stream);
+/* loss = acc2[0] / norm2[0] + acc2[1] / norm2[1]; the accumulators are consumed (zeroed for the next step). */
+SRFRD_API int srfrd_loss_finalize(float* acc2, const float* norm2, float* loss, void* stream);
 
 /* ---- K7: Adam(lr, betas, eps), dense, torch.optim.Adam arithmetic (trainer.py:390) ----
  * state3 = {step, 1-beta1^step, 1-beta2^step} lives on the device (CUDA-graph replayable). */
@@ -199,9 +200,14 @@ SRFRD_API int srfrd_adam_step(float* p, float* g, float* m, float* v, int64_t n,
 SRFRD_API int srfrd_catalogue_topk_plan(int64_t U, int64_t n_rows, int64_t row_lo, int D, int n_split, int* chunks_out);
 SRFRD_API int srfrd_catalogue_topk(const void* feats_bf16, int64_t U, int64_t u_pad, int n_split, const void* table_bf16,
                          int64_t n_rows, int64_t row_lo, int64_t id_base, int D, int ld_feats, int ld_table,
-                         int chunks, float* part_scores, int* part_ids, void* stream);
+                         int chunks, float* part_scores, int* part_ids, float* packed_out, void* stream);
 SRFRD_API int srfrd_merge_topk(const float* scores, const int* ids, int64_t U, int nlists, int k, float* out_scores,
                      int64_t* out_ids, void* stream);
+/* Row-sharded scoring: packed_out (nullable, (U, 20) fp32 words) receives each user's final local list as 10 fp32 scores
+ * followed by 10 int32 global ids -- 80 B per user, the send buffer of ONE all-gather; srfrd_merge_topk_packed merges the
+ * gathered (nlists, U, 20) buffer (list l of user u at word (l * U + u) * 20) into the global top-k, identical on every rank. */
+SRFRD_API int srfrd_merge_topk_packed(const float* packed, int64_t U, int nlists, int k, float* out_scores,
+                            int64_t* out_ids, void* stream);
 
 /* ---- on-device batch sampler (next row 8f #1) ----
  * replaces: WarpSampler_fr / sample_function_fr (utils.py:14-90) and the seven LongTensor.to(device) copies per
@@ -214,6 +220,24 @@ SRFRD_API int srfrd_sample_batch(const int64_t* offsets, const int* items, const
                        const int* eligible, int n_eligible, int itemnum, int B, int L, int policy, uint64_t seed,
                        const float* step, int64_t* users, int64_t* seq, int64_t* rsq, int64_t* pos, int64_t* prs,
                        int64_t* neg, int64_t* nrs, float* w_pos, void* stream);
+
+/* ---- sampled-candidate evaluation (row A10 / next row 8f #2) ----
+ * replaces: the per-user loop of evaluation() / evaluation_with_label() (utils.py:558-597, :650-720): the rejection
+ * draw of 100 negatives (utils.py:578-583), the batch-1 predict() call (utils.py:589 -> SRFR_model.py:144-152) and the
+ * double argsort (utils.py:591).
+ * sample_candidates: cand[u, 0] = target[users0[u]], cand[u, 1..C) = uniform ids in 1..itemnum not in the user's TRAIN
+ *   row of the CSR (offsets, items).
+ * candidate_rank: logits[u, c] = <feats[u, :D], E[cand[u, c]]> (+ <feats[u, D:D+F], Fe[user_label[u]]> when fake_table
+ *   != NULL: SRFRN rows, SRFR_model.py:244-257); rank[u] = #{c >= 1 : logits[u, c] > logits[u, 0]}.  Ids outside
+ *   [0, n_rows) are clamped to row 0 and *err_flag (nullable device int) is set to 1 (the reference raises IndexError).
+ * add_user_term: logits[u, 0..I) += <feats_tail[u, 0..F), Fe[label[u]]>  (the same SRFRN term for predict()). */
+SRFRD_API int srfrd_sample_candidates(const int64_t* offsets, const int* items, const int* users0, const int* target,
+                            int64_t U, int itemnum, int C, uint64_t seed, int64_t* cand, void* stream);
+SRFRD_API int srfrd_candidate_rank(const float* feats, int ldf, const float* item_table, int64_t n_rows, int D,
+                         const int64_t* cand, int64_t U, int C, const float* fake_table, int F,
+                         const int64_t* user_label, float* logits, int ldl, int* rank, int* err_flag, void* stream);
+SRFRD_API int srfrd_add_user_term(float* logits, int ldl, int64_t U, int I, const float* feats_tail, int ldf,
+                        const float* fake_table, const int64_t* label, int F, void* stream);
 
 #ifdef __cplusplus
 }

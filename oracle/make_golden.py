@@ -78,6 +78,7 @@ def build(kind, SR, N, L, D, Fw, nb, heads):
 
 
 def one_fixture(kind, SR, seed, N=60, L=12, D=16, Fw=16, nb=2, heads=1, B=6):
+    torch.manual_seed(seed)                  # the constructors' default init (conv biases ...) draws from the GLOBAL stream
     gen = torch.Generator().manual_seed(seed)
     rng = np.random.default_rng(seed)
     model = build(kind, SR, N, L, D, Fw, nb, heads)
@@ -134,6 +135,7 @@ def legacy_sasrec_fixture(RM, seed, N=60, L=12, D=16, nb=2, B=6):
     """model.py SASRec (numpy inputs, args namespace)."""
     import types
     args = types.SimpleNamespace(device="cpu", hidden_units=D, maxlen=L, dropout_rate=0.0, num_blocks=nb, num_heads=1)
+    torch.manual_seed(seed)                  # the constructors' default init (conv biases ...) draws from the GLOBAL stream
     gen = torch.Generator().manual_seed(seed)
     rng = np.random.default_rng(seed)
     model = RM.SASRec(10, N, args)

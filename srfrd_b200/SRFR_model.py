@@ -49,8 +49,11 @@ class _EncodeAndScore(torch.autograd.Function):
     def forward(ctx, model, seq, rsq, pos, prs, neg, nrs, *params):
         eng: HotPath = model._engine
         train = any(ctx.needs_input_grad)    # (grad mode is always off inside Function.forward)
+        if model.training and eng.spec.dropout > 0:
+            eng.host_drop_counter += 1           # a fresh dropout mask per training forward (reference: torch's RNG stream)
         with torch.no_grad():
             hidden = eng.forward(seq, rsq, training=model.training, save=train)
+            ctx.version = eng.fwd_version
             B, L = seq.shape
             zp = zn = None
             if pos is not None or neg is not None:
@@ -76,6 +79,10 @@ class _EncodeAndScore(torch.autograd.Function):
         seq, rsq, pos, prs, neg, nrs = ctx.ids
         B, L = seq.shape
         T = B * L
+        if eng.saved is None or eng.saved.get("version") != ctx.version or eng.fwd_version != ctx.version:
+            raise RuntimeError("srfrd_b200: backward() of a stale forward -- another forward() (training, validation or "
+                               "predict) ran on this model after the one being back-propagated and overwrote the shared "
+                               "activation workspace; run backward() before the next forward()")
         ws = eng._ws
         dh = ws["dh"][:T]
         eng.P.grad.zero_()
@@ -94,7 +101,7 @@ class _EncodeAndScore(torch.autograd.Function):
             dh.zero_()
         if d_hidden is not None:
             dh[:, :eng.spec.Dout].add_(d_hidden.reshape(T, -1))
-        eng.backward(dh)
+        eng.backward(dh, ctx.version)
         grads = tuple(eng.P.view(n, grad=True).clone() for n in model._param_names)
         return (None,) * 7 + grads
 
@@ -190,8 +197,8 @@ class _HotPathModule(nn.Module):
             fid = torch.as_tensor(fake_ids, device=eng.device).long()
             lab = torch.empty(fid.shape[0], dtype=torch.int64, device=eng.device)
             ops.srfu_labels(fid.contiguous(), 3, lab)
-            fe = eng.P.view("embedding_layer.fake_embed.weight")[lab]
-            logits = logits + (feats[:, self.spec.D:] * fe).sum(-1, keepdim=True)
+            logits = logits.contiguous()
+            ops.add_user_term(logits, feats[:, self.spec.D:], eng.P.view("embedding_layer.fake_embed.weight"), lab)
         return logits.squeeze()
 
 

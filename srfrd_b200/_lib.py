@@ -59,8 +59,12 @@ SIGNATURES = {
     "srfrd_adam_tick": [vp, f32, f32, vp],
     "srfrd_adam_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, i32, vp],
     "srfrd_catalogue_topk_plan": [i64, i64, i64, i32, i32, C.POINTER(i32)],
-    "srfrd_catalogue_topk": [vp, i64, i64, i32, vp, i64, i64, i64, i32, i32, i32, i32, vp, vp, vp],
+    "srfrd_catalogue_topk": [vp, i64, i64, i32, vp, i64, i64, i64, i32, i32, i32, i32, vp, vp, vp, vp],
+    "srfrd_merge_topk_packed": [vp, i64, i32, i32, vp, vp, vp],
     "srfrd_merge_topk": [vp, vp, i64, i32, i32, vp, vp, vp],
+    "srfrd_sample_candidates": [vp, vp, vp, vp, i64, i32, i32, u64, vp, vp],
+    "srfrd_candidate_rank": [vp, i32, vp, i64, i32, vp, i64, i32, vp, i32, vp, vp, i32, vp, vp, vp],
+    "srfrd_add_user_term": [vp, i32, i64, i32, vp, i32, vp, vp, i32, vp],
     "srfrd_sample_batch": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
 }
 
@@ -85,7 +89,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)            # AttributeError if the symbol is not exported
         fn.argtypes = argtypes
         fn.restype = C.c_int
-    if lib.srfrd_abi_version() != 3:
+    if lib.srfrd_abi_version() != 4:
         raise RuntimeError("srfrd_b200: ABI version mismatch between _lib.py and the built library")
     _lib = lib
     return lib

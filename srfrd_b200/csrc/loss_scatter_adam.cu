@@ -186,11 +186,13 @@ __global__ void __launch_bounds__(256) weight_sums_kernel(const int64_t* pos, co
   }
 }
 
-__global__ void loss_finalize_kernel(const float* acc, const float* norm, float* loss) {
+// The accumulators are CONSUMED (zeroed for the next step): no separate fill kernel in the step graph.
+__global__ void loss_finalize_kernel(float* acc, const float* norm, float* loss) {
   pdl_prologue_done();
   const float a = norm[0] > 0.f ? acc[0] / norm[0] : 0.f;
   const float b = norm[1] > 0.f ? acc[1] / norm[1] : 0.f;
   loss[0] = a + b;
+  acc[0] = 0.f; acc[1] = 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -240,12 +242,13 @@ __global__ void embed_bwd_kernel(EmbedBwdParams p) {
 }
 
 // out[(n / seg_in) * seg_out + n % seg_in] += in[n] where n % seg_in < seg_out
-__global__ void add_segments_kernel(const float* in, int64_t n, int seg_in, int seg_out, float* out) {
+__global__ void add_segments_kernel(float* in, int64_t n, int seg_in, int seg_out, float* out) {
   pdl_prologue_done();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int c = (int)(i % seg_in);
   if (c < seg_out) out[(i / seg_in) * seg_out + c] += in[i];
+  in[i] = 0.f;                           // consumed: the scratch accumulator is zero again for the next step
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -257,6 +260,9 @@ __global__ void adam_tick_kernel(float* state, float beta1, float beta2) {
   state[0] = step;
   state[1] = (float)(1.0 - pow((double)beta1, (double)step));
   state[2] = (float)(1.0 - pow((double)beta2, (double)step));
+  // state[3]: the same counter as a 32-bit INTEGER bit pattern (the fp32 step stalls at 2^24); this word is what the
+  // dropout masks and the on-device sampler mix into their seeds (mix_seed reads the raw bits)
+  state[3] = __uint_as_float(__float_as_uint(state[3]) + 1u);
 }
 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
@@ -367,7 +373,7 @@ extern "C" int srfrd_weight_sums(const int64_t* pos, const float* w_pos, const f
   return 0;
 }
 
-extern "C" int srfrd_loss_finalize(const float* acc2, const float* norm2, float* loss, void* stream) {
+extern "C" int srfrd_loss_finalize(float* acc2, const float* norm2, float* loss, void* stream) {
   SRFRD_REQUIRE(acc2 && norm2 && loss, "loss_finalize: null pointer");
   SRFRD_CUDA(launch_pdl(loss_finalize_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, acc2, norm2, loss));
   SRFRD_LAUNCH_CHECK();
@@ -391,7 +397,7 @@ extern "C" int srfrd_embed_bwd(const void* dx0, int ldx, const int64_t* seq, con
   return 0;
 }
 
-extern "C" int srfrd_add_segments(const float* in, int64_t n, int seg_in, int seg_out, float* out, void* stream) {
+extern "C" int srfrd_add_segments(float* in, int64_t n, int seg_in, int seg_out, float* out, void* stream) {
   SRFRD_REQUIRE(in && out && seg_in > 0 && seg_out <= seg_in, "add_segments: bad arguments");
   if (n == 0) return 0;
   SRFRD_CUDA(launch_pdl(add_segments_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, in, n, seg_in,

@@ -49,12 +49,22 @@ __global__ void __launch_bounds__(256) sample_batch_kernel(SampleParams p) {
       const float pf = p.p_fake ? p.p_fake[a + src + 1] : 0.f;
       w = p.policy == 2 ? 1.f - pf : (p.policy == 1 ? (pf < 0.5f ? 1.f : 0.f) : 1.f);
       // rejection sampling against the user's own (short) item list
-      for (uint32_t tries = 0;; ++tries) {
-        const int cand = 1 + (int)(hash_u32(seed, 0x4E65u + tries, (uint64_t)o) % (uint32_t)p.itemnum);
-        bool hit = false;
+      // random_neq (utils.py:14-18) loops until the draw is outside the user's set; after 256 failed draws (a user who
+      // rated almost the whole catalogue) walk upwards from the last draw to the next free id -- never a colliding id
+      // while one exists (the reference would spin forever if none does; here the last draw is kept)
+      int cand = 1;
+      bool hit = true;
+      for (uint32_t tries = 0; hit && tries < 256; ++tries) {
+        cand = 1 + (int)(hash_u32(seed, 0x4E65u + tries, (uint64_t)o) % (uint32_t)p.itemnum);
+        hit = false;
         for (int k = 0; k < n; ++k) hit |= p.items[a + k] == cand;
-        if (!hit || tries >= 64) { ng = cand; break; }
       }
+      for (int walk = 0; hit && walk < p.itemnum; ++walk) {
+        cand = cand % p.itemnum + 1;
+        hit = false;
+        for (int k = 0; k < n; ++k) hit |= p.items[a + k] == cand;
+      }
+      ng = cand;
     }
     p.seq[o] = sq; p.rsq[o] = rq; p.pos[o] = ps; p.prs[o] = pr; p.neg[o] = ng; p.nrs[o] = valid ? 1 : 0;
     if (p.w_pos) p.w_pos[o] = w;

@@ -47,6 +47,8 @@ struct TopkShape {
   const bf16* table; int ld_table;
   float* out_scores;      // (U, slots, TK)  phase 1: tile maxima; phase 2 writes the row's exact top-10 into slot 0
   int* out_ids;           // (U, slots, TK)  phase 1: tile indices (-1 = empty); phase 2: global item ids in slot 0
+  float* packed;          // optional (U, 2 * TK): the row's final list as TK fp32 scores followed by TK int32 global ids
+                          // -- the send buffer of the row-sharded all-gather (80 B per user), written by phase 2
 };
 
 // D[tmem] (+)= A[tmem] * B[smem]
@@ -447,7 +449,11 @@ __global__ void __launch_bounds__(256) catalogue_refine_kernel(TopkShape s) {
       const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
       if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; bl = ol; }
     }
-    if (lane == 0) { osc[r] = bv; oid[r] = bi < 0 ? -1 : (int)(s.id_base + bi); }
+    if (lane == 0) {
+      const int gid = bi < 0 ? -1 : (int)(s.id_base + bi);
+      osc[r] = bv; oid[r] = gid;
+      if (s.packed) { s.packed[(size_t)u * 2 * TK + r] = bv; reinterpret_cast<int*>(s.packed)[(size_t)u * 2 * TK + TK + r] = gid; }
+    }
     if (lane == bl && bi >= 0) {                        // pop my head
 #pragma unroll
       for (int k = 0; k < TK - 1; ++k) { ts[k] = ts[k + 1]; ti[k] = ti[k + 1]; }
@@ -478,6 +484,38 @@ __global__ void merge_topk_kernel(const float* sc, const int* ids, int64_t U, in
       if (up) {
         const float fs = ts[r]; ts[r] = ts[r - 1]; ts[r - 1] = fs;
         const int is = ti[r]; ti[r] = ti[r - 1]; ti[r - 1] = is;
+      }
+    }
+  }
+  for (int r = 0; r < k; ++r) {
+    out_sc[u * k + r] = ts[r];
+    out_ids[u * k + r] = ti[r];
+  }
+}
+
+// K9 over the all-gathered send buffers: list l of user u is packed[(l * U + u) * 2 TK ...] = TK scores, TK int32 ids.
+__global__ void merge_topk_packed_kernel(const float* packed, int64_t U, int nlists, int k, float* out_sc, int64_t* out_ids) {
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= U) return;
+  float ts[TK]; int ti[TK];
+#pragma unroll
+  for (int r = 0; r < TK; ++r) { ts[r] = -INFINITY; ti[r] = -1; }
+  for (int l = 0; l < nlists; ++l) {
+    const float* s0 = packed + ((size_t)l * U + u) * 2 * TK;
+    const int* i0 = reinterpret_cast<const int*>(s0) + TK;
+    for (int n = 0; n < TK; ++n) {
+      const float v = s0[n]; const int id = i0[n];
+      if (id < 0) continue;
+      const bool better = (ti[TK - 1] < 0) || v > ts[TK - 1] || (v == ts[TK - 1] && id < ti[TK - 1]);
+      if (!better) continue;
+      ts[TK - 1] = v; ti[TK - 1] = id;
+#pragma unroll
+      for (int r = TK - 1; r > 0; --r) {
+        const bool up = (ti[r - 1] < 0) || ts[r] > ts[r - 1] || (ts[r] == ts[r - 1] && ti[r] < ti[r - 1]);
+        if (up) {
+          const float fs = ts[r]; ts[r] = ts[r - 1]; ts[r - 1] = fs;
+          const int is = ti[r]; ti[r] = ti[r - 1]; ti[r - 1] = is;
+        }
       }
     }
   }
@@ -552,7 +590,7 @@ static int launch_tilemax(const CUtensorMap& tmE, TopkShape& s, int grid, cudaSt
 
 extern "C" int srfrd_catalogue_topk(const void* feats_bf16, int64_t U, int64_t u_pad, int n_split, const void* table_bf16,
                                     int64_t n_rows, int64_t row_lo, int64_t id_base, int D, int ld_feats, int ld_table,
-                                    int chunks, float* part_scores, int* part_ids, void* stream_) {
+                                    int chunks, float* part_scores, int* part_ids, float* packed_out, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SRFRD_REQUIRE(feats_bf16 && table_bf16 && part_scores && part_ids, "catalogue_topk: null pointer");
   SRFRD_REQUIRE(n_split >= 1 && n_split <= 3, "catalogue_topk: n_split must be 1..3");
@@ -573,7 +611,7 @@ extern "C" int srfrd_catalogue_topk(const void* feats_bf16, int64_t U, int64_t u
   s.tiles_total = pl.tiles_total; s.ugroups = pl.ugroups; s.share = pl.share; s.slots = pl.slots;
   s.feats = (const bf16*)feats_bf16; s.ld_feats = ld_feats;
   s.table = (const bf16*)table_bf16; s.ld_table = ld_table;
-  s.out_scores = part_scores; s.out_ids = part_ids;
+  s.out_scores = part_scores; s.out_ids = part_ids; s.packed = packed_out;
   { const char* dbg = getenv("SRFRD_TOPK_DEBUG"); s.debug = dbg ? atoi(dbg) : 0; }
   // list slots a user group does not use stay empty (index -1)
   SRFRD_CUDA(cudaMemsetAsync(part_ids, 0xFF, (size_t)U * pl.slots * TK * sizeof(int), stream));
@@ -597,6 +635,16 @@ extern "C" int srfrd_merge_topk(const float* scores, const int* ids, int64_t U, 
   SRFRD_REQUIRE(k >= 1 && k <= TK, "merge_topk: k must be in 1..%d", TK);
   if (U == 0) return 0;
   merge_topk_kernel<<<(unsigned)((U + 127) / 128), 128, 0, (cudaStream_t)stream>>>(scores, ids, U, nlists, k, out_scores, out_ids);
+  SRFRD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int srfrd_merge_topk_packed(const float* packed, int64_t U, int nlists, int k, float* out_scores,
+                                       int64_t* out_ids, void* stream) {
+  SRFRD_REQUIRE(packed && out_scores && out_ids, "merge_topk_packed: null pointer");
+  SRFRD_REQUIRE(k >= 1 && k <= TK && nlists >= 1, "merge_topk_packed: k must be in 1..%d", TK);
+  if (U == 0) return 0;
+  merge_topk_packed_kernel<<<(unsigned)((U + 127) / 128), 128, 0, (cudaStream_t)stream>>>(packed, U, nlists, k, out_scores, out_ids);
   SRFRD_LAUNCH_CHECK();
   return 0;
 }

@@ -139,7 +139,11 @@ class FlatParams:
             off += (n + 3) // 4 * 4                      # keep every view 16-byte aligned
         self.numel = off
         self.data = torch.zeros(off, dtype=torch.float32, device=device)
-        self.grad = torch.zeros(off, dtype=torch.float32, device=device)
+        # gradient bucket = every parameter gradient followed by a 4-float tail that carries the step's loss accumulators:
+        # data-parallel training moves gradients AND loss with ONE all-reduce over `grad_bucket`
+        self.grad_bucket = torch.zeros(off + 4, dtype=torch.float32, device=device)
+        self.grad = self.grad_bucket[:off]
+        self.grad_tail = self.grad_bucket[off:]
 
     def view(self, name: str, grad: bool = False) -> torch.Tensor:
         off, shape = self.offsets[name]
@@ -160,8 +164,13 @@ class HotPath:
         self.device = params.data.device
         self._ws_tokens = 0
         self._ws: Dict[str, torch.Tensor] = {}
+        # bumped whenever the workspace is re-allocated: a captured CUDA graph holds raw pointers into it, so
+        # FusedTrainer keys its graph on this and re-captures after a larger forward (evaluation chunk, bigger batch)
+        self.ws_generation = 0
+        self.fwd_version = 0            # stamps every forward; backward() of anything but the latest forward raises
+        self.host_drop_counter = 0      # mixed into the dropout seed on the autograd path (no device step counter there)
         self._build_shadows()
-        self.step_state = torch.zeros(4, dtype=torch.float32, device=self.device)   # Adam {step, bc1, bc2}
+        self.step_state = torch.zeros(4, dtype=torch.float32, device=self.device)   # Adam {step, bc1, bc2, uint32 step bits}
         # Independent branches of the step (the k/v projection next to LN1 + the q projection; every weight-gradient
         # GEMM next to the data-gradient chain) are enqueued on a second stream: captured into the CUDA graph they
         # become parallel branches, so one kernel's launch latency, tail and CTA skew are filled by the other's CTAs.
@@ -250,9 +259,12 @@ class HotPath:
 
     # ------------------------------------------------------------------ workspaces
     def _workspace(self, T: int, L: int) -> Dict[str, torch.Tensor]:
+        """Activation / gradient buffers for up to T tokens.  Everything whose size depends on the sequence length
+        (pos_tmp, the long-sequence softmax statistics) is sized by spec.max_len, so reuse depends on T only."""
         if T <= self._ws_tokens:
             return self._ws
         s, dev = self.spec, self.device
+        Lmax = max(L, s.max_len)
         H, nb = s.Hp, s.num_blocks               # padded widths; padding columns stay zero (buffers start zeroed and
         ws: Dict[str, torch.Tensor] = {}         # no kernel ever writes a non-zero value there)
 
@@ -267,7 +279,7 @@ class HotPath:
             act(f"kv{i}", 2 * H)
             act(f"st1_{i}", 2, torch.float32)
             act(f"st2_{i}", 2, torch.float32)
-            if L > 128:                              # softmax row statistics for the tile-pair backward (maxlen > 128)
+            if Lmax > 128:                           # softmax row statistics for the tile-pair backward (maxlen > 128)
                 ws[f"ast{i}"] = torch.zeros(T * s.num_heads, 4, dtype=torch.float32, device=dev)
         if s.kind == "SRFR":
             act("c", s.Dp)
@@ -286,8 +298,9 @@ class HotPath:
         if s.dropout > 0:
             for i in range(nb):
                 act(f"gE_{i}")
-        ws["pos_tmp"] = torch.zeros(L * H, dtype=torch.float32, device=dev)
+        ws["pos_tmp"] = torch.zeros(Lmax * H, dtype=torch.float32, device=dev)
         self._ws, self._ws_tokens = ws, T
+        self.ws_generation += 1
         return ws
 
     # ------------------------------------------------------------------ forward
@@ -301,9 +314,13 @@ class HotPath:
             raise RuntimeError(f"sequence length {L} exceeds max_len {s.max_len} (pos_embed rows, SRFR_model.py:12)")
         T, H, Hp, nb = B * L, s.H, s.Hp, s.num_blocks
         ws = self._workspace(T, L)
+        self.fwd_version += 1                   # EVERY forward overwrites the shared activations (saving or not)
         p_drop = s.dropout if training else 0.0
-        step = self.step_state[0:1] if p_drop > 0 else None
-        seed = self.drop_seed
+        step = self.step_state[3:4] if p_drop > 0 else None      # integer step counter bits (adam_tick), never stalls
+        # FusedTrainer advances the device step counter (step_state[0]) once per step, which gives a captured graph a fresh
+        # mask per replay; the autograd path (model.forward + a torch optimizer, trainer.simulate) has no such counter, so
+        # _EncodeAndScore bumps host_drop_counter per training forward and it is folded into the seed here
+        seed = (self.drop_seed + self.host_drop_counter * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
         seq = seq.contiguous()
         aux_ids = None
         if s.mode == 1:
@@ -311,6 +328,14 @@ class HotPath:
         elif s.mode == 2:
             aux_ids = torch.empty(B, dtype=torch.int64, device=self.device)
             ops.srfu_labels(fake_ids.contiguous(), {"SRFU_B": 0, "SRFU_F": 1, "SRFU_R": 2}[s.kind], aux_ids)
+            # label ranges are static per kind: B {1, 2}, F [0, L], R [0, 10] (SRFR_model.py:546-570; the reference's own
+            # zoo passes 3 / maxlen + 1 / 11 rows, trainer.py:173-205).  A smaller table (e.g. the constructor default
+            # number_of_labels = 2) makes the reference raise IndexError when such a label occurs; only in that
+            # under-provisioned case the labels are checked here (one D2H sync) instead of reading past the table.
+            need = {"SRFU_B": 3, "SRFU_F": L + 1, "SRFU_R": 11}[s.kind]
+            if s.n_labels < need and B > 0 and int(aux_ids.max()) >= s.n_labels:
+                raise IndexError(f"index out of range in self: {s.kind} user label {int(aux_ids.max())} needs "
+                                 f"number_of_labels >= {need}, got {s.n_labels}")
         aux_table = P.view(s.aux_key) if s.aux_key else None
         x = [ws[f"x{i}"][:T] for i in range(nb + 1)]
         ops.embed_ln_fwd(P.view(s.item_key), P.view(s.pos_key), aux_table, s.mode, seq, aux_ids, s.item_scale,
@@ -361,16 +386,23 @@ class HotPath:
         ops.layernorm_fwd(fin_in, P.view("last_layernorm.weight"), P.view("last_layernorm.bias"), LN_EPS, y_f32=hfin,
                           stats=ws["stF"][:T], H=s.Dout)
         if training if save is None else save:
-            self.saved = dict(seq=seq, aux_ids=aux_ids, B=B, L=L, p_drop=p_drop, seed=seed, step=step)
+            self.saved = dict(seq=seq, aux_ids=aux_ids, B=B, L=L, p_drop=p_drop, seed=seed, step=step,
+                              version=self.fwd_version)
         return hfin.view(B, L, s.Doutp)[..., :s.Dout]
 
     # ------------------------------------------------------------------ backward
-    def backward(self, dh: torch.Tensor) -> None:
+    def backward(self, dh: torch.Tensor, version: Optional[int] = None) -> None:
         """Given dL/dhidden (T, Dout) fp32, accumulate every parameter gradient into P.grad
-        (the score kernels have already added the pos/neg rows of the item table)."""
+        (the score kernels have already added the pos/neg rows of the item table).  The activations live in the
+        engine's shared workspace, so only the LATEST saving forward can be back-propagated: `version` (the stamp the
+        autograd node took at forward time) is checked against it."""
         s, P, sv = self.spec, self.P, self.saved
         if sv is None:
             raise RuntimeError("backward() without a training forward()")
+        if sv["version"] != self.fwd_version or (version is not None and version != sv["version"]):
+            raise RuntimeError("srfrd_b200: backward() of a stale forward -- another forward() (training, validation or "
+                               "predict) ran on this model after the one being back-propagated and overwrote the shared "
+                               "activation workspace; run backward() before the next forward()")
         B, L = sv["B"], sv["L"]
         T, H, Hp, nb = B * L, s.H, s.Hp, s.num_blocks
         ws = self._ws
@@ -444,8 +476,7 @@ class HotPath:
         aux_grad = G(s.aux_key) if s.aux_key else None
         ops.embed_bwd(dx0, sv["seq"], sv["aux_ids"], s.D, s.F if s.mode == 1 else 0, s.mode, s.item_scale,
                       G(s.item_key), aux_grad)
-        pos_tmp = ws["pos_tmp"][:L * Hp]
-        pos_tmp.zero_()
+        pos_tmp = ws["pos_tmp"][:L * Hp]          # zero on entry: allocated zeroed, and add_segments consumes (re-zeroes) it
         ops.colsum(dx0, pos_tmp, M=B, N=L * Hp, ld=L * Hp)
         ops.add_segments(pos_tmp, L * Hp, Hp, s.D, G(s.pos_key))
         self._join()                                # every weight gradient has landed in P.grad

@@ -1,5 +1,5 @@
 """Evaluation on the hot path: full-catalogue top-k (tcgen05 scoring fused with a streaming top-10)
-and the reference's sampled-101 protocol (utils.py:544-602), both batched.
+and the reference's sampled-101 protocol (utils.py:544-602), both batched and both on the library's own kernels.
 
 Full-catalogue scoring is the reference's ``predict(user_ids, seq, rsq, label)`` called with
 ``label = arange(1, itemnum + 1)`` followed by ``(-logits).argsort().argsort()`` (utils.py:589-591),
@@ -41,11 +41,9 @@ class CatalogueIndex:
         return min(rank * S, n_rows_total), min((rank + 1) * S, n_rows_total)
 
 
-def local_topk(feats_f32: torch.Tensor, index: CatalogueIndex, n_split: int = 1):
-    """Per-user top-10 of feats (U, D) against the local shard -> (scores (U,10) fp32, ids (U,10) int64)."""
+def _split_feats(feats_f32: torch.Tensor, Dp: int, n_split: int):
     U, D = feats_f32.shape
     dev = feats_f32.device
-    Dp = index.Dp
     u_pad = (U + 255) // 256 * 256          # whole user groups (2 tiles of 128) per split
     fb = torch.zeros(n_split * u_pad, Dp, dtype=bf16, device=dev)
     f = feats_f32.contiguous()
@@ -59,12 +57,29 @@ def local_topk(feats_f32: torch.Tensor, index: CatalogueIndex, n_split: int = 1)
         ops.f32_to_bf16_split(f, hi, mid)
         rest = f - hi.float() - mid.float()
         ops.f32_to_bf16_split(rest.contiguous(), fb[2 * u_pad:2 * u_pad + U, :D], None)
-    if index.n_rows <= index.row_lo:                      # empty shard
-        return (torch.full((U, TK), float("-inf"), device=dev), torch.full((U, TK), -1, dtype=torch.int64, device=dev))
-    chunks = ops.catalogue_topk_plan(U, index.n_rows, index.row_lo, Dp, n_split)
+    return fb, u_pad
+
+
+def _local_lists(feats_f32: torch.Tensor, index: CatalogueIndex, n_split: int, packed: Optional[torch.Tensor]):
+    """Run K8 on the local shard; returns the (U, chunks, 10) list buffers whose slot 0 holds each user's exact local
+    top-10 (sorted, global ids) and, when `packed` is given, the same list in the all-gather wire format."""
+    U = feats_f32.shape[0]
+    dev = feats_f32.device
+    fb, u_pad = _split_feats(feats_f32, index.Dp, n_split)
+    chunks = ops.catalogue_topk_plan(U, index.n_rows, index.row_lo, index.Dp, n_split)
     ps = torch.empty(U, chunks, TK, dtype=torch.float32, device=dev)
     pi = torch.empty(U, chunks, TK, dtype=torch.int32, device=dev)
-    ops.catalogue_topk(fb, U, u_pad, n_split, index.table, index.row_lo, index.id_base, chunks, ps, pi)
+    ops.catalogue_topk(fb, U, u_pad, n_split, index.table, index.row_lo, index.id_base, chunks, ps, pi, packed)
+    return ps, pi, chunks
+
+
+def local_topk(feats_f32: torch.Tensor, index: CatalogueIndex, n_split: int = 1):
+    """Per-user top-10 of feats (U, D) against the local shard -> (scores (U,10) fp32, ids (U,10) int64)."""
+    U = feats_f32.shape[0]
+    dev = feats_f32.device
+    if index.n_rows <= index.row_lo:                      # empty shard
+        return (torch.full((U, TK), float("-inf"), device=dev), torch.full((U, TK), -1, dtype=torch.int64, device=dev))
+    ps, pi, chunks = _local_lists(feats_f32, index, n_split, None)
     out_s = torch.empty(U, TK, dtype=torch.float32, device=dev)
     out_i = torch.empty(U, TK, dtype=torch.int64, device=dev)
     ops.merge_topk(ps, pi, U, chunks, TK, out_s, out_i)
@@ -81,18 +96,25 @@ def merge_shards(scores: torch.Tensor, ids: torch.Tensor, k: int = TK):
 
 
 def sharded_topk(feats_f32: torch.Tensor, index: CatalogueIndex, process_group=None, n_split: int = 1):
-    """Row-sharded catalogue scoring: local top-10, all-gather (80 B / user / rank), merge -> identical
-    (U, 10) on every rank."""
-    s, i = local_topk(feats_f32, index, n_split)
+    """Row-sharded catalogue scoring: local top-10, ONE all-gather of the packed lists (10 fp32 scores + 10 int32 global
+    ids = 80 B / user / rank, written in wire format by the scoring kernel itself), merge straight out of the gathered
+    buffer -> identical (U, 10) on every rank.  No int64 on the wire, no permute / contiguous copies."""
+    from . import parallel
     if process_group is None or torch.distributed.get_world_size(process_group) == 1:
-        return s, i
+        return local_topk(feats_f32, index, n_split)
     G = torch.distributed.get_world_size(process_group)
-    U = s.shape[0]
-    gs = torch.empty(G, U, TK, dtype=torch.float32, device=s.device)
-    gi = torch.empty(G, U, TK, dtype=torch.int64, device=s.device)
-    torch.distributed.all_gather_into_tensor(gs, s.contiguous(), group=process_group)
-    torch.distributed.all_gather_into_tensor(gi, i.contiguous(), group=process_group)
-    return merge_shards(gs.permute(1, 0, 2).contiguous(), gi.permute(1, 0, 2).contiguous())
+    U = feats_f32.shape[0]
+    dev = feats_f32.device
+    packed = torch.empty(U, 2 * TK, dtype=torch.float32, device=dev)
+    if index.n_rows <= index.row_lo:                      # empty shard: ids -1 (bit pattern of int32 -1 in every id word)
+        packed.view(torch.int32).fill_(-1)
+    else:
+        _local_lists(feats_f32, index, n_split, packed)
+    gathered = parallel.allgather_packed_topk(packed, process_group)        # (G, U, 20)
+    out_s = torch.empty(U, TK, dtype=torch.float32, device=dev)
+    out_i = torch.empty(U, TK, dtype=torch.int64, device=dev)
+    ops.merge_topk_packed(gathered, U, G, TK, out_s, out_i)
+    return out_s, out_i
 
 
 def hr_ndcg_from_topk(topk_ids: torch.Tensor, target: torch.Tensor, k: int = 10) -> Tuple[float, float]:
@@ -125,42 +147,106 @@ def evaluate_full_catalogue(model, seq, rsq, target, batch_users: int = 16384, n
     return ndcg, hr, ids
 
 
-@torch.no_grad()
-def evaluation(model, dataset, maxlen, device, max_users: int = 10000, seed: Optional[int] = None, chunk: int = 2048):
-    """Batched restatement of the reference's evaluation() (utils.py:544-602): per user 1 held-out target +
-    100 uniform negatives not in the user's train set, rank of the target among the 101, HR@10 / NDCG@10.
-    Returns (NDCG@10, HR@10).  The candidate scoring goes through model.predict's tensor-core path."""
+def dataset_to_csr(dataset):
+    """The reference's [user_train, user_test, usernum, itemnum] dicts (utils.py:92-139) -> CSR arrays over user rows
+    0..usernum-1 (row u-1 = user u): offsets int64, items int32, labels int8, first held-out item (0 = none)."""
     train, test, usernum, itemnum = dataset
-    rng = np.random.default_rng(seed)
-    users = list(range(1, usernum + 1))
+    lens = np.fromiter((len(train["item_ids"].get(u, ())) for u in range(1, usernum + 1)), np.int64, usernum)
+    offsets = np.zeros(usernum + 1, np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    items = np.fromiter((i for u in range(1, usernum + 1) for i in train["item_ids"].get(u, ())), np.int32, int(offsets[-1]))
+    labels = np.fromiter((r for u in range(1, usernum + 1) for r in train["review_ids"].get(u, ())), np.int8, int(offsets[-1]))
+    target = np.fromiter((test["item_ids"][u][0] if len(test["item_ids"].get(u, ())) >= 1 else 0
+                          for u in range(1, usernum + 1)), np.int32, usernum)
+    return offsets, items, labels, target, int(usernum), int(itemnum)
+
+
+def eval_users(csr, max_users: int = 10000, rng: Optional[np.random.Generator] = None) -> np.ndarray:
+    """User rows the reference would evaluate (utils.py:551-559): at most ``max_users`` sampled without replacement,
+    then those with at least one train and one held-out interaction."""
+    offsets, _, _, target, usernum, _ = csr
+    rows = np.arange(usernum)
     if usernum > max_users:
-        users = rng.choice(np.arange(1, usernum + 1), max_users, replace=False).tolist()
-    users = [u for u in users if len(train["item_ids"][u]) >= 1 and len(test["item_ids"][u]) >= 1]
-    NDCG = HT = 0.0
-    for s in range(0, len(users), chunk):
-        us = users[s:s + chunk]
-        seq = np.zeros((len(us), maxlen), np.int64)
-        rsq = np.zeros((len(us), maxlen), np.int64)
-        cand = np.zeros((len(us), 101), np.int64)
-        for r, u in enumerate(us):
-            it, rv = train["item_ids"][u][-maxlen:], train["review_ids"][u][-maxlen:]
-            seq[r, maxlen - len(it):] = it
-            rsq[r, maxlen - len(rv):] = rv
-            rated = set(train["item_ids"][u]) | {0}
-            cand[r, 0] = test["item_ids"][u][0]
-            j = 1
-            while j < 101:
-                t = int(rng.integers(1, itemnum + 1))
-                if t not in rated:
-                    cand[r, j] = t
-                    j += 1
-        feats = model.encode_last(torch.from_numpy(seq).to(device), torch.from_numpy(rsq).to(device))
-        table = model._engine.P.view(model.spec.item_key)
-        rows = table[torch.from_numpy(cand).to(device)]                     # (u, 101, D) candidate gather
-        logits = torch.einsum("ud,ucd->uc", feats[:, :model.spec.D], rows)   # 101 dots per user: not the hot path
-        rank = (logits[:, 1:] > logits[:, :1]).sum(1).cpu().numpy()
-        hit = rank < 10
-        NDCG += float(np.where(hit, 1.0 / np.log2(rank + 2.0), 0.0).sum())
-        HT += float(hit.sum())
-    n = max(len(users), 1)
-    return NDCG / n, HT / n
+        rng = rng or np.random.default_rng()
+        rows = np.sort(rng.choice(usernum, max_users, replace=False))
+    ok = (np.diff(offsets)[rows] >= 1) & (target[rows] != 0)
+    return rows[ok].astype(np.int32)
+
+
+def right_aligned(csr, rows: np.ndarray, maxlen: int):
+    """seq / rsq as evaluation() builds them (utils.py:561-574): the last ``maxlen`` train items, right-aligned."""
+    offsets, items, labels = csr[0], csr[1], csr[2]
+    a, b = offsets[rows], offsets[rows + 1]
+    t = np.arange(maxlen)[None, :]
+    src = (b - a)[:, None] - (maxlen - t)
+    valid = src >= 0
+    gi = np.where(valid, a[:, None] + src, 0)
+    if len(items) == 0:
+        z = np.zeros((len(rows), maxlen), np.int64)
+        return z, z.copy()
+    return (np.where(valid, items[gi], 0).astype(np.int64), np.where(valid, labels[gi], 0).astype(np.int64))
+
+
+@torch.no_grad()
+def sampled_ranks(model, csr, rows: np.ndarray, maxlen: int, device, seed: int = 0, n_neg: int = 100,
+                  candidates: Optional[np.ndarray] = None, chunk: int = 8192, return_logits: bool = False):
+    """0-based rank of each user's held-out item among itself + ``n_neg`` sampled negatives (utils.py:576-591), on the
+    device: candidate draw (srfrd_sample_candidates, rejection against the user's train row), encoder on the hot-path
+    kernels, candidate scoring + rank (srfrd_candidate_rank).  ``candidates`` (len(rows), 1 + n_neg) overrides the
+    draw (parity tests feed the reference's own sets).  Returns ranks (numpy int64)[, logits (numpy)]."""
+    offsets, items, labels, target, usernum, itemnum = csr
+    dev = torch.device(device)
+    eng = model._sync_flat()
+    spec = model.spec
+    d_off = torch.from_numpy(offsets).to(dev)
+    d_items = torch.from_numpy(items if len(items) else np.zeros(1, np.int32)).to(dev)
+    d_target = torch.from_numpy(target).to(dev)
+    C = 1 + n_neg if candidates is None else candidates.shape[1]
+    ranks, logits_out = [], []
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    for s in range(0, len(rows), chunk):
+        r = rows[s:s + chunk]
+        seq, rsq = right_aligned(csr, r, maxlen)
+        seq_d, rsq_d = torch.from_numpy(seq).to(dev), torch.from_numpy(rsq).to(dev)
+        if candidates is None:
+            cand = torch.empty(len(r), C, dtype=torch.int64, device=dev)
+            ops.sample_candidates(d_off, d_items, torch.from_numpy(np.ascontiguousarray(r, np.int32)).to(dev), d_target,
+                                  itemnum, C, seed + s, cand)
+        else:
+            cand = torch.from_numpy(np.ascontiguousarray(candidates[s:s + chunk], np.int64)).to(dev)
+        feats = model.encode_last(seq_d, rsq_d)                          # (u, Dout) fp32
+        rank = torch.empty(len(r), dtype=torch.int32, device=dev)
+        lg = torch.empty(len(r), C, dtype=torch.float32, device=dev) if return_logits else None
+        ft = lab = None
+        if spec.kind == "SRFRN":                                         # rows E[id] || Fe[user label], SRFR_model.py:244-257
+            ft = eng.P.view("embedding_layer.fake_embed.weight")
+            lab = torch.empty(len(r), dtype=torch.int64, device=dev)
+            ops.srfu_labels(rsq_d.contiguous(), 3, lab)
+        ops.candidate_rank(feats, eng.P.view(spec.item_key), cand, spec.D, ft, lab, lg, rank, err)
+        ranks.append(rank)
+        if return_logits:
+            logits_out.append(lg)
+    if not ranks:
+        return (np.zeros(0, np.int64), np.zeros((0, C), np.float32)) if return_logits else np.zeros(0, np.int64)
+    out = torch.cat(ranks).cpu().numpy().astype(np.int64)                # one D2H read for all users
+    if int(err.item()):
+        raise IndexError("index out of range in self: a candidate item id is outside the item table")
+    if return_logits:
+        return out, torch.cat(logits_out).cpu().numpy()
+    return out
+
+
+@torch.no_grad()
+def evaluation(model, dataset, maxlen, device, max_users: int = 10000, seed: Optional[int] = None, chunk: int = 8192,
+               candidates: Optional[np.ndarray] = None, users: Optional[np.ndarray] = None):
+    """The reference's evaluation() (utils.py:544-602), batched on the device: per user 1 held-out target + 100 uniform
+    negatives not in the user's train set, rank of the target among the 101, HR@10 / NDCG@10.  Returns
+    (NDCG@10, HR@10).  Candidate draw, encoder and candidate scoring / ranking all run on the library's kernels
+    (sampled_ranks); ``users`` (1-based ids) / ``candidates`` pin the user order and candidate sets for parity tests."""
+    csr = dataset_to_csr(dataset)
+    rng = np.random.default_rng(seed)
+    rows = eval_users(csr, max_users, rng) if users is None else (np.asarray(users, np.int64) - 1).astype(np.int32)
+    rank = sampled_ranks(model, csr, rows, maxlen, device, seed=int(rng.integers(1 << 31)), candidates=candidates, chunk=chunk)
+    hit = rank < 10
+    n = max(len(rows), 1)
+    return float(np.where(hit, 1.0 / np.log2(rank + 2.0), 0.0).sum() / n), float(hit.sum() / n)

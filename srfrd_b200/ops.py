@@ -220,11 +220,17 @@ def catalogue_topk_plan(U, n_rows, row_lo, D, n_split) -> int:
     return out.value
 
 
-def catalogue_topk(feats, U, u_pad, n_split, table, row_lo, id_base, chunks, part_scores, part_ids):
+def catalogue_topk(feats, U, u_pad, n_split, table, row_lo, id_base, chunks, part_scores, part_ids, packed=None):
+    """packed: optional (U, 20) fp32 -- each user's final local list as 10 scores + 10 int32 ids (all-gather send buffer)."""
     _lib.require_device()
     D = table.shape[1]
     call("srfrd_catalogue_topk", _p(feats), U, u_pad, n_split, _p(table), table.shape[0], row_lo, id_base, D,
-         feats.stride(0), table.stride(0), chunks, _p(part_scores), _p(part_ids), _stream())
+         feats.stride(0), table.stride(0), chunks, _p(part_scores), _p(part_ids), _p(packed), _stream())
+
+
+def merge_topk_packed(packed, U, nlists, k, out_scores, out_ids):
+    _lib.require_device()
+    call("srfrd_merge_topk_packed", _p(packed), U, nlists, k, _p(out_scores), _p(out_ids), _stream())
 
 
 def merge_topk(scores, ids, U, nlists, k, out_scores, out_ids):
@@ -238,3 +244,27 @@ def sample_batch(offsets, items, labels, p_fake, eligible, itemnum, B, L, policy
     call("srfrd_sample_batch", _p(offsets), _p(items), _p(labels), _p(p_fake), _p(eligible), eligible.numel(), int(itemnum),
          B, L, int(policy), int(seed), _p(step), _p(out.get("users")), _p(out["seq"]), _p(out["rsq"]), _p(out["pos"]),
          _p(out["prs"]), _p(out["neg"]), _p(out["nrs"]), _p(w_pos), _stream())
+
+
+def sample_candidates(offsets, items, users0, target, itemnum, C, seed, cand):
+    """cand (U, C) int64: column 0 = the held-out item, the rest uniform ids outside the user's train row."""
+    _lib.require_device()
+    call("srfrd_sample_candidates", _p(offsets), _p(items), _p(users0), _p(target), users0.numel(), int(itemnum), int(C),
+         int(seed), _p(cand), _stream())
+
+
+def candidate_rank(feats, item_table, cand, D, fake_table=None, user_label=None, logits=None, rank=None, err_flag=None):
+    _lib.require_device()
+    _chk(feats, torch.float32, "feats"); _chk(item_table, torch.float32, "item_table"); _chk(cand, torch.int64, "cand")
+    U, Cn = cand.shape
+    F = 0 if fake_table is None else fake_table.shape[1]
+    call("srfrd_candidate_rank", _p(feats), feats.stride(0), _p(item_table), item_table.shape[0], int(D), _p(cand), U, Cn,
+         _p(fake_table), F, _p(user_label), _p(logits), 0 if logits is None else logits.stride(0), _p(rank), _p(err_flag),
+         _stream())
+
+
+def add_user_term(logits, feats_tail, fake_table, label):
+    _lib.require_device()
+    U, I = logits.shape
+    call("srfrd_add_user_term", _p(logits), logits.stride(0), U, I, _p(feats_tail), feats_tail.stride(0), _p(fake_table),
+         _p(label), fake_table.shape[1], _stream())

@@ -31,18 +31,13 @@ def shard_batch(batch: Dict[str, torch.Tensor], rank: int, world: int) -> Dict[s
     return {k: v[lo:hi] for k, v in batch.items()}
 
 
-def global_weight_sums(local_sums: torch.Tensor, group=None) -> torch.Tensor:
-    """All-reduce the per-rank (sum w_pos, sum w_neg) pair so each rank normalises by the global sums."""
-    out = local_sums.clone()
-    if dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
-    return out
-
-
-def allreduce_gradients(flat_grad: torch.Tensor, group=None) -> None:
-    """One SUM all-reduce over the flat fp32 gradient buffer (3.4 MB at C2)."""
-    if dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+def allreduce_sum_(t: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place SUM all-reduce (no-op without a process group / at world size 1).  FusedTrainer uses it for the weight
+    sums (loss normaliser, global count of pos != 0 -- trainer.py:36-38) and for the flat gradient bucket whose tail
+    carries the loss accumulators, so one collective per step moves gradients AND loss."""
+    if group is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
 
 
 def broadcast_parameters(flat_params: torch.Tensor, src: int = 0, group=None) -> None:
@@ -50,11 +45,23 @@ def broadcast_parameters(flat_params: torch.Tensor, src: int = 0, group=None) ->
         dist.broadcast(flat_params, src, group=group)
 
 
-def allgather_topk(scores: torch.Tensor, ids: torch.Tensor, group=None):
-    """(U, 10) per rank -> (U, G, 10) candidate lists on every rank."""
+def allgather_packed_topk(packed: torch.Tensor, group=None) -> torch.Tensor:
+    """(U, 20) per rank (10 fp32 scores + 10 int32 ids per user, the scoring kernel's wire format) -> (G, U, 20) on
+    every rank with ONE all-gather."""
     G = dist.get_world_size(group)
-    gs = [torch.empty_like(scores) for _ in range(G)]
-    gi = [torch.empty_like(ids) for _ in range(G)]
-    dist.all_gather(gs, scores.contiguous(), group=group)
-    dist.all_gather(gi, ids.contiguous(), group=group)
-    return torch.stack(gs, 1), torch.stack(gi, 1)
+    U, W = packed.shape
+    out = torch.empty(G * U, W, dtype=packed.dtype, device=packed.device)      # (G * U, W): rank-major concatenation
+    dist.all_gather_into_tensor(out, packed.contiguous(), group=group)
+    return out.view(G, U, W)
+
+
+def merge_packed_topk_host(gathered: torch.Tensor, k: int = 10):
+    """Host restatement of srfrd_merge_topk_packed (tie-break: score desc, id asc) for the CPU protocol tests."""
+    import numpy as np
+    g = gathered.cpu().numpy()
+    G, U, W = g.shape
+    sc = g[:, :, :W // 2].transpose(1, 0, 2).reshape(U, -1)
+    ids = g[:, :, W // 2:].view(np.int32).transpose(1, 0, 2).reshape(U, -1).astype(np.int64)
+    sc = np.where(ids < 0, -np.inf, sc)
+    order = np.lexsort((ids, -sc), axis=1)[:, :k]
+    return np.take_along_axis(sc, order, 1), np.take_along_axis(ids, order, 1)

@@ -106,7 +106,7 @@ CONFIGS: Dict[str, dict] = {
                D=64, F=16, L=50, blocks=2, heads=1, batch=16384),
     "C4": dict(seed=1238, usernum=22363, itemnum=12101, min_len=20, mean_extra=60.0, max_len=200,
                D=256, F=16, L=200, blocks=4, heads=1, batch=1024),
-    "C5": dict(seed=1239, usernum=500_000, itemnum=150_000, min_len=3, mean_extra=20.0, max_len=50,
+    "C5": dict(seed=1239, usernum=500_000, itemnum=150_000, min_len=3, mean_extra=24.5, max_len=50,
                D=64, F=16, L=50, blocks=2, heads=1, batch=4096, fake_rate=0.30, lognormal=True),
 }
 

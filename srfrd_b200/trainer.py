@@ -16,7 +16,7 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
-from . import ops
+from . import ops, parallel
 from .engine import HotPath
 
 __all__ = ["simulate", "FusedTrainer", "DeviceSampler", "discriminator_weights"]
@@ -106,12 +106,15 @@ class FusedTrainer:
         dev = self.eng.device
         self.m = torch.zeros_like(self.P.data)
         self.v = torch.zeros_like(self.P.data)
-        self.scal = torch.zeros(8, dtype=torch.float32, device=dev)   # [0:2] norm, [2:4] loss acc, [4] loss
+        self.scal = torch.zeros(8, dtype=torch.float32, device=dev)   # [0:2] norm (weight sums), [4] loss
+        # the loss accumulators live in the tail of the gradient bucket (one all-reduce moves gradients and loss)
+        self.comm = torch.cuda.Stream(device=dev) if process_group is not None else None
         self._static: Optional[Dict[str, torch.Tensor]] = None
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._graph_key = None
+        self._eager_key = None
         self._has_w = (False, False)
-        self.P.grad.zero_()
+        self.P.grad_bucket.zero_()
         self.eng.refresh_shadows()
         self.steps = 0
 
@@ -142,26 +145,30 @@ class FusedTrainer:
         pos, neg = st["pos"].view(-1), st["neg"].view(-1)
         w_pos = st["w_pos"].view(-1) if has_wp else None
         w_neg = st["w_neg"].view(-1) if has_wn else None
-        norm, acc, loss = self.scal[0:2], self.scal[2:4], self.scal[4:5]
+        norm, acc, loss = self.scal[0:2], P.grad_tail[0:2], self.scal[4:5]
         smp = getattr(self, "_sampler", None)
         if smp is not None:
-            smp.sample_into(st, st["w_pos"] if has_wp else None, self._sampler_policy, step=eng.step_state[0:1])
+            smp.sample_into(st, st["w_pos"] if has_wp else None, self._sampler_policy, step=eng.step_state[3:4])
         ops.weight_sums(pos, w_pos, w_neg, norm)
-        acc.zero_()
         if self.pg is not None:
-            torch.distributed.all_reduce(norm, group=self.pg)             # global sum of weights
+            # global sum of weights (the reference's mean over ALL pos != 0 of the batch, trainer.py:36-38): a side stream
+            # carries this tiny all-reduce so that the forward pass does not wait for it -- only the loss kernel does
+            self.comm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm):
+                parallel.allreduce_sum_(norm, self.pg)
         hidden = eng.forward(st["seq"], st["rsq"], training=True)
         ws = eng._ws
         ft = eng.fake_table()
+        if self.pg is not None:
+            torch.cuda.current_stream().wait_stream(self.comm)
         ops.score_loss_fused(ws["hfin"][:T], P.view(s.item_key), ft, pos, neg,
                              st["prs"].view(-1) if ft is not None else None,
                              st["nrs"].view(-1) if ft is not None else None, w_pos, w_neg, norm, acc, ws["dh"][:T],
                              P.view(s.item_key, grad=True), eng.fake_table_grad())
         eng.backward(ws["dh"][:T])
         if self.pg is not None:
-            torch.distributed.all_reduce(P.grad, group=self.pg)           # NCCL sum over NVLink
-            torch.distributed.all_reduce(acc, group=self.pg)
-        ops.loss_finalize(acc, norm, loss)
+            parallel.allreduce_sum_(P.grad_bucket, self.pg)               # ONE NCCL sum over NVLink: gradients + loss sums
+        ops.loss_finalize(acc, norm, loss)                                # (consumes acc: zero again for the next step)
         ops.adam_tick(eng.step_state, self.betas[0], self.betas[1])
         ops.adam_step(P.data, P.grad, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, eng.step_state,
                       zero_grad=True)
@@ -185,6 +192,31 @@ class FusedTrainer:
         if w_neg is not None:
             st["w_neg"].copy_(torch.as_tensor(w_neg), non_blocking=non_blocking)
         self._has_w = (w_pos is not None, w_neg is not None)
+
+    def pack_batch(self, batch: Dict[str, torch.Tensor], w_pos=None, w_neg=None) -> torch.Tensor:
+        """One flat device buffer holding a whole batch in the layout of the step's static inputs (six int64 (B, L) id
+        arrays + two fp32 (B, L) weight arrays): ``step_packed`` then needs ONE device-to-device copy per step."""
+        B, L = batch["seq"].shape
+        flat = torch.zeros(7 * B * L, dtype=torch.int64, device=self.eng.device)
+        v = self._carve(flat, B, L)
+        for k in self._KEYS:
+            if batch.get(k) is not None:
+                v[k].copy_(torch.as_tensor(batch[k]))
+        if w_pos is not None:
+            v["w_pos"].copy_(torch.as_tensor(w_pos))
+        if w_neg is not None:
+            v["w_neg"].copy_(torch.as_tensor(w_neg))
+        flat._srfrd_shape, flat._srfrd_w = (B, L), (w_pos is not None, w_neg is not None)
+        return flat
+
+    def step_packed(self, flat: torch.Tensor) -> torch.Tensor:
+        """One step on a batch prepared by ``pack_batch`` (device resident)."""
+        B, L = flat._srfrd_shape
+        if self._static is None or self._static["seq"].shape != (B, L):
+            self._alloc_static(B, L)
+        self._static_flat.copy_(flat, non_blocking=True)
+        self._has_w = flat._srfrd_w
+        return self.run_step()
 
     # ---- host batches pipelined across steps: H2D of batch n+1 (copy stream) overlaps the compute of batch n ----------
     def prefetch(self, batch: Dict[str, torch.Tensor], w_pos=None, w_neg=None):
@@ -227,10 +259,12 @@ class FusedTrainer:
 
     def run_step(self) -> torch.Tensor:
         """Run one step on the loaded batch; returns the device scalar holding the loss (no sync)."""
-        key = (tuple(self._static["seq"].shape), self._has_w, id(getattr(self, "_sampler", None)))
+        # the graph holds raw pointers into the engine's workspace: a re-allocation (a larger evaluation / encode_last
+        # forward between training steps) bumps ws_generation and forces a re-capture instead of a replay into freed memory
+        key = (tuple(self._static["seq"].shape), self._has_w, id(getattr(self, "_sampler", None)), self.eng.ws_generation)
         if self.use_graph and self._graph is not None and self._graph_key == key:
             self._graph.replay()
-        elif self.use_graph and self.steps >= 1:
+        elif self.use_graph and self.steps >= 1 and self._eager_key == key[:3] + (self.eng.ws_generation,):
             # capture after one eager step has sized the workspaces, set kernel attributes and (data parallel) warmed
             # up the NCCL communicator; the gradient all-reduce is captured into the same graph
             g = torch.cuda.CUDAGraph()
@@ -241,6 +275,8 @@ class FusedTrainer:
             g.replay()
         else:
             self._step_body(*self._has_w)
+            # an eager step may itself have re-allocated the workspace: remember the generation it LEFT behind
+            self._eager_key = key[:3] + (self.eng.ws_generation,)
         self.steps += 1
         return self.scal[4]
 

@@ -97,53 +97,28 @@ def label_breakdown(ranks: np.ndarray, labels: np.ndarray) -> Dict[int, list]:
 
 @torch.no_grad()
 def evaluation_with_label(model, dataset, maxlen, device, max_users: int = 10000, seed: Optional[int] = None,
-                          chunk: int = 2048):
-    """utils.py:628-752, batched.  Returns (NDCG@10, HT@10, userResults, Binary_Metric, Frequency_Metric,
-    Ratio_Metric); userResults[user] = [rank, HIT, NDCG, label_B, label_F, label_R]."""
-    train, test, usernum, itemnum = dataset
+                          chunk: int = 8192, candidates: Optional[np.ndarray] = None, users: Optional[np.ndarray] = None):
+    """utils.py:628-752, batched on the device kernels (evaluation.sampled_ranks).  Returns (NDCG@10, HT@10, userResults,
+    Binary_Metric, Frequency_Metric, Ratio_Metric); userResults[user] = [rank, HIT, NDCG, label_B, label_F, label_R]."""
+    from . import evaluation as EV
+    csr = EV.dataset_to_csr(dataset)
     rng = np.random.default_rng(seed)
-    users = list(range(1, usernum + 1))
-    if usernum > max_users:
-        users = rng.choice(np.arange(1, usernum + 1), max_users, replace=False).tolist()
-    users = [u for u in users if len(train["item_ids"].get(u, [])) >= 1 and len(test["item_ids"].get(u, [])) >= 1]
-    ranks, labs = [], {0: [], 1: [], 2: []}
-    for s in range(0, len(users), chunk):
-        us = users[s:s + chunk]
-        seq = np.zeros((len(us), maxlen), np.int64)
-        rsq = np.zeros((len(us), maxlen), np.int64)
-        cand = np.zeros((len(us), 101), np.int64)
-        for r, u in enumerate(us):
-            it, rv = train["item_ids"][u][-maxlen:], train["review_ids"][u][-maxlen:]
-            seq[r, maxlen - len(it):] = it
-            rsq[r, maxlen - len(rv):] = rv
-            rated = set(train["item_ids"][u]) | {0}
-            cand[r, 0] = test["item_ids"][u][0]
-            j = 1
-            while j < 101:
-                t = int(rng.integers(1, itemnum + 1))
-                if t not in rated:
-                    cand[r, j] = t
-                    j += 1
-        seq_d, rsq_d = torch.from_numpy(seq).to(device), torch.from_numpy(rsq).to(device)
-        feats = model.encode_last(seq_d, rsq_d)
-        table = model._engine.P.view(model.spec.item_key)
-        rows = table[torch.from_numpy(cand).to(device)]
-        logits = torch.einsum("ud,ucd->uc", feats[:, :model.spec.D], rows)      # 101 dots per user: not the hot path
-        ranks.append((logits[:, 1:] > logits[:, :1]).sum(1).cpu().numpy())
-        # user labels of utils.py:604-626.  NOTE the binary rule here (1 = mostly fake) is the INVERSE of
-        # SRFU_B.get_Labels (SRFR_model.py:546-552, 2 = mostly fake): both are reproduced as written.
-        nf, nr = (rsq == 1).sum(1), (rsq == 2).sum(1)
-        labs[0].append(np.where(nf > nr, 1, 2))
-        labs[1].append(nf)
-        labs[2].append(np.floor(nf / np.maximum(nf + nr, 1) * 10).astype(np.int64))
-    if not users:
+    rows = EV.eval_users(csr, max_users, rng) if users is None else (np.asarray(users, np.int64) - 1).astype(np.int32)
+    if len(rows) == 0:
         return 0.0, 0.0, {}, {}, {}, {}
-    rank = np.concatenate(ranks)
-    lb, lf, lr = (np.concatenate(labs[k]) for k in (0, 1, 2))
+    rank = EV.sampled_ranks(model, csr, rows, maxlen, device, seed=int(rng.integers(1 << 31)), candidates=candidates,
+                            chunk=chunk)
+    # user labels of utils.py:604-626.  NOTE the binary rule here (1 = mostly fake) is the INVERSE of
+    # SRFU_B.get_Labels (SRFR_model.py:546-552, 2 = mostly fake): both are reproduced as written.
+    _, rsq = EV.right_aligned(csr, rows, maxlen)
+    nf, nr = (rsq == 1).sum(1), (rsq == 2).sum(1)
+    lb = np.where(nf > nr, 1, 2)
+    lf = nf
+    lr = np.floor(nf / np.maximum(nf + nr, 1) * 10).astype(np.int64)
     hit = rank < 10
     ndcg = np.where(hit, 1.0 / np.log2(rank + 2.0), 0.0)
-    user_results = {u: [int(rank[i]), float(hit[i]), float(ndcg[i]), int(lb[i]), int(lf[i]), int(lr[i])]
-                    for i, u in enumerate(users)}
-    n = len(users)
+    user_results = {int(u) + 1: [int(rank[i]), float(hit[i]), float(ndcg[i]), int(lb[i]), int(lf[i]), int(lr[i])]
+                    for i, u in enumerate(rows)}
+    n = len(rows)
     return (float(ndcg.sum() / n), float(hit.sum() / n), user_results, label_breakdown(rank, lb),
             label_breakdown(rank, lf), label_breakdown(rank, lr))

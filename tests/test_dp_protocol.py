@@ -1,7 +1,9 @@
-"""world_size-2 gloo tests (CPU) of the data-parallel protocol in srfrd_b200/parallel.py, with the CPU oracle
-standing in for the CUDA kernels: (1) batch-sharded gradients normalised by the all-reduced weight sums and
-SUM-all-reduced equal the single-process gradient; (2) row-sharded top-10 + all-gather + merge equals the
-unsharded top-10 bit for bit."""
+"""world_size-2 gloo tests (CPU) of the data-parallel protocol in srfrd_b200/parallel.py -- the SAME functions
+FusedTrainer._step_body and evaluation.sharded_topk call on the GPU (allreduce_sum_ on the weight sums and on the
+gradient bucket whose tail carries the loss accumulators; allgather_packed_topk on the 80-byte wire format) -- with the
+CPU oracle standing in for the CUDA kernels: (1) batch-sharded gradients normalised by the all-reduced weight sums and
+SUM-all-reduced in one bucket equal the single-process gradient and loss; (2) row-sharded top-10 + ONE packed
+all-gather + merge equals the unsharded top-10 bit for bit."""
 import os
 
 import numpy as np
@@ -43,16 +45,17 @@ def _grad_job(rank, world):
     tr = O.OracleTrainer(fx["param"], "SRFR", 1)
     _, zp, zn = O.forward(tr.sd, "SRFR", shard["seq"], shard["rsq"], shard["pos"], shard["prs"], shard["neg"], shard["nrs"], 1)
     w = shard["w"]
-    W = P.global_weight_sums(torch.stack([w.sum(), w.sum()]))
-    loss = (w * torch.nn.functional.softplus(-zp)).sum() / W[0] + (w * torch.nn.functional.softplus(zn)).sum() / W[1]
+    W = P.allreduce_sum_(torch.stack([w.sum(), w.sum()]), dist.group.WORLD)      # trainer: norm on the comm stream
+    acc = torch.stack([(w * torch.nn.functional.softplus(-zp)).sum(), (w * torch.nn.functional.softplus(zn)).sum()])
+    loss = acc[0] / W[0] + acc[1] / W[1]
     loss.backward()
     tr._zero_pad_rows()
     names = sorted(tr.sd)
     flat = torch.cat([(tr.sd[n].grad if tr.sd[n].grad is not None else torch.zeros_like(tr.sd[n])).flatten() for n in names])
-    P.allreduce_gradients(flat)
-    total = loss.detach().clone()
-    dist.all_reduce(total)
-    return flat.numpy(), float(total)
+    bucket = torch.cat([flat, acc.detach(), torch.zeros(2)])                     # FlatParams.grad_bucket: grads + 4-float tail
+    P.allreduce_sum_(bucket, dist.group.WORLD)                                   # trainer: ONE collective per step
+    total = bucket[-4] / W[0] + bucket[-3] / W[1]                                # loss_finalize
+    return bucket[:-4].numpy(), float(total)
 
 
 def test_sharded_gradients_equal_single_process():
@@ -81,8 +84,14 @@ def _topk_job(rank, world):
     first = 1 if lo == 0 else 0                                   # id 0 is the pad row, never a candidate
     sc = (feats @ table[lo + first:hi].T).numpy()
     v, i = O.topk_stable(sc, 10, first_id=lo + first)
-    vs, is_ = P.allgather_topk(torch.from_numpy(v), torch.from_numpy(i))
-    mv, mi = O.merge_topk(vs.reshape(37, -1).numpy(), is_.reshape(37, -1).numpy(), 10)
+    # the scoring kernel's wire format: 10 fp32 scores + 10 int32 global ids per user (80 B), one all-gather
+    packed = torch.from_numpy(np.concatenate([v.astype(np.float32), i.astype(np.int32).view(np.float32)], 1))
+    gathered = P.allgather_packed_topk(packed, dist.group.WORLD)
+    assert gathered.shape == (world, 37, 20)
+    mv, mi = P.merge_packed_topk_host(gathered, 10)
+    mv2, mi2 = O.merge_topk(gathered[:, :, :10].permute(1, 0, 2).reshape(37, -1).numpy(),
+                            gathered[:, :, 10:].contiguous().view(torch.int32).permute(1, 0, 2).reshape(37, -1).numpy().astype(np.int64), 10)
+    assert np.array_equal(mi, mi2)
     return mi
 
 

@@ -1,0 +1,277 @@
+"""Round-2 parity / safety tests on the B200: the benchmarked catalogue size, the `mask` discriminator policy, C4-shape
+gradients at scale, dropout statistics, and the regression tests of the advisor's findings (graph re-capture after a
+workspace re-allocation, fresh dropout masks on the autograd path, SRFU label range, stale backward)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _xavier(m):
+    for _, p in m.named_parameters():                      # trainer.py:364-369
+        if p.dim() >= 2:
+            torch.nn.init.xavier_normal_(p.data)
+    return m
+
+
+# --------------------------------------------------------------------------------------------- catalogue at C3 size
+def test_catalogue_top10_bit_exact_at_one_million_items():
+    """The configuration bench.py quotes (N = 1 000 000 items, D = 64; here 768 users = 3 user groups, so the 148 CTAs cut
+    user groups into pieces exactly as in the benchmark): dyadic inputs (entries k/8, |k| <= 16 -> every partial sum is
+    exact in fp32 under any accumulation order), ties -> lower id.  The oracle ranks a spread subset of the users."""
+    from oracle import srfrd_oracle as O
+    from srfrd_b200 import evaluation as EV
+    g = torch.Generator().manual_seed(1003)
+    N, D, U = 1_000_000, 64, 768
+    table = torch.randint(-16, 17, (N + 1, D), generator=g, dtype=torch.int8).float() / 8
+    feats = torch.randint(-16, 17, (U, D), generator=g, dtype=torch.int8).float() / 8
+    index = EV.CatalogueIndex(table.cuda(), 0)
+    s, ids = EV.local_topk(feats.cuda(), index, 1)
+    sub = np.r_[0:24, 250:262, 255:270, 500:524, 744:768]
+    sub = np.unique(sub)
+    s_ref, ids_ref = O.catalogue_topk(feats[sub], table, 10, chunk=32)
+    assert np.array_equal(ids.cpu().numpy()[sub], ids_ref), "top-10 ids differ from the oracle at N = 1M"
+    assert np.array_equal(s.cpu().numpy()[sub], s_ref)
+    # 8-way row sharding + merge (what the 8-GPU run does, emulated on one device) == unsharded, for every user
+    parts_s, parts_i = [], []
+    for r in range(8):
+        lo, hi = EV.CatalogueIndex.shard_bounds(N + 1, r, 8)
+        ps, pi = EV.local_topk(feats.cuda(), EV.CatalogueIndex(table[lo:hi].cuda(), lo), 1)
+        parts_s.append(ps); parts_i.append(pi)
+    ms, mi = EV.merge_shards(torch.stack(parts_s, 1), torch.stack(parts_i, 1))
+    assert torch.equal(mi, ids) and torch.equal(ms, s)
+
+
+# --------------------------------------------------------------------------------------------- mask policy
+def test_mask_policy_step_matches_the_weighted_oracle():
+    """`mask` (g = 1[p_fake < 0.5] == the hard label the BERT discriminator emits): three fused steps vs the oracle's
+    weighted loss + autograd + Adam; then the on-device sampler's in-graph `mask` / `soft` weights equal the host rule."""
+    from oracle import srfrd_oracle as O
+    from srfrd_b200 import SRFR_model as M, synth
+    from srfrd_b200.trainer import DeviceSampler, FusedTrainer, discriminator_weights
+    data = synth.make_interactions(61, 3000, 2500, 5, 6.0, 50, fake_rate=0.3)
+    torch.manual_seed(4)
+    m = _xavier(M.SRFR(data.itemnum, 50, 64, 16, 0.0, 2, 1, "cuda")).to("cuda")
+    sd0 = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    orc = O.OracleTrainer(sd0, "SRFR", 1)
+    tr = FusedTrainer(m, use_graph=True)
+    smp = synth.BatchSampler(data, 50, 8)
+    for step in range(3):
+        tb = {k: torch.from_numpy(v) for k, v in smp.next_batch(192).items()}
+        w_cpu = O.discriminator_weights(tb["pos"], tb["p_fake"], "mask")
+        assert 0.55 < float(w_cpu.sum() / (tb["pos"] != 0).sum()) < 0.85          # ~30 % of the positions are masked out
+        ref = orc.step(tb, w_cpu)
+        cb = {k: v.cuda() for k, v in tb.items()}
+        w = discriminator_weights(cb["pos"], cb["p_fake"], "mask")
+        assert torch.equal(w.cpu(), w_cpu)
+        loss = float(tr.step(cb, w_pos=w))
+        assert abs(loss - ref) < 5e-3, f"mask step {step}: {loss} vs oracle {ref}"
+    ds = DeviceSampler(data, 50, "cuda", seed=3)
+    out = ds.alloc(256)
+    for pol in ("mask", "soft", "none"):
+        w = torch.zeros(256, 50, device="cuda")
+        ds.sample_into(out, w, pol)
+        # recover p_fake of every drawn positive from the CSR and apply the host rule
+        u0 = (out["users"] - 1).cpu().numpy()
+        pos = out["pos"].cpu().numpy()
+        exp = np.zeros((256, 50), np.float32)
+        for b in range(256):
+            a, e = data.offsets[u0[b]], data.offsets[u0[b] + 1]
+            pf = dict(zip(data.items[a:e].tolist(), data.p_fake[a:e].tolist()))
+            for t in range(50):
+                if pos[b, t]:
+                    p = pf[int(pos[b, t])]
+                    exp[b, t] = (1.0 if p < 0.5 else 0.0) if pol == "mask" else (1.0 - p if pol == "soft" else 1.0)
+        np.testing.assert_allclose(w.cpu().numpy(), exp, rtol=0, atol=1e-6)
+
+
+# --------------------------------------------------------------------------------------------- C4 shape at scale
+def test_c4_shape_gradients_match_oracle_at_128_sequences():
+    """C4 shape (maxlen 200, D = 256, F = 16 -> H = 272, 4 blocks; tcgen05 tile-pair attention for maxlen > 128) on 128
+    sequences = 25 600 tokens: loss and every parameter gradient vs the fp32 oracle's autograd."""
+    from oracle import srfrd_oracle as O
+    from srfrd_b200 import SRFR_model as M, synth
+    data = synth.make_interactions(33, 600, 1500, 20, 60.0, 200)
+    batch = synth.BatchSampler(data, 200, 5).next_batch(128)
+    torch.manual_seed(7)
+    m = M.SRFR(data.itemnum, 200, 256, 16, 0.0, 4, 1, "cuda")
+    for _, p in m.named_parameters():
+        if p.dim() >= 2:
+            torch.nn.init.xavier_normal_(p.data)
+        else:
+            p.data.add_(0.1 * torch.randn_like(p))
+    m = m.to("cuda").train()
+    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    tb = {k: torch.from_numpy(v) for k, v in batch.items()}
+    ref_loss, ref = O.OracleTrainer(sd, "SRFR", 1).grads(tb)
+    cb = {k: v.cuda() for k, v in tb.items()}
+    h, zp, zn = m(None, cb["seq"], cb["rsq"], cb["pos"], cb["prs"], cb["neg"], cb["nrs"])
+    idx = torch.where(cb["pos"] != 0)
+    crit = torch.nn.BCEWithLogitsLoss()
+    loss = crit(zp[idx], torch.ones_like(zp[idx])) + crit(zn[idx], torch.zeros_like(zn[idx]))
+    loss.backward()
+    assert abs(float(loss) - ref_loss) < 5e-3
+    worst = (0.0, "")
+    for k, p in m.named_parameters():
+        g, r = p.grad.cpu().flatten(), ref[k].flatten()
+        if k.endswith("in_proj_bias"):                     # d loss / d b_k == 0 (softmax shift invariance): q and v thirds
+            H = r.numel() // 3
+            g, r = torch.cat([g[:H], g[2 * H:]]), torch.cat([r[:H], r[2 * H:]])
+        rel = float((g - r).norm() / (r.norm() + 1e-30))
+        cos = float(torch.dot(g, r) / (g.norm() * r.norm() + 1e-30))
+        worst = max(worst, (rel, k))
+        assert rel <= 0.10 and cos >= 0.995, f"{k}: rel L2 err {rel:.4f}, cos {cos:.5f}"
+    print("C4-shape gradients: worst relative L2 error %.4f (%s)" % worst)
+
+
+# --------------------------------------------------------------------------------------------- dropout statistics
+def test_dropout_keep_rate_and_mean_preservation():
+    """In-kernel dropout (hash(seed ^ step, stream, element) >= p) against p: the FFN epilogue's keep rate is 1 - p within
+    4 sigma, kept values are scaled by 1 / (1 - p) (the mean is preserved), two streams / two steps give independent
+    masks, and attention dropout on the probabilities preserves the row mean of P V for V = 1."""
+    from srfrd_b200 import ops
+    M_, N, K = 8192, 80, 80
+    A = torch.zeros(M_, K, dtype=torch.bfloat16, device="cuda")
+    Bw = torch.zeros(N, K, dtype=torch.bfloat16, device="cuda")
+    bias = torch.full((N,), 2.0, device="cuda")
+    step = torch.zeros(1, device="cuda")
+    masks = []
+    for p in (0.5, 0.2):
+        for stream, st in ((11, 0.0), (12, 0.0), (11, 1.0)):
+            step.fill_(st)
+            out = torch.empty(M_, N, dtype=torch.bfloat16, device="cuda")
+            ops.gemm_tn(A, Bw, out_bf16=out, bias=bias, drop_p=p, drop_seed=1234, drop_stream=stream, drop_step=step)
+            o = out.float()
+            keep = o != 0
+            n = keep.numel()
+            rate = float(keep.float().mean())
+            assert abs(rate - (1 - p)) < 4 * np.sqrt(p * (1 - p) / n), (p, rate)
+            vals = o[keep]
+            assert torch.allclose(vals, torch.full_like(vals, 2.0 / (1 - p)), rtol=1e-2)       # bf16 rounding of 2 / (1 - p)
+            assert abs(float(o.mean()) - 2.0) < 4 * 2.0 * np.sqrt(p / (1 - p) / n) + 2e-2
+            # no structure along rows or columns
+            assert float(keep.float().mean(0).std()) < 3 * np.sqrt(p * (1 - p) / M_)
+            assert float(keep.float().mean(1).std()) < 3 * np.sqrt(p * (1 - p) / N)
+            if p == 0.5:
+                masks.append(keep)
+    # different stream / different step -> (nearly) independent masks: agreement rate ~ 0.5
+    for a, b in ((0, 1), (0, 2)):
+        agree = float((masks[a] == masks[b]).float().mean())
+        assert abs(agree - 0.5) < 0.01, agree
+    # attention: O = (P * keep / (1 - p)) V with V = 1 -> E[O] = 1 for every row; variance shrinks with the causal width
+    Bq, L, H = 64, 50, 64
+    g = torch.Generator(device="cpu").manual_seed(5)
+    q = (torch.randn(Bq * L, H, generator=g) * 0.3).to(torch.bfloat16).cuda()
+    k = (torch.randn(Bq * L, H, generator=g) * 0.3).to(torch.bfloat16).cuda()
+    v = torch.ones(Bq * L, H, dtype=torch.bfloat16, device="cuda")
+    o = torch.empty_like(q)
+    ops.attention_fwd(q, k, v, o, Bq, L, H, 1, 0.5, 99, 10, None)
+    of = o.float().view(Bq, L, H)
+    assert abs(float(of.mean()) - 1.0) < 0.02
+    assert abs(float(of[:, -10:, :].mean()) - 1.0) < 0.03          # late positions: ~45 keys each
+    assert set(np.unique(of[:, 0, 0].cpu().numpy()).tolist()) <= {0.0, 2.0}      # one key: kept (x2) or dropped
+
+
+# --------------------------------------------------------------------------------------------- advisor regressions
+def test_graph_is_recaptured_after_the_workspace_grows():
+    """a captured step graph holds raw pointers into the engine workspace; a larger forward in between
+    (evaluation chunk) re-allocates it.  The trainer must re-capture, not replay into freed memory: its losses stay equal
+    to a twin trainer that never uses graphs, and the freed blocks are deliberately re-used by junk tensors."""
+    from srfrd_b200 import SRFR_model as M, synth
+    from srfrd_b200.trainer import FusedTrainer
+    data = synth.make_interactions(12, 2000, 1500, 5, 4.0, 50)
+    smp = synth.BatchSampler(data, 50, 2)
+    batches = [{k: torch.from_numpy(v).cuda() for k, v in smp.next_batch(64).items()} for _ in range(8)]
+    big = {k: torch.from_numpy(v).cuda() for k, v in smp.next_batch(1024).items()}
+
+    def make():
+        torch.manual_seed(9)
+        return _xavier(M.SRFR(data.itemnum, 50, 64, 16, 0.0, 2, 1, "cuda")).to("cuda")
+    mg, me = make(), make()
+    tg, te = FusedTrainer(mg, use_graph=True), FusedTrainer(me, use_graph=False)
+    lg, le = [], []
+    for i, b in enumerate(batches):
+        if i == 4:                                         # graph already captured (steps 1..3 replayed it)
+            gen0 = tg.eng.ws_generation
+            mg.eval(); me.eval()
+            fg = mg.encode_last(big["seq"], big["rsq"]); fe = me.encode_last(big["seq"], big["rsq"])
+            mg.train(); me.train()
+            assert tg.eng.ws_generation == gen0 + 1      # the workspace was re-allocated
+            junk = [torch.full((64 * 50, 80), float("nan"), dtype=torch.bfloat16, device="cuda") for _ in range(64)]
+            assert torch.allclose(fg, fe, atol=1e-5)
+        lg.append(float(tg.step(b))); le.append(float(te.step(b)))
+    assert all(np.isfinite(lg)), lg
+    np.testing.assert_allclose(lg, le, rtol=0, atol=3e-3)
+    assert tg._graph is not None and tg._graph_key[-1] == tg.eng.ws_generation
+    del junk
+    # a longer sequence at a smaller token count reuses the buffers (pos_tmp / long-sequence statistics are sized by max_len)
+    m2 = _xavier(M.SRFR(500, 200, 64, 16, 0.0, 1, 1, "cuda")).to("cuda")
+    t2 = FusedTrainer(m2, use_graph=False)
+    d2 = synth.make_interactions(5, 300, 500, 20, 60.0, 200)
+    s2 = synth.BatchSampler(d2, 200, 1)
+    short = {k: torch.from_numpy(v[:, -50:].copy()).cuda() for k, v in s2.next_batch(256).items() if k != "u"}
+    longb = {k: torch.from_numpy(v).cuda() for k, v in s2.next_batch(32).items() if k != "u"}
+    l_a = float(t2.step(short)); l_b = float(t2.step(longb))
+    assert np.isfinite(l_a) and np.isfinite(l_b)
+
+
+def test_autograd_path_draws_a_fresh_dropout_mask_every_forward():
+    """on the drop-in path (model.forward + torch optimizer, trainer.simulate at dropout 0.5) the
+    device step counter never advances; the engine mixes a host-side forward counter into the seed instead."""
+    from srfrd_b200 import SRFR_model as M, synth
+    data = synth.make_interactions(3, 500, 400, 5, 4.0, 20)
+    b = {k: torch.from_numpy(v).cuda() for k, v in synth.BatchSampler(data, 20, 1).next_batch(32).items()}
+    for ctor in (lambda: M.SRFR(400, 20, 32, 16, 0.5, 2, 1, "cuda"), lambda: M.SASRec(400, 20, 32, 0.5, 2, 1, "cuda")):
+        torch.manual_seed(1)
+        m = ctor().to("cuda").train()
+        h1 = m(None, b["seq"], b["rsq"], b["pos"], b["prs"], b["neg"], b["nrs"])[0].clone()
+        h2 = m(None, b["seq"], b["rsq"], b["pos"], b["prs"], b["neg"], b["nrs"])[0].clone()
+        assert not torch.equal(h1, h2), "two training forwards used the same dropout mask"
+        m.eval()
+        e1 = m(None, b["seq"], b["rsq"])[0].clone()
+        e2 = m(None, b["seq"], b["rsq"])[0].clone()
+        assert torch.equal(e1, e2)
+        # forward and backward of one step agree on the mask: a finite-difference-free check through linearity --
+        # the gradient of sum(hidden) w.r.t. last_layernorm.bias is the number of rows, whatever the mask
+        m.train()
+        m.zero_grad()
+        h = m(None, b["seq"], b["rsq"])[0]
+        h.sum().backward()
+        gb = dict(m.named_parameters())["last_layernorm.bias"].grad
+        assert torch.allclose(gb, torch.full_like(gb, float(h.shape[0] * h.shape[1])), rtol=1e-4)
+
+
+def test_srfu_label_outside_an_underprovisioned_table_raises_like_the_reference():
+    """SRFU_B with the constructor default number_of_labels = 2 emits label 2 for a mostly-fake user;
+    the reference raises IndexError (nn.Embedding), the kernels must not read past the table."""
+    from srfrd_b200 import SRFR_model as M
+    m = M.SRFU_B(100, 10, 32, 2, 0.0, 1, 1, "cuda").to("cuda").eval()
+    seq = torch.randint(1, 101, (4, 10), device="cuda")
+    real = torch.full((4, 10), 2, device="cuda")               # mostly real -> label 1: fine with 2 rows
+    m(None, seq, real)
+    fake = real.clone(); fake[2] = 1                           # user 2 mostly fake -> label 2 -> out of range
+    with pytest.raises(IndexError, match="out of range"):
+        m(None, seq, fake)
+    ok = M.SRFU_B(100, 10, 32, 3, 0.0, 1, 1, "cuda").to("cuda").eval()
+    ok(None, seq, fake)
+
+
+def test_backward_of_a_stale_forward_raises():
+    """activations live in one shared workspace, so only the latest saving forward can be back-propagated."""
+    from srfrd_b200 import SRFR_model as M
+    torch.manual_seed(0)
+    m = M.SRFR(50, 8, 16, 16, 0.0, 1, 1, "cuda").to("cuda").train()
+    seq = torch.randint(1, 51, (3, 8), device="cuda"); rsq = torch.randint(1, 3, (3, 8), device="cuda")
+    h1 = m(None, seq, rsq)[0]
+    h2 = m(None, seq, rsq)[0]
+    with pytest.raises(RuntimeError, match="stale forward"):
+        h1.sum().backward()
+    h2.sum().backward()                                        # the latest one is fine
+    h3 = m(None, seq, rsq)[0]
+    m.eval()
+    with torch.no_grad():                                      # a validation forward in between also overwrites the
+        m(None, seq, rsq)                                      # workspace: refused instead of silently wrong gradients
+    m.train()
+    with pytest.raises(RuntimeError, match="stale forward"):
+        h3.sum().backward()
