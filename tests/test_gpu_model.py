@@ -78,10 +78,13 @@ def test_autograd_gradients_match_reference_golden(name, kind):
         scale = float(ref.abs().max()) + 1e-6
         err = float((got - ref).abs().max())
         cos = float(torch.dot(got.flatten(), ref.flatten()) / (got.norm() * ref.norm() + 1e-30))
-        # 6-sequence batches: no averaging of the bf16 activation-gradient rounding noise.  Direction must
-        # agree to 1 % (cos >= 0.99); the worst single element within 25 % of the tensor's largest gradient
-        # (test_gradients_match_oracle_at_scale below is the tight check, where the noise averages out).
-        assert cos >= 0.99 and err <= 0.25 * scale + 1e-5, f"{k}: cos {cos:.4f}, max err {err:.3e} vs scale {scale:.3e}"
+        rel = float((got - ref).norm() / (ref.norm() + 1e-30))
+        # 6-sequence batches: no averaging of the bf16 activation-gradient rounding noise.  Direction must agree to
+        # 1 % (cos >= 0.99), relative L2 error <= 15 %, the worst single element within 35 % of the tensor's largest
+        # gradient (test_gradients_match_oracle_at_scale and the C4-shape test are the tight checks, where the noise
+        # averages out: <= 8 % / 10 % relative L2).
+        assert cos >= 0.99 and rel <= 0.15 and err <= 0.35 * scale + 1e-5, \
+            f"{k}: cos {cos:.4f}, rel L2 {rel:.4f}, max err {err:.3e} vs scale {scale:.3e}"
 
 
 @pytest.mark.parametrize("name,kind", CASES)
