@@ -239,6 +239,64 @@ SRFRD_API int srfrd_candidate_rank(const float* feats, int ldf, const float* ite
 SRFRD_API int srfrd_add_user_term(float* logits, int ldl, int64_t U, int I, const float* feats_tail, int ldf,
                         const float* fake_table, const int64_t* label, int F, void* stream);
 
+/* ---- packed token layout: do not compute padding (SRFR_model.py:98-99, :113, :121) ----
+ * The sampler's batches are mostly pad slots (88 % at C2).  A pad slot enters the encoder as x = 0 and is re-zeroed after
+ * every block; with no key-padding mask it still is a key / value (k = b_k, v = b_v), identical for every pad of a
+ * sequence.  The packed layout keeps per sequence ONE pad-representative row followed by the kept tokens (input id != 0,
+ * or `keep` id != 0) in position order, rounded up with filler rows to a multiple of 128.  Attention weights the
+ * representative's key column by the number of dropped pads before the query's position, which reproduces the dense
+ * result exactly (forward and backward).  All maps are built on the device (srfrd_pack_plan; the row count is data
+ * dependent and the step runs inside a CUDA graph); rows[0] is the dynamic row count every other kernel reads. */
+typedef struct {
+  int* rows;        /* [4] device: {M = rows incl. filler (multiple of 128), T' = real rows, attention tiles, 0} */
+  int* cnt;         /* [B] scratch: kept tokens per sequence */
+  int* seq_first;   /* [B + 1] first packed row of each sequence (its pad representative); [B] = T' */
+  int* tok_row;     /* [B * L] packed row of each dense token, -1 = dropped pad */
+  int* row_tok;     /* [cap] dense token (b * L + l) of each packed row, -1 = pad representative / filler row */
+  int64_t* row_ids; /* [cap] input item id of the row, 0 for representative / kept pad / filler rows: the pad mask */
+  int* row_info;    /* [cap][4] {first row of the row's sequence, one past its last row, float bits of the pad column's
+                       weight for this row, position l}; 16-byte aligned */
+  int* tile_row0;   /* [B + 130] first row of each attention tile (whole sequences, <= 128 rows); entry [tiles] = M */
+  int* last_row;    /* [B] packed row that holds position L - 1 of each sequence (its representative if that slot is a pad) */
+  int64_t cap;      /* capacity in rows, >= roundup(B * (L + 1), 128) */
+} srfrd_pack_t;
+/* seq, keep: (B, L) int64 (keep nullable).  Needs L + 1 <= 128 and B <= 16384. */
+SRFRD_API int srfrd_pack_plan(const int64_t* seq, const int64_t* keep, int64_t B, int L, const srfrd_pack_t* pk, void* stream);
+/* Dynamic row count for the row-wise entry points: after srfrd_set_row_limit(rows_dev), srfrd_gemm_tn (M), srfrd_gemm_wgrad
+ * (T), srfrd_layernorm_fwd / _bwd (T) and srfrd_dropout_apply (M) launched from THIS host thread treat their row argument
+ * as a capacity and process min(argument, *rows_dev) rows, *rows_dev being read on the device when the kernel runs
+ * (a multiple of 128 for the GEMMs).  NULL restores static counts.  Thread-local; captured into CUDA graphs by value. */
+SRFRD_API int srfrd_set_row_limit(const int* rows_dev);
+/* K1 on the packed layout: output row t holds dense token row_tok[t] (id 0 -> a zero row).  Widths multiples of 8. */
+SRFRD_API int srfrd_embed_ln_fwd_packed(const float* item_table, int64_t n_rows, int D, const float* pos_table,
+                              const float* aux_table, int64_t n_aux, int F, int mode, const int64_t* seq,
+                              const int64_t* aux_ids, int64_t B, int L, float item_scale, const float* ln_w,
+                              const float* ln_b, float eps, void* x0_bf16, void* q_bf16, float* stats, int ldx,
+                              float drop_p, uint64_t drop_seed, uint32_t drop_stream, const float* drop_step,
+                              const int* row_tok, const int* rows_dev, int64_t cap_rows, void* stream);
+/* y[t] = LN(x[row_index[t]]) for t < n (fp32 out): the final LayerNorm of each sequence's last position only. */
+SRFRD_API int srfrd_layernorm_fwd_rows(const void* x_bf16, int ldx, const float* w, const float* b, float eps, float* y_f32,
+                             int ldy, const int* row_index, int64_t n, int H, void* stream);
+/* Causal attention over packed rows (tcgen05; L + 1 <= 128, head width a multiple of 16, one head or 64-column heads). */
+SRFRD_API int srfrd_attention_packed_supported(int L, int H, int heads);
+SRFRD_API int srfrd_attention_fwd_packed(const void* q, int ldq, const void* k, const void* v, int ldkv, void* o, int ldo,
+                               const srfrd_pack_t* pk, int L, int H, int heads, float drop_p, uint64_t seed,
+                               uint32_t stream_id, const float* drop_step, void* stream);
+SRFRD_API int srfrd_attention_bwd_packed(const void* dout, int lddo, const void* q, int ldq, const void* k, const void* v,
+                               int ldkv, void* dq, int lddq, void* dk, void* dv, int lddkv, const srfrd_pack_t* pk,
+                               int L, int H, int heads, float drop_p, uint64_t seed, uint32_t stream_id,
+                               const float* drop_step, void* stream);
+/* K4 on the packed layout: h / dh are packed rows; ids, weights stay (B * L) dense and are reached through row_tok. */
+SRFRD_API int srfrd_score_loss_fused_packed(const float* h, int ldh, const float* item_table, const float* fake_table,
+                                  const int64_t* pos, const int64_t* neg, const int64_t* prs, const int64_t* nrs,
+                                  const float* w_pos, const float* w_neg, const float* norm, int D, int F,
+                                  float* loss_acc, float* dh, int lddh, float* d_item, float* d_fake,
+                                  const int* row_tok, const int* rows_dev, int64_t cap_rows, void* stream);
+/* K5 on the packed layout (+ the positional-table gradient, which the dense path takes from srfrd_colsum). */
+SRFRD_API int srfrd_embed_bwd_packed(const void* dx0_bf16, int ldx, const int64_t* seq, const int64_t* aux_ids,
+                           const int* tok_row, int64_t B, int L, int D, int F, int mode, float item_scale,
+                           float* d_item, float* d_aux, float* d_pos, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

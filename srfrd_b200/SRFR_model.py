@@ -184,7 +184,9 @@ class _HotPathModule(nn.Module):
         eng = self._sync_flat()
         eng.refresh_shadows()
         to = lambda t: None if t is None else torch.as_tensor(t, device=eng.device).long()
-        return eng.forward(to(input_ids), to(fake_ids), training=False, last_only=True).clone()
+        seq = to(input_ids)
+        packed = eng.packed_default and eng.packed_ok(seq.shape[0], seq.shape[1])
+        return eng.forward(seq, to(fake_ids), training=False, last_only=True, packed=packed).clone()
 
     @torch.no_grad()
     def predict(self, user_ids, input_ids, fake_ids, label):

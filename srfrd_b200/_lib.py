@@ -27,6 +27,12 @@ class CastDesc(C.Structure):
                 ("rows", i32), ("cols", i32), ("dst_is_f32", i32)]
 
 
+class PackDesc(C.Structure):
+    """srfrd_pack_t: device buffers of the packed token layout (include/srfrd_b200.h)."""
+    _fields_ = [("rows", vp), ("cnt", vp), ("seq_first", vp), ("tok_row", vp), ("row_tok", vp), ("row_ids", vp),
+                ("row_info", vp), ("tile_row0", vp), ("last_row", vp), ("cap", i64)]
+
+
 # name -> argtypes, exactly the prototypes of include/srfrd_b200.h
 SIGNATURES = {
     "srfrd_abi_version": [],
@@ -62,6 +68,18 @@ SIGNATURES = {
     "srfrd_catalogue_topk": [vp, i64, i64, i32, vp, i64, i64, i64, i32, i32, i32, i32, vp, vp, vp, vp],
     "srfrd_merge_topk_packed": [vp, i64, i32, i32, vp, vp, vp],
     "srfrd_merge_topk": [vp, vp, i64, i32, i32, vp, vp, vp],
+    "srfrd_pack_plan": [vp, vp, i64, i32, C.POINTER(PackDesc), vp],
+    "srfrd_set_row_limit": [vp],
+    "srfrd_embed_ln_fwd_packed": [vp, i64, i32, vp, vp, i64, i32, i32, vp, vp, i64, i32, f32, vp, vp, f32, vp, vp, vp, i32,
+                                  f32, u64, u32, vp, vp, vp, i64, vp],
+    "srfrd_layernorm_fwd_rows": [vp, i32, vp, vp, f32, vp, i32, vp, i64, i32, vp],
+    "srfrd_attention_packed_supported": [i32, i32, i32],
+    "srfrd_attention_fwd_packed": [vp, i32, vp, vp, i32, vp, i32, C.POINTER(PackDesc), i32, i32, i32, f32, u64, u32, vp, vp],
+    "srfrd_attention_bwd_packed": [vp, i32, vp, i32, vp, vp, i32, vp, i32, vp, vp, i32, C.POINTER(PackDesc), i32, i32, i32,
+                                   f32, u64, u32, vp, vp],
+    "srfrd_score_loss_fused_packed": [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, i32, vp, vp, vp, vp,
+                                      i64, vp],
+    "srfrd_embed_bwd_packed": [vp, i32, vp, vp, vp, i64, i32, i32, i32, i32, f32, vp, vp, vp, vp],
     "srfrd_sample_candidates": [vp, vp, vp, vp, i64, i32, i32, u64, vp, vp],
     "srfrd_candidate_rank": [vp, i32, vp, i64, i32, vp, i64, i32, vp, i32, vp, vp, i32, vp, vp, vp],
     "srfrd_add_user_term": [vp, i32, i64, i32, vp, i32, vp, vp, i32, vp],

@@ -17,6 +17,9 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static thread_local const int* g_row_limit = nullptr;
+const int* row_limit() { return g_row_limit; }
+
 bool pdl_enabled() {
   static int v = -1;
   // measured at C2: no gain (1.83 vs 1.81 ms / step) -- the persistent kernels fill every SM's shared memory, so a
@@ -70,6 +73,11 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 extern "C" const char* srfrd_last_error(void) { return srfrd::g_err; }
 
 extern "C" int srfrd_abi_version(void) { return SRFRD_ABI_VERSION; }
+
+extern "C" int srfrd_set_row_limit(const int* rows_dev) {
+  srfrd::g_row_limit = rows_dev;
+  return 0;
+}
 
 extern "C" int srfrd_device_check(void) {
   int n = 0;

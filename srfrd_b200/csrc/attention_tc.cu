@@ -44,6 +44,11 @@ struct AttnTc {
   bf16* o; int ldo;                       // forward output
   bf16 *dq, *dk, *dv; int lddq, lddkv;    // backward outputs
   uint64_t drop_seed; uint32_t drop_thresh, drop_stream; float drop_scale; const float* drop_step;
+  // packed token layout (pack.cu): tiles start at pk_tile_row0[tile] and hold whole variable-length sequences; per row
+  // pk_info = {first row of its sequence, one past its last row, float bits of the pad column's weight, position}
+  const int* pk_rows;                     // device {M, T', n_tiles}
+  const int4* pk_info;
+  const int* pk_tile_row0;
 };
 
 // byte offset of element (row r, column c) inside a [128 x 64] bf16 block with the 128-byte swizzle
@@ -53,7 +58,31 @@ __device__ __forceinline__ uint32_t sw128(int r, int c) {
 
 struct RowInfo {
   int r; int64_t t; bool owned; int jlo, jhi, l; int64_t bh;
+  float pm;        // packed layout: weight of the key column at the window start (the pad representative stands for
+                   // `pm` dropped pad slots); 1 otherwise
+  int jbase;       // packed layout: un-shifted window start (dropout hash index)
 };
+// Packed layout.  Row r of the tile that starts at packed row `row0`: the row is owned when its whole sequence lies inside
+// the tile (tiles start at sequence boundaries; a trailing partial sequence belongs to the next tile).  Keys: the rows of
+// the same sequence up to the row itself; the first of them is the pad representative, weighted by the number of
+// dropped pad slots before this row's position -- with weight 0 the window simply starts one column later.
+__device__ __forceinline__ RowInfo row_info_pk(const AttnTc& p, int row0, int M, int h, int quarter, int lane) {
+  RowInfo ri;
+  ri.r = quarter * 32 + lane;
+  ri.t = (int64_t)row0 + ri.r;
+  int4 inf = make_int4(0, 0, 0, 0);
+  const bool in = ri.t < M;
+  if (in) inf = __ldg(p.pk_info + ri.t);
+  ri.owned = in && inf.x >= row0 && inf.y <= row0 + TILE;
+  const float mult = __int_as_float(inf.z);
+  ri.jbase = inf.x - row0;
+  ri.jlo = ri.jbase + (mult == 0.f ? 1 : 0);
+  ri.jhi = ri.r;
+  ri.pm = mult == 0.f ? 1.f : mult;
+  ri.l = 0;
+  ri.bh = ri.t * p.heads + h;
+  return ri;
+}
 __device__ __forceinline__ RowInfo row_info(const AttnTc& p, int tile, int h, int quarter, int lane) {
   RowInfo ri;
   ri.r = quarter * 32 + lane;
@@ -64,11 +93,14 @@ __device__ __forceinline__ RowInfo row_info(const AttnTc& p, int tile, int h, in
   ri.jlo = sidx * p.L;
   ri.jhi = ri.jlo + ri.l;
   ri.bh = (ri.t / p.L) * p.heads + h;
+  ri.pm = 1.f;
+  ri.jbase = ri.jlo;
   return ri;
 }
 __device__ __forceinline__ float drop_f(const AttnTc& p, const RowInfo& ri, int col) {
   if (!p.drop_thresh) return 1.f;
-  const uint64_t idx = ((uint64_t)ri.bh * p.L + ri.l) * p.L + (col - ri.jlo);
+  const uint64_t idx = p.pk_info ? (uint64_t)ri.bh * 256u + (uint64_t)(col - ri.jbase)
+                                 : ((uint64_t)ri.bh * p.L + ri.l) * p.L + (col - ri.jlo);
   return dropout_keep(p.drop_seed, p.drop_stream, idx, p.drop_thresh) ? p.drop_scale : 0.f;
 }
 
@@ -153,6 +185,18 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// Packed layout: a tile owns a data-dependent number of rows, so its results leave through coalesced 16-byte stores of the
+// owned rows (all 256 epilogue threads) instead of a TMA store with a fixed box.
+__device__ __forceinline__ void store_staged_rows(bf16* dst, int ld, int64_t row0, int col0, const uint8_t* blocks, int hd,
+                                                  int n_own, int tid256) {
+  const int cpr = hd >> 3;                                   // 16-byte chunks per row
+  for (int i = tid256; i < n_own * cpr; i += 256) {
+    const int r = i / cpr, ch = i - r * cpr;
+    const uint4 v = *reinterpret_cast<const uint4*>(blocks + (ch >> 3) * OPB + sw128(r, (ch & 7) * 8));
+    *reinterpret_cast<uint4*>(dst + (row0 + r) * ld + col0 + ch * 8) = v;
+  }
+}
+
 static constexpr int AF_THREADS = 320;   // forward: 8 softmax / epilogue warps + TMA warp + MMA warp
 
 // Forward, two CTAs per SM (smem <= 98 KB, 256 TMEM columns each): a tile is a chain of TMA -> S MMA -> softmax ->
@@ -165,7 +209,7 @@ static constexpr int AF_THREADS = 320;   // forward: 8 softmax / epilogue warps 
 // 17 k-cycle tile -- single-warp instruction latency, not bandwidth.
 // Warp roles (320 threads): warps 0..7 softmax + epilogue (quarter = warp & 3, part = warp >> 2), warp 8 TMA,
 // warp 9 MMA (control warps have the highest ids: the scheduler favours them).
-template <bool DROP>
+template <bool DROP, bool PK>
 __global__ void __launch_bounds__(AF_THREADS, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, AttnTc p) {
@@ -182,7 +226,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
            *kv_free = bars + 5, *q_free = bars + 6;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_items = p.n_tiles * p.heads;
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmO);
@@ -198,12 +241,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tS = tmem_base, tO = tmem_base + 128;
   pdl_prologue_done();
   if (DROP) p.drop_seed = mix_seed(p.drop_seed, p.drop_step);
+  const int pk_M = PK ? __ldg(p.pk_rows) : 0;
+  const int n_items = (PK ? __ldg(p.pk_rows + 2) : p.n_tiles) * p.heads;
 
   if (warp == 8) {
     uint32_t ph = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x, ph ^= 1) {
       const int tile = it / p.heads, h = it % p.heads;
-      const int row0 = tile * p.spt * p.L, col0 = h * p.hd;
+      const int row0 = PK ? __ldg(p.pk_tile_row0 + tile) : tile * p.spt * p.L, col0 = h * p.hd;
       mbar_wait(q_free, ph ^ 1);                   // O of the previous item has left Q's smem
       mbar_wait(kv_free, ph ^ 1);                  // previous PV MMA is done with P (K's smem) and V
       AT_STAMP(0, it / gridDim.x);
@@ -261,11 +306,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // key chunks (32 columns) that any row of this quarter needs: from the first row's window start to the quarter's
     // own diagonal chunk (causal: row r needs columns jlo..r); this warp takes c_lo + part, c_lo + part + 2
     const int r_first = quarter * 32;
-    const int c_lo = min(((r_first / p.L) * p.L) >> 5, quarter), c_hi = quarter;
+    // packed layout: a sequence has at most L + 1 rows, so a row's window starts at most L columns before it
+    const int c_lo = PK ? (max(0, r_first - p.L) >> 5) : min(((r_first / p.L) * p.L) >> 5, quarter), c_hi = quarter;
     uint32_t ph = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x, ph ^= 1) {
       const int tile = it / p.heads, h = it % p.heads;
-      RowInfo ri = row_info(p, tile, h, quarter, lane);
+      const int pk_row0 = PK ? __ldg(p.pk_tile_row0 + tile) : 0;
+      RowInfo ri = PK ? row_info_pk(p, pk_row0, pk_M, h, quarter, lane) : row_info(p, tile, h, quarter, lane);
       if (!ri.owned) { ri.jlo = 1 << 20; ri.jhi = ri.jlo; }         // empty window; TMEM loads stay warp-collective
       const unsigned span = (unsigned)(ri.jhi - ri.jlo);
       mbar_wait(s_full, ph);
@@ -307,6 +354,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               const int j = 8 * g + i;
               float x = ex2_approx(fmaf(__uint_as_float(raw[j]), p.scale_log2e, -mb));   // un-normalised; O is scaled by 1/sum
               x = ((unsigned)(j - lo) <= span) ? x : 0.f;
+              if (PK) x = (j == lo) ? x * ri.pm : x;       // the pad representative's column counts pm times
               sum += x;
               if (DROP) x *= drop_f(p, ri, c * 32 + j);
               e[i] = x;
@@ -365,7 +413,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       fence_proxy_async();
       named_bar_sync_a(9, 256);
       if (warp == 0) AT_STAMP(8, it / gridDim.x);
-      if (warp == 0 && lane == 0) {
+      if (PK) {
+        const int n_own = __ldg(p.pk_tile_row0 + tile + 1) - pk_row0;
+        store_staged_rows(p.o, p.ldo, pk_row0, h * p.hd, Qs, p.hd, n_own, threadIdx.x);
+        named_bar_sync_a(9, 256);                  // every thread has read its chunks: Q's smem may be refilled
+        if (warp == 0 && lane == 0) mbar_arrive(q_free);
+      } else if (warp == 0 && lane == 0) {
         const int row0 = tile * p.spt * p.L, col0 = h * p.hd;
         for (int kb = 0; kb < p.kblocks; ++kb) tma_store_2d_a(&tmO, Qs + kb * OPB, col0 + kb * 64, row0);
         bulk_commit_wait_read_all();
@@ -386,7 +439,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // TMEM round trip), and exchange row max, row sum and delta = sum_j P_ij dP_ij through shared memory.  dQ / dK / dV
 // leave through TMA stores from the (dead) dO / K / Q operand blocks.
 // Warp roles (320 threads): warps 0..7 softmax + epilogue (quarter = warp & 3, part = warp >> 2), warp 8 TMA, warp 9 MMA.
-template <bool DROP>
+template <bool DROP, bool PK>
 __global__ void __launch_bounds__(AF_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
@@ -406,7 +459,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t *in_full = bars, *in_free = bars + 1, *sdp_full = bars + 2, *ds_full = bars + 3, *out_full = bars + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_items = p.n_tiles * p.heads;
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
@@ -421,6 +473,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   pdl_prologue_done();
   if (DROP) p.drop_seed = mix_seed(p.drop_seed, p.drop_step);
+  const int pk_M = PK ? __ldg(p.pk_rows) : 0;
+  const int n_items = (PK ? __ldg(p.pk_rows + 2) : p.n_tiles) * p.heads;
   // S and dP live in columns [0,128) and [128,256); once the softmax backward has consumed them the same
   // columns receive dK and dV, and dQ goes to [256, 256+hd).
   const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDK = tmem_base, tDV = tmem_base + 128, tDQ = tmem_base + 256;
@@ -429,7 +483,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint32_t ph = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x, ph ^= 1) {
       const int tile = it / p.heads, h = it % p.heads;
-      const int row0 = tile * p.spt * p.L, col0 = h * p.hd;
+      const int row0 = PK ? __ldg(p.pk_tile_row0 + tile) : tile * p.spt * p.L, col0 = h * p.hd;
       mbar_wait(in_free, ph ^ 1);            // previous item's outputs have left the operand blocks
       if (elect_one()) {
         mbar_expect_tx(in_full, 4 * opbytes);
@@ -441,7 +495,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         if (!(p.debug & 256) && it + (int)gridDim.x < n_items) {        // next item's operands: HBM -> L2 while this one computes
           const int itn = it + gridDim.x;
-          const int rown = (itn / p.heads) * p.spt * p.L, coln = (itn % p.heads) * p.hd;
+          const int rown = PK ? __ldg(p.pk_tile_row0 + itn / p.heads) : (itn / p.heads) * p.spt * p.L, coln = (itn % p.heads) * p.hd;
           for (int kb = 0; kb < p.kblocks; ++kb) {
             tma_prefetch_l2_2d(&tmQ, coln + kb * 64, rown);
             tma_prefetch_l2_2d(&tmK, coln + kb * 64, rown);
@@ -498,12 +552,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int quarter = warp & 3, part = warp >> 2;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const int r_first = quarter * 32;
-    const int c_lo = min(((r_first / p.L) * p.L) >> 5, quarter), c_hi = quarter;
+    const int c_lo = PK ? (max(0, r_first - p.L) >> 5) : min(((r_first / p.L) * p.L) >> 5, quarter), c_hi = quarter;
     float* xmax = xch; float* xsum = xch + 2 * TILE; float* xdel = xch + 4 * TILE;
     uint32_t ph = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x, ph ^= 1) {
       const int tile = it / p.heads, h = it % p.heads;
-      RowInfo ri = row_info(p, tile, h, quarter, lane);
+      const int pk_row0 = PK ? __ldg(p.pk_tile_row0 + tile) : 0;
+      RowInfo ri = PK ? row_info_pk(p, pk_row0, pk_M, h, quarter, lane) : row_info(p, tile, h, quarter, lane);
       const bool own = ri.owned;
       if (!own) { ri.jlo = 1 << 20; ri.jhi = ri.jlo; }              // empty window, loads stay warp-collective
       const unsigned span = (unsigned)(ri.jhi - ri.jlo);
@@ -536,6 +591,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         float e1 = ex2_approx(fmaf(__uint_as_float(s1[j]), p.scale_log2e, -mb));
         e0 = ((unsigned)(j - lo0) <= span) ? e0 : 0.f;
         e1 = ((unsigned)(j - lo1) <= span) ? e1 : 0.f;
+        if (PK) {                                   // the pad representative's column counts pm times (P is the total mass)
+          e0 = (j == lo0) ? e0 * ri.pm : e0;
+          e1 = (j == lo1) ? e1 * ri.pm : e1;
+        }
         float d0 = __uint_as_float(g0[j]), d1 = __uint_as_float(g1[j]);
         if (DROP) {
           const float k0 = drop_f(p, ri, c0 * 32 + j), k1 = drop_f(p, ri, c1 * 32 + j);
@@ -643,7 +702,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_before();
       fence_proxy_async();
       named_bar_sync_a(9, 256);
-      if (warp == 0 && lane == 0) {
+      if (PK) {
+        const int n_own = __ldg(p.pk_tile_row0 + tile + 1) - pk_row0;
+        store_staged_rows(p.dq, p.lddq, pk_row0, h * p.hd, Ds, p.hd, n_own, threadIdx.x);
+        store_staged_rows(p.dk, p.lddkv, pk_row0, h * p.hd, Ks, p.hd, n_own, threadIdx.x);
+        store_staged_rows(p.dv, p.lddkv, pk_row0, h * p.hd, Qs, p.hd, n_own, threadIdx.x);
+        named_bar_sync_a(9, 256);                  // every thread has read its chunks: the operand blocks may be refilled
+        if (warp == 0 && lane == 0) mbar_arrive(in_free);
+      } else if (warp == 0 && lane == 0) {
         const int row0 = tile * p.spt * p.L, col0 = h * p.hd;
         for (int kb = 0; kb < p.kblocks; ++kb) {
           tma_store_2d_a(&tmDQ, Ds + kb * OPB, col0 + kb * 64, row0);
@@ -718,16 +784,16 @@ extern "C" int srfrd_attention_fwd(const void* q, int ldq, const void* k, const 
   const size_t smem = (size_t)(2 * p.kblocks + (p.kblocks > 2 ? p.kblocks : 2)) * OPB + 4 * TILE * sizeof(float) + 1024 + 256;
   static bool attr = false;
   if (!attr) {
-    SRFRD_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-    SRFRD_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    SRFRD_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    SRFRD_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
     attr = true;
   }
   int grid = p.n_tiles * heads;
   if (grid > 2 * num_sms()) grid = 2 * num_sms();
   if (p.drop_thresh)
-    SRFRD_CUDA(launch_pdl(attn_fwd_tc_kernel<true>, dim3(grid), dim3(AF_THREADS), smem, (cudaStream_t)stream, tmQ, tmK, tmV, tmO, p));
+    SRFRD_CUDA(launch_pdl(attn_fwd_tc_kernel<true, false>, dim3(grid), dim3(AF_THREADS), smem, (cudaStream_t)stream, tmQ, tmK, tmV, tmO, p));
   else
-    SRFRD_CUDA(launch_pdl(attn_fwd_tc_kernel<false>, dim3(grid), dim3(AF_THREADS), smem, (cudaStream_t)stream, tmQ, tmK, tmV, tmO, p));
+    SRFRD_CUDA(launch_pdl(attn_fwd_tc_kernel<false, false>, dim3(grid), dim3(AF_THREADS), smem, (cudaStream_t)stream, tmQ, tmK, tmV, tmO, p));
   SRFRD_LAUNCH_CHECK();
   return 0;
 }
@@ -762,18 +828,102 @@ extern "C" int srfrd_attention_bwd(const void* dout, int lddo, const void* q, in
   const size_t smem = (size_t)(4 * p.kblocks + 4) * OPB + 6 * TILE * sizeof(float) + 1024 + 256;
   static bool attr = false;
   if (!attr) {
-    SRFRD_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SRFRD_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SRFRD_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SRFRD_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
   int grid = p.n_tiles * heads;
   if (grid > num_sms()) grid = num_sms();
   if (p.drop_thresh)
-    SRFRD_CUDA(launch_pdl(attn_bwd_tc_kernel<true>, dim3(grid), dim3(AF_THREADS), smem, (cudaStream_t)stream, tmQ, tmK, tmV,
+    SRFRD_CUDA(launch_pdl(attn_bwd_tc_kernel<true, false>, dim3(grid), dim3(AF_THREADS), smem, (cudaStream_t)stream, tmQ, tmK, tmV,
                           tmDO, tmDQ, tmDK, tmDV, p));
   else
-    SRFRD_CUDA(launch_pdl(attn_bwd_tc_kernel<false>, dim3(grid), dim3(AF_THREADS), smem, (cudaStream_t)stream, tmQ, tmK, tmV,
+    SRFRD_CUDA(launch_pdl(attn_bwd_tc_kernel<false, false>, dim3(grid), dim3(AF_THREADS), smem, (cudaStream_t)stream, tmQ, tmK, tmV,
                           tmDO, tmDQ, tmDK, tmDV, p));
+  SRFRD_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Packed token layout (pack.cu): the same kernels with tiles, row windows and the pad column's weight read from the
+// device-resident plan; q / k / v / o (and the gradients) are (capacity, ld) buffers of packed rows.
+static int packed_supported(int L, int H, int heads, int ldq, int ldkv) {
+  if (!tc_supported(L, H, heads, ldq, ldkv)) return 0;
+  const int hd = H / heads;
+  return (L + 1 <= TILE) && (heads == 1 || hd % 64 == 0);
+}
+
+extern "C" int srfrd_attention_packed_supported(int L, int H, int heads) {
+  return packed_supported(L, H, heads, 8, 8) && !getenv("SRFRD_ATTN_SIMT");
+}
+
+extern "C" int srfrd_attention_fwd_packed(const void* q, int ldq, const void* k, const void* v, int ldkv, void* o, int ldo,
+                                          const srfrd_pack_t* pk, int L, int H, int heads, float drop_p, uint64_t seed,
+                                          uint32_t stream_id, const float* drop_step, void* stream) {
+  SRFRD_REQUIRE(q && k && v && o && pk && pk->rows && pk->row_info && pk->tile_row0, "attention_fwd_packed: null pointer");
+  SRFRD_REQUIRE(packed_supported(L, H, heads, ldq, ldkv) && ldo % 8 == 0 && ((uintptr_t)o & 15) == 0,
+                "attention_fwd_packed: unsupported shape (L=%d H=%d heads=%d)", L, H, heads);
+  AttnTc p = {};
+  if (int rc = fill(p, 1, L, H, heads, drop_p, seed, stream_id, drop_step)) return rc;
+  p.T = pk->cap;
+  p.o = (bf16*)o; p.ldo = ldo; p.tma_o = 1;
+  p.pk_rows = pk->rows; p.pk_info = (const int4*)pk->row_info; p.pk_tile_row0 = pk->tile_row0;
+  CUtensorMap tmQ, tmK, tmV;
+  if (int rc = make_tmap_bf16_2d(&tmQ, q, p.T, H, ldq, TILE, 64)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tmK, k, p.T, H, ldkv, TILE, 64)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tmV, v, p.T, H, ldkv, TILE, 64)) return rc;
+  const size_t smem = (size_t)(2 * p.kblocks + (p.kblocks > 2 ? p.kblocks : 2)) * OPB + 4 * TILE * sizeof(float) + 1024 + 256;
+  static bool attr = false;
+  if (!attr) {
+    SRFRD_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    SRFRD_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    attr = true;
+  }
+  int64_t grid = (pk->cap / 64 + 1) * heads;               // more tiles than this cannot exist
+  if (grid > 2 * num_sms()) grid = 2 * num_sms();
+  if (p.drop_thresh)
+    SRFRD_CUDA(launch_pdl(attn_fwd_tc_kernel<true, true>, dim3((unsigned)grid), dim3(AF_THREADS), smem, (cudaStream_t)stream, tmQ, tmK, tmV, tmQ, p));
+  else
+    SRFRD_CUDA(launch_pdl(attn_fwd_tc_kernel<false, true>, dim3((unsigned)grid), dim3(AF_THREADS), smem, (cudaStream_t)stream, tmQ, tmK, tmV, tmQ, p));
+  SRFRD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int srfrd_attention_bwd_packed(const void* dout, int lddo, const void* q, int ldq, const void* k, const void* v,
+                                          int ldkv, void* dq, int lddq, void* dk, void* dv, int lddkv, const srfrd_pack_t* pk,
+                                          int L, int H, int heads, float drop_p, uint64_t seed, uint32_t stream_id,
+                                          const float* drop_step, void* stream) {
+  SRFRD_REQUIRE(dout && q && k && v && dq && dk && dv && pk && pk->rows && pk->row_info && pk->tile_row0,
+                "attention_bwd_packed: null pointer");
+  SRFRD_REQUIRE(packed_supported(L, H, heads, ldq, ldkv) && lddo % 8 == 0 && lddq % 8 == 0 && lddkv % 8 == 0 &&
+                    (((uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv) & 15) == 0,
+                "attention_bwd_packed: unsupported shape (L=%d H=%d heads=%d)", L, H, heads);
+  AttnTc p = {};
+  if (int rc = fill(p, 1, L, H, heads, drop_p, seed, stream_id, drop_step)) return rc;
+  p.T = pk->cap;
+  p.dq = (bf16*)dq; p.dk = (bf16*)dk; p.dv = (bf16*)dv; p.lddq = lddq; p.lddkv = lddkv; p.tma_o = 1;
+  p.pk_rows = pk->rows; p.pk_info = (const int4*)pk->row_info; p.pk_tile_row0 = pk->tile_row0;
+  { const char* l2 = getenv("SRFRD_L2_PREFETCH"); if (l2 && atoi(l2) == 0) p.debug |= 256; }
+  CUtensorMap tmQ, tmK, tmV, tmDO;
+  if (int rc = make_tmap_bf16_2d(&tmQ, q, p.T, H, ldq, TILE, 64)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tmK, k, p.T, H, ldkv, TILE, 64)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tmV, v, p.T, H, ldkv, TILE, 64)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tmDO, dout, p.T, H, lddo, TILE, 64)) return rc;
+  const size_t smem = (size_t)(4 * p.kblocks + 4) * OPB + 6 * TILE * sizeof(float) + 1024 + 256;
+  static bool attr = false;
+  if (!attr) {
+    SRFRD_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SRFRD_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  int64_t grid = (pk->cap / 64 + 1) * heads;
+  if (grid > num_sms()) grid = num_sms();
+  if (p.drop_thresh)
+    SRFRD_CUDA(launch_pdl(attn_bwd_tc_kernel<true, true>, dim3((unsigned)grid), dim3(AF_THREADS), smem, (cudaStream_t)stream, tmQ, tmK, tmV,
+                          tmDO, tmQ, tmQ, tmQ, p));
+  else
+    SRFRD_CUDA(launch_pdl(attn_bwd_tc_kernel<false, true>, dim3((unsigned)grid), dim3(AF_THREADS), smem, (cudaStream_t)stream, tmQ, tmK, tmV,
+                          tmDO, tmQ, tmQ, tmQ, p));
   SRFRD_LAUNCH_CHECK();
   return 0;
 }

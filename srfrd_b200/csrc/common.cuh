@@ -41,6 +41,8 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 // allocation, descriptor prefetch) while the previous kernel of the stream / graph is still draining; it must call
 // pdl_prologue_done() before it touches anything an earlier kernel wrote.  Opt-in: SRFRD_PDL=1 (see api.cu).
 bool pdl_enabled();
+// Dynamic row count (srfrd_set_row_limit): device pointer the row-wise entry points read their row count from, or null.
+const int* row_limit();
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                               Args&&... args) {

@@ -51,6 +51,7 @@ __device__ long long g_gemm_cta[2 * 160];     // per-CTA start / end globaltimer
 #define TN_STAMP(ev, tile) do { if (s.debug == 5 && blockIdx.x == 0 && (tile) < 16) { if (elect_one()) g_gemm_dbg[(ev) * 16 + (tile)] = clock64(); } } while (0)
 
 struct GemmShape {
+  const int* rows_dev;      // dynamic row count: M = min(M, *rows_dev) (packed token layout), or null
   int M, N, K;
   int block_n, m_tiles, n_tiles, stages;
   int has_aux;              // residual or gate present: the tile's aux block(s) arrive by TMA in the set's tile buffer
@@ -149,7 +150,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ring + TN_RING);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = s.m_tiles * s.n_tiles;
   int* sched = g_tn_sched + 2 * s.sched_slot;
 
   if (warp == 16) {                                      // barrier initialisation spread over the lanes
@@ -177,6 +177,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 17) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
   pdl_prologue_done();                                   // everything below may read what earlier kernels wrote
+  if (s.rows_dev) {                                      // data-dependent row count (packed layout): capacity stays static
+    s.M = min(s.M, __ldg(s.rows_dev));
+    s.m_tiles = (s.M + BLOCK_M - 1) / BLOCK_M;
+  }
+  const int total_tiles = s.m_tiles * s.n_tiles;
   for (int i = threadIdx.x; i < MAX_BIAS; i += blockDim.x) sbias[i] = (e.bias && i < s.N) ? __ldg(e.bias + i) : 0.f;
   if (LNF) {
     for (int i = threadIdx.x; i < MAX_LN; i += blockDim.x) {
@@ -206,6 +211,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // tiles static).  Measured at C2 the dynamic order gains nothing: a tile has to be claimed when its loads are issued,
     // 4-6 tiles before it completes, which is as long as the imbalance it could correct.
     int t = blockIdx.x, t1 = blockIdx.x + (int)gridDim.x;
+    if (t >= total_tiles) t = -1;                        // (dynamic row count: this CTA may have nothing to do)
     if (t1 >= total_tiles) t1 = -1;
     for (int tl = 0;; ++tl) {
       int fetched = -1;
@@ -535,6 +541,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // weight gradient: split-K over tokens, MN-major operands
 // ---------------------------------------------------------------------------------------------
 struct WgradShape {
+  const int* rows_dev; // dynamic token count: T = min(T, *rows_dev), a multiple of 128 (packed token layout), or null.
+                       // Written by the pack-plan kernels at the very start of a step, never by the preceding kernel.
   int T, Mo, No;       // tokens, output rows (dY width), output cols (X width)
   int block_n;         // columns per CTA tile (multiple of 16, <= 256)
   int a_atoms, b_atoms;  // 64-wide MN atoms per stage
@@ -567,7 +575,9 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int i = threadIdx.x; i < ATOM_BYTES / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
     fence_proxy_async();
   }
-  const int kblocks_total = (s.T + BLOCK_K - 1) / BLOCK_K;
+  // dynamic token count (packed layout): read before anything else so that a CTA without work skips cleanly
+  const int T_eff = s.rows_dev ? min(s.T, *s.rows_dev) : s.T;
+  const int kblocks_total = (T_eff + BLOCK_K - 1) / BLOCK_K;
   const int per = (kblocks_total + s.k_splits - 1) / s.k_splits;
   const int kb_begin = blockIdx.x * per, kb_end = min(kblocks_total, kb_begin + per);
   const int nkb = max(0, kb_end - kb_begin);
@@ -770,6 +780,7 @@ static int plan_gemm_tn(int M, int N, int K, bool has_aux, bool tma_out, bool ln
 extern "C" int srfrd_gemm_tn_plan(int M, int N, int K, int has_aux, int bf16_out, int fused_ln, int* out) {
   SRFRD_REQUIRE(out && M > 0 && N > 0 && K > 0 && N % 16 == 0 && K % 8 == 0, "gemm_tn_plan: bad arguments");
   GemmShape s;
+  s.rows_dev = nullptr;
   size_t smem = 0;
   if (int rc = plan_gemm_tn(M, N, K, has_aux != 0, bf16_out != 0, fused_ln != 0, s, smem)) return rc;
   const int kblocks = (K + BLOCK_K - 1) / BLOCK_K;
@@ -807,6 +818,7 @@ extern "C" int srfrd_gemm_tn(const void* A, int lda, const void* B, int ldb, int
   }
   size_t smem = 0;
   if (int rc = plan_gemm_tn(M, N, K, aux != nullptr, tma_out, lnf, s, smem)) return rc;
+  s.rows_dev = row_limit();
   const int b_stage_bytes = ((s.block_n * BLOCK_K * 2) + 1023) & ~1023;
   (void)b_stage_bytes;
   static int next_slot = 0;
@@ -871,6 +883,7 @@ extern "C" int srfrd_gemm_wgrad(const void* dY, int lda, const void* X, int ldb,
   SRFRD_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && lda >= Mo && ldb >= No, "gemm_wgrad: leading dims must be multiples of 8 and cover the widths");
   SRFRD_REQUIRE(T < (1ll << 31), "gemm_wgrad: too many tokens");
   WgradShape s;
+  s.rows_dev = row_limit();
   s.T = (int)T; s.Mo = Mo; s.No = No;
   // one column tile up to 480 columns (H = 272: X is then read once per 128-row tile of dY instead of once per
   // (row tile, column tile) pair); wider outputs are split evenly

@@ -23,6 +23,8 @@ struct ScoreParams {
   float* d_item; float* d_fake;         // gradient tables (red.add) or null
   int64_t T; int D, F;
   int mode;                             // 0 = logits only, 1 = fused loss fwd+bwd, 2 = bwd from dz
+  const int* row_tok;                   // packed layout: h / dh row t belongs to dense token row_tok[t] (-1: no token); ids,
+  const int* rows_dev;                  // weights and logits stay indexed by the dense token.  rows_dev: device row count
 };
 
 __device__ __forceinline__ float softplus(float x) { return fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x))); }
@@ -34,7 +36,7 @@ __device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + __expf(
 // Gradients of the 3-row fake table are kept in registers and flushed once per warp: every active token hits the same two
 // rows, which made them the most contended addresses of the step.
 template <int NC>
-__global__ void __launch_bounds__(256) score_kernel(ScoreParams p) {
+__global__ void __launch_bounds__(256, (NC <= 9 ? 2 : 1)) score_kernel(ScoreParams p) {
   __shared__ float red[2][8];
   pdl_prologue_done();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -51,27 +53,31 @@ __global__ void __launch_bounds__(256) score_kernel(ScoreParams p) {
 #pragma unroll
   for (int i = 0; i < NC; ++i) fk1[i] = fk2[i] = 0.f;
   const bool dh_vec = p.dh && (p.lddh == W) && (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.dh) & 15) == 0);
+  if (p.rows_dev) p.T = min(p.T, (int64_t)__ldg(p.rows_dev));
   for (int64_t t0 = warp0 * 32; t0 < p.T; t0 += nwarps * 32) {
     const int64_t tl = t0 + lane;
-    const bool in = tl < p.T;
+    bool in = tl < p.T;
+    int my_tok = 0;                           // packed layout: dense token whose ids / weights / logits this row uses
+    if (p.row_tok && in) { my_tok = __ldg(p.row_tok + tl); in = my_tok >= 0; }
+    const int64_t my_src = p.row_tok ? (int64_t)my_tok : tl;
     int64_t my_pid = 0, my_nid = 0, my_pf = 0, my_nf = 0;
     float my_a = 0.f, my_b = 0.f;             // mode 1: (w_pos, w_neg); mode 2: (dz+, dz-)
     bool my_active = false;
     if (in) {
-      my_pid = __ldg(p.pos + tl);
-      my_nid = __ldg(p.neg + tl);
+      my_pid = __ldg(p.pos + my_src);
+      my_nid = __ldg(p.neg + my_src);
       if (p.mode == 1) {
-        my_a = p.w_pos ? __ldg(p.w_pos + tl) : (my_pid != 0 ? 1.f : 0.f);
-        my_b = p.w_neg ? __ldg(p.w_neg + tl) : my_a;
+        my_a = p.w_pos ? __ldg(p.w_pos + my_src) : (my_pid != 0 ? 1.f : 0.f);
+        my_b = p.w_neg ? __ldg(p.w_neg + my_src) : my_a;
         my_active = (my_a != 0.f) || (my_b != 0.f) || p.zp;
       } else if (p.mode == 2) {
-        my_a = __ldg(p.dzp_in + tl);
-        my_b = __ldg(p.dzn_in + tl);
+        my_a = __ldg(p.dzp_in + my_src);
+        my_b = __ldg(p.dzn_in + my_src);
         my_active = (my_a != 0.f) || (my_b != 0.f);
       } else {
         my_active = true;
       }
-      if (p.fake_table && my_active) { my_pf = __ldg(p.prs + tl); my_nf = __ldg(p.nrs + tl); }
+      if (p.fake_table && my_active) { my_pf = __ldg(p.prs + my_src); my_nf = __ldg(p.nrs + my_src); }
     }
     unsigned mask = __ballot_sync(0xffffffffu, my_active);
     if (p.dh) {                               // zero rows of the inactive tokens
@@ -92,6 +98,7 @@ __global__ void __launch_bounds__(256) score_kernel(ScoreParams p) {
       const int r = __ffs(mask) - 1;
       mask &= mask - 1;
       const int64_t t = t0 + r;
+      const int64_t tsrc = p.row_tok ? (int64_t)__shfl_sync(0xffffffffu, my_tok, r) : t;
       const int64_t pid = __shfl_sync(0xffffffffu, my_pid, r), nid = __shfl_sync(0xffffffffu, my_nid, r);
       const int pf = (int)__shfl_sync(0xffffffffu, (int)my_pf, r), nf = (int)__shfl_sync(0xffffffffu, (int)my_nf, r);
       const float ta = __shfl_sync(0xffffffffu, my_a, r), tb = __shfl_sync(0xffffffffu, my_b, r);
@@ -115,7 +122,7 @@ __global__ void __launch_bounds__(256) score_kernel(ScoreParams p) {
         }
       }
       const float zp = warp_sum(sp), zn = warp_sum(sn);
-      if (p.zp && lane == 0) { p.zp[t] = zp; p.zn[t] = zn; }
+      if (p.zp && lane == 0) { p.zp[tsrc] = zp; p.zn[tsrc] = zn; }
       if (p.mode == 0) continue;
       float dzp = ta, dzn = tb;
       if (p.mode == 1) {
@@ -241,6 +248,54 @@ __global__ void embed_bwd_kernel(EmbedBwdParams p) {
     red_add_f32(p.d_aux + p.aux_ids[b] * p.D + c, accu);
 }
 
+// K5 on the packed layout: sequences are walked by a persistent grid; dx0 rows are found through tok_row (the packed row of
+// each dense token, -1 = dropped pad).  The positional-table gradient (dense layout: a column sum over the (B, L*H) view)
+// is accumulated per block in shared memory [L][D] -- thread c owns column c, so no atomics -- and flushed once per block.
+__global__ void embed_bwd_packed_kernel(EmbedBwdParams p, const int* tok_row, int64_t B, float* d_pos) {
+  extern __shared__ float spos[];            // [L * D] positional gradient partials, then [2 * L] ids as int64
+  pdl_prologue_done();
+  const int c = threadIdx.x;
+  const int H = p.D + (p.mode == 1 ? p.F : 0);
+  int64_t* ids = reinterpret_cast<int64_t*>(spos + ((p.L * p.D + 1) & ~1));
+  int* rows = reinterpret_cast<int*>(ids + 2 * p.L);
+  for (int i = threadIdx.x; i < p.L * p.D; i += blockDim.x) spos[i] = 0.f;
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    for (int l = threadIdx.x; l < p.L; l += blockDim.x) {
+      ids[l] = p.seq[b * p.L + l];
+      ids[p.L + l] = (p.mode == 1 && p.aux_ids) ? p.aux_ids[b * p.L + l] : 0;
+      rows[l] = tok_row[b * p.L + l];
+    }
+    __syncthreads();
+    if (c >= H) continue;
+    float acc1 = 0.f, acc2 = 0.f, accu = 0.f;
+    for (int l = 0; l < p.L; ++l) {
+      const int64_t id = ids[l];
+      if (id == 0) continue;                 // (a kept pad row has id 0: masked input, no gradient)
+      const float v = bf2f(p.dx0[(int64_t)rows[l] * p.ldx + c]);
+      if (c < p.D) {
+        red_add_f32(p.d_item + id * p.D + c, v * p.item_scale);
+        spos[l * p.D + c] += v;
+        accu += v;
+      } else {
+        const int64_t f = ids[p.L + l];
+        if (f == 1) acc1 += v;
+        else if (f == 2) acc2 += v;
+      }
+    }
+    if (p.mode == 1 && c >= p.D && p.d_aux) {        // fake_embed padding_idx = 0: row 0 gets nothing
+      if (acc1 != 0.f) red_add_f32(p.d_aux + 1 * p.F + (c - p.D), acc1);
+      if (acc2 != 0.f) red_add_f32(p.d_aux + 2 * p.F + (c - p.D), acc2);
+    }
+    if (p.mode == 2 && c < p.D && p.d_aux && accu != 0.f)
+      red_add_f32(p.d_aux + p.aux_ids[b] * p.D + c, accu);
+  }
+  __syncthreads();
+  if (d_pos)
+    for (int i = threadIdx.x; i < p.L * p.D; i += blockDim.x)
+      if (spos[i] != 0.f) red_add_f32(d_pos + i, spos[i]);
+}
+
 // out[(n / seg_in) * seg_out + n % seg_in] += in[n] where n % seg_in < seg_out
 __global__ void add_segments_kernel(float* in, int64_t n, int seg_in, int seg_out, float* out) {
   pdl_prologue_done();
@@ -361,6 +416,21 @@ extern "C" int srfrd_score_loss_fused(const float* h, int ldh, const float* item
   return score_launch(p, stream);
 }
 
+extern "C" int srfrd_score_loss_fused_packed(const float* h, int ldh, const float* item_table, const float* fake_table,
+                                             const int64_t* pos, const int64_t* neg, const int64_t* prs, const int64_t* nrs,
+                                             const float* w_pos, const float* w_neg, const float* norm, int D, int F,
+                                             float* loss_acc, float* dh, int lddh, float* d_item, float* d_fake,
+                                             const int* row_tok, const int* rows_dev, int64_t cap_rows, void* stream) {
+  SRFRD_REQUIRE(h && item_table && pos && neg && norm && loss_acc && row_tok && rows_dev, "score_loss_fused_packed: null pointer");
+  SRFRD_REQUIRE(!fake_table || (prs && nrs), "score_loss_fused_packed: fake ids required with a fake table");
+  ScoreParams p = {};
+  p.h = h; p.ldh = ldh; p.item_table = item_table; p.fake_table = fake_table; p.pos = pos; p.neg = neg; p.prs = prs;
+  p.nrs = nrs; p.w_pos = w_pos; p.w_neg = w_neg; p.norm = norm; p.T = cap_rows; p.D = D; p.F = F;
+  p.loss_acc = loss_acc; p.dh = dh; p.lddh = lddh; p.d_item = d_item; p.d_fake = d_fake; p.mode = 1;
+  p.row_tok = row_tok; p.rows_dev = rows_dev;
+  return score_launch(p, stream);
+}
+
 extern "C" int srfrd_weight_sums(const int64_t* pos, const float* w_pos, const float* w_neg, int64_t T, float* out2,
                                  void* stream) {
   SRFRD_REQUIRE(pos && out2, "weight_sums: null pointer");
@@ -393,6 +463,33 @@ extern "C" int srfrd_embed_bwd(const void* dx0, int ldx, const int64_t* seq, con
   p.item_scale = item_scale; p.d_item = d_item; p.d_aux = d_aux;
   const int threads = (H + 31) & ~31;
   SRFRD_CUDA(launch_pdl(embed_bwd_kernel, dim3((unsigned)B), dim3(threads), 2 * L * sizeof(int64_t), (cudaStream_t)stream, p));
+  SRFRD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int srfrd_embed_bwd_packed(const void* dx0, int ldx, const int64_t* seq, const int64_t* aux_ids,
+                                      const int* tok_row, int64_t B, int L, int D, int F, int mode, float item_scale,
+                                      float* d_item, float* d_aux, float* d_pos, void* stream) {
+  SRFRD_REQUIRE(dx0 && seq && d_item && tok_row, "embed_bwd_packed: null pointer");
+  SRFRD_REQUIRE(mode >= 0 && mode <= 2, "embed_bwd_packed: bad mode");
+  SRFRD_REQUIRE(mode != 2 || aux_ids, "embed_bwd_packed: labels required for mode 2");
+  const int H = D + (mode == 1 ? F : 0);
+  SRFRD_REQUIRE(H <= 1024, "embed_bwd_packed: width %d unsupported", H);
+  if (B == 0) return 0;
+  EmbedBwdParams p;
+  p.dx0 = (const bf16*)dx0; p.ldx = ldx; p.seq = seq; p.aux_ids = aux_ids; p.L = L; p.D = D; p.F = F; p.mode = mode;
+  p.item_scale = item_scale; p.d_item = d_item; p.d_aux = d_aux;
+  const int threads = (H + 31) & ~31;
+  const size_t smem = (size_t)((L * D + 1) & ~1) * sizeof(float) + 2 * L * sizeof(int64_t) + L * sizeof(int);
+  SRFRD_REQUIRE(smem <= 200 * 1024, "embed_bwd_packed: L * D = %d too large for the shared positional accumulator", L * D);
+  static bool attr = false;
+  if (!attr) {
+    SRFRD_CUDA(cudaFuncSetAttribute(embed_bwd_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  int64_t grid = (int64_t)num_sms() * (smem > 48 * 1024 ? 1 : 4);
+  if (grid > B) grid = B;
+  SRFRD_CUDA(launch_pdl(embed_bwd_packed_kernel, dim3((unsigned)grid), dim3(threads), smem, (cudaStream_t)stream, p, tok_row, B, d_pos));
   SRFRD_LAUNCH_CHECK();
   return 0;
 }

@@ -57,6 +57,8 @@ struct EmbedParams {
   const float* aux_table;    // mode 1: fake_embed (3, F); mode 2: user_label_embed (labels, D)
   const int64_t* seq;        // (B, L)
   const int64_t* aux_ids;    // mode 1: (B, L) fake ids or null (-> all 0); mode 2: (B,) labels
+  const int* row_tok;        // packed layout: dense token (b * L + l) of output row t, -1 = pad representative / filler
+  const int* rows_dev;       // packed layout: device row count (rows beyond it are not touched)
   int64_t T;
   int L, D, F, mode;
   float item_scale;
@@ -214,10 +216,19 @@ __global__ void __launch_bounds__(256, 4) embed_ln_vec_kernel(EmbedParams p) {
   int64_t t = warp * RPW + grp;
   int l = (int)(t % p.L);
   const bool has_ln = p.ln_w != nullptr;
+  if (p.rows_dev) p.T = min(p.T, (int64_t)__ldg(p.rows_dev));
   for (; t - grp < p.T; t += stride, l = (l + lstep >= p.L) ? l + lstep - p.L : l + lstep) {
     const bool row_ok = t < p.T;
     int64_t id = 0, aid = 0;
-    if (row_ok) {
+    if (p.row_tok) {                   // packed layout: output row t holds dense token row_tok[t] (or a row with id 0)
+      const int src = row_ok ? __ldg(p.row_tok + t) : -1;
+      if (src >= 0) {
+        l = src % p.L;
+        id = __ldg(p.seq + src);
+        if (MODE == 1) aid = p.aux_ids ? __ldg(p.aux_ids + src) : 0;
+        if (MODE == 2) aid = __ldg(p.aux_ids + src / p.L);
+      }
+    } else if (row_ok) {
       id = __ldg(p.seq + t);
       if (MODE == 1) aid = p.aux_ids ? __ldg(p.aux_ids + t) : 0;
       if (MODE == 2) aid = __ldg(p.aux_ids + t / p.L);
@@ -318,6 +329,8 @@ struct LnFwdParams {
   int64_t T; int H;
   int64_t row_stride;   // process rows t*row_stride + row_offset (used to normalise only the last position)
   int64_t row_offset;
+  const int* row_index; // optional: input row of output row t (packed layout: the row that holds each sequence's last position)
+  const int* rows_dev;  // optional: device row count (packed layout)
 };
 
 // p.H is the number of VALID columns (LayerNorm width); rows are processed in 8-column chunks up to Hc = roundup(H, 8),
@@ -329,6 +342,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(LnFwdParams p) {
   const int Hc = (p.H + 7) & ~7;
   constexpr bool ragged = RAGGED;
   pdl_prologue_done();
+  if (p.rows_dev) p.T = min(p.T, (int64_t)__ldg(p.rows_dev));
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t t0 = warp * RPW * UN; t0 < p.T; t0 += nwarps * RPW * UN) {
@@ -341,7 +355,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(LnFwdParams p) {
         const int c = (ch * LPR + sub) * 8;
         raw[u][ch] = make_uint4(0, 0, 0, 0);
         if (t < p.T && c < Hc)
-          raw[u][ch] = __ldg(reinterpret_cast<const uint4*>(p.x + (t * p.row_stride + p.row_offset) * p.ldx + c));
+          raw[u][ch] = __ldg(reinterpret_cast<const uint4*>(
+              p.x + (p.row_index ? (int64_t)__ldg(p.row_index + t) : t * p.row_stride + p.row_offset) * p.ldx + c));
       }
     }
 #pragma unroll
@@ -402,6 +417,7 @@ struct LnBwdParams {
   bf16* dx; int lddx;
   float* dw; float* db;              // (H) accumulated with red.add
   int64_t T; int H;
+  const int* rows_dev;               // optional: device row count (packed layout)
 };
 
 // Lean register layout: the per-lane column accumulators (dw, db: 2 x CH x 8) are the only persistent state; the LN
@@ -418,6 +434,7 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(LnBwdParams p) {
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   pdl_prologue_done();
+  if (p.rows_dev) p.T = min(p.T, (int64_t)__ldg(p.rows_dev));
   for (int i = threadIdx.x; i < MAXW; i += blockDim.x) { sdw[i] = sdb[i] = 0.f; sw[i] = i < p.H ? __ldg(p.w + i) : 0.f; }
   __syncthreads();
   float adw[CH][8], adb[CH][8];
@@ -543,10 +560,11 @@ __global__ void __launch_bounds__(256, 4) ln_fwd_vec_kernel(LnFwdParams p) {
   for (int ch = 0; ch < CH; ++ch) col[ch] = (ch * LPR + sub) * 8;
   if (!last_ok) col[LAST] = 0;
   const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 5) * RPW;
+  if (p.rows_dev) p.T = min(p.T, (int64_t)__ldg(p.rows_dev));
   for (int64_t t = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + grp; t - grp < p.T; t += stride) {
     const bool ok = t < p.T;
     const int64_t tt = ok ? t : p.T - 1;
-    const bf16* xrow = p.x + (tt * p.row_stride + p.row_offset) * p.ldx;
+    const bf16* xrow = p.x + (p.row_index ? (int64_t)__ldg(p.row_index + tt) : tt * p.row_stride + p.row_offset) * p.ldx;
     uint4 raw[CH];
 #pragma unroll
     for (int ch = 0; ch < CH; ++ch) raw[ch] = __ldg(reinterpret_cast<const uint4*>(xrow + col[ch]));
@@ -593,6 +611,7 @@ __global__ void __launch_bounds__(TPB, BPS) ln_bwd_vec_kernel(LnBwdParams p) {
   constexpr int RPW = 32 / LPR, LAST = CH - 1;
   const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
   pdl_prologue_done();
+  if (p.rows_dev) p.T = min(p.T, (int64_t)__ldg(p.rows_dev));
   for (int i = threadIdx.x; i < MAXW; i += blockDim.x) { sdw[i] = sdb[i] = 0.f; sw[i] = i < p.H ? __ldg(p.w + i) : 0.f; }
   __syncthreads();
   float adw[CH][8], adb[CH][8];
@@ -811,8 +830,10 @@ __global__ void f32_to_bf16_rows_kernel(const float* src, int64_t src_ld, const 
 }
 
 __global__ void dropout_apply_kernel(const bf16* x, int ldx, bf16* out, int ldo, int64_t M, int N, uint64_t seed,
-                                     uint32_t thresh, uint32_t stream_id, float scale, const float* step) {
+                                     uint32_t thresh, uint32_t stream_id, float scale, const float* step,
+                                     const int* rows_dev) {
   pdl_prologue_done();
+  if (rows_dev) M = min(M, (int64_t)__ldg(rows_dev));
   seed = mix_seed(seed, step);
   const int64_t n2 = M * (N / 2);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
@@ -834,12 +855,13 @@ static int grid_for_rows(int64_t T, int rows_per_block, int max_blocks_per_sm) {
 
 using namespace srfrd;
 
-extern "C" int srfrd_embed_ln_fwd(const float* item_table, int64_t n_rows, int D, const float* pos_table,
-                                  const float* aux_table, int64_t n_aux, int F, int mode, const int64_t* seq,
-                                  const int64_t* aux_ids, int64_t B, int L, float item_scale, const float* ln_w,
-                                  const float* ln_b, float eps, void* x0_bf16, float* x0_f32, void* q_bf16,
-                                  float* stats, int ldx, float drop_p, uint64_t drop_seed, uint32_t drop_stream,
-                                  const float* drop_step, void* stream) {
+static int embed_ln_fwd_impl(const float* item_table, int64_t n_rows, int D, const float* pos_table,
+                             const float* aux_table, int64_t n_aux, int F, int mode, const int64_t* seq,
+                             const int64_t* aux_ids, int64_t B, int L, float item_scale, const float* ln_w,
+                             const float* ln_b, float eps, void* x0_bf16, float* x0_f32, void* q_bf16,
+                             float* stats, int ldx, float drop_p, uint64_t drop_seed, uint32_t drop_stream,
+                             const float* drop_step, const int* row_tok, const int* rows_dev, int64_t cap_rows,
+                             void* stream) {
   SRFRD_REQUIRE(item_table && pos_table && seq, "embed_ln_fwd: null input");
   SRFRD_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "embed_ln_fwd: dropout p must be in [0, 1)");
   SRFRD_REQUIRE(mode >= 0 && mode <= 2, "embed_ln_fwd: mode must be 0 (none), 1 (concat fake) or 2 (add user label)");
@@ -852,9 +874,12 @@ extern "C" int srfrd_embed_ln_fwd(const float* item_table, int64_t n_rows, int D
   SRFRD_REQUIRE((!x0_bf16 && !q_bf16) || (ldx >= ((H + 7) & ~7) && ldx % 8 == 0), "embed_ln_fwd: bad ldx %d", ldx);
   (void)n_rows; (void)n_aux;
   if (B * L == 0) return 0;
+  SRFRD_REQUIRE(!row_tok || (vec && rows_dev && cap_rows > 0 && !x0_f32),
+                "embed_ln_fwd_packed: needs widths that are multiples of 8, the device row count and a capacity");
   EmbedParams p;
   p.item_table = item_table; p.pos_table = pos_table; p.aux_table = aux_table; p.seq = seq; p.aux_ids = aux_ids;
-  p.T = B * L; p.L = L; p.D = D; p.F = F; p.mode = mode; p.item_scale = item_scale;
+  p.row_tok = row_tok; p.rows_dev = rows_dev;
+  p.T = row_tok ? cap_rows : B * L; p.L = L; p.D = D; p.F = F; p.mode = mode; p.item_scale = item_scale;
   p.ln_w = ln_w; p.ln_b = ln_b; p.eps = eps; p.x0 = (bf16*)x0_bf16; p.x0_f32 = x0_f32; p.q = (bf16*)q_bf16;
   p.stats = stats; p.ldx = ldx;
   p.drop_seed = drop_seed; p.drop_stream = drop_stream; p.drop_step = drop_step;
@@ -880,9 +905,32 @@ extern "C" int srfrd_embed_ln_fwd(const float* item_table, int64_t n_rows, int D
   return 0;
 }
 
-extern "C" int srfrd_layernorm_fwd(const void* x, int ldx, const float* w, const float* b, float eps, void* y_bf16,
-                                   float* y_f32, int ldy, float* stats, int64_t T, int H, int64_t row_stride,
-                                   int64_t row_offset, void* stream) {
+extern "C" int srfrd_embed_ln_fwd(const float* item_table, int64_t n_rows, int D, const float* pos_table,
+                                  const float* aux_table, int64_t n_aux, int F, int mode, const int64_t* seq,
+                                  const int64_t* aux_ids, int64_t B, int L, float item_scale, const float* ln_w,
+                                  const float* ln_b, float eps, void* x0_bf16, float* x0_f32, void* q_bf16,
+                                  float* stats, int ldx, float drop_p, uint64_t drop_seed, uint32_t drop_stream,
+                                  const float* drop_step, void* stream) {
+  return embed_ln_fwd_impl(item_table, n_rows, D, pos_table, aux_table, n_aux, F, mode, seq, aux_ids, B, L, item_scale, ln_w,
+                           ln_b, eps, x0_bf16, x0_f32, q_bf16, stats, ldx, drop_p, drop_seed, drop_stream, drop_step, nullptr,
+                           nullptr, 0, stream);
+}
+
+extern "C" int srfrd_embed_ln_fwd_packed(const float* item_table, int64_t n_rows, int D, const float* pos_table,
+                                         const float* aux_table, int64_t n_aux, int F, int mode, const int64_t* seq,
+                                         const int64_t* aux_ids, int64_t B, int L, float item_scale, const float* ln_w,
+                                         const float* ln_b, float eps, void* x0_bf16, void* q_bf16, float* stats, int ldx,
+                                         float drop_p, uint64_t drop_seed, uint32_t drop_stream, const float* drop_step,
+                                         const int* row_tok, const int* rows_dev, int64_t cap_rows, void* stream) {
+  SRFRD_REQUIRE(row_tok && rows_dev, "embed_ln_fwd_packed: null row map");
+  return embed_ln_fwd_impl(item_table, n_rows, D, pos_table, aux_table, n_aux, F, mode, seq, aux_ids, B, L, item_scale, ln_w,
+                           ln_b, eps, x0_bf16, nullptr, q_bf16, stats, ldx, drop_p, drop_seed, drop_stream, drop_step, row_tok,
+                           rows_dev, cap_rows, stream);
+}
+
+static int layernorm_fwd_impl(const void* x, int ldx, const float* w, const float* b, float eps, void* y_bf16,
+                              float* y_f32, int ldy, float* stats, int64_t T, int H, int64_t row_stride,
+                              int64_t row_offset, const int* row_index, const int* rows_dev, void* stream) {
   SRFRD_REQUIRE(x && w && b && (y_bf16 || y_f32), "layernorm_fwd: null pointer");
   SRFRD_REQUIRE(H <= MAXW && ldx % 8 == 0 && ldy % 8 == 0 && ldx >= ((H + 7) & ~7) && ldy >= ((H + 7) & ~7),
                 "layernorm_fwd: width %d / ld (%d, %d) unsupported (rows are padded to a multiple of 8 columns)", H, ldx, ldy);
@@ -890,6 +938,7 @@ extern "C" int srfrd_layernorm_fwd(const void* x, int ldx, const float* w, const
   LnFwdParams p;
   p.x = (const bf16*)x; p.ldx = ldx; p.w = w; p.b = b; p.eps = eps; p.y_bf16 = (bf16*)y_bf16; p.y_f32 = y_f32;
   p.ldy = ldy; p.stats = stats; p.T = T; p.H = H; p.row_stride = row_stride; p.row_offset = row_offset;
+  p.row_index = row_index; p.rows_dev = rows_dev;
 #define CALL(LPR, CH)                                                                                                   \
   do {                                                                                                                  \
     const dim3 grid(grid_for_rows(T, 16 * (32 / LPR), 8));                                                              \
@@ -901,6 +950,19 @@ extern "C" int srfrd_layernorm_fwd(const void* x, int ldx, const float* w, const
 #undef CALL
   SRFRD_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int srfrd_layernorm_fwd(const void* x, int ldx, const float* w, const float* b, float eps, void* y_bf16,
+                                   float* y_f32, int ldy, float* stats, int64_t T, int H, int64_t row_stride,
+                                   int64_t row_offset, void* stream) {
+  return layernorm_fwd_impl(x, ldx, w, b, eps, y_bf16, y_f32, ldy, stats, T, H, row_stride, row_offset, nullptr, row_limit(),
+                            stream);
+}
+
+extern "C" int srfrd_layernorm_fwd_rows(const void* x, int ldx, const float* w, const float* b, float eps, float* y_f32,
+                                        int ldy, const int* row_index, int64_t n, int H, void* stream) {
+  SRFRD_REQUIRE(row_index, "layernorm_fwd_rows: null row index");
+  return layernorm_fwd_impl(x, ldx, w, b, eps, nullptr, y_f32, ldy, nullptr, n, H, 1, 0, row_index, nullptr, stream);
 }
 
 extern "C" int srfrd_layernorm_bwd(const void* dy_bf16, const float* dy_f32, int lddy, const void* x, int ldx,
@@ -916,7 +978,7 @@ extern "C" int srfrd_layernorm_bwd(const void* dy_bf16, const float* dy_f32, int
   LnBwdParams p;
   p.dy_bf16 = (const bf16*)dy_bf16; p.dy_f32 = dy_f32; p.lddy = lddy; p.x = (const bf16*)x; p.ldx = ldx;
   p.stats = stats; p.w = w; p.add = (const bf16*)add; p.ldadd = ldadd; p.row_ids = row_ids; p.dx = (bf16*)dx;
-  p.lddx = lddx; p.dw = dw; p.db = db; p.T = T; p.H = H;
+  p.lddx = lddx; p.dw = dw; p.db = db; p.T = T; p.H = H; p.rows_dev = row_limit();
 #define CALL(LPR, CH)                                                                                             \
   do {                                                                                                            \
     const int grid = grid_for_rows(T, 8 * (32 / LPR) * 8, 2);                                                     \
@@ -995,7 +1057,7 @@ extern "C" int srfrd_dropout_apply(const void* x, int ldx, void* out, int ldo, i
   if (blocks > num_sms() * 16) blocks = num_sms() * 16;
   SRFRD_CUDA(launch_pdl(dropout_apply_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, ldx,
                         (bf16*)out, ldo, M, N, seed, (uint32_t)((double)drop_p * 4294967296.0), stream_id,
-                        1.f / (1.f - drop_p), drop_step));
+                        1.f / (1.f - drop_p), drop_step, row_limit()));
   SRFRD_LAUNCH_CHECK();
   return 0;
 }

@@ -178,6 +178,8 @@ class HotPath:
         self.overlap = os.environ.get("SRFRD_OVERLAP", "1") != "0"
         self.drop_seed = 0x5EED5EED
         self.saved: Optional[dict] = None
+        self._plans: Dict[Tuple[int, int], ops.PackedPlan] = {}
+        self.packed_default = os.environ.get("SRFRD_PACKED", "1") != "0"
 
     # ------------------------------------------------------------------ bf16 operand shadows
     def _build_shadows(self):
@@ -303,15 +305,40 @@ class HotPath:
         self.ws_generation += 1
         return ws
 
+    # ------------------------------------------------------------------ packed token layout
+    def packed_ok(self, B: int, L: int) -> bool:
+        """Can this batch shape run on the packed token layout (csrc/pack.cu: no work on pad slots)?  Needs widths that
+        are multiples of 16 (no ragged padding columns), tcgen05 attention with a whole sequence + its pad representative
+        in one 128-row tile, and at most 16384 sequences per call."""
+        s = self.spec
+        if s.padded or s.H % 16 or s.D % 8 or B > 16384 or B < 1:
+            return False
+        return ops.attention_packed_supported(L, s.H, s.num_heads)
+
+    def _plan(self, B: int, L: int) -> "ops.PackedPlan":
+        key = (B, L)
+        if key not in self._plans:
+            if len(self._plans) >= 4:                 # a captured graph may hold pointers into a plan: bump the generation
+                self._plans.clear()
+                self.ws_generation += 1
+            self._plans[key] = ops.PackedPlan(B, L, self.device)
+        return self._plans[key]
+
     # ------------------------------------------------------------------ forward
     def forward(self, seq: torch.Tensor, fake_ids: Optional[torch.Tensor], training: bool,
-                last_only: bool = False, save: Optional[bool] = None) -> torch.Tensor:
+                last_only: bool = False, save: Optional[bool] = None, packed: bool = False,
+                keep: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Encoder forward.  Returns hidden (B, L, Dout) fp32 -- or (B, Dout) for last_only (predict uses
-        hidden[:, -1, :] only, SRFR_model.py:147).  Saves what backward needs when training."""
+        hidden[:, -1, :] only, SRFR_model.py:147).  Saves what backward needs when training.
+        packed=True runs on the packed token layout (pad slots are not computed; `keep` (B, L) marks pad slots that must
+        still get a row because they carry a loss term): the full hidden state is then left in PACKED rows in the
+        workspace (ws["hfin"], row maps in the plan) and only last_only returns a dense result."""
         s, P = self.spec, self.P
         B, L = seq.shape
         if L > s.max_len:
             raise RuntimeError(f"sequence length {L} exceeds max_len {s.max_len} (pos_embed rows, SRFR_model.py:12)")
+        if packed:
+            return self._forward_packed(seq, fake_ids, training, last_only, save, keep)
         T, H, Hp, nb = B * L, s.H, s.Hp, s.num_blocks
         ws = self._workspace(T, L)
         self.fwd_version += 1                   # EVERY forward overwrites the shared activations (saving or not)
@@ -403,6 +430,8 @@ class HotPath:
             raise RuntimeError("srfrd_b200: backward() of a stale forward -- another forward() (training, validation or "
                                "predict) ran on this model after the one being back-propagated and overwrote the shared "
                                "activation workspace; run backward() before the next forward()")
+        if sv.get("plan") is not None:
+            return self._backward_packed(dh)
         B, L = sv["B"], sv["L"]
         T, H, Hp, nb = B * L, s.H, s.Hp, s.num_blocks
         ws = self._ws
@@ -480,6 +509,152 @@ class HotPath:
         ops.colsum(dx0, pos_tmp, M=B, N=L * Hp, ld=L * Hp)
         ops.add_segments(pos_tmp, L * Hp, Hp, s.D, G(s.pos_key))
         self._join()                                # every weight gradient has landed in P.grad
+        self.saved = None
+
+    # ------------------------------------------------------------------ packed forward / backward
+    def _forward_packed(self, seq, fake_ids, training, last_only, save, keep):
+        """The same kernel sequence as forward() over M packed rows (M is data dependent and lives on the device:
+        every row-wise kernel reads it through ops.row_limit, the packed kernels take the plan)."""
+        s, P = self.spec, self.P
+        B, L = seq.shape
+        H, Hp, nb = s.H, s.Hp, s.num_blocks
+        plan = self._plan(B, L)
+        T = plan.cap
+        ws = self._workspace(T, L)
+        self.fwd_version += 1
+        p_drop = s.dropout if training else 0.0
+        step = self.step_state[3:4] if p_drop > 0 else None
+        seed = (self.drop_seed + self.host_drop_counter * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        seq = seq.contiguous()
+        aux_ids = None
+        if s.mode == 1:
+            aux_ids = None if fake_ids is None else fake_ids.contiguous()
+        elif s.mode == 2:
+            aux_ids = torch.empty(B, dtype=torch.int64, device=self.device)
+            ops.srfu_labels(fake_ids.contiguous(), {"SRFU_B": 0, "SRFU_F": 1, "SRFU_R": 2}[s.kind], aux_ids)
+            need = {"SRFU_B": 3, "SRFU_F": L + 1, "SRFU_R": 11}[s.kind]
+            if s.n_labels < need and int(aux_ids.max()) >= s.n_labels:
+                raise IndexError(f"index out of range in self: {s.kind} user label {int(aux_ids.max())} needs "
+                                 f"number_of_labels >= {need}, got {s.n_labels}")
+        aux_table = P.view(s.aux_key) if s.aux_key else None
+        plan.build(seq, None if keep is None else keep.contiguous())
+        x = [ws[f"x{i}"][:T] for i in range(nb + 1)]
+        row_ids = plan.row_ids
+        fuse_ln = Hp <= 128 and os.environ.get("SRFRD_FUSE_LN", "1") != "0"
+        with ops.row_limit(plan.rows):
+            ops.embed_ln_fwd_packed(P.view(s.item_key), P.view(s.pos_key), aux_table, s.mode, seq, aux_ids, s.item_scale,
+                                    P.view("attention_layernorms.0.weight"), P.view("attention_layernorms.0.bias"), LN_EPS,
+                                    x[0], ws["Q0"][:T], ws["st1_0"][:T], plan,
+                                    drop_p=p_drop if s.kind == "SASRec" else 0.0, drop_seed=seed, drop_stream=1, drop_step=step)
+            for i in range(nb):
+                Q, q, kv, o, r, y, h1 = (ws[f"{n}{i}"][:T] for n in ("Q", "q", "kv", "o", "r", "y", "h1"))
+                with self._branch():                                   # k | v need the un-normalised x only
+                    ops.gemm_tn(x[i], self.sh[f"wkv{i}"], out_bf16=kv, bias=self.bias("bkv", i))
+                if i > 0 and not fuse_ln:
+                    ops.layernorm_fwd(x[i], P.view(f"attention_layernorms.{i}.weight"), P.view(f"attention_layernorms.{i}.bias"),
+                                      LN_EPS, y_bf16=Q, stats=ws[f"st1_{i}"][:T], H=H)
+                ops.gemm_tn(Q, self.sh[f"wq{i}"], out_bf16=q, bias=self.bias("bq", i))
+                self._join()
+                ops.attention_fwd_packed(q, kv[:, :Hp], kv[:, Hp:], o, plan, L, H, s.num_heads, p_drop, seed, 10 + 4 * i, step)
+                if fuse_ln:
+                    ops.gemm_tn(o, self.sh[f"wo{i}"], out_bf16=r, bias=self.bias("bo", i), residual=Q, ln_out=y,
+                                ln_w=P.view(f"forward_layernorms.{i}.weight"), ln_b=P.view(f"forward_layernorms.{i}.bias"),
+                                ln_eps=LN_EPS, ln_stats=ws[f"st2_{i}"][:T])
+                else:
+                    ops.gemm_tn(o, self.sh[f"wo{i}"], out_bf16=r, bias=self.bias("bo", i), residual=Q)
+                    ops.layernorm_fwd(r, P.view(f"forward_layernorms.{i}.weight"), P.view(f"forward_layernorms.{i}.bias"),
+                                      LN_EPS, y_bf16=y, stats=ws[f"st2_{i}"][:T], H=H)
+                ops.gemm_tn(y, self.sh[f"w1{i}"], out_bf16=h1, bias=self.bias("b1", i), relu=True,
+                            drop_p=p_drop, drop_seed=seed, drop_stream=11 + 4 * i, drop_step=step)
+                nxt = {}
+                if fuse_ln and i + 1 < nb:
+                    nxt = dict(ln_out=ws[f"Q{i + 1}"][:T], ln_w=P.view(f"attention_layernorms.{i + 1}.weight"),
+                               ln_b=P.view(f"attention_layernorms.{i + 1}.bias"), ln_eps=LN_EPS,
+                               ln_stats=ws[f"st1_{i + 1}"][:T])
+                ops.gemm_tn(h1, self.sh[f"w2{i}"], out_bf16=x[i + 1], bias=self.bias("b2", i), residual=y, row_ids=row_ids,
+                            drop_p=p_drop, drop_seed=seed, drop_stream=12 + 4 * i, drop_step=step, **nxt)
+            fin_in = x[nb]
+            if s.kind == "SRFR":
+                ops.gemm_tn(x[nb], self.sh["wc"], out_bf16=ws["c"][:T], bias=self.bias("bc"))
+                fin_in = ws["c"][:T]
+            if not last_only:
+                ops.layernorm_fwd(fin_in, P.view("last_layernorm.weight"), P.view("last_layernorm.bias"), LN_EPS,
+                                  y_f32=ws["hfin"][:T], stats=ws["stF"][:T], H=s.Dout)
+        if last_only:
+            out = ws["hfin"][:B]
+            ops.layernorm_fwd_rows(fin_in, P.view("last_layernorm.weight"), P.view("last_layernorm.bias"), LN_EPS, out,
+                                   plan.last_row, B, s.Dout)
+            return out[:, :s.Dout]
+        if training if save is None else save:
+            self.saved = dict(seq=seq, aux_ids=aux_ids, B=B, L=L, p_drop=p_drop, seed=seed, step=step,
+                              version=self.fwd_version, plan=plan)
+        return ws["hfin"][:T]
+
+    def _backward_packed(self, dh: torch.Tensor) -> None:
+        s, P, sv = self.spec, self.P, self.saved
+        plan = sv["plan"]
+        B, L = sv["B"], sv["L"]
+        T, H, Hp, nb = plan.cap, s.H, s.Hp, s.num_blocks
+        ws = self._ws
+        row_ids = plan.row_ids
+        p_drop, seed, step = sv["p_drop"], sv["seed"], sv["step"]
+        gA, gC, gD, gX = (ws[n][:T] for n in ("gA", "gC", "gD", "gX"))
+        G = lambda name: P.view(name, grad=True)
+        GM = lambda name: P.mat(name, grad=True)
+        x = [ws[f"x{i}"][:T] for i in range(nb + 1)]
+        dz_top = ws[f"gdz_{nb - 1}"][:T]
+        with ops.row_limit(plan.rows):
+            if s.kind == "SRFR":
+                gc = ws["gc"][:T]
+                ops.layernorm_bwd(dh, ws["c"][:T], ws["stF"][:T], P.view("last_layernorm.weight"), gc,
+                                  G("last_layernorm.weight"), G("last_layernorm.bias"), H=s.D)
+                with self._branch():
+                    ops.gemm_wgrad(gc, x[nb], GM("last_conv.weight"), G("last_conv.bias"), Mo=s.D, No=H)
+                ops.gemm_tn(gc, self.sh["wcT"], out_bf16=dz_top, row_ids=row_ids)
+            else:
+                ops.layernorm_bwd(dh, x[nb], ws["stF"][:T], P.view("last_layernorm.weight"), dz_top,
+                                  G("last_layernorm.weight"), G("last_layernorm.bias"), row_ids=row_ids, H=s.Dout)
+            for i in reversed(range(nb)):
+                Q, q, kv, o, r, y, h1 = (ws[f"{n}{i}"][:T] for n in ("Q", "q", "kv", "o", "r", "y", "h1"))
+                dz, da1, dr, dq, dkv = (ws[f"{n}{i}"][:T] for n in ("gdz_", "gda1_", "gdr_", "gdq_", "gdkv_"))
+                dx_out = ws[f"gdz_{i - 1}"][:T] if i > 0 else gA
+                dz2 = dz
+                if p_drop > 0:
+                    dz2 = ws[f"gE_{i}"][:T]
+                    ops.dropout_apply(dz, dz2, Hp, p_drop, seed, 12 + 4 * i, step)
+                with self._branch():
+                    ops.gemm_wgrad(dz2, h1, GM(f"forward_layers.{i}.conv2.weight"), G(f"forward_layers.{i}.conv2.bias"), Mo=H, No=H)
+                ops.gemm_tn(dz2, self.sh[f"w2T{i}"], out_bf16=da1, gate=h1, drop_p=p_drop, drop_seed=seed,
+                            drop_stream=11 + 4 * i, drop_step=step)
+                with self._branch():
+                    ops.gemm_wgrad(da1, y, GM(f"forward_layers.{i}.conv1.weight"), G(f"forward_layers.{i}.conv1.bias"), Mo=H, No=H)
+                ops.gemm_tn(da1, self.sh[f"w1T{i}"], out_bf16=gC, residual=dz)
+                ops.layernorm_bwd(gC, r, ws[f"st2_{i}"][:T], P.view(f"forward_layernorms.{i}.weight"), dr,
+                                  G(f"forward_layernorms.{i}.weight"), G(f"forward_layernorms.{i}.bias"), H=H)
+                with self._branch():
+                    ops.gemm_wgrad(dr, o, GM(f"attention_layers.{i}.out_proj.weight"),
+                                   G(f"attention_layers.{i}.out_proj.bias"), Mo=H, No=H)
+                ops.gemm_tn(dr, self.sh[f"woT{i}"], out_bf16=gC)
+                ops.attention_bwd_packed(gC, q, kv[:, :Hp], kv[:, Hp:], dq, dkv[:, :Hp], dkv[:, Hp:], plan, L, H, s.num_heads,
+                                         p_drop, seed, 10 + 4 * i, step)
+                gin = GM(f"attention_layers.{i}.in_proj_weight")
+                gbin = G(f"attention_layers.{i}.in_proj_bias")
+                with self._branch():
+                    ops.gemm_wgrad(dq, Q, gin[:H], gbin[:H], Mo=H, No=H)
+                    ops.gemm_wgrad(dkv, x[i], gin[H:], gbin[H:], Mo=2 * H, No=H)
+                ops.gemm_tn(dq, self.sh[f"wqT{i}"], out_bf16=gD, residual=dr)
+                ops.gemm_tn(dkv, self.sh[f"wkvT{i}"], out_bf16=gX)
+                ops.layernorm_bwd(gD, x[i], ws[f"st1_{i}"][:T], P.view(f"attention_layernorms.{i}.weight"), dx_out,
+                                  G(f"attention_layernorms.{i}.weight"), G(f"attention_layernorms.{i}.bias"),
+                                  add=gX, row_ids=row_ids, H=H)
+            dx0 = gA
+            if s.kind == "SASRec" and p_drop > 0:
+                ops.dropout_apply(gA, gC, H, p_drop, seed, 1, step)
+                dx0 = gC
+        aux_grad = G(s.aux_key) if s.aux_key else None
+        ops.embed_bwd_packed(dx0, sv["seq"], sv["aux_ids"], plan, s.D, s.F if s.mode == 1 else 0, s.mode, s.item_scale,
+                             G(s.item_key), aux_grad, G(s.pos_key))
+        self._join()
         self.saved = None
 
     # ------------------------------------------------------------------ scoring helpers

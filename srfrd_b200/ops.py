@@ -12,7 +12,9 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import CastDesc, GemmEpilogue, call
+from contextlib import contextmanager
+
+from ._lib import CastDesc, GemmEpilogue, PackDesc, call
 
 bf16 = torch.bfloat16
 
@@ -268,3 +270,89 @@ def add_user_term(logits, feats_tail, fake_table, label):
     U, I = logits.shape
     call("srfrd_add_user_term", _p(logits), logits.stride(0), U, I, _p(feats_tail), feats_tail.stride(0), _p(fake_table),
          _p(label), fake_table.shape[1], _stream())
+
+
+# ---------------------------------------------------------------------------------------------------- packed token layout
+class PackedPlan:
+    """Device buffers of the packed token layout for up to B sequences of length L (srfrd_pack_t).  `build` runs the
+    three plan kernels; afterwards `rows[0]` holds the dynamic row count every packed / row-limited kernel reads."""
+
+    def __init__(self, B: int, L: int, device):
+        self.B, self.L = B, L
+        self.cap = (B * (L + 1) + 127) // 128 * 128
+        i32 = lambda n: torch.zeros(n, dtype=torch.int32, device=device)
+        self.rows, self.cnt, self.seq_first = i32(4), i32(B), i32(B + 1)
+        self.tok_row, self.row_tok = i32(B * L), i32(self.cap)
+        self.row_ids = torch.zeros(self.cap, dtype=torch.int64, device=device)
+        self.row_info = i32(4 * self.cap)
+        self.tile_row0, self.last_row = i32(B + 130), i32(B)
+        self.desc = PackDesc(_p(self.rows), _p(self.cnt), _p(self.seq_first), _p(self.tok_row), _p(self.row_tok),
+                             _p(self.row_ids), _p(self.row_info), _p(self.tile_row0), _p(self.last_row), self.cap)
+
+    def build(self, seq, keep=None):
+        _lib.require_device()
+        B, L = seq.shape
+        assert (B, L) == (self.B, self.L)
+        _chk(seq, torch.int64, "seq")
+        call("srfrd_pack_plan", _p(seq), _p(keep), B, L, C.byref(self.desc), _stream())
+
+
+@contextmanager
+def row_limit(rows_dev):
+    """Within the block, gemm_tn / gemm_wgrad / layernorm_fwd / layernorm_bwd / dropout_apply process
+    min(their row argument, rows_dev[0]) rows (rows_dev: int32 device tensor, read when the kernel runs)."""
+    call("srfrd_set_row_limit", _p(rows_dev))
+    try:
+        yield
+    finally:
+        call("srfrd_set_row_limit", None)
+
+
+def attention_packed_supported(L: int, H: int, heads: int) -> bool:
+    return bool(_lib.load().srfrd_attention_packed_supported(int(L), int(H), int(heads)))
+
+
+def embed_ln_fwd_packed(item_table, pos_table, aux_table, mode, seq, aux_ids, item_scale, ln_w, ln_b, eps, x0_bf16, q_bf16,
+                        stats, plan: PackedPlan, drop_p=0.0, drop_seed=0, drop_stream=0, drop_step=None):
+    _lib.require_device()
+    B, L = seq.shape
+    D = item_table.shape[1]
+    F = aux_table.shape[1] if (aux_table is not None and mode == 1) else 0
+    call("srfrd_embed_ln_fwd_packed", _p(item_table), item_table.shape[0], D, _p(pos_table), _p(aux_table),
+         0 if aux_table is None else aux_table.shape[0], F, mode, _p(seq), _p(aux_ids), B, L, float(item_scale), _p(ln_w),
+         _p(ln_b), float(eps), _p(x0_bf16), _p(q_bf16), _p(stats), x0_bf16.stride(0), float(drop_p), int(drop_seed),
+         int(drop_stream), _p(drop_step), _p(plan.row_tok), _p(plan.rows), plan.cap, _stream())
+
+
+def layernorm_fwd_rows(x, w, b, eps, y_f32, row_index, n, H):
+    _lib.require_device()
+    call("srfrd_layernorm_fwd_rows", _p(x), x.stride(0), _p(w), _p(b), float(eps), _p(y_f32), y_f32.stride(0), _p(row_index),
+         n, H, _stream())
+
+
+def attention_fwd_packed(q, k, v, o, plan: PackedPlan, L, H, heads, drop_p=0.0, seed=0, stream_id=0, drop_step=None):
+    _lib.require_device()
+    call("srfrd_attention_fwd_packed", _p(q), q.stride(0), _p(k), _p(v), k.stride(0), _p(o), o.stride(0), C.byref(plan.desc),
+         L, H, heads, float(drop_p), int(seed), int(stream_id), _p(drop_step), _stream())
+
+
+def attention_bwd_packed(dout, q, k, v, dq, dk, dv, plan: PackedPlan, L, H, heads, drop_p=0.0, seed=0, stream_id=0,
+                         drop_step=None):
+    call("srfrd_attention_bwd_packed", _p(dout), dout.stride(0), _p(q), q.stride(0), _p(k), _p(v), k.stride(0), _p(dq),
+         dq.stride(0), _p(dk), _p(dv), dk.stride(0), C.byref(plan.desc), L, H, heads, float(drop_p), int(seed),
+         int(stream_id), _p(drop_step), _stream())
+
+
+def score_loss_fused_packed(h, item_table, fake_table, pos, neg, prs, nrs, w_pos, w_neg, norm, loss_acc, dh, d_item, d_fake,
+                            plan: PackedPlan):
+    D = item_table.shape[1]
+    F = 0 if fake_table is None else fake_table.shape[1]
+    call("srfrd_score_loss_fused_packed", _p(h), h.stride(0), _p(item_table), _p(fake_table), _p(pos), _p(neg), _p(prs),
+         _p(nrs), _p(w_pos), _p(w_neg), _p(norm), D, F, _p(loss_acc), _p(dh), dh.stride(0), _p(d_item), _p(d_fake),
+         _p(plan.row_tok), _p(plan.rows), plan.cap, _stream())
+
+
+def embed_bwd_packed(dx0, seq, aux_ids, plan: PackedPlan, D, F, mode, item_scale, d_item, d_aux, d_pos):
+    B, L = seq.shape
+    call("srfrd_embed_bwd_packed", _p(dx0), dx0.stride(0), _p(seq), _p(aux_ids), _p(plan.tok_row), B, L, D, F, mode,
+         float(item_scale), _p(d_item), _p(d_aux), _p(d_pos), _stream())

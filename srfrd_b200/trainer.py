@@ -89,10 +89,12 @@ class FusedTrainer:
                    Gradients are SUM-all-reduced and the loss is normalised by the all-reduced weight
                    sums, so N ranks on B/N sequences each reproduce one rank on B sequences.
     use_graph    : capture the step in a CUDA graph after the first (eager) step.
+    packed       : run the encoder on the packed token layout (csrc/pack.cu) -- pad slots, ~88 % of a Beauty-shaped batch,
+                   are not computed; results equal the dense path (None = on when the shape supports it).
     """
 
     def __init__(self, model, lr: float = 1e-3, betas=(0.9, 0.98), eps: float = 1e-8, process_group=None,
-                 use_graph: bool = True, l2_emb: float = 0.0):
+                 use_graph: bool = True, l2_emb: float = 0.0, packed: Optional[bool] = None):
         if l2_emb != 0.0:
             raise NotImplementedError("FusedTrainer implements the reference default l2_emb = 0.0 (trainer.py:123); "
                                       "use simulate() with a torch optimizer for l2_emb != 0")
@@ -103,6 +105,8 @@ class FusedTrainer:
         self.lr, self.betas, self.eps = lr, betas, eps
         self.pg = process_group
         self.use_graph = use_graph
+        # packed token layout (no work on pad slots) whenever the shape supports it; SRFRD_PACKED=0 / packed=False = dense
+        self.packed = self.eng.packed_default if packed is None else bool(packed)
         dev = self.eng.device
         self.m = torch.zeros_like(self.P.data)
         self.v = torch.zeros_like(self.P.data)
@@ -156,16 +160,26 @@ class FusedTrainer:
             self.comm.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.comm):
                 parallel.allreduce_sum_(norm, self.pg)
-        hidden = eng.forward(st["seq"], st["rsq"], training=True)
+        packed = self.packed and eng.packed_ok(B, L)
+        # packed token layout: pad slots (88 % of a C2 batch) get no rows; slots whose POSITIVE id is set keep one even if
+        # their input is a pad, because the loss reads their hidden state
+        hidden = eng.forward(st["seq"], st["rsq"], training=True, packed=packed, keep=st["pos"] if packed else None)
         ws = eng._ws
         ft = eng.fake_table()
         if self.pg is not None:
             torch.cuda.current_stream().wait_stream(self.comm)
-        ops.score_loss_fused(ws["hfin"][:T], P.view(s.item_key), ft, pos, neg,
-                             st["prs"].view(-1) if ft is not None else None,
-                             st["nrs"].view(-1) if ft is not None else None, w_pos, w_neg, norm, acc, ws["dh"][:T],
-                             P.view(s.item_key, grad=True), eng.fake_table_grad())
-        eng.backward(ws["dh"][:T])
+        prs_ = st["prs"].view(-1) if ft is not None else None
+        nrs_ = st["nrs"].view(-1) if ft is not None else None
+        if packed:
+            plan = eng.saved["plan"]
+            Tp = plan.cap
+            ops.score_loss_fused_packed(ws["hfin"][:Tp], P.view(s.item_key), ft, pos, neg, prs_, nrs_, w_pos, w_neg, norm, acc,
+                                        ws["dh"][:Tp], P.view(s.item_key, grad=True), eng.fake_table_grad(), plan)
+            eng.backward(ws["dh"][:Tp])
+        else:
+            ops.score_loss_fused(ws["hfin"][:T], P.view(s.item_key), ft, pos, neg, prs_, nrs_, w_pos, w_neg, norm, acc,
+                                 ws["dh"][:T], P.view(s.item_key, grad=True), eng.fake_table_grad())
+            eng.backward(ws["dh"][:T])
         if self.pg is not None:
             parallel.allreduce_sum_(P.grad_bucket, self.pg)               # ONE NCCL sum over NVLink: gradients + loss sums
         ops.loss_finalize(acc, norm, loss)                                # (consumes acc: zero again for the next step)

@@ -275,3 +275,188 @@ def test_backward_of_a_stale_forward_raises():
     m.train()
     with pytest.raises(RuntimeError, match="stale forward"):
         h3.sum().backward()
+
+
+# --------------------------------------------------------------------------------------------- packed token layout
+def _plan_reference(seq, keep):
+    """Host restatement of srfrd_pack_plan (csrc/pack.cu)."""
+    B, L = seq.shape
+    kept = (seq != 0) | ((keep != 0) if keep is not None else False)
+    rows_per = kept.sum(1) + 1
+    first = np.concatenate([[0], np.cumsum(rows_per)])
+    Tp = int(first[-1]); M = (Tp + 127) // 128 * 128
+    row_tok = -np.ones(M, np.int64); row_ids = np.zeros(M, np.int64); info = np.zeros((M, 4), np.int64)
+    tok_row = -np.ones((B, L), np.int64); last_row = np.zeros(B, np.int64)
+    for b in range(B):
+        r0, end = first[b], first[b + 1]
+        info[r0] = (r0, end, np.float32(1.0).view(np.int32), 0)
+        j = 0
+        last_row[b] = r0
+        for l in range(L):
+            if kept[b, l]:
+                r = r0 + 1 + j
+                row_tok[r] = b * L + l; row_ids[r] = seq[b, l]; tok_row[b, l] = r
+                info[r] = (r0, end, np.float32(l - j).view(np.int32), l)
+                if l == L - 1:
+                    last_row[b] = r
+                j += 1
+    for r in range(Tp, M):
+        info[r] = (r, r + 1, np.float32(1.0).view(np.int32), 0)
+    bounds = list(first) + list(range(Tp + 1, M + 1))
+    tiles, i = [], 0
+    while bounds[i] < M:
+        tiles.append(bounds[i])
+        k = i + 1
+        while k + 1 < len(bounds) and bounds[k + 1] <= bounds[i] + 128:
+            k += 1
+        i = k
+    return dict(M=M, Tp=Tp, first=first, row_tok=row_tok, row_ids=row_ids, info=info, tok_row=tok_row, last_row=last_row,
+                tiles=np.array(tiles + [M]))
+
+
+def _ragged_batch(B, L, N, seed, interior=True):
+    """Left-padded sequences as the sampler emits them, plus the cases the API allows: empty rows, full rows, pad slots in
+    the middle of a sequence and slots whose input is a pad but whose positive id is set."""
+    rng = np.random.default_rng(seed)
+    seq = np.zeros((B, L), np.int64); pos = np.zeros((B, L), np.int64); neg = np.zeros((B, L), np.int64)
+    for b in range(B):
+        n = int(rng.integers(0, L + 1)) if b % 7 else (L if b % 14 else 0)
+        if n:
+            seq[b, L - n:] = rng.integers(1, N + 1, n)
+            pos[b, L - n:] = rng.integers(1, N + 1, n)
+            neg[b, L - n:] = rng.integers(1, N + 1, n)
+        if interior and n > 4 and b % 3 == 0:
+            holes = rng.choice(np.arange(L - n + 1, L - 1), size=min(3, n - 3), replace=False)
+            seq[b, holes] = 0                                   # interior pads: still keys for later queries
+            pos[b, holes[:1]] = 0; neg[b, holes[:1]] = 0        # one of them also drops its loss term
+        if interior and n and n < L and b % 5 == 0:
+            pos[b, L - n - 1] = int(rng.integers(1, N + 1)); neg[b, L - n - 1] = int(rng.integers(1, N + 1))   # loss on a pad input
+    rsq = np.where(seq != 0, rng.integers(1, 3, (B, L)), 0); prs = np.where(pos != 0, rng.integers(1, 3, (B, L)), 0)
+    nrs = (pos != 0).astype(np.int64)
+    return {k: torch.from_numpy(v).cuda() for k, v in dict(seq=seq, rsq=rsq, pos=pos, prs=prs, neg=neg, nrs=nrs).items()}
+
+
+def test_pack_plan_matches_host_restatement():
+    from srfrd_b200 import ops
+    for B, L, seed in ((37, 50, 1), (300, 20, 2), (64, 127, 3), (1, 5, 4)):
+        b = _ragged_batch(B, L, 500, seed)
+        plan = ops.PackedPlan(B, L, "cuda")
+        for keep in (None, b["pos"]):
+            plan.build(b["seq"], keep)
+            ref = _plan_reference(b["seq"].cpu().numpy(), None if keep is None else keep.cpu().numpy())
+            rows = plan.rows.cpu().numpy()
+            M = ref["M"]
+            assert rows[0] == M and rows[1] == ref["Tp"] and rows[2] == len(ref["tiles"]) - 1
+            assert np.array_equal(plan.seq_first.cpu().numpy(), ref["first"])
+            assert np.array_equal(plan.row_tok.cpu().numpy()[:M], ref["row_tok"])
+            assert np.array_equal(plan.row_ids.cpu().numpy()[:M], ref["row_ids"])
+            assert np.array_equal(plan.row_info.cpu().numpy().reshape(-1, 4)[:M], ref["info"])
+            assert np.array_equal(plan.tok_row.cpu().numpy().reshape(B, L), ref["tok_row"])
+            assert np.array_equal(plan.last_row.cpu().numpy(), ref["last_row"])
+            assert np.array_equal(plan.tile_row0.cpu().numpy()[:rows[2] + 1], ref["tiles"])
+            t = ref["tiles"]
+            assert (np.diff(t) <= 128).all() and (np.diff(t) > 0).all()
+
+
+@pytest.mark.parametrize("kind,heads,drop", [("SRFR", 1, 0.0), ("SRFRN", 1, 0.0), ("SASRec", 1, 0.0), ("SRFU_F", 1, 0.0),
+                                             ("SASRec", 2, 0.0), ("SRFR", 1, 0.5)])
+def test_packed_layout_equals_dense_layout(kind, heads, drop):
+    """The packed token layout (no rows for pad slots, one weighted pad-representative key per sequence) against the
+    dense layout on the SAME kernels: loss, the hidden state of every kept token and every parameter gradient, on
+    batches with empty / full rows, interior pads and loss terms on pad inputs.  Both paths compute in bf16, so they
+    agree to rounding (not bit for bit: GEMM tiles group different rows)."""
+    from srfrd_b200 import SRFR_model as M, ops
+    from srfrd_b200.trainer import FusedTrainer
+    B, L, N = 96, 50, 800
+    torch.manual_seed(11)
+    hd = 128 if heads == 2 else 64
+    ctor = {"SRFR": lambda: M.SRFR(N, L, 64, 16, drop, 2, heads, "cuda"), "SRFRN": lambda: M.SRFRN(N, L, 64, 16, drop, 2, heads, "cuda"),
+            "SASRec": lambda: M.SASRec(N, L, hd, drop, 2, heads, "cuda"), "SRFU_F": lambda: M.SRFU_F(N, L, 64, L + 1, drop, 2, heads, "cuda")}[kind]
+    m = ctor()
+    for _, p in m.named_parameters():
+        if p.dim() >= 2:
+            torch.nn.init.xavier_normal_(p.data)
+        else:
+            p.data.add_(0.1 * torch.randn_like(p))
+    m = m.to("cuda").train()
+    b = _ragged_batch(B, L, N, 5)
+    w = (torch.rand(B, L, device="cuda") * (b["pos"] != 0)).contiguous()
+    outs = {}
+    for packed in (False, True):
+        tr = FusedTrainer(m, use_graph=False, packed=packed)
+        eng, P = tr.eng, tr.P
+        assert (not packed) or eng.packed_ok(B, L)
+        tr.load_batch(b, w_pos=w)
+        # the body of one step up to (not including) Adam, so the gradients can be compared
+        st = tr._static
+        norm, acc = tr.scal[0:2], P.grad_tail[0:2]
+        P.grad_bucket.zero_()
+        ops.weight_sums(st["pos"].view(-1), st["w_pos"].view(-1), None, norm)
+        h = eng.forward(st["seq"], st["rsq"], training=True, packed=packed, keep=st["pos"] if packed else None)
+        ft = eng.fake_table()
+        prs_ = st["prs"].view(-1) if ft is not None else None
+        nrs_ = st["nrs"].view(-1) if ft is not None else None
+        if packed:
+            plan = eng.saved["plan"]
+            hid = eng._ws["hfin"][:plan.cap].clone()
+            ops.score_loss_fused_packed(eng._ws["hfin"][:plan.cap], P.view(eng.spec.item_key), ft, st["pos"].view(-1),
+                                        st["neg"].view(-1), prs_, nrs_, st["w_pos"].view(-1), None, norm, acc,
+                                        eng._ws["dh"][:plan.cap], P.view(eng.spec.item_key, grad=True), eng.fake_table_grad(), plan)
+            eng.backward(eng._ws["dh"][:plan.cap])
+            tok_row = plan.tok_row.long()
+            dense_h = torch.zeros(B * L, hid.shape[1], device="cuda")
+            keep = tok_row >= 0
+            dense_h[keep] = hid[tok_row[keep]]
+            outs[packed] = (float(acc[0] / norm[0] + acc[1] / norm[1]), dense_h, P.grad.clone(), keep)
+        else:
+            hid = eng._ws["hfin"][:B * L].clone()
+            ops.score_loss_fused(eng._ws["hfin"][:B * L], P.view(eng.spec.item_key), ft, st["pos"].view(-1), st["neg"].view(-1),
+                                 prs_, nrs_, st["w_pos"].view(-1), None, norm, acc, eng._ws["dh"][:B * L],
+                                 P.view(eng.spec.item_key, grad=True), eng.fake_table_grad())
+            eng.backward(eng._ws["dh"][:B * L])
+            outs[packed] = (float(acc[0] / norm[0] + acc[1] / norm[1]), hid, P.grad.clone(), None)
+        P.grad_bucket.zero_()
+    (l_d, h_d, g_d, _), (l_p, h_p, g_p, keep) = outs[False], outs[True]
+    if drop == 0.0:
+        assert abs(l_d - l_p) < 2e-3, (l_d, l_p)
+        torch.testing.assert_close(h_p[keep], h_d[keep], rtol=2e-2, atol=3e-2)
+        # dropped pad slots all equal the pad representative's hidden state in the dense layout too
+        for name, (off, shape) in P.offsets.items():
+            n = int(np.prod(shape))
+            a, c = g_d[off:off + n], g_p[off:off + n]
+            if name.endswith("in_proj_bias"):
+                H = n // 3
+                a, c = torch.cat([a[:H], a[2 * H:]]), torch.cat([c[:H], c[2 * H:]])
+            rel = float((a - c).norm() / (a.norm() + 1e-20))
+            assert rel < 0.06, f"{name}: packed vs dense gradient rel L2 {rel:.4f}"
+    else:
+        # different dropout streams (the mask index is the row index): statistically equal, not element-wise
+        assert np.isfinite(l_p) and abs(l_d - l_p) < 0.3
+        assert torch.isfinite(g_p).all()
+        cos = float(torch.dot(g_d, g_p) / (g_d.norm() * g_p.norm()))
+        ratio = float(g_p.norm() / g_d.norm())
+        assert cos > 0.1 and 0.5 < ratio < 2.0, (cos, ratio)     # two independent p = 0.5 masks on 96 sequences
+
+
+def test_packed_encode_last_and_fused_steps_match_dense():
+    """encode_last / predict and whole FusedTrainer steps (CUDA graph) on the packed layout vs the dense layout."""
+    from srfrd_b200 import SRFR_model as M, synth
+    from srfrd_b200.trainer import FusedTrainer
+    data = synth.make_interactions(8, 3000, 2000, 5, 4.0, 50)
+    smp = synth.BatchSampler(data, 50, 2)
+
+    def make():
+        torch.manual_seed(21)
+        return _xavier(M.SRFR(data.itemnum, 50, 64, 16, 0.0, 2, 1, "cuda")).to("cuda")
+    md, mp = make(), make()
+    b = _ragged_batch(200, 50, data.itemnum, 9)
+    md._sync_flat().packed_default = False
+    fd = md.encode_last(b["seq"], b["rsq"]); fp = mp.encode_last(b["seq"], b["rsq"])
+    torch.testing.assert_close(fp, fd, rtol=2e-2, atol=3e-2)
+    td, tp = FusedTrainer(md, packed=False), FusedTrainer(mp, packed=True)
+    for i in range(6):
+        nb = {k: torch.from_numpy(v).cuda() for k, v in smp.next_batch(512).items()}
+        ld, lp = float(td.step(nb)), float(tp.step(nb))
+        assert abs(ld - lp) < 3e-3, (i, ld, lp)
+    a, c = md.flat_parameters().data, mp.flat_parameters().data
+    assert float((a - c).abs().max()) < 8e-3          # six Adam steps of lr 1e-3 each
