@@ -297,7 +297,7 @@ def bench_train_config(name, dev, rank, world, pg, timed, pk, steps, model_kw, d
     out = dict(value=round(world * B * steps / (ms / 1e3), 1), unit="seqs/s", ms_per_step=round(ms / steps, 4), steps=steps,
                warmup=W, batch_per_gpu=B, n_gpus=world, valid_slot_fraction=round(valid_frac, 4), policy=policy,
                dropout=dropout, loss=round(float(tr.scal[4]), 5))
-    if breakdown and rank == 0:
+    if breakdown:                                    # EVERY rank runs the eager pass (it steps through the all-reduce)
         if sampler == "device":                      # the eager pass needs the sampler attached for its step body
             tr._sampler, tr._sampler_policy = smp, policy
         agg, calls = kernel_breakdown(tr, 2, valid_frac)
@@ -364,7 +364,9 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     pg = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a collective mismatch must fail in minutes, not hold the GPUs for NCCL's default 10-minute watchdog
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=150))
         pg = dist.group.WORLD
     c = CFG
     B, L = c["batch"], c["L"]

@@ -22,9 +22,11 @@ const int* row_limit() { return g_row_limit; }
 
 bool pdl_enabled() {
   static int v = -1;
-  // measured at C2: no gain (1.83 vs 1.81 ms / step) -- the persistent kernels fill every SM's shared memory, so a
-  // dependent CTA cannot become resident before its predecessor's CTAs exit.  Off unless SRFRD_PDL=1.
-  if (v < 0) { const char* e = getenv("SRFRD_PDL"); v = (e && e[0] == '1') ? 1 : 0; }
+  // Programmatic dependent launch: a kernel's prologue (barrier init, TMEM allocation, descriptor prefetch) overlaps the
+  // tail of its predecessor.  Round 1 (dense layout, 0.2 GB per kernel): no gain, 1.83 vs 1.81 ms / step -- the persistent
+  // kernels filled every SM.  With the packed token layout a kernel moves ~5 MB and the step is a chain of ~40 launch
+  // latencies: 0.558 -> 0.517 ms / step at C2.  On unless SRFRD_PDL=0.
+  if (v < 0) { const char* e = getenv("SRFRD_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
   return v == 1;
 }
 

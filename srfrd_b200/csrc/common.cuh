@@ -160,19 +160,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Spin with a watchdog: a mis-programmed pipeline traps (-> launch error) instead of hanging the GPU.
-// The spin itself is three instructions (try_wait, branch, counter): the first version evaluated the watchdog's
-// clock64() on EVERY failed test -- the compiler speculates the side-effect-free clock read past the `spins & 1023`
-// guard -- which made a waiting warp burn 12 issue slots per test (ncu source view of the catalogue kernel: 300 M of
-// 2 250 M warp instructions were watchdog arithmetic, competing with the epilogue warps of the same scheduler).
-// The clock now lives behind a call that cannot be inlined or speculated.
-static __device__ __noinline__ void mbar_watchdog(long long* t0) {
-  const long long now = clock64();
-  if (*t0 == 0) { *t0 = now; return; }
-  if (now - *t0 > 4000000000ll) {
-    printf("srfrd_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-    __trap();
-  }
-}
+// (A leaner spin -- try_wait + branch + counter with the clock behind an out-of-line call -- was tried in round 2: ncu's
+//  source view shows the watchdog arithmetic below is evaluated on every failed test, 12 issue slots each.  It measured
+//  WORSE in the catalogue kernel, 4.9 vs 3.0 ms: the extra instructions act as a back-off, and a tight try_wait loop in
+//  13 waiting warps starves the warps that would complete the barriers.  Kept as it was.)
 __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar_addr, uint32_t parity) {   // bar_addr: shared-space address
   uint32_t ok;
   asm volatile(
@@ -186,10 +177,13 @@ __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar_addr, uint32_t pari
 }
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity) {
   if (mbar_try_wait_a(bar_addr, parity)) return;
-  long long t0 = 0;
+  long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait_a(bar_addr, parity)) {
-    if (((++spins) & 0xffffu) == 0) mbar_watchdog(&t0);
+    if (((++spins) & 0x3ffu) == 0 && (clock64() - t0) > 4000000000ll) {
+      printf("srfrd_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
   }
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_a(smem_u32(bar), parity); }

@@ -299,7 +299,6 @@ catalogue_tilemax_kernel(const __grid_constant__ CUtensorMap tmE, TopkShape s) {
         tc_fence_before();                                // scores are in registers: hand the accumulator back now
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[a]);
-        if (s.debug == 4) continue;                       // timing experiment only: accumulator round trip without the scan
         if (t == s.tiles_total - 1) {                     // last tile of the table: columns past row_hi are not items
           const int col_row0 = s.row_lo + t * NT;
 #pragma unroll
