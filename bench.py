@@ -133,11 +133,33 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
-def algorithmic_bytes(name, a, valid_frac):
-    """Algorithmic (minimum) HBM bytes of one C-ABI call, from its arguments (DESIGN.md 'bytes per unit')."""
+def algorithmic_bytes(name, a, valid_frac, packed=None):
+    """Algorithmic (minimum) HBM bytes of one C-ABI call, from its arguments (DESIGN.md 'bytes per unit').
+    packed = (capacity rows, actual rows M, sequences B, maxlen L) when the step ran on the packed token layout: the
+    row-wise calls are then launched with the CAPACITY as their row argument and read the actual count on the device."""
     g = lambda i: a[i] or 0
+    rows = (lambda r: packed[1] if (packed and r == packed[0]) else r)
+    if packed:
+        cap, Mp, Bp, Lp = packed
+        if name == "srfrd_embed_ln_fwd_packed":
+            D, F, mode = a[2], a[6], a[7]
+            H = D + (F if mode == 1 else 0)
+            return Mp * (4 + 16 + D * 4 + 2 * H * 2 + 8), 0.0
+        if name in ("srfrd_attention_fwd_packed", "srfrd_attention_bwd_packed"):
+            H = a[9] if name.endswith("fwd_packed") else a[14]
+            n = 4 if name.endswith("fwd_packed") else 7
+            avg = Mp / max(Bp, 1)                                     # rows per sequence incl. its pad representative
+            return n * Mp * H * 2 + Mp * 16, (2.0 if n == 4 else 5.0) * Mp * avg * H
+        if name == "srfrd_score_loss_fused_packed":
+            D = a[11]
+            return Mp * (4 + 16 + D * 4 + 2 * D * 4 + D * 4 + 2 * 2 * D * 4), 0.0
+        if name == "srfrd_embed_bwd_packed":
+            D, F, mode = a[8], a[9], a[10]
+            return Mp * (4 + 8 + (D + (F if mode == 1 else 0)) * 2 + D * 8), 0.0
+        if name == "srfrd_pack_plan":
+            return Bp * Lp * (16 + 4) + Mp * (4 + 8 + 16), 0.0
     if name == "srfrd_gemm_tn":
-        M, N, K = a[4], a[5], a[6]
+        M, N, K = rows(a[4]), a[5], a[6]
         ep = a[7]._obj
         b = M * K * 2 + N * K * 2 + M * N * (2 if ep.out_bf16 else 4)
         b += (M * N * 2 if ep.residual else 0) + (M * N * 2 if ep.gate else 0) + (M * 8 if ep.row_ids else 0)
@@ -145,7 +167,7 @@ def algorithmic_bytes(name, a, valid_frac):
             b += M * N * 2 + (M * 8 if ep.ln_stats else 0)
         return b, 2.0 * M * N * K
     if name == "srfrd_gemm_wgrad":
-        T, Mo, No = a[4], a[5], a[6]
+        T, Mo, No = rows(a[4]), a[5], a[6]
         return T * (Mo + No) * 2 + Mo * No * 4, 2.0 * T * Mo * No
     if name == "srfrd_attention_fwd":
         B, L, H = a[8], a[9], a[10]
@@ -154,10 +176,10 @@ def algorithmic_bytes(name, a, valid_frac):
         B, L, H = a[15], a[16], a[17]
         return 7 * B * L * H * 2, 5.0 * B * L * L * H
     if name == "srfrd_layernorm_fwd":
-        T, H = a[9], a[10]
+        T, H = rows(a[9]), a[10]
         return T * H * 2 + T * H * (2 if a[5] else 4) + T * 8, 0.0
     if name == "srfrd_layernorm_bwd":
-        T, H = a[14], a[15]
+        T, H = rows(a[14]), a[15]
         return T * H * (2 if a[0] else 4) + 2 * T * H * 2 + T * 8 + (T * H * 2 if a[7] else 0) + (T * 8 if a[9] else 0), 0.0
     if name == "srfrd_embed_ln_fwd":
         D, F, mode, T = a[2], a[6], a[7], a[10] * a[11]
@@ -174,7 +196,7 @@ def algorithmic_bytes(name, a, valid_frac):
         T, D, F, mode = a[4] * a[5], a[6], a[7], a[8]
         return T * 16 + valid_frac * T * ((D + (F if mode == 1 else 0)) * 2 + D * 8), 0.0
     if name == "srfrd_dropout_apply":
-        return a[4] * a[5] * 4, 0.0
+        return rows(a[4]) * a[5] * 4, 0.0
     return 0, 0.0
 
 
@@ -193,13 +215,22 @@ def kernel_breakdown(tr, steps, valid_frac):
     torch.cuda.synchronize()
     _lib.set_profile(None)
     tr.use_graph, tr.eng.overlap = tr_graph, ov
+    packed = None
+    plans = getattr(tr.eng, "_plans", {})
+    st = tr._static["seq"].shape if tr._static is not None else None
+    if tr.packed and st is not None and tuple(st) in plans:          # row count of the last batch (device -> host, after the run)
+        pl = plans[tuple(st)]
+        packed = (pl.cap, int(pl.rows[0].item()), int(st[0]), int(st[1]))
     agg = {}
     for name, args, e0, e1 in recs:
+        if name == "srfrd_set_row_limit":                             # host-side state, no launch
+            continue
         ms = e0.elapsed_time(e1)
-        by, fl = algorithmic_bytes(name, args, valid_frac)
+        by, fl = algorithmic_bytes(name, args, valid_frac, packed)
         d = agg.setdefault(name, dict(ms=0.0, n=0, bytes=0.0, flops=0.0))
         d["ms"] += ms; d["n"] += 1; d["bytes"] += by; d["flops"] += fl
-    return agg, len(recs) // max(steps, 1)
+    n_launch = sum(1 for r in recs if r[0] != "srfrd_set_row_limit")
+    return agg, n_launch // max(steps, 1), packed
 
 
 # ---------------------------------------------------------------------------------------------
@@ -300,8 +331,10 @@ def bench_train_config(name, dev, rank, world, pg, timed, pk, steps, model_kw, d
     if breakdown:                                    # EVERY rank runs the eager pass (it steps through the all-reduce)
         if sampler == "device":                      # the eager pass needs the sampler attached for its step body
             tr._sampler, tr._sampler_policy = smp, policy
-        agg, calls = kernel_breakdown(tr, 2, valid_frac)
+        agg, calls, packed_rows = kernel_breakdown(tr, 2, valid_frac)
         out["roofline"] = top_kernel_roofline(agg, 2, pk)
+        if packed_rows:
+            out["packed_rows"] = dict(capacity=packed_rows[0], rows=packed_rows[1], dense_tokens=packed_rows[2] * packed_rows[3])
         out["gpu_launches_per_step"] = calls
     if world > 1:
         torch.cuda.synchronize()
@@ -428,8 +461,10 @@ def run_ours(args):
     e2e = world * B * args.steps / (ms_e2e / 1e3)
 
     # ---- per-kernel breakdown + roofline of the dominant kernel (rank 0) ----
-    agg, calls_per_step = kernel_breakdown(tr, 3, valid_frac)
+    agg, calls_per_step, packed_rows = kernel_breakdown(tr, 3, valid_frac)
     roofline = top_kernel_roofline(agg, 3, pk)
+    if packed_rows:
+        roofline["packed_rows"] = dict(capacity=packed_rows[0], rows=packed_rows[1], dense_tokens=packed_rows[2] * packed_rows[3])
     roofline["how"] = ("event-bracketed pass of 3 eager steps right after the timed region (which replays a CUDA graph); the "
                        "GPU is parked behind a spin kernel while the host enqueues each step, so the deltas are GPU time")
     if world > 1:

@@ -191,6 +191,13 @@ SRFRD_API int srfrd_adam_tick(float* state3, float beta1, float beta2, void* str
 SRFRD_API int srfrd_adam_step(float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                     const float* state3, int zero_grad, void* stream);
 
+/* The tail of a training step in ONE launch: srfrd_adam_tick + srfrd_adam_step + srfrd_loss_finalize (acc2 nullable).
+ * state8 = {step, 1-beta1^step, 1-beta2^step, uint32 step bits (seed of dropout / sampler), int scratch counter, -, -, -}:
+ * every block derives the new state from the old one, the last block to finish publishes it. */
+SRFRD_API int srfrd_adam_step_fused(float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                          float eps, float* state8, int zero_grad, float* acc2, const float* norm2, float* loss,
+                          void* stream);
+
 /* ---- K8/K9: full-catalogue scoring fused with a streaming per-row top-10 ----
  * replaces: SRFR_model.py:144-152 predict() called with label = arange(1, N+1) + the double argsort of
  * utils.py:591, i.e. rank by (score desc, item id asc).
@@ -294,8 +301,8 @@ SRFRD_API int srfrd_score_loss_fused_packed(const float* h, int ldh, const float
                                   const int* row_tok, const int* rows_dev, int64_t cap_rows, void* stream);
 /* K5 on the packed layout (+ the positional-table gradient, which the dense path takes from srfrd_colsum). */
 SRFRD_API int srfrd_embed_bwd_packed(const void* dx0_bf16, int ldx, const int64_t* seq, const int64_t* aux_ids,
-                           const int* tok_row, int64_t B, int L, int D, int F, int mode, float item_scale,
-                           float* d_item, float* d_aux, float* d_pos, void* stream);
+                           const int* row_tok, const int* rows_dev, int64_t cap_rows, int L, int D, int F, int mode,
+                           float item_scale, float* d_item, float* d_aux, float* d_pos, void* stream);
 
 #ifdef __cplusplus
 }

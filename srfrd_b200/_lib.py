@@ -64,6 +64,7 @@ SIGNATURES = {
     "srfrd_loss_finalize": [vp, vp, vp, vp],
     "srfrd_adam_tick": [vp, f32, f32, vp],
     "srfrd_adam_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, i32, vp],
+    "srfrd_adam_step_fused": [vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, i32, vp, vp, vp, vp],
     "srfrd_catalogue_topk_plan": [i64, i64, i64, i32, i32, C.POINTER(i32)],
     "srfrd_catalogue_topk": [vp, i64, i64, i32, vp, i64, i64, i64, i32, i32, i32, i32, vp, vp, vp, vp],
     "srfrd_merge_topk_packed": [vp, i64, i32, i32, vp, vp, vp],
@@ -79,7 +80,7 @@ SIGNATURES = {
                                    f32, u64, u32, vp, vp],
     "srfrd_score_loss_fused_packed": [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, i32, vp, vp, vp, vp,
                                       i64, vp],
-    "srfrd_embed_bwd_packed": [vp, i32, vp, vp, vp, i64, i32, i32, i32, i32, f32, vp, vp, vp, vp],
+    "srfrd_embed_bwd_packed": [vp, i32, vp, vp, vp, vp, i64, i32, i32, i32, i32, f32, vp, vp, vp, vp],
     "srfrd_sample_candidates": [vp, vp, vp, vp, i64, i32, i32, u64, vp, vp],
     "srfrd_candidate_rank": [vp, i32, vp, i64, i32, vp, i64, i32, vp, i32, vp, vp, i32, vp, vp, vp],
     "srfrd_add_user_term": [vp, i32, i64, i32, vp, i32, vp, vp, i32, vp],

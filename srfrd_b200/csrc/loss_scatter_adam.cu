@@ -25,6 +25,7 @@ struct ScoreParams {
   int mode;                             // 0 = logits only, 1 = fused loss fwd+bwd, 2 = bwd from dz
   const int* row_tok;                   // packed layout: h / dh row t belongs to dense token row_tok[t] (-1: no token); ids,
   const int* rows_dev;                  // weights and logits stay indexed by the dense token.  rows_dev: device row count
+  int group;                            // rows a warp takes per pass: 32 (dense: ~4 of them are active), 8 (packed: nearly all are)
 };
 
 __device__ __forceinline__ float softplus(float x) { return fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x))); }
@@ -54,9 +55,10 @@ __global__ void __launch_bounds__(256, (NC <= 9 ? 2 : 1)) score_kernel(ScorePara
   for (int i = 0; i < NC; ++i) fk1[i] = fk2[i] = 0.f;
   const bool dh_vec = p.dh && (p.lddh == W) && (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.dh) & 15) == 0);
   if (p.rows_dev) p.T = min(p.T, (int64_t)__ldg(p.rows_dev));
-  for (int64_t t0 = warp0 * 32; t0 < p.T; t0 += nwarps * 32) {
+  const int G = p.group;
+  for (int64_t t0 = warp0 * G; t0 < p.T; t0 += nwarps * G) {
     const int64_t tl = t0 + lane;
-    bool in = tl < p.T;
+    bool in = lane < G && tl < p.T;
     int my_tok = 0;                           // packed layout: dense token whose ids / weights / logits this row uses
     if (p.row_tok && in) { my_tok = __ldg(p.row_tok + tl); in = my_tok >= 0; }
     const int64_t my_src = p.row_tok ? (int64_t)my_tok : tl;
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(256, (NC <= 9 ? 2 : 1)) score_kernel(ScorePara
     }
     unsigned mask = __ballot_sync(0xffffffffu, my_active);
     if (p.dh) {                               // zero rows of the inactive tokens
-      const int nrow = (int)min((int64_t)32, p.T - t0);
+      const int nrow = (int)min((int64_t)G, p.T - t0);
       if (dh_vec) {
         const int per_row = W >> 2, total = nrow * per_row;
         float4* base = reinterpret_cast<float4*>(p.dh + t0 * p.lddh);
@@ -248,51 +250,44 @@ __global__ void embed_bwd_kernel(EmbedBwdParams p) {
     red_add_f32(p.d_aux + p.aux_ids[b] * p.D + c, accu);
 }
 
-// K5 on the packed layout: sequences are walked by a persistent grid; dx0 rows are found through tok_row (the packed row of
-// each dense token, -1 = dropped pad).  The positional-table gradient (dense layout: a column sum over the (B, L*H) view)
-// is accumulated per block in shared memory [L][D] -- thread c owns column c, so no atomics -- and flushed once per block.
-__global__ void embed_bwd_packed_kernel(EmbedBwdParams p, const int* tok_row, int64_t B, float* d_pos) {
-  extern __shared__ float spos[];            // [L * D] positional gradient partials, then [2 * L] ids as int64
+// K5 on the packed layout, row-parallel: a block takes RPB packed rows per pass, thread (y, c) owns column c of row y.
+// A row with a dense token (row_tok >= 0) and a non-zero input id adds its dx0 row to the item table (red.add), to the
+// positional table through a per-block shared accumulator [L][D] (shared-memory atomics, flushed once per block; the
+// dense path takes this gradient from a column sum over the (B, L*H) view) and to the fake / user-label table.
+__global__ void __launch_bounds__(512) embed_bwd_packed_kernel(EmbedBwdParams p, const int* row_tok, const int* rows_dev, int64_t cap,
+                                                              float* d_pos) {
+  extern __shared__ float spos[];            // [L * D]
   pdl_prologue_done();
-  const int c = threadIdx.x;
+  const int c = threadIdx.x, y = threadIdx.y, RPB = blockDim.y;
   const int H = p.D + (p.mode == 1 ? p.F : 0);
-  int64_t* ids = reinterpret_cast<int64_t*>(spos + ((p.L * p.D + 1) & ~1));
-  int* rows = reinterpret_cast<int*>(ids + 2 * p.L);
-  for (int i = threadIdx.x; i < p.L * p.D; i += blockDim.x) spos[i] = 0.f;
-  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
-    __syncthreads();
-    for (int l = threadIdx.x; l < p.L; l += blockDim.x) {
-      ids[l] = p.seq[b * p.L + l];
-      ids[p.L + l] = (p.mode == 1 && p.aux_ids) ? p.aux_ids[b * p.L + l] : 0;
-      rows[l] = tok_row[b * p.L + l];
+  const int tid = y * blockDim.x + c, nthr = blockDim.x * blockDim.y;
+  for (int i = tid; i < p.L * p.D; i += nthr) spos[i] = 0.f;
+  __syncthreads();
+  const int64_t M = min(cap, (int64_t)__ldg(rows_dev));
+  float acc1 = 0.f, acc2 = 0.f;
+  for (int64_t r = (int64_t)blockIdx.x * RPB + y; r < M; r += (int64_t)gridDim.x * RPB) {
+    const int tok = __ldg(row_tok + r);
+    if (tok < 0 || c >= H) continue;
+    const int64_t id = __ldg(p.seq + tok);
+    if (id == 0) continue;                   // (a kept pad row has id 0: masked input, no gradient)
+    const float v = bf2f(p.dx0[r * p.ldx + c]);
+    if (c < p.D) {
+      red_add_f32(p.d_item + id * p.D + c, v * p.item_scale);
+      atomicAdd(&spos[(tok % p.L) * p.D + c], v);
+      if (p.mode == 2 && p.d_aux) red_add_f32(p.d_aux + p.aux_ids[tok / p.L] * p.D + c, v);
+    } else if (p.aux_ids) {
+      const int64_t f = __ldg(p.aux_ids + tok);
+      if (f == 1) acc1 += v;
+      else if (f == 2) acc2 += v;
     }
-    __syncthreads();
-    if (c >= H) continue;
-    float acc1 = 0.f, acc2 = 0.f, accu = 0.f;
-    for (int l = 0; l < p.L; ++l) {
-      const int64_t id = ids[l];
-      if (id == 0) continue;                 // (a kept pad row has id 0: masked input, no gradient)
-      const float v = bf2f(p.dx0[(int64_t)rows[l] * p.ldx + c]);
-      if (c < p.D) {
-        red_add_f32(p.d_item + id * p.D + c, v * p.item_scale);
-        spos[l * p.D + c] += v;
-        accu += v;
-      } else {
-        const int64_t f = ids[p.L + l];
-        if (f == 1) acc1 += v;
-        else if (f == 2) acc2 += v;
-      }
-    }
-    if (p.mode == 1 && c >= p.D && p.d_aux) {        // fake_embed padding_idx = 0: row 0 gets nothing
-      if (acc1 != 0.f) red_add_f32(p.d_aux + 1 * p.F + (c - p.D), acc1);
-      if (acc2 != 0.f) red_add_f32(p.d_aux + 2 * p.F + (c - p.D), acc2);
-    }
-    if (p.mode == 2 && c < p.D && p.d_aux && accu != 0.f)
-      red_add_f32(p.d_aux + p.aux_ids[b] * p.D + c, accu);
+  }
+  if (p.mode == 1 && c >= p.D && c < H && p.d_aux) {        // fake_embed padding_idx = 0: row 0 gets nothing
+    if (acc1 != 0.f) red_add_f32(p.d_aux + 1 * p.F + (c - p.D), acc1);
+    if (acc2 != 0.f) red_add_f32(p.d_aux + 2 * p.F + (c - p.D), acc2);
   }
   __syncthreads();
   if (d_pos)
-    for (int i = threadIdx.x; i < p.L * p.D; i += blockDim.x)
+    for (int i = tid; i < p.L * p.D; i += nthr)
       if (spos[i] != 0.f) red_add_f32(d_pos + i, spos[i]);
 }
 
@@ -318,6 +313,66 @@ __global__ void adam_tick_kernel(float* state, float beta1, float beta2) {
   // state[3]: the same counter as a 32-bit INTEGER bit pattern (the fp32 step stalls at 2^24); this word is what the
   // dropout masks and the on-device sampler mix into their seeds (mix_seed reads the raw bits)
   state[3] = __uint_as_float(__float_as_uint(state[3]) + 1u);
+}
+
+// One launch for the tail of a training step: Adam tick (step counters, bias corrections), the dense Adam update, and
+// the loss read-out.  Every block derives the NEW step state from the old one (thread 0: two pow() per block), the last
+// block to finish publishes it -- by then every block has read the old state -- and block 0 finalises the loss.
+// state8 = {step, 1 - beta1^step, 1 - beta2^step, uint32 step bits, int blocks-done counter, -, -, -}.
+__global__ void __launch_bounds__(256) adam_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                                         float* __restrict__ v, int64_t n, float lr, float beta1, float beta2,
+                                                         float eps, float* state, int zero_grad, float* acc, const float* norm,
+                                                         float* loss) {
+  __shared__ float s_bc[2];
+  pdl_prologue_done();
+  if (threadIdx.x == 0) {
+    const float step = state[0] + 1.f;
+    s_bc[0] = (float)(1.0 - pow((double)beta1, (double)step));
+    s_bc[1] = (float)(1.0 - pow((double)beta2, (double)step));
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 32 && acc) {
+    const float a = norm[0] > 0.f ? acc[0] / norm[0] : 0.f;
+    const float b = norm[1] > 0.f ? acc[1] / norm[1] : 0.f;
+    loss[0] = a + b;
+    acc[0] = 0.f; acc[1] = 0.f;
+  }
+  __syncthreads();
+  const float step_size = lr / s_bc[0];
+  const float inv_sqrt_bc2 = rsqrtf(s_bc[1]);
+  const int64_t n4 = n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i], gg = reinterpret_cast<float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    float* pa = &pp.x; float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      ma[j] = beta1 * ma[j] + (1.f - beta1) * ga[j];
+      va[j] = beta2 * va[j] + (1.f - beta2) * ga[j] * ga[j];
+      pa[j] -= step_size * ma[j] / (sqrtf(va[j]) * inv_sqrt_bc2 + eps);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    m[i] = beta1 * m[i] + (1.f - beta1) * g[i];
+    v[i] = beta2 * v[i] + (1.f - beta2) * g[i] * g[i];
+    p[i] -= step_size * m[i] / (sqrtf(v[i]) * inv_sqrt_bc2 + eps);
+    if (zero_grad) g[i] = 0.f;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int* done = reinterpret_cast<int*>(state + 4);
+    if (atomicAdd(done, 1) == (int)gridDim.x - 1) {        // last block: every block has read the old state
+      *done = 0;
+      state[0] = state[0] + 1.f;
+      state[1] = s_bc[0];
+      state[2] = s_bc[1];
+      state[3] = __uint_as_float(__float_as_uint(state[3]) + 1u);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
@@ -360,7 +415,8 @@ static int score_launch(ScoreParams& p, void* stream) {
   const int W = p.D + (p.fake_table ? p.F : 0);
   SRFRD_REQUIRE(W <= 32 * MAXC, "score: width %d unsupported", W);
   if (p.T == 0) return 0;
-  int64_t blocks = (p.T + 255) / 256;              // a warp takes 32 tokens per pass
+  if (p.group != 8) p.group = 32;
+  int64_t blocks = (p.T + 8 * p.group - 1) / (8 * p.group);     // a warp takes `group` rows per pass
   const int64_t cap = (int64_t)num_sms() * 8;
   if (blocks > cap) blocks = cap;
   const int nc = (W + 31) / 32;
@@ -427,7 +483,7 @@ extern "C" int srfrd_score_loss_fused_packed(const float* h, int ldh, const floa
   p.h = h; p.ldh = ldh; p.item_table = item_table; p.fake_table = fake_table; p.pos = pos; p.neg = neg; p.prs = prs;
   p.nrs = nrs; p.w_pos = w_pos; p.w_neg = w_neg; p.norm = norm; p.T = cap_rows; p.D = D; p.F = F;
   p.loss_acc = loss_acc; p.dh = dh; p.lddh = lddh; p.d_item = d_item; p.d_fake = d_fake; p.mode = 1;
-  p.row_tok = row_tok; p.rows_dev = rows_dev;
+  p.row_tok = row_tok; p.rows_dev = rows_dev; p.group = 8;
   return score_launch(p, stream);
 }
 
@@ -468,28 +524,31 @@ extern "C" int srfrd_embed_bwd(const void* dx0, int ldx, const int64_t* seq, con
 }
 
 extern "C" int srfrd_embed_bwd_packed(const void* dx0, int ldx, const int64_t* seq, const int64_t* aux_ids,
-                                      const int* tok_row, int64_t B, int L, int D, int F, int mode, float item_scale,
-                                      float* d_item, float* d_aux, float* d_pos, void* stream) {
-  SRFRD_REQUIRE(dx0 && seq && d_item && tok_row, "embed_bwd_packed: null pointer");
+                                      const int* row_tok, const int* rows_dev, int64_t cap_rows, int L, int D, int F,
+                                      int mode, float item_scale, float* d_item, float* d_aux, float* d_pos, void* stream) {
+  SRFRD_REQUIRE(dx0 && seq && d_item && row_tok && rows_dev, "embed_bwd_packed: null pointer");
   SRFRD_REQUIRE(mode >= 0 && mode <= 2, "embed_bwd_packed: bad mode");
   SRFRD_REQUIRE(mode != 2 || aux_ids, "embed_bwd_packed: labels required for mode 2");
   const int H = D + (mode == 1 ? F : 0);
-  SRFRD_REQUIRE(H <= 1024, "embed_bwd_packed: width %d unsupported", H);
-  if (B == 0) return 0;
+  SRFRD_REQUIRE(H <= 512, "embed_bwd_packed: width %d unsupported", H);
+  if (cap_rows == 0) return 0;
   EmbedBwdParams p;
   p.dx0 = (const bf16*)dx0; p.ldx = ldx; p.seq = seq; p.aux_ids = aux_ids; p.L = L; p.D = D; p.F = F; p.mode = mode;
   p.item_scale = item_scale; p.d_item = d_item; p.d_aux = d_aux;
-  const int threads = (H + 31) & ~31;
-  const size_t smem = (size_t)((L * D + 1) & ~1) * sizeof(float) + 2 * L * sizeof(int64_t) + L * sizeof(int);
+  const int tx = (H + 31) & ~31;
+  const int ty = 512 / tx > 0 ? 512 / tx : 1;
+  const size_t smem = (size_t)L * D * sizeof(float);
   SRFRD_REQUIRE(smem <= 200 * 1024, "embed_bwd_packed: L * D = %d too large for the shared positional accumulator", L * D);
   static bool attr = false;
   if (!attr) {
     SRFRD_CUDA(cudaFuncSetAttribute(embed_bwd_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
-  int64_t grid = (int64_t)num_sms() * (smem > 48 * 1024 ? 1 : 4);
-  if (grid > B) grid = B;
-  SRFRD_CUDA(launch_pdl(embed_bwd_packed_kernel, dim3((unsigned)grid), dim3(threads), smem, (cudaStream_t)stream, p, tok_row, B, d_pos));
+  int64_t grid = (int64_t)num_sms() * (smem > 48 * 1024 ? 1 : 2);
+  const int64_t need = (cap_rows + ty - 1) / ty;
+  if (grid > need) grid = need;
+  SRFRD_CUDA(launch_pdl(embed_bwd_packed_kernel, dim3((unsigned)grid), dim3(tx, ty), smem, (cudaStream_t)stream, p, row_tok,
+                        rows_dev, cap_rows, d_pos));
   SRFRD_LAUNCH_CHECK();
   return 0;
 }
@@ -520,6 +579,21 @@ extern "C" int srfrd_adam_step(float* p, float* g, float* m, float* v, int64_t n
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
   SRFRD_CUDA(launch_pdl(adam_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, n, lr, beta1, beta2,
                         eps, state3, zero_grad));
+  SRFRD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int srfrd_adam_step_fused(float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                                     float eps, float* state8, int zero_grad, float* acc2, const float* norm2, float* loss,
+                                     void* stream) {
+  SRFRD_REQUIRE(p && g && m && v && state8, "adam_step_fused: null pointer");
+  SRFRD_REQUIRE(!acc2 || (norm2 && loss), "adam_step_fused: the loss read-out needs norm and loss");
+  SRFRD_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "adam_step_fused: buffers must be 16-byte aligned");
+  int64_t blocks = (n / 4 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+  SRFRD_CUDA(launch_pdl(adam_fused_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, n, lr, beta1,
+                        beta2, eps, state8, zero_grad, acc2, norm2, loss));
   SRFRD_LAUNCH_CHECK();
   return 0;
 }

@@ -170,11 +170,12 @@ class HotPath:
         self.fwd_version = 0            # stamps every forward; backward() of anything but the latest forward raises
         self.host_drop_counter = 0      # mixed into the dropout seed on the autograd path (no device step counter there)
         self._build_shadows()
-        self.step_state = torch.zeros(4, dtype=torch.float32, device=self.device)   # Adam {step, bc1, bc2, uint32 step bits}
+        self.step_state = torch.zeros(8, dtype=torch.float32, device=self.device)   # Adam {step, bc1, bc2, uint32 step bits}
         # Independent branches of the step (the k/v projection next to LN1 + the q projection; every weight-gradient
         # GEMM next to the data-gradient chain) are enqueued on a second stream: captured into the CUDA graph they
         # become parallel branches, so one kernel's launch latency, tail and CTA skew are filled by the other's CTAs.
         self.side = torch.cuda.Stream(device=self.device)
+        self.side2 = torch.cuda.Stream(device=self.device)     # a second independent branch (backward: dx through k | v)
         self.overlap = os.environ.get("SRFRD_OVERLAP", "1") != "0"
         self.drop_seed = 0x5EED5EED
         self.saved: Optional[dict] = None
@@ -245,19 +246,20 @@ class HotPath:
         ops.cast_weights(self._cast_table, self._cast_n)
 
     @contextmanager
-    def _branch(self):
-        """Run the enclosed launches on the side stream, ordered after everything enqueued so far on the main one."""
+    def _branch(self, second: bool = False):
+        """Run the enclosed launches on a side stream, ordered after everything enqueued so far on the main one."""
         if not self.overlap:
             yield
             return
         main = torch.cuda.current_stream()
-        self.side.wait_stream(main)
-        with torch.cuda.stream(self.side):
+        st = self.side2 if second else self.side
+        st.wait_stream(main)
+        with torch.cuda.stream(st):
             yield
 
-    def _join(self):
+    def _join(self, second: bool = False):
         if self.overlap:
-            torch.cuda.current_stream().wait_stream(self.side)
+            torch.cuda.current_stream().wait_stream(self.side2 if second else self.side)
 
     # ------------------------------------------------------------------ workspaces
     def _workspace(self, T: int, L: int) -> Dict[str, torch.Tensor]:
@@ -490,8 +492,10 @@ class HotPath:
                 else:   # k and v gradients sit at column offsets 0 and Hp: two row blocks of in_proj_weight
                     ops.gemm_wgrad(dkv[:, :Hp], x[i], gin[H:2 * H], gbin[H:2 * H], Mo=H, No=H)
                     ops.gemm_wgrad(dkv[:, Hp:], x[i], gin[2 * H:], gbin[2 * H:], Mo=H, No=H)
+            with self._branch(second=True):                                                        # independent of dQ
+                ops.gemm_tn(dkv, self.sh[f"wkvT{i}"], out_bf16=gX)                                 # dx via k, v
             ops.gemm_tn(dq, self.sh[f"wqT{i}"], out_bf16=gD, residual=dr)                          # dQ = dr + dq Wq
-            ops.gemm_tn(dkv, self.sh[f"wkvT{i}"], out_bf16=gX)                                     # dx via k, v
+            self._join(second=True)
             # LN1 + the un-normalised k/v path; pad rows zeroed (x_i was masked, SRFR_model.py:99,121)
             ops.layernorm_bwd(gD, x[i], ws[f"st1_{i}"][:T], P.view(f"attention_layernorms.{i}.weight"), dx_out,
                               G(f"attention_layernorms.{i}.weight"), G(f"attention_layernorms.{i}.bias"),
@@ -642,8 +646,10 @@ class HotPath:
                 with self._branch():
                     ops.gemm_wgrad(dq, Q, gin[:H], gbin[:H], Mo=H, No=H)
                     ops.gemm_wgrad(dkv, x[i], gin[H:], gbin[H:], Mo=2 * H, No=H)
+                with self._branch(second=True):                        # dx through k | v: independent of dQ
+                    ops.gemm_tn(dkv, self.sh[f"wkvT{i}"], out_bf16=gX)
                 ops.gemm_tn(dq, self.sh[f"wqT{i}"], out_bf16=gD, residual=dr)
-                ops.gemm_tn(dkv, self.sh[f"wkvT{i}"], out_bf16=gX)
+                self._join(second=True)
                 ops.layernorm_bwd(gD, x[i], ws[f"st1_{i}"][:T], P.view(f"attention_layernorms.{i}.weight"), dx_out,
                                   G(f"attention_layernorms.{i}.weight"), G(f"attention_layernorms.{i}.bias"),
                                   add=gX, row_ids=row_ids, H=H)

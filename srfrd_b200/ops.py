@@ -216,6 +216,13 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, state3, zero_grad=True):
          _p(state3), int(zero_grad), _stream())
 
 
+def adam_step_fused(p, g, m, v, lr, beta1, beta2, eps, state8, zero_grad=True, acc2=None, norm2=None, loss=None):
+    """adam_tick + adam_step + loss_finalize in one launch (state8: 8 floats, see the header)."""
+    _lib.require_device()
+    call("srfrd_adam_step_fused", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
+         _p(state8), int(zero_grad), _p(acc2), _p(norm2), _p(loss), _stream())
+
+
 def catalogue_topk_plan(U, n_rows, row_lo, D, n_split) -> int:
     out = C.c_int(0)
     call("srfrd_catalogue_topk_plan", U, n_rows, row_lo, D, n_split, C.byref(out))
@@ -354,5 +361,5 @@ def score_loss_fused_packed(h, item_table, fake_table, pos, neg, prs, nrs, w_pos
 
 def embed_bwd_packed(dx0, seq, aux_ids, plan: PackedPlan, D, F, mode, item_scale, d_item, d_aux, d_pos):
     B, L = seq.shape
-    call("srfrd_embed_bwd_packed", _p(dx0), dx0.stride(0), _p(seq), _p(aux_ids), _p(plan.tok_row), B, L, D, F, mode,
-         float(item_scale), _p(d_item), _p(d_aux), _p(d_pos), _stream())
+    call("srfrd_embed_bwd_packed", _p(dx0), dx0.stride(0), _p(seq), _p(aux_ids), _p(plan.row_tok), _p(plan.rows), plan.cap,
+         L, D, F, mode, float(item_scale), _p(d_item), _p(d_aux), _p(d_pos), _stream())

@@ -112,7 +112,7 @@ class FusedTrainer:
         self.v = torch.zeros_like(self.P.data)
         self.scal = torch.zeros(8, dtype=torch.float32, device=dev)   # [0:2] norm (weight sums), [4] loss
         # the loss accumulators live in the tail of the gradient bucket (one all-reduce moves gradients and loss)
-        self.comm = torch.cuda.Stream(device=dev) if process_group is not None else None
+        self.comm = torch.cuda.Stream(device=dev)
         self._static: Optional[Dict[str, torch.Tensor]] = None
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._graph_key = None
@@ -153,12 +153,13 @@ class FusedTrainer:
         smp = getattr(self, "_sampler", None)
         if smp is not None:
             smp.sample_into(st, st["w_pos"] if has_wp else None, self._sampler_policy, step=eng.step_state[3:4])
-        ops.weight_sums(pos, w_pos, w_neg, norm)
-        if self.pg is not None:
-            # global sum of weights (the reference's mean over ALL pos != 0 of the batch, trainer.py:36-38): a side stream
-            # carries this tiny all-reduce so that the forward pass does not wait for it -- only the loss kernel does
-            self.comm.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(self.comm):
+        # The weight sums (loss normaliser: the reference's mean over ALL pos != 0 of the batch, trainer.py:36-38) and, data
+        # parallel, their tiny all-reduce run on a side stream: the forward pass does not wait for them, only the loss
+        # kernel does.
+        self.comm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm):
+            ops.weight_sums(pos, w_pos, w_neg, norm)
+            if self.pg is not None:
                 parallel.allreduce_sum_(norm, self.pg)
         packed = self.packed and eng.packed_ok(B, L)
         # packed token layout: pad slots (88 % of a C2 batch) get no rows; slots whose POSITIVE id is set keep one even if
@@ -166,8 +167,7 @@ class FusedTrainer:
         hidden = eng.forward(st["seq"], st["rsq"], training=True, packed=packed, keep=st["pos"] if packed else None)
         ws = eng._ws
         ft = eng.fake_table()
-        if self.pg is not None:
-            torch.cuda.current_stream().wait_stream(self.comm)
+        torch.cuda.current_stream().wait_stream(self.comm)
         prs_ = st["prs"].view(-1) if ft is not None else None
         nrs_ = st["nrs"].view(-1) if ft is not None else None
         if packed:
@@ -182,10 +182,9 @@ class FusedTrainer:
             eng.backward(ws["dh"][:T])
         if self.pg is not None:
             parallel.allreduce_sum_(P.grad_bucket, self.pg)               # ONE NCCL sum over NVLink: gradients + loss sums
-        ops.loss_finalize(acc, norm, loss)                                # (consumes acc: zero again for the next step)
-        ops.adam_tick(eng.step_state, self.betas[0], self.betas[1])
-        ops.adam_step(P.data, P.grad, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, eng.step_state,
-                      zero_grad=True)
+        # Adam tick + dense Adam + loss read-out (consumes acc: zero again for the next step) in one launch
+        ops.adam_step_fused(P.data, P.grad, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, eng.step_state,
+                            zero_grad=True, acc2=acc, norm2=norm, loss=loss)
         eng.refresh_shadows()
 
     # ------------------------------------------------------------------
