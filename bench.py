@@ -327,7 +327,7 @@ def bench_train_config(name, dev, rank, world, pg, timed, pk, steps, model_kw, d
     ms = timed(fn, steps, W)
     out = dict(value=round(world * B * steps / (ms / 1e3), 1), unit="seqs/s", ms_per_step=round(ms / steps, 4), steps=steps,
                warmup=W, batch_per_gpu=B, n_gpus=world, valid_slot_fraction=round(valid_frac, 4), policy=policy,
-               dropout=dropout, loss=round(float(tr.scal[4]), 5))
+               dropout=dropout, loss=round(float(tr.loss_dev), 5))
     if breakdown:                                    # EVERY rank runs the eager pass (it steps through the all-reduce)
         if sampler == "device":                      # the eager pass needs the sampler attached for its step body
             tr._sampler, tr._sampler_policy = smp, policy

@@ -304,6 +304,19 @@ SRFRD_API int srfrd_embed_bwd_packed(const void* dx0_bf16, int ldx, const int64_
                            const int* row_tok, const int* rows_dev, int64_t cap_rows, int L, int D, int F, int mode,
                            float item_scale, float* d_item, float* d_aux, float* d_pos, void* stream);
 
+/* ---- data-parallel gradient exchange fused with Adam over NVLink peer memory ----
+ * One launch per rank: reduce-scatter (rank r sums slice r of every rank's gradient bucket through peer pointers),
+ * torch.optim.Adam arithmetic on that slice with the rank's own slice of the moments, all-gather (the new parameters are
+ * written into every rank's parameter buffer, every rank's gradient slice is zeroed), loss read-out (rank 0 reduces the
+ * two accumulators in the bucket's tail [n, n+1] and writes the loss to param[n] of every rank), entry / exit barriers
+ * through release / acquire flags in each rank's signal words.  grad / param / signal pointer arrays are DEVICE arrays of
+ * `world` peer-mapped pointers (torch.distributed._symmetric_memory buffer_ptrs_dev); buckets and parameter buffers hold
+ * n + 4 floats; local4 = 4 zero-initialised device words (epoch, grid barrier).  Replaces an NCCL all-reduce of the bucket
+ * followed by srfrd_adam_step_fused on every rank; with world == 1 it is the same arithmetic as srfrd_adam_step_fused. */
+SRFRD_API int srfrd_dp_adam_step(float* const* grad_ptrs_dev, float* const* param_ptrs_dev, uint32_t* const* signal_ptrs_dev,
+                       int rank, int world, int64_t n, float* m, float* v, float lr, float beta1, float beta2, float eps,
+                       float* state8, const float* norm2, uint32_t* local4, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

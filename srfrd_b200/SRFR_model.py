@@ -164,6 +164,21 @@ class _HotPathModule(nn.Module):
             self._engine = HotPath(self.spec, flat)
         return self._engine
 
+    def rehome(self, alloc) -> HotPath:
+        """Move the flat parameter store into buffers from `alloc(numel)` (symmetric / peer-mapped memory for the fused
+        data-parallel optimizer) and rebuild the engine around them; parameter values are preserved."""
+        self._sync_flat()
+        params = dict(self.named_parameters())
+        dev = params[self._param_names[0]].device
+        flat = FlatParams(self.spec, dev, alloc)
+        with torch.no_grad():
+            for n in self._param_names:
+                flat.view(n).copy_(params[n].detach().to(torch.float32))
+                params[n].data = flat.view(n)
+        self._flat = flat
+        self._engine = HotPath(self.spec, flat)
+        return self._engine
+
     def flat_parameters(self) -> FlatParams:
         self._sync_flat()
         return self._flat

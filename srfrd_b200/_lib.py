@@ -69,6 +69,7 @@ SIGNATURES = {
     "srfrd_catalogue_topk": [vp, i64, i64, i32, vp, i64, i64, i64, i32, i32, i32, i32, vp, vp, vp, vp],
     "srfrd_merge_topk_packed": [vp, i64, i32, i32, vp, vp, vp],
     "srfrd_merge_topk": [vp, vp, i64, i32, i32, vp, vp, vp],
+    "srfrd_dp_adam_step": [vp, vp, vp, i32, i32, i64, vp, vp, f32, f32, f32, f32, vp, vp, vp, vp],
     "srfrd_pack_plan": [vp, vp, i64, i32, C.POINTER(PackDesc), vp],
     "srfrd_set_row_limit": [vp],
     "srfrd_embed_ln_fwd_packed": [vp, i64, i32, vp, vp, i64, i32, i32, vp, vp, i64, i32, f32, vp, vp, f32, vp, vp, vp, i32,

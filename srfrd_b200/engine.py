@@ -129,7 +129,9 @@ class FlatParams:
     """All parameters in ONE fp32 buffer (plus a same-shaped gradient buffer): the Adam kernel, the
     gradient all-reduce and the bf16 shadow refresh each touch it in a single launch."""
 
-    def __init__(self, spec: ModelSpec, device):
+    def __init__(self, spec: ModelSpec, device, alloc=None):
+        """alloc(numel) -> fp32 tensor: lets the data-parallel trainer place the parameter buffer and the gradient bucket
+        in symmetric (peer-mapped) memory; default = ordinary device memory."""
         self.spec = spec
         self.offsets: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
         off = 0
@@ -138,10 +140,14 @@ class FlatParams:
             self.offsets[name] = (off, shape)
             off += (n + 3) // 4 * 4                      # keep every view 16-byte aligned
         self.numel = off
-        self.data = torch.zeros(off, dtype=torch.float32, device=device)
+        zeros = (lambda n: alloc(n).zero_()) if alloc is not None else (lambda n: torch.zeros(n, dtype=torch.float32, device=device))
+        # parameter buffer + a 4-float tail (the fused data-parallel optimizer writes the step's loss there on every rank)
+        self.data_ext = zeros(off + 4)
+        self.data = self.data_ext[:off]
+        self.data_tail = self.data_ext[off:]
         # gradient bucket = every parameter gradient followed by a 4-float tail that carries the step's loss accumulators:
         # data-parallel training moves gradients AND loss with ONE all-reduce over `grad_bucket`
-        self.grad_bucket = torch.zeros(off + 4, dtype=torch.float32, device=device)
+        self.grad_bucket = zeros(off + 4)
         self.grad = self.grad_bucket[:off]
         self.grad_tail = self.grad_bucket[off:]
 

@@ -363,3 +363,12 @@ def embed_bwd_packed(dx0, seq, aux_ids, plan: PackedPlan, D, F, mode, item_scale
     B, L = seq.shape
     call("srfrd_embed_bwd_packed", _p(dx0), dx0.stride(0), _p(seq), _p(aux_ids), _p(plan.row_tok), _p(plan.rows), plan.cap,
          L, D, F, mode, float(item_scale), _p(d_item), _p(d_aux), _p(d_pos), _stream())
+
+
+def dp_adam_step(grad_ptrs_dev: int, param_ptrs_dev: int, signal_ptrs_dev: int, rank, world, n, m, v, lr, beta1, beta2, eps,
+                 state8, norm2, local4):
+    """Reduce-scatter + Adam + all-gather over peer memory in one launch (csrc/dp_adam.cu); the *_ptrs_dev arguments are
+    device addresses of arrays of `world` peer-mapped pointers (symmetric memory handles' buffer_ptrs_dev)."""
+    _lib.require_device()
+    call("srfrd_dp_adam_step", grad_ptrs_dev, param_ptrs_dev, signal_ptrs_dev, int(rank), int(world), int(n), _p(m), _p(v),
+         float(lr), float(beta1), float(beta2), float(eps), _p(state8), _p(norm2), _p(local4), _stream())

@@ -99,6 +99,9 @@ class FusedTrainer:
             raise NotImplementedError("FusedTrainer implements the reference default l2_emb = 0.0 (trainer.py:123); "
                                       "use simulate() with a torch optimizer for l2_emb != 0")
         self.model = model
+        self._dp = None
+        if process_group is not None and torch.distributed.get_world_size(process_group) > 1:
+            self._dp = self._setup_fused_dp(model, process_group)
         self.eng: HotPath = model._sync_flat()
         self.P = self.eng.P
         self.spec = self.eng.spec
@@ -123,6 +126,45 @@ class FusedTrainer:
         self.steps = 0
 
     # ------------------------------------------------------------------
+    @staticmethod
+    def _setup_fused_dp(model, pg):
+        """Place the flat parameter buffer and the gradient bucket in symmetric memory (mapped into every rank of the
+        node) so that ONE kernel per rank can do reduce-scatter -> Adam -> all-gather through NVLink peer pointers
+        (csrc/dp_adam.cu).  Returns None -- the NCCL all-reduce path stays -- when symmetric memory is unavailable or
+        SRFRD_FUSED_DP=0."""
+        import os
+        if os.environ.get("SRFRD_FUSED_DP", "1") == "0":
+            return None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            dev = next(model.parameters()).device
+            gname = pg.group_name
+            try:
+                symm.enable_symm_mem_for_group(gname)
+            except Exception:  # noqa: BLE001  (newer torch: not needed / deprecated)
+                pass
+            eng = model.rehome(lambda n: symm.empty(n, dtype=torch.float32, device=dev))
+            P = eng.P
+            sig = symm.empty(64, dtype=torch.int32, device=dev).zero_()
+            torch.cuda.synchronize()
+            hg, hp, hs = (symm.rendezvous(t, gname) for t in (P.grad_bucket, P.data_ext, sig))
+            dp = dict(g=int(hg.buffer_ptrs_dev), p=int(hp.buffer_ptrs_dev), s=int(hs.buffer_ptrs_dev), rank=int(hg.rank),
+                      world=int(hg.world_size), keep=(hg, hp, hs, sig),
+                      local=torch.zeros(4, dtype=torch.int32, device=dev))
+            torch.cuda.synchronize()
+            torch.distributed.barrier(group=pg)
+            return dp
+        except Exception as ex:  # noqa: BLE001
+            import warnings
+            warnings.warn(f"srfrd_b200: fused data-parallel optimizer unavailable ({type(ex).__name__}: {ex}); "
+                          "falling back to the NCCL all-reduce + replicated Adam")
+            return None
+
+    @property
+    def loss_dev(self) -> torch.Tensor:
+        """Device scalar holding the last step's loss."""
+        return self.P.data_tail[0] if self._dp is not None else self.scal[4]
+
     _KEYS = ("seq", "rsq", "pos", "prs", "neg", "nrs")
 
     @staticmethod
@@ -180,11 +222,18 @@ class FusedTrainer:
             ops.score_loss_fused(ws["hfin"][:T], P.view(s.item_key), ft, pos, neg, prs_, nrs_, w_pos, w_neg, norm, acc,
                                  ws["dh"][:T], P.view(s.item_key, grad=True), eng.fake_table_grad())
             eng.backward(ws["dh"][:T])
-        if self.pg is not None:
-            parallel.allreduce_sum_(P.grad_bucket, self.pg)               # ONE NCCL sum over NVLink: gradients + loss sums
-        # Adam tick + dense Adam + loss read-out (consumes acc: zero again for the next step) in one launch
-        ops.adam_step_fused(P.data, P.grad, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, eng.step_state,
-                            zero_grad=True, acc2=acc, norm2=norm, loss=loss)
+        if self._dp is not None:
+            # reduce-scatter -> Adam on this rank's slice -> all-gather of the new parameters + loss, one kernel over NVLink
+            # peer memory (csrc/dp_adam.cu) instead of an NCCL all-reduce followed by the same Adam on every rank
+            d = self._dp
+            ops.dp_adam_step(d["g"], d["p"], d["s"], d["rank"], d["world"], P.numel, self.m, self.v, self.lr, self.betas[0],
+                             self.betas[1], self.eps, eng.step_state, norm, d["local"])
+        else:
+            if self.pg is not None:
+                parallel.allreduce_sum_(P.grad_bucket, self.pg)           # ONE NCCL sum over NVLink: gradients + loss sums
+            # Adam tick + dense Adam + loss read-out (consumes acc: zero again for the next step) in one launch
+            ops.adam_step_fused(P.data, P.grad, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps,
+                                eng.step_state, zero_grad=True, acc2=acc, norm2=norm, loss=loss)
         eng.refresh_shadows()
 
     # ------------------------------------------------------------------
@@ -291,7 +340,7 @@ class FusedTrainer:
             # an eager step may itself have re-allocated the workspace: remember the generation it LEFT behind
             self._eager_key = key[:3] + (self.eng.ws_generation,)
         self.steps += 1
-        return self.scal[4]
+        return self.loss_dev
 
     def step(self, batch, w_pos=None, w_neg=None) -> torch.Tensor:
         self.load_batch(batch, w_pos, w_neg)

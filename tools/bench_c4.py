@@ -31,7 +31,7 @@ for i in range(n):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
-print(f"C4 B={B} L={L} valid={valid:.2f}: {ms:.3f} ms/step, {B / ms * 1e3:.0f} seqs/s, loss {float(tr.scal[4]):.4f}")
+print(f"C4 B={B} L={L} valid={valid:.2f}: {ms:.3f} ms/step, {B / ms * 1e3:.0f} seqs/s, loss {float(tr.loss_dev):.4f}")
 recs = []
 tr.use_graph = False
 _lib.set_profile(recs)

@@ -25,10 +25,13 @@ def make_model():
 
 data = synth.make_interactions(77, 4000, 3000, 5, 4.0, 50)
 smp = synth.BatchSampler(data, 50, 5)
-batches = [smp.next_batch(64 * world) for _ in range(4)]
+batches = [smp.next_batch(64 * world) for _ in range(6)]
 m_dp, m_one = make_model(), make_model()
 P.broadcast_parameters(m_dp.flat_parameters().data, 0)
-tr_dp = FusedTrainer(m_dp, process_group=dist.group.WORLD, use_graph=False)
+use_graph = os.environ.get("DP_CHECK_GRAPH", "0") == "1"
+tr_dp = FusedTrainer(m_dp, process_group=dist.group.WORLD, use_graph=use_graph)
+if rank == 0:
+    print("fused reduce-scatter/Adam/all-gather kernel:", tr_dp._dp is not None, "graph:", use_graph)
 tr_one = FusedTrainer(m_one, use_graph=False)
 ok = True
 for nb in batches:
@@ -42,6 +45,13 @@ for nb in batches:
     ok &= abs(l1 - l2) < 2e-3
 a, b = m_one.flat_parameters().data, m_dp.flat_parameters().data
 drift = float((a - b).abs().max())
+# replicas must be bit-identical (every element is computed by exactly one rank and written everywhere)
+mine = m_dp.flat_parameters().data.clone()
+other = mine.clone()
+dist.broadcast(other, 0)
+ok &= bool(torch.equal(mine, other))
+if rank == 0:
+    print("replicas bit-identical:", bool(torch.equal(mine, other)))
 cos = float(torch.dot(a - 0, b - 0) / (a.norm() * b.norm()))
 ok &= drift < 5e-3
 # sharded catalogue top-10
@@ -56,6 +66,12 @@ ok &= same
 flag = torch.tensor([1.0 if ok else 0.0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print(f"param drift after 4 steps {drift:.2e}; sharded top-10 == unsharded: {same}; ALL OK: {bool(flag.item())}")
-dist.destroy_process_group()
-sys.exit(0 if flag.item() else 1)
+    print(f"param drift after 6 steps {drift:.2e}; sharded top-10 == unsharded: {same}; ALL OK: {bool(flag.item())}")
+# (no destroy_process_group(): with NCCL work captured in live CUDA graphs the communicator teardown can block for minutes)
+rc = 0 if flag.item() else 1
+torch.cuda.synchronize()
+dist.barrier()
+tr_dp._graph = None
+torch.cuda.synchronize()
+sys.stdout.flush()
+os._exit(rc)
