@@ -515,6 +515,11 @@ def run_ours(args):
     if not args.no_catalogue and rank == 0:
         gat = guarded(bench_gather, dev, pk)
 
+    scale_k = None
+    if not args.no_catalogue and rank == 0:
+        scale_k = guarded(bench_scale_kernels, dev, pk)
+        torch.cuda.empty_cache()
+
     # ---- CPU baseline (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -541,6 +546,8 @@ def run_ours(args):
             line["catalogue"] = cat
         if gat is not None:
             line["gather"] = gat
+        if scale_k is not None:
+            line["scale_kernels"] = scale_k
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if eager is not None:
@@ -589,6 +596,68 @@ def bench_gather(dev, pk):
                 roofline=dict(bound="hbm", achieved=round(gbs, 1), peak=pk["hbm"], unit="GB/s", frac=round(gbs / pk["hbm"], 4),
                               traffic=measured_traffic("srfrd_embed_ln_fwd@C3"), bytes_per_token=600, peak_source=pk["src"]),
                 config="C3 table (1M x 64 fp32, 256 MB > L2), 81920 x 50 tokens, all slots valid, SRFR D=64 F=16")
+
+
+def bench_scale_kernels(dev, pk):
+    """K4 (fused gather-dot + weighted BCE fwd/bwd), K5 (sparse embedding-gradient scatter-add) and K7 (dense Adam) at
+    catalogue scale -- 1 M x 64 fp32 item table and gradient (256 MB each, beyond L2), 2 M tokens with every slot valid --
+    each against the HBM roofline (at C2 the 3 MB table is L2-resident, so the HBM fraction must be shown here).
+    K5's destination rows are random (uniform over 1 M rows): the bound there is the L2 atomic unit, not HBM."""
+    from srfrd_b200 import ops
+    N, D, F, L, B = 1_000_000, 64, 16, 50, 40960
+    T, H = B * L, D + F
+    g = torch.Generator(device="cpu").manual_seed(1240)
+    E = torch.randn(N + 1, D, generator=g).to(dev)
+    dE = torch.zeros(N + 1, D, device=dev)
+    pos = torch.randint(1, N + 1, (T,), generator=g).to(dev)
+    neg = torch.randint(1, N + 1, (T,), generator=g).to(dev)
+    h = torch.randn(T, D, generator=g).to(dev) * 0.1
+    dh = torch.empty(T, D, device=dev)
+    norm, acc = torch.zeros(2, device=dev), torch.zeros(2, device=dev)
+    ops.weight_sums(pos, None, None, norm)
+
+    def timeit(fn):
+        iters = int(os.environ.get("SRFRD_SCALE_ITERS", 5))          # (1 under ncu: one launch of each kernel)
+        for _ in range(2 if iters > 1 else 0):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    def roof(ms, by, key, per):
+        gbs = by / (ms * 1e-3) / 1e9
+        return dict(ms=round(ms, 4), roofline=dict(bound="hbm", achieved=round(gbs, 1), peak=pk["hbm"], unit="GB/s",
+                                                   frac=round(gbs / pk["hbm"], 4), traffic=measured_traffic(key),
+                                                   algorithmic_bytes=int(by), bytes_per_unit=per, peak_source=pk["src"]))
+    out = {}
+    ms = timeit(lambda: ops.score_loss_fused(h, E, None, pos, neg, None, None, None, None, norm, acc, dh, dE, None))
+    per = 16 + D * 4 + 2 * D * 4 + D * 4 + 2 * 2 * D * 4          # ids, h, two gathered rows, dh, two read-modify-write rows
+    out["k4"] = dict(kernel="srfrd_score_loss_fused", tokens=T, **roof(ms, T * per, "srfrd_score_loss_fused@C3", f"{per} B/token"))
+    del h, dh
+    dx0 = (torch.randn(T, H, generator=g) * 0.1).to(torch.bfloat16).to(dev)
+    seq = torch.randint(1, N + 1, (B, L), generator=g).to(dev)
+    rsq = torch.randint(1, 3, (B, L), generator=g).to(dev)
+    dF = torch.zeros(3, F, device=dev)
+    ms = timeit(lambda: ops.embed_bwd(dx0, seq, rsq, D, F, 1, 1.0, dE, dF))
+    per = 16 + H * 2 + D * 8
+    out["k5"] = dict(kernel="srfrd_embed_bwd", tokens=T, **roof(ms, T * per, "srfrd_embed_bwd@C3", f"{per} B/token"),
+                     note="uniform random destination rows over a 256 MB fp32 gradient table: bound by the L2 atomic units "
+                          "(red.global.add.f32, one 4-byte reduction per element), see tools/microbench")
+    del dx0
+    n = (N + 1) * D
+    p_, g_, m_, v_ = (torch.zeros(n, device=dev) for _ in range(4))
+    g_.normal_(generator=None)
+    st = torch.zeros(8, device=dev)
+    ops.adam_tick(st, 0.9, 0.98)
+    ms = timeit(lambda: ops.adam_step(p_, g_, m_, v_, 1e-3, 0.9, 0.98, 1e-8, st, zero_grad=True))
+    out["k7"] = dict(kernel="srfrd_adam_step", params=n, **roof(ms, n * 32.0, "srfrd_adam_step@C3", "32 B/param (read p g m v, write p m v g)"))
+    out["config"] = "C3-scale: 1M x 64 fp32 item table + gradient, 40960 x 50 tokens all valid, uniform random ids"
+    return out
 
 
 def bench_catalogue(dev, rank, world, pg, args, pk, timed):

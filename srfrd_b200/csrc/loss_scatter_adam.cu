@@ -96,58 +96,85 @@ __global__ void __launch_bounds__(256, (NC <= 9 ? 2 : 1)) score_kernel(ScorePara
         }
       }
     }
-    while (mask) {
-      const int r = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const int64_t t = t0 + r;
-      const int64_t tsrc = p.row_tok ? (int64_t)__shfl_sync(0xffffffffu, my_tok, r) : t;
-      const int64_t pid = __shfl_sync(0xffffffffu, my_pid, r), nid = __shfl_sync(0xffffffffu, my_nid, r);
-      const int pf = (int)__shfl_sync(0xffffffffu, (int)my_pf, r), nf = (int)__shfl_sync(0xffffffffu, (int)my_nf, r);
-      const float ta = __shfl_sync(0xffffffffu, my_a, r), tb = __shfl_sync(0xffffffffu, my_b, r);
+    // One token per pass; for narrow rows (NC <= 4) the NEXT active token's three rows (h, E[pos], E[neg]) are fetched
+    // before the current token's reductions and atomics, so two tokens' gathers are in flight per warp: at catalogue
+    // scale the kernel is bound by memory-level parallelism (ncu: 37 % of HBM peak with one token in flight).
+    struct Tok {
+      int64_t t, tsrc, pid, nid; int pf, nf; float ta, tb;
       float hv[NC], ep[NC], en[NC];
+    };
+    auto fetch = [&](Tok& k, int r) {
+      k.t = t0 + r;
+      k.tsrc = p.row_tok ? (int64_t)__shfl_sync(0xffffffffu, my_tok, r) : k.t;
+      k.pid = __shfl_sync(0xffffffffu, my_pid, r); k.nid = __shfl_sync(0xffffffffu, my_nid, r);
+      k.pf = (int)__shfl_sync(0xffffffffu, (int)my_pf, r); k.nf = (int)__shfl_sync(0xffffffffu, (int)my_nf, r);
+      k.ta = __shfl_sync(0xffffffffu, my_a, r); k.tb = __shfl_sync(0xffffffffu, my_b, r);
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        const int c = lane + 32 * i;
+        k.hv[i] = k.ep[i] = k.en[i] = 0.f;
+        if (c < W) {
+          k.hv[i] = p.h[k.t * p.ldh + c];
+          if (c < p.D) {
+            k.ep[i] = __ldg(p.item_table + k.pid * p.D + c);
+            k.en[i] = __ldg(p.item_table + k.nid * p.D + c);
+          } else {
+            k.ep[i] = __ldg(p.fake_table + (int64_t)k.pf * p.F + (c - p.D));
+            k.en[i] = __ldg(p.fake_table + (int64_t)k.nf * p.F + (c - p.D));
+          }
+        }
+      }
+    };
+    auto finish = [&](const Tok& k) {
       float sp = 0.f, sn = 0.f;
 #pragma unroll
-      for (int i = 0; i < NC; ++i) {
-        const int c = lane + 32 * i;
-        hv[i] = ep[i] = en[i] = 0.f;
-        if (c < W) {
-          hv[i] = p.h[t * p.ldh + c];
-          if (c < p.D) {
-            ep[i] = __ldg(p.item_table + pid * p.D + c);
-            en[i] = __ldg(p.item_table + nid * p.D + c);
-          } else {
-            ep[i] = __ldg(p.fake_table + (int64_t)pf * p.F + (c - p.D));
-            en[i] = __ldg(p.fake_table + (int64_t)nf * p.F + (c - p.D));
-          }
-          sp = fmaf(hv[i], ep[i], sp);
-          sn = fmaf(hv[i], en[i], sn);
-        }
-      }
+      for (int i = 0; i < NC; ++i) { sp = fmaf(k.hv[i], k.ep[i], sp); sn = fmaf(k.hv[i], k.en[i], sn); }
       const float zp = warp_sum(sp), zn = warp_sum(sn);
-      if (p.zp && lane == 0) { p.zp[tsrc] = zp; p.zn[tsrc] = zn; }
-      if (p.mode == 0) continue;
-      float dzp = ta, dzn = tb;
+      if (p.zp && lane == 0) { p.zp[k.tsrc] = zp; p.zn[k.tsrc] = zn; }
+      if (p.mode == 0) return;
+      float dzp = k.ta, dzn = k.tb;
       if (p.mode == 1) {
-        lp_acc += ta * softplus(-zp);
-        ln_acc += tb * softplus(zn);
-        dzp = ta * (sigmoidf(zp) - 1.f) * inv_np;
-        dzn = tb * sigmoidf(zn) * inv_nn;
+        lp_acc += k.ta * softplus(-zp);
+        ln_acc += k.tb * softplus(zn);
+        dzp = k.ta * (sigmoidf(zp) - 1.f) * inv_np;
+        dzn = k.tb * sigmoidf(zn) * inv_nn;
       }
 #pragma unroll
       for (int i = 0; i < NC; ++i) {
         const int c = lane + 32 * i;
         if (c < W) {
-          if (p.dh) p.dh[t * p.lddh + c] = dzp * ep[i] + dzn * en[i];
+          if (p.dh) p.dh[k.t * p.lddh + c] = dzp * k.ep[i] + dzn * k.en[i];
           if (c < p.D) {
             // padding_idx = 0: the pad row never receives gradient (SRFR_model.py:10)
-            if (p.d_item && pid != 0 && dzp != 0.f) red_add_f32(p.d_item + pid * p.D + c, dzp * hv[i]);
-            if (p.d_item && nid != 0 && dzn != 0.f) red_add_f32(p.d_item + nid * p.D + c, dzn * hv[i]);
+            if (p.d_item && k.pid != 0 && dzp != 0.f) red_add_f32(p.d_item + k.pid * p.D + c, dzp * k.hv[i]);
+            if (p.d_item && k.nid != 0 && dzn != 0.f) red_add_f32(p.d_item + k.nid * p.D + c, dzn * k.hv[i]);
           } else {
-            const float gp = dzp * hv[i], gn = dzn * hv[i];
-            fk1[i] += (pf == 1 ? gp : 0.f) + (nf == 1 ? gn : 0.f);
-            fk2[i] += (pf == 2 ? gp : 0.f) + (nf == 2 ? gn : 0.f);
+            const float gp = dzp * k.hv[i], gn = dzn * k.hv[i];
+            fk1[i] += (k.pf == 1 ? gp : 0.f) + (k.nf == 1 ? gn : 0.f);
+            fk2[i] += (k.pf == 2 ? gp : 0.f) + (k.nf == 2 ? gn : 0.f);
           }
         }
+      }
+    };
+    if (NC <= 4) {
+      if (mask) {
+        Tok cur, nxt;
+        { const int r = __ffs(mask) - 1; mask &= mask - 1; fetch(cur, r); }
+        while (true) {
+          const bool more = mask != 0;
+          if (more) { const int r = __ffs(mask) - 1; mask &= mask - 1; fetch(nxt, r); }
+          finish(cur);
+          if (!more) break;
+          cur = nxt;
+        }
+      }
+    } else {
+      while (mask) {
+        const int r = __ffs(mask) - 1;
+        mask &= mask - 1;
+        Tok cur;
+        fetch(cur, r);
+        finish(cur);
       }
     }
   }

@@ -96,13 +96,20 @@ __global__ void __launch_bounds__(SCAN_THREADS) pack_scan_kernel(srfrd_pack_t pk
     nxt[i] = lo;
   }
   __syncthreads();
+  // the chase itself touches shared memory only (one dependent load per tile); the visited boundaries are recorded in
+  // place (the slots of nxt[] already passed are dead) and written out by all threads afterwards
+  __shared__ int s_ntiles;
   if (tid == 0) {
     int k = 0;
-    for (int i = 0; i < NB; i = nxt[i]) pk.tile_row0[k++] = pack_bound(first, (int)B, Tp, i);
-    pk.tile_row0[k] = M;
+    for (int i = 0; i < NB;) { const int j = nxt[i]; nxt[k++] = i; i = j; }      // k <= i always: slot k is already consumed
+    s_ntiles = k;
     pk.rows[2] = k;
     pk.rows[3] = 0;
   }
+  __syncthreads();
+  const int nt = s_ntiles;
+  for (int k = tid; k < nt; k += SCAN_THREADS) pk.tile_row0[k] = pack_bound(first, (int)B, Tp, nxt[k]);
+  if (tid == 0) pk.tile_row0[nt] = M;
 }
 
 __global__ void __launch_bounds__(256) pack_fill_kernel(const int64_t* seq, const int64_t* keep, int64_t B, int L, srfrd_pack_t pk) {

@@ -96,3 +96,9 @@ if what in ("k1", "all"):
     nvalid = int((seq != 0).sum())
     mode = 1 if H > 64 else 0                       # KB_H=64: no fake-review columns (SASRec / SRFU shaped)
     timeit(f"embed_ln_fwd (K1) N={N} valid={nvalid / T:.2f}", lambda i: ops.embed_ln_fwd(E, P, Fe if mode else None, mode, seq, rsq if mode else None, 1.0, w, b, 1e-8, x0_bf16=outs[i % NBUF], q_bf16=acts[i % NBUF], stats=st), 2 * A + T * 24 + nvalid * 256)
+
+if what in ("c3scale",):
+    # K4 / K5 / K7 at catalogue scale (for ncu --set full: dram__bytes of one launch each); same shapes as bench.py
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    print(bench.bench_scale_kernels(torch.device("cuda"), bench.peaks()))

@@ -2,7 +2,7 @@
 <tag>_bench_launches.txt, <tag>_<kernel>_ncu.txt and traffic.json (DRAM bytes per launch, read by bench.py)."""
 import csv, json, os, subprocess, sys
 
-tag = sys.argv[1] if len(sys.argv) > 1 else "r1c"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r2"
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out = os.path.join(root, "gpurun_out")
 prof = os.path.join(root, sys.argv[2]) if len(sys.argv) > 2 else os.path.join(root, "profiles")
@@ -26,7 +26,7 @@ try:                                     # keep entries of captures that are not
 except Exception:
     pass
 for name, key, match in [("gemm_tn", "srfrd_gemm_tn", "gemm_tn"), ("topk", "srfrd_catalogue_topk", "catalogue_"),
-                         ("k1", "srfrd_embed_ln_fwd@C3", "embed_ln"), ("misc", None, "")]:
+                         ("k1", "srfrd_embed_ln_fwd@C3", "embed_ln"), ("c3k", "c3k", ""), ("misc", None, "")]:
     rep = os.path.join(out, f"{tag}_{name}.ncu-rep")
     if not os.path.exists(rep):
         print("missing", rep)
@@ -38,6 +38,16 @@ for name, key, match in [("gemm_tn", "srfrd_gemm_tn", "gemm_tn"), ("topk", "srfr
     recs, units = raw(rep)
     per = [to_bytes(r["dram__bytes_read.sum"], units["dram__bytes_read.sum"]) + to_bytes(r["dram__bytes_write.sum"], units["dram__bytes_write.sum"])
            for r in recs if match in r["Kernel Name"]]
+    if name == "c3k":            # three kernels, one launch each: key per kernel
+        for r in recs:
+            kn = r["Kernel Name"]
+            k2 = ("srfrd_score_loss_fused@C3" if "score_kernel" in kn else "srfrd_embed_bwd@C3" if "embed_bwd" in kn
+                  else "srfrd_adam_step@C3" if "adam_kernel" in kn else None)
+            if k2:
+                traffic[k2] = round(to_bytes(r["dram__bytes_read.sum"], units["dram__bytes_read.sum"]) +
+                                    to_bytes(r["dram__bytes_write.sum"], units["dram__bytes_write.sum"]))
+                print(k2, traffic[k2])
+        continue
     if name == "topk":           # one pass = streaming kernel + refine kernel
         traffic[key] = round(sum(per))
     else:
