@@ -267,7 +267,8 @@ typedef struct {
   int* last_row;    /* [B] packed row that holds position L - 1 of each sequence (its representative if that slot is a pad) */
   int64_t cap;      /* capacity in rows, >= roundup(B * (L + 1), 128) */
 } srfrd_pack_t;
-/* seq, keep: (B, L) int64 (keep nullable).  Needs L + 1 <= 128 and B <= 16384. */
+/* seq, keep: (B, L) int64 (keep nullable).  B <= 16384; the attention tile plan is built only when L + 1 <= 128
+ * (longer sequences use the row maps with the dense-layout attention kernels, see srfrd_unpack_rows). */
 SRFRD_API int srfrd_pack_plan(const int64_t* seq, const int64_t* keep, int64_t B, int L, const srfrd_pack_t* pk, void* stream);
 /* Dynamic row count for the row-wise entry points: after srfrd_set_row_limit(rows_dev), srfrd_gemm_tn (M), srfrd_gemm_wgrad
  * (T), srfrd_layernorm_fwd / _bwd (T) and srfrd_dropout_apply (M) launched from THIS host thread treat their row argument
@@ -303,6 +304,22 @@ SRFRD_API int srfrd_score_loss_fused_packed(const float* h, int ldh, const float
 SRFRD_API int srfrd_embed_bwd_packed(const void* dx0_bf16, int ldx, const int64_t* seq, const int64_t* aux_ids,
                            const int* row_tok, const int* rows_dev, int64_t cap_rows, int L, int D, int F, int mode,
                            float item_scale, float* d_item, float* d_aux, float* d_pos, void* stream);
+
+/* Packed <-> dense row movement for sequence lengths whose attention kernels work on the dense (B, L) layout
+ * (128 < maxlen <= 256): the row-wise bulk of a block runs on packed rows, attention on dense tensors.
+ * unpack: dense[t] = packed[tok_row[t]]; a dropped pad slot takes its sequence's pad-representative row (mode 0: q, k, v)
+ *         or zeros (mode 1: dO).   pack: packed[r] = dense[row_tok[r]]; representative rows take zeros (mode 0: o, dq) or
+ *         the sum over the sequence's dropped pad slots (mode 1: dk, dv); filler rows zeros.  Up to 3 tensors per call. */
+typedef struct {
+  const void* src; int ld_s;   /* bf16 rows: packed (unpack) / dense (pack) */
+  void* dst; int ld_d;         /* bf16 rows: dense (unpack) / packed (pack) */
+  int W;                       /* columns, multiple of 8 */
+  int mode;
+} srfrd_repack_part_t;
+SRFRD_API int srfrd_unpack_rows(const srfrd_repack_part_t* parts, int n_parts, const srfrd_pack_t* pk, int64_t B, int L,
+                      void* stream);
+SRFRD_API int srfrd_pack_rows(const srfrd_repack_part_t* parts, int n_parts, const srfrd_pack_t* pk, int64_t B, int L,
+                    void* stream);
 
 /* ---- data-parallel gradient exchange fused with Adam over NVLink peer memory ----
  * One launch per rank: reduce-scatter (rank r sums slice r of every rank's gradient bucket through peer pointers),

@@ -33,6 +33,10 @@ class PackDesc(C.Structure):
                 ("row_info", vp), ("tile_row0", vp), ("last_row", vp), ("cap", i64)]
 
 
+class RepackPart(C.Structure):
+    _fields_ = [("src", vp), ("ld_s", i32), ("dst", vp), ("ld_d", i32), ("W", i32), ("mode", i32)]
+
+
 # name -> argtypes, exactly the prototypes of include/srfrd_b200.h
 SIGNATURES = {
     "srfrd_abi_version": [],
@@ -69,6 +73,8 @@ SIGNATURES = {
     "srfrd_catalogue_topk": [vp, i64, i64, i32, vp, i64, i64, i64, i32, i32, i32, i32, vp, vp, vp, vp],
     "srfrd_merge_topk_packed": [vp, i64, i32, i32, vp, vp, vp],
     "srfrd_merge_topk": [vp, vp, i64, i32, i32, vp, vp, vp],
+    "srfrd_unpack_rows": [C.POINTER(RepackPart), i32, C.POINTER(PackDesc), i64, i32, vp],
+    "srfrd_pack_rows": [C.POINTER(RepackPart), i32, C.POINTER(PackDesc), i64, i32, vp],
     "srfrd_dp_adam_step": [vp, vp, vp, i32, i32, i64, vp, vp, f32, f32, f32, f32, vp, vp, vp, vp],
     "srfrd_pack_plan": [vp, vp, i64, i32, C.POINTER(PackDesc), vp],
     "srfrd_set_row_limit": [vp],

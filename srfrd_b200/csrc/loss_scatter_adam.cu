@@ -277,18 +277,23 @@ __global__ void embed_bwd_kernel(EmbedBwdParams p) {
     red_add_f32(p.d_aux + p.aux_ids[b] * p.D + c, accu);
 }
 
-// K5 on the packed layout, row-parallel: a block takes RPB packed rows per pass, thread (y, c) owns column c of row y.
-// A row with a dense token (row_tok >= 0) and a non-zero input id adds its dx0 row to the item table (red.add), to the
-// positional table through a per-block shared accumulator [L][D] (shared-memory atomics, flushed once per block; the
-// dense path takes this gradient from a column sum over the (B, L*H) view) and to the fake / user-label table.
+// K5 on the packed layout, row-parallel: a block takes RPB packed rows per pass and a SLICE of up to 64 columns
+// (blockIdx.y), thread (y, x) owns column slice*64 + x of row y.  A row with a dense token (row_tok >= 0) and a non-zero
+// input id adds its dx0 row to the item table (red.add), to the positional table through a per-block shared accumulator
+// [L][slice width] (shared-memory atomics, flushed once per block; the dense path takes this gradient from a column sum
+// over the (B, L*H) view) and to the fake / user-label table.  Column slices keep the accumulator at L * 256 bytes, so
+// several blocks fit an SM also at maxlen 200, D = 256 (one 200 KB accumulator per SM measured 0.52 ms at C4).
+static constexpr int EB_SLICE = 64;
 __global__ void __launch_bounds__(512) embed_bwd_packed_kernel(EmbedBwdParams p, const int* row_tok, const int* rows_dev, int64_t cap,
                                                               float* d_pos) {
-  extern __shared__ float spos[];            // [L * D]
+  extern __shared__ float spos[];            // [L * EB_SLICE]
   pdl_prologue_done();
-  const int c = threadIdx.x, y = threadIdx.y, RPB = blockDim.y;
+  const int x = threadIdx.x, y = threadIdx.y, RPB = blockDim.y;
+  const int c = blockIdx.y * EB_SLICE + x;
   const int H = p.D + (p.mode == 1 ? p.F : 0);
-  const int tid = y * blockDim.x + c, nthr = blockDim.x * blockDim.y;
-  for (int i = tid; i < p.L * p.D; i += nthr) spos[i] = 0.f;
+  const int tid = y * blockDim.x + x, nthr = blockDim.x * blockDim.y;
+  const bool pos_slice = blockIdx.y * EB_SLICE < p.D;
+  if (pos_slice) for (int i = tid; i < p.L * EB_SLICE; i += nthr) spos[i] = 0.f;
   __syncthreads();
   const int64_t M = min(cap, (int64_t)__ldg(rows_dev));
   float acc1 = 0.f, acc2 = 0.f;
@@ -300,7 +305,7 @@ __global__ void __launch_bounds__(512) embed_bwd_packed_kernel(EmbedBwdParams p,
     const float v = bf2f(p.dx0[r * p.ldx + c]);
     if (c < p.D) {
       red_add_f32(p.d_item + id * p.D + c, v * p.item_scale);
-      atomicAdd(&spos[(tok % p.L) * p.D + c], v);
+      atomicAdd(&spos[(tok % p.L) * EB_SLICE + x], v);
       if (p.mode == 2 && p.d_aux) red_add_f32(p.d_aux + p.aux_ids[tok / p.L] * p.D + c, v);
     } else if (p.aux_ids) {
       const int64_t f = __ldg(p.aux_ids + tok);
@@ -313,9 +318,11 @@ __global__ void __launch_bounds__(512) embed_bwd_packed_kernel(EmbedBwdParams p,
     if (acc2 != 0.f) red_add_f32(p.d_aux + 2 * p.F + (c - p.D), acc2);
   }
   __syncthreads();
-  if (d_pos)
-    for (int i = tid; i < p.L * p.D; i += nthr)
-      if (spos[i] != 0.f) red_add_f32(d_pos + i, spos[i]);
+  if (d_pos && pos_slice)
+    for (int i = tid; i < p.L * EB_SLICE; i += nthr) {
+      const int l = i / EB_SLICE, cc = blockIdx.y * EB_SLICE + i % EB_SLICE;
+      if (cc < p.D && spos[i] != 0.f) red_add_f32(d_pos + l * p.D + cc, spos[i]);
+    }
 }
 
 // out[(n / seg_in) * seg_out + n % seg_in] += in[n] where n % seg_in < seg_out
@@ -562,20 +569,25 @@ extern "C" int srfrd_embed_bwd_packed(const void* dx0, int ldx, const int64_t* s
   EmbedBwdParams p;
   p.dx0 = (const bf16*)dx0; p.ldx = ldx; p.seq = seq; p.aux_ids = aux_ids; p.L = L; p.D = D; p.F = F; p.mode = mode;
   p.item_scale = item_scale; p.d_item = d_item; p.d_aux = d_aux;
-  const int tx = (H + 31) & ~31;
-  const int ty = 512 / tx > 0 ? 512 / tx : 1;
-  const size_t smem = (size_t)L * D * sizeof(float);
-  SRFRD_REQUIRE(smem <= 200 * 1024, "embed_bwd_packed: L * D = %d too large for the shared positional accumulator", L * D);
+  const int slices = (H + EB_SLICE - 1) / EB_SLICE;
+  const int tx = EB_SLICE, ty = 8;
+  const size_t smem = (size_t)L * EB_SLICE * sizeof(float);
+  SRFRD_REQUIRE(smem <= 200 * 1024, "embed_bwd_packed: L = %d too long for the shared positional accumulator", L);
   static bool attr = false;
   if (!attr) {
     SRFRD_CUDA(cudaFuncSetAttribute(embed_bwd_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
-  int64_t grid = (int64_t)num_sms() * (smem > 48 * 1024 ? 1 : 2);
+  int per_sm = (int)((200 * 1024) / (smem + 1024));
+  if (per_sm > 4) per_sm = 4;
+  if (per_sm < 1) per_sm = 1;
+  int64_t gx = ((int64_t)num_sms() * per_sm + slices - 1) / slices;
   const int64_t need = (cap_rows + ty - 1) / ty;
-  if (grid > need) grid = need;
-  SRFRD_CUDA(launch_pdl(embed_bwd_packed_kernel, dim3((unsigned)grid), dim3(tx, ty), smem, (cudaStream_t)stream, p, row_tok,
-                        rows_dev, cap_rows, d_pos));
+  if (gx > need) gx = need;
+  if (gx < 1) gx = 1;
+  const dim3 grid((unsigned)gx, (unsigned)slices);
+  SRFRD_CUDA(launch_pdl(embed_bwd_packed_kernel, grid, dim3(tx, ty), smem, (cudaStream_t)stream, p, row_tok, rows_dev, cap_rows,
+                        d_pos));
   SRFRD_LAUNCH_CHECK();
   return 0;
 }

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256) pack_count_kernel(const int64_t* seq, con
 // bound(i): first row of "sequence" i, where the filler rows count as single-row sequences after the B real ones
 __device__ __forceinline__ int pack_bound(const int* first, int B, int Tp, int i) { return i <= B ? first[min(i, B)] + 0 : Tp + (i - B); }
 
-__global__ void __launch_bounds__(SCAN_THREADS) pack_scan_kernel(srfrd_pack_t pk, int64_t B) {
+__global__ void __launch_bounds__(SCAN_THREADS) pack_scan_kernel(srfrd_pack_t pk, int64_t B, int plan_tiles) {
   extern __shared__ int sm[];                 // [B + 1] first rows, then [NBmax] next-tile pointers
   __shared__ int wsum[32];
   __shared__ int s_total;
@@ -84,6 +84,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) pack_scan_kernel(srfrd_pack_t pk
   // ---- greedy tile plan.  A tile starts at a sequence boundary and holds every following whole sequence that fits in
   // 128 rows.  nxt[i] = index of the boundary where the tile that starts at boundary i ends (largest k with
   // bound(k) <= bound(i) + 128): one binary search per boundary, all in parallel; the plan is then a pointer chase.
+  if (!plan_tiles) {                          // sequences longer than a tile: row maps only (dense-layout attention)
+    if (tid == 0) { pk.rows[2] = 0; pk.rows[3] = 0; pk.tile_row0[0] = M; }
+    return;
+  }
   const int NB = (int)B + (M - Tp);           // boundaries 0 .. NB (bound(NB) = M)
   int* nxt = sm + B + 1;
   for (int i = tid; i < NB; i += SCAN_THREADS) {
@@ -162,7 +166,7 @@ extern "C" int srfrd_pack_plan(const int64_t* seq, const int64_t* keep, int64_t 
   const srfrd_pack_t pk = *pk_host;
   SRFRD_REQUIRE(pk.rows && pk.cnt && pk.seq_first && pk.tok_row && pk.row_tok && pk.row_ids && pk.row_info && pk.tile_row0 &&
                 pk.last_row, "pack_plan: null output");
-  SRFRD_REQUIRE(B >= 1 && L >= 1 && L + 1 <= PACK_TILE, "pack_plan: a sequence plus its pad representative must fit one 128-row tile (L=%d)", L);
+  SRFRD_REQUIRE(B >= 1 && L >= 1 && L <= 4096, "pack_plan: bad shape (B=%lld L=%d)", (long long)B, L);
   SRFRD_REQUIRE(B <= 16384, "pack_plan: at most 16384 sequences per call (B=%lld)", (long long)B);
   const int64_t need = (B * (L + 1) + PACK_TILE - 1) / PACK_TILE * PACK_TILE;
   SRFRD_REQUIRE(pk.cap >= need, "pack_plan: capacity %lld rows < %lld", (long long)pk.cap, (long long)need);
@@ -175,7 +179,7 @@ extern "C" int srfrd_pack_plan(const int64_t* seq, const int64_t* keep, int64_t 
     SRFRD_CUDA(cudaFuncSetAttribute(pack_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr = true;
   }
-  pack_scan_kernel<<<1, SCAN_THREADS, smem, stream>>>(pk, B);
+  pack_scan_kernel<<<1, SCAN_THREADS, smem, stream>>>(pk, B, L + 1 <= PACK_TILE ? 1 : 0);
   SRFRD_LAUNCH_CHECK();
   pack_fill_kernel<<<(unsigned)((B + 7) / 8), 256, 0, stream>>>(seq, keep, B, L, pk);
   SRFRD_LAUNCH_CHECK();

@@ -318,10 +318,36 @@ class HotPath:
         """Can this batch shape run on the packed token layout (csrc/pack.cu: no work on pad slots)?  Needs widths that
         are multiples of 16 (no ragged padding columns), tcgen05 attention with a whole sequence + its pad representative
         in one 128-row tile, and at most 16384 sequences per call."""
+        return self.packed_mode(B, L) is not None
+
+    def packed_mode(self, B: int, L: int) -> Optional[str]:
+        """'tile': everything incl. attention on packed rows (a sequence + its pad representative fit one 128-row tile);
+        'hybrid': row-wise kernels on packed rows, attention on the dense (B, L) layout with pack / unpack copies around it
+        (128 <= maxlen: the tile-pair kernels of attention_long.cu); None: dense layout only."""
         s = self.spec
         if s.padded or s.H % 16 or s.D % 8 or B > 16384 or B < 1:
-            return False
-        return ops.attention_packed_supported(L, s.H, s.num_heads)
+            return None
+        if ops.attention_packed_supported(L, s.H, s.num_heads):
+            return "tile"
+        if os.environ.get("SRFRD_HYBRID", "1") != "0" and L <= 4096:
+            return "hybrid"
+        return None
+
+    def _hybrid_ws(self, Td: int) -> Dict[str, torch.Tensor]:
+        """Dense-layout attention operands of the hybrid mode: q, k|v, o per block (kept for backward) + gradient scratch."""
+        hw = getattr(self, "_hws", None)
+        if hw is not None and hw["_rows"] >= Td:
+            return hw
+        s, dev = self.spec, self.device
+        Hp = s.Hp
+        hw = {"_rows": Td}
+        z = lambda w: torch.zeros(Td, w, dtype=bf16, device=dev)
+        for i in range(s.num_blocks):
+            hw[f"qd{i}"], hw[f"kvd{i}"], hw[f"od{i}"] = z(Hp), z(2 * Hp), z(Hp)
+        hw["dod"], hw["dqd"], hw["dkvd"] = z(Hp), z(Hp), z(2 * Hp)
+        self._hws = hw
+        self.ws_generation += 1
+        return hw
 
     def _plan(self, B: int, L: int) -> "ops.PackedPlan":
         key = (B, L)
@@ -548,6 +574,7 @@ class HotPath:
                                  f"number_of_labels >= {need}, got {s.n_labels}")
         aux_table = P.view(s.aux_key) if s.aux_key else None
         plan.build(seq, None if keep is None else keep.contiguous())
+        hyb = self._hybrid_ws(B * L) if self.packed_mode(B, L) == "hybrid" else None
         x = [ws[f"x{i}"][:T] for i in range(nb + 1)]
         row_ids = plan.row_ids
         fuse_ln = Hp <= 128 and os.environ.get("SRFRD_FUSE_LN", "1") != "0"
@@ -565,7 +592,14 @@ class HotPath:
                                       LN_EPS, y_bf16=Q, stats=ws[f"st1_{i}"][:T], H=H)
                 ops.gemm_tn(Q, self.sh[f"wq{i}"], out_bf16=q, bias=self.bias("bq", i))
                 self._join()
-                ops.attention_fwd_packed(q, kv[:, :Hp], kv[:, Hp:], o, plan, L, H, s.num_heads, p_drop, seed, 10 + 4 * i, step)
+                if hyb is None:
+                    ops.attention_fwd_packed(q, kv[:, :Hp], kv[:, Hp:], o, plan, L, H, s.num_heads, p_drop, seed, 10 + 4 * i, step)
+                else:       # dense-layout attention between an unpack and a pack copy
+                    qd, kvd, od = hyb[f"qd{i}"][:B * L], hyb[f"kvd{i}"][:B * L], hyb[f"od{i}"][:B * L]
+                    ops.unpack_rows([(q, qd, Hp, 0), (kv, kvd, 2 * Hp, 0)], plan)
+                    ops.attention_fwd(qd, kvd[:, :Hp], kvd[:, Hp:], od, B, L, H, s.num_heads, p_drop, seed, 10 + 4 * i, step,
+                                      stats=ws.get(f"ast{i}"))
+                    ops.pack_rows([(od, o, Hp, 0)], plan)
                 if fuse_ln:
                     ops.gemm_tn(o, self.sh[f"wo{i}"], out_bf16=r, bias=self.bias("bo", i), residual=Q, ln_out=y,
                                 ln_w=P.view(f"forward_layernorms.{i}.weight"), ln_b=P.view(f"forward_layernorms.{i}.bias"),
@@ -597,12 +631,12 @@ class HotPath:
             return out[:, :s.Dout]
         if training if save is None else save:
             self.saved = dict(seq=seq, aux_ids=aux_ids, B=B, L=L, p_drop=p_drop, seed=seed, step=step,
-                              version=self.fwd_version, plan=plan)
+                              version=self.fwd_version, plan=plan, hyb=hyb)
         return ws["hfin"][:T]
 
     def _backward_packed(self, dh: torch.Tensor) -> None:
         s, P, sv = self.spec, self.P, self.saved
-        plan = sv["plan"]
+        plan, hyb = sv["plan"], sv.get("hyb")
         B, L = sv["B"], sv["L"]
         T, H, Hp, nb = plan.cap, s.H, s.Hp, s.num_blocks
         ws = self._ws
@@ -645,8 +679,18 @@ class HotPath:
                     ops.gemm_wgrad(dr, o, GM(f"attention_layers.{i}.out_proj.weight"),
                                    G(f"attention_layers.{i}.out_proj.bias"), Mo=H, No=H)
                 ops.gemm_tn(dr, self.sh[f"woT{i}"], out_bf16=gC)
-                ops.attention_bwd_packed(gC, q, kv[:, :Hp], kv[:, Hp:], dq, dkv[:, :Hp], dkv[:, Hp:], plan, L, H, s.num_heads,
-                                         p_drop, seed, 10 + 4 * i, step)
+                if hyb is None:
+                    ops.attention_bwd_packed(gC, q, kv[:, :Hp], kv[:, Hp:], dq, dkv[:, :Hp], dkv[:, Hp:], plan, L, H,
+                                             s.num_heads, p_drop, seed, 10 + 4 * i, step)
+                else:
+                    Td = B * L
+                    qd, kvd, od = hyb[f"qd{i}"][:Td], hyb[f"kvd{i}"][:Td], hyb[f"od{i}"][:Td]
+                    dod, dqd, dkvd = hyb["dod"][:Td], hyb["dqd"][:Td], hyb["dkvd"][:Td]
+                    ops.unpack_rows([(gC, dod, Hp, 1)], plan)                  # a pad query's output is dead: dO = 0
+                    ops.attention_bwd(dod, qd, kvd[:, :Hp], kvd[:, Hp:], dqd, dkvd[:, :Hp], dkvd[:, Hp:], B, L, H, s.num_heads,
+                                      p_drop, seed, 10 + 4 * i, step, o=od, stats=ws.get(f"ast{i}"))
+                    # dk, dv of the pad representative = the sum over its sequence's pad slots (every copy of the pad key)
+                    ops.pack_rows([(dqd, dq, Hp, 0), (dkvd, dkv, 2 * Hp, 1)], plan)
                 gin = GM(f"attention_layers.{i}.in_proj_weight")
                 gbin = G(f"attention_layers.{i}.in_proj_bias")
                 with self._branch():

@@ -14,7 +14,7 @@ import torch
 from . import _lib
 from contextlib import contextmanager
 
-from ._lib import CastDesc, GemmEpilogue, PackDesc, call
+from ._lib import CastDesc, GemmEpilogue, PackDesc, RepackPart, call
 
 bf16 = torch.bfloat16
 
@@ -372,3 +372,24 @@ def dp_adam_step(grad_ptrs_dev: int, param_ptrs_dev: int, signal_ptrs_dev: int, 
     _lib.require_device()
     call("srfrd_dp_adam_step", grad_ptrs_dev, param_ptrs_dev, signal_ptrs_dev, int(rank), int(world), int(n), _p(m), _p(v),
          float(lr), float(beta1), float(beta2), float(eps), _p(state8), _p(norm2), _p(local4), _stream())
+
+
+def _parts(parts):
+    arr = (RepackPart * len(parts))()
+    for i, (src, dst, W, mode) in enumerate(parts):
+        arr[i] = RepackPart(_p(src), src.stride(0), _p(dst), dst.stride(0), int(W), int(mode))
+    return arr
+
+
+def unpack_rows(parts, plan: PackedPlan):
+    """parts: [(packed src, dense dst, columns, mode)]; mode 0: pad slots take the representative row, 1: zeros."""
+    _lib.require_device()
+    arr = _parts(parts)
+    call("srfrd_unpack_rows", arr, len(parts), C.byref(plan.desc), plan.B, plan.L, _stream())
+
+
+def pack_rows(parts, plan: PackedPlan):
+    """parts: [(dense src, packed dst, columns, mode)]; mode 0: representative rows zero, 1: sum of the dropped pad slots."""
+    _lib.require_device()
+    arr = _parts(parts)
+    call("srfrd_pack_rows", arr, len(parts), C.byref(plan.desc), plan.B, plan.L, _stream())

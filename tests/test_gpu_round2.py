@@ -358,16 +358,18 @@ def test_pack_plan_matches_host_restatement():
             assert (np.diff(t) <= 128).all() and (np.diff(t) > 0).all()
 
 
-@pytest.mark.parametrize("kind,heads,drop", [("SRFR", 1, 0.0), ("SRFRN", 1, 0.0), ("SASRec", 1, 0.0), ("SRFU_F", 1, 0.0),
-                                             ("SASRec", 2, 0.0), ("SRFR", 1, 0.5)])
-def test_packed_layout_equals_dense_layout(kind, heads, drop):
+@pytest.mark.parametrize("kind,heads,drop,L", [("SRFR", 1, 0.0, 50), ("SRFRN", 1, 0.0, 50), ("SASRec", 1, 0.0, 50),
+                                               ("SRFU_F", 1, 0.0, 50), ("SASRec", 2, 0.0, 50), ("SRFR", 1, 0.5, 50),
+                                               ("SRFR", 1, 0.0, 160), ("SASRec", 1, 0.0, 200), ("SRFR", 1, 0.5, 160)])
+def test_packed_layout_equals_dense_layout(kind, heads, drop, L):
     """The packed token layout (no rows for pad slots, one weighted pad-representative key per sequence) against the
     dense layout on the SAME kernels: loss, the hidden state of every kept token and every parameter gradient, on
     batches with empty / full rows, interior pads and loss terms on pad inputs.  Both paths compute in bf16, so they
-    agree to rounding (not bit for bit: GEMM tiles group different rows)."""
+    agree to rounding (not bit for bit: GEMM tiles group different rows).  maxlen 160 / 200 exercise the HYBRID mode
+    (row-wise kernels on packed rows, tile-pair attention on the dense layout between unpack / pack copies)."""
     from srfrd_b200 import SRFR_model as M, ops
     from srfrd_b200.trainer import FusedTrainer
-    B, L, N = 96, 50, 800
+    B, N = (96, 800) if L == 50 else (40, 800)
     torch.manual_seed(11)
     hd = 128 if heads == 2 else 64
     ctor = {"SRFR": lambda: M.SRFR(N, L, 64, 16, drop, 2, heads, "cuda"), "SRFRN": lambda: M.SRFRN(N, L, 64, 16, drop, 2, heads, "cuda"),
@@ -385,7 +387,7 @@ def test_packed_layout_equals_dense_layout(kind, heads, drop):
     for packed in (False, True):
         tr = FusedTrainer(m, use_graph=False, packed=packed)
         eng, P = tr.eng, tr.P
-        assert (not packed) or eng.packed_ok(B, L)
+        assert (not packed) or eng.packed_mode(B, L) == ("tile" if L == 50 else "hybrid")
         tr.load_batch(b, w_pos=w)
         # the body of one step up to (not including) Adam, so the gradients can be compared
         st = tr._static
