@@ -7,9 +7,11 @@ import bench
 
 def test_traffic_lookup_reads_the_committed_capture():
     t = bench.measured_traffic("srfrd_gemm_tn")
-    assert isinstance(t, int) and 10e6 < t < 200e6          # DRAM bytes per launch of the dominant kernel at C2
+    assert isinstance(t, int) and 1e6 < t < 200e6           # DRAM bytes per launch of the dominant kernel at C2 (packed rows: ~7 MB)
     assert bench.measured_traffic("srfrd_catalogue_topk") > 1e9
     assert bench.measured_traffic("no_such_kernel") is None
+    for k in ("srfrd_score_loss_fused@C3", "srfrd_embed_bwd@C3", "srfrd_adam_step@C3", "srfrd_embed_ln_fwd@C3"):
+        assert bench.measured_traffic(k) > 1e9              # catalogue-scale captures of K4 / K5 / K7 / K1
 
 
 def test_algorithmic_bytes_of_the_gemm_variants():
