@@ -166,6 +166,12 @@ def algorithmic_bytes(name, a, valid_frac, packed=None):
         if ep.ln_out_bf16:                       # fused LayerNorm: its output and (mean, rstd) are extra stores
             b += M * N * 2 + (M * 8 if ep.ln_stats else 0)
         return b, 2.0 * M * N * K
+    if name == "srfrd_mlp2_tn":                      # A, mid, out (+ LayerNorm output), two square weights; residual = A
+        M, N = rows(a[6]), a[7]
+        ep = a[8]._obj
+        b = 3 * M * N * 2 + 2 * N * N * 2 + (M * N * 2 if ep.gate else 0) + (M * N * 2 if ep.residual else 0)
+        b += (M * N * 2 + M * 8) if ep.ln_out else 0
+        return b, 4.0 * M * N * N
     if name == "srfrd_gemm_wgrad":
         T, Mo, No = rows(a[4]), a[5], a[6]
         return T * (Mo + No) * 2 + Mo * No * 4, 2.0 * T * Mo * No

@@ -305,6 +305,28 @@ SRFRD_API int srfrd_embed_bwd_packed(const void* dx0_bf16, int ldx, const int64_
                            const int* row_tok, const int* rows_dev, int64_t cap_rows, int L, int D, int F, int mode,
                            float item_scale, float* d_item, float* d_aux, float* d_pos, void* stream);
 
+/* Two chained GEMMs with square weights (N = K <= 128, multiple of 16) in ONE launch:
+ *   mid = stage1(A W1^T):  + bias1, dropout (drop1), ReLU (relu1), gate (v = gate > 0 ? v : 0)       -> mid_out (bf16)
+ *   out = stage2(mid W2^T): + bias2, dropout (drop2), + residual, * (row_ids != 0)                    -> out (bf16)
+ *   optional ln_out = LayerNorm(out) * ln_w + ln_b with ln_stats = (mean, rstd)
+ * replaces: PointWiseFeedForward's two 1x1 Conv1d (SRFR_model.py:41,44,47-51) in the forward (residual = A, the FFN input)
+ * and their data-gradient pair in the backward (gate = h1, residual = the incoming gradient), i.e. two srfrd_gemm_tn
+ * launches; the intermediate tile goes from epilogue 1 to MMA 2 through shared memory.  Honours srfrd_set_row_limit. */
+typedef struct {
+  const float* bias1; const float* bias2;     /* [N] or NULL */
+  const void* gate; int ldg;                  /* bf16 [M, ldg] or NULL */
+  int relu1;
+  float drop1_p, drop2_p; uint32_t drop1_stream, drop2_stream; uint64_t drop_seed; const float* drop_step;
+  const void* residual; int ldr;              /* bf16 [M, ldr]; NULL + residual_is_a = 1 (or == A): the A operand itself */
+  int residual_is_a;
+  const int64_t* row_ids;                     /* [M] or NULL */
+  void* mid_out; int ldm;                     /* bf16 [M, ldm] */
+  void* out; int ldc;                         /* bf16 [M, ldc] */
+  void* ln_out; int ld_ln; const float* ln_w; const float* ln_b; float* ln_stats; float ln_eps;   /* ln_out NULL = off */
+} srfrd_mlp2_t;
+SRFRD_API int srfrd_mlp2_tn(const void* A_bf16, int lda, const void* W1_bf16, int ldw1, const void* W2_bf16, int ldw2, int M, int N,
+                  const srfrd_mlp2_t* ep, void* stream);
+
 /* Packed <-> dense row movement for sequence lengths whose attention kernels work on the dense (B, L) layout
  * (128 < maxlen <= 256): the row-wise bulk of a block runs on packed rows, attention on dense tensors.
  * unpack: dense[t] = packed[tok_row[t]]; a dropped pad slot takes its sequence's pad-representative row (mode 0: q, k, v)

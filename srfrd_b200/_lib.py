@@ -27,6 +27,14 @@ class CastDesc(C.Structure):
                 ("rows", i32), ("cols", i32), ("dst_is_f32", i32)]
 
 
+class Mlp2Epilogue(C.Structure):
+    """srfrd_mlp2_t (include/srfrd_b200.h)."""
+    _fields_ = [("bias1", vp), ("bias2", vp), ("gate", vp), ("ldg", i32), ("relu1", i32), ("drop1_p", f32), ("drop2_p", f32),
+                ("drop1_stream", u32), ("drop2_stream", u32), ("drop_seed", u64), ("drop_step", vp), ("residual", vp), ("ldr", i32),
+                ("residual_is_a", i32), ("row_ids", vp), ("mid_out", vp), ("ldm", i32), ("out", vp), ("ldc", i32),
+                ("ln_out", vp), ("ld_ln", i32), ("ln_w", vp), ("ln_b", vp), ("ln_stats", vp), ("ln_eps", f32)]
+
+
 class PackDesc(C.Structure):
     """srfrd_pack_t: device buffers of the packed token layout (include/srfrd_b200.h)."""
     _fields_ = [("rows", vp), ("cnt", vp), ("seq_first", vp), ("tok_row", vp), ("row_tok", vp), ("row_ids", vp),
@@ -48,6 +56,7 @@ SIGNATURES = {
     "srfrd_layernorm_fwd": [vp, i32, vp, vp, f32, vp, vp, i32, vp, i64, i32, i64, i64, vp],
     "srfrd_layernorm_bwd": [vp, vp, i32, vp, i32, vp, vp, vp, i32, vp, vp, i32, vp, vp, i64, i32, vp],
     "srfrd_gemm_tn": [vp, i32, vp, i32, i32, i32, i32, C.POINTER(GemmEpilogue), vp],
+    "srfrd_mlp2_tn": [vp, i32, vp, i32, vp, i32, i32, i32, C.POINTER(Mlp2Epilogue), vp],
     "srfrd_gemm_tn_plan": [i32, i32, i32, i32, i32, i32, vp],
     "srfrd_gemm_debug_read": [vp],
     "srfrd_attn_debug_read": [vp],

@@ -15,6 +15,11 @@
 
 namespace srfrd {
 
+// ffn.cu: the lean one-tile-per-CTA path for small inputs (see srfrd_gemm_tn)
+bool gemm_small_eligible(int M, int N, int K, const srfrd_gemm_epilogue_t* ep, int lda, int ldb);
+int gemm_small_launch(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const srfrd_gemm_epilogue_t* ep,
+                      cudaStream_t stream);
+
 static constexpr int BLOCK_M = 128;
 static constexpr int BLOCK_K = 64;                       // 64 bf16 = one 128-byte swizzle row
 static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
@@ -804,6 +809,10 @@ extern "C" int srfrd_gemm_tn(const void* A, int lda, const void* B, int ldb, int
   SRFRD_REQUIRE(!ep->gate || ep->ldg % 8 == 0, "gemm_tn: bad ldg");
   SRFRD_REQUIRE(!(ep->residual && ep->gate), "gemm_tn: residual and gate cannot be combined (one aux operand)");
   SRFRD_REQUIRE(!ep->bias || N <= MAX_BIAS, "gemm_tn: bias with N=%d > %d unsupported", N, MAX_BIAS);
+  if (gemm_small_eligible(M, N, K, ep, lda, ldb)) {
+    SRFRD_REQUIRE(!(ep->drop_p > 0.f) || ep->drop_p < 1.f, "gemm_tn: dropout p must be < 1");
+    return gemm_small_launch(A, lda, B, ldb, M, N, K, ep, stream);
+  }
   GemmShape s;
   const void* aux = ep->residual ? ep->residual : ep->gate;
   const int ldaux = ep->residual ? ep->ldr : ep->ldg;

@@ -187,6 +187,7 @@ class HotPath:
         self.saved: Optional[dict] = None
         self._plans: Dict[Tuple[int, int], ops.PackedPlan] = {}
         self.packed_default = os.environ.get("SRFRD_PACKED", "1") != "0"
+        self.fuse_ffn = os.environ.get("SRFRD_FUSE_FFN", "1") != "0"    # FFN1 + FFN2 (and their backward pair) in one launch
 
     # ------------------------------------------------------------------ bf16 operand shadows
     def _build_shadows(self):
@@ -608,15 +609,21 @@ class HotPath:
                     ops.gemm_tn(o, self.sh[f"wo{i}"], out_bf16=r, bias=self.bias("bo", i), residual=Q)
                     ops.layernorm_fwd(r, P.view(f"forward_layernorms.{i}.weight"), P.view(f"forward_layernorms.{i}.bias"),
                                       LN_EPS, y_bf16=y, stats=ws[f"st2_{i}"][:T], H=H)
-                ops.gemm_tn(y, self.sh[f"w1{i}"], out_bf16=h1, bias=self.bias("b1", i), relu=True,
-                            drop_p=p_drop, drop_seed=seed, drop_stream=11 + 4 * i, drop_step=step)
                 nxt = {}
                 if fuse_ln and i + 1 < nb:
                     nxt = dict(ln_out=ws[f"Q{i + 1}"][:T], ln_w=P.view(f"attention_layernorms.{i + 1}.weight"),
                                ln_b=P.view(f"attention_layernorms.{i + 1}.bias"), ln_eps=LN_EPS,
                                ln_stats=ws[f"st1_{i + 1}"][:T])
-                ops.gemm_tn(h1, self.sh[f"w2{i}"], out_bf16=x[i + 1], bias=self.bias("b2", i), residual=y, row_ids=row_ids,
-                            drop_p=p_drop, drop_seed=seed, drop_stream=12 + 4 * i, drop_step=step, **nxt)
+                if self.fuse_ffn and Hp <= 128:            # FFN1 + FFN2 (+ the next LayerNorm) in one launch, h1 through smem
+                    ops.mlp2_tn(y, self.sh[f"w1{i}"], self.sh[f"w2{i}"], h1, x[i + 1], bias1=self.bias("b1", i),
+                                bias2=self.bias("b2", i), relu1=True, drop1_p=p_drop, drop2_p=p_drop, drop1_stream=11 + 4 * i,
+                                drop2_stream=12 + 4 * i, drop_seed=seed, drop_step=step, residual_is_a=True, row_ids=row_ids,
+                                **nxt)
+                else:
+                    ops.gemm_tn(y, self.sh[f"w1{i}"], out_bf16=h1, bias=self.bias("b1", i), relu=True,
+                                drop_p=p_drop, drop_seed=seed, drop_stream=11 + 4 * i, drop_step=step)
+                    ops.gemm_tn(h1, self.sh[f"w2{i}"], out_bf16=x[i + 1], bias=self.bias("b2", i), residual=y, row_ids=row_ids,
+                                drop_p=p_drop, drop_seed=seed, drop_stream=12 + 4 * i, drop_step=step, **nxt)
             fin_in = x[nb]
             if s.kind == "SRFR":
                 ops.gemm_tn(x[nb], self.sh["wc"], out_bf16=ws["c"][:T], bias=self.bias("bc"))
@@ -668,11 +675,19 @@ class HotPath:
                     ops.dropout_apply(dz, dz2, Hp, p_drop, seed, 12 + 4 * i, step)
                 with self._branch():
                     ops.gemm_wgrad(dz2, h1, GM(f"forward_layers.{i}.conv2.weight"), G(f"forward_layers.{i}.conv2.bias"), Mo=H, No=H)
-                ops.gemm_tn(dz2, self.sh[f"w2T{i}"], out_bf16=da1, gate=h1, drop_p=p_drop, drop_seed=seed,
-                            drop_stream=11 + 4 * i, drop_step=step)
-                with self._branch():
-                    ops.gemm_wgrad(da1, y, GM(f"forward_layers.{i}.conv1.weight"), G(f"forward_layers.{i}.conv1.bias"), Mo=H, No=H)
-                ops.gemm_tn(da1, self.sh[f"w1T{i}"], out_bf16=gC, residual=dz)
+                if self.fuse_ffn and Hp <= 128:            # da1 = (dz2 W2) * drop1 * (h1 > 0);  dy = da1 W1 + dz: one launch
+                    ops.mlp2_tn(dz2, self.sh[f"w2T{i}"], self.sh[f"w1T{i}"], da1, gC, gate=h1, drop1_p=p_drop,
+                                drop1_stream=11 + 4 * i, drop_seed=seed, drop_step=step, residual=dz)
+                    with self._branch():
+                        ops.gemm_wgrad(da1, y, GM(f"forward_layers.{i}.conv1.weight"), G(f"forward_layers.{i}.conv1.bias"),
+                                       Mo=H, No=H)
+                else:
+                    ops.gemm_tn(dz2, self.sh[f"w2T{i}"], out_bf16=da1, gate=h1, drop_p=p_drop, drop_seed=seed,
+                                drop_stream=11 + 4 * i, drop_step=step)
+                    with self._branch():
+                        ops.gemm_wgrad(da1, y, GM(f"forward_layers.{i}.conv1.weight"), G(f"forward_layers.{i}.conv1.bias"),
+                                       Mo=H, No=H)
+                    ops.gemm_tn(da1, self.sh[f"w1T{i}"], out_bf16=gC, residual=dz)
                 ops.layernorm_bwd(gC, r, ws[f"st2_{i}"][:T], P.view(f"forward_layernorms.{i}.weight"), dr,
                                   G(f"forward_layernorms.{i}.weight"), G(f"forward_layernorms.{i}.bias"), H=H)
                 with self._branch():

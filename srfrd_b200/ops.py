@@ -14,7 +14,7 @@ import torch
 from . import _lib
 from contextlib import contextmanager
 
-from ._lib import CastDesc, GemmEpilogue, PackDesc, RepackPart, call
+from ._lib import CastDesc, GemmEpilogue, Mlp2Epilogue, PackDesc, RepackPart, call
 
 bf16 = torch.bfloat16
 
@@ -393,3 +393,18 @@ def pack_rows(parts, plan: PackedPlan):
     _lib.require_device()
     arr = _parts(parts)
     call("srfrd_pack_rows", arr, len(parts), C.byref(plan.desc), plan.B, plan.L, _stream())
+
+
+def mlp2_tn(A, W1, W2, mid_out, out, bias1=None, bias2=None, gate=None, relu1=False, drop1_p=0.0, drop2_p=0.0, drop1_stream=0,
+            drop2_stream=0, drop_seed=0, drop_step=None, residual=None, residual_is_a=False, row_ids=None, ln_out=None,
+            ln_w=None, ln_b=None, ln_stats=None, ln_eps=0.0, M=None):
+    """out = stage2(stage1(A W1^T) W2^T) in one launch (csrc/ffn.cu); W1, W2 square (N, N) bf16, N <= 128."""
+    _lib.require_device()
+    M = A.shape[0] if M is None else M
+    N = W1.shape[0]
+    ep = Mlp2Epilogue(_p(bias1), _p(bias2), _p(gate), 0 if gate is None else gate.stride(0), int(relu1), float(drop1_p),
+                      float(drop2_p), int(drop1_stream), int(drop2_stream), int(drop_seed), _p(drop_step), _p(residual),
+                      0 if residual is None else residual.stride(0), int(residual_is_a), _p(row_ids), _p(mid_out),
+                      mid_out.stride(0), _p(out), out.stride(0), _p(ln_out), 0 if ln_out is None else ln_out.stride(0),
+                      _p(ln_w), _p(ln_b), _p(ln_stats), float(ln_eps))
+    call("srfrd_mlp2_tn", _p(A), A.stride(0), _p(W1), W1.stride(0), _p(W2), W2.stride(0), M, N, C.byref(ep), _stream())

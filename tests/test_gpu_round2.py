@@ -462,3 +462,48 @@ def test_packed_encode_last_and_fused_steps_match_dense():
         assert abs(ld - lp) < 3e-3, (i, ld, lp)
     a, c = md.flat_parameters().data, mp.flat_parameters().data
     assert float((a - c).abs().max()) < 8e-3          # six Adam steps of lr 1e-3 each
+
+
+# --------------------------------------------------------------------------------------------- fused two-GEMM kernel
+@pytest.mark.parametrize("M,N,case", [(1000, 80, "fwd"), (384, 64, "fwd_ln"), (777, 128, "fwd_drop"), (1000, 80, "bwd"),
+                                      (640, 96, "bwd_drop"), (50, 16, "fwd_ln")])
+def test_mlp2_equals_two_gemm_tn_launches(M, N, case):
+    """srfrd_mlp2_tn (FFN1 + FFN2 in one launch, the intermediate tile through shared memory) against the two
+    srfrd_gemm_tn launches it replaces, same epilogues: intermediate bit-equal, result within one bf16 ulp of rounding
+    (the second GEMM consumes the same bf16 intermediate; its fp32 accumulation order may differ), fused LayerNorm within
+    1 bf16 ulp, statistics 1e-4, dropout masks identical (same hash, same element index)."""
+    from srfrd_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(M + N)
+    bf = torch.bfloat16
+    A = (torch.randn(M, N, generator=g) * 0.7).to(bf).cuda()
+    W1 = (torch.randn(N, N, generator=g) * 0.2).to(bf).cuda()
+    W2 = (torch.randn(N, N, generator=g) * 0.2).to(bf).cuda()
+    b1, b2 = torch.randn(N, generator=g).cuda() * 0.1, torch.randn(N, generator=g).cuda() * 0.1
+    ids = (torch.rand(M, generator=g) > 0.2).long().cuda()
+    lw, lb = torch.randn(N, generator=g).cuda(), torch.randn(N, generator=g).cuda()
+    step = torch.zeros(1, device="cuda")
+    mid_r, out_r = torch.empty(M, N, dtype=bf, device="cuda"), torch.empty(M, N, dtype=bf, device="cuda")
+    mid, out = torch.empty_like(mid_r), torch.empty_like(out_r)
+    ln_r, ln = torch.empty_like(out_r), torch.empty_like(out_r)
+    st_r, st = torch.empty(M, 2, device="cuda"), torch.empty(M, 2, device="cuda")
+    p = 0.3 if "drop" in case else 0.0
+    if case.startswith("fwd"):
+        lnk = dict(ln_out=ln_r, ln_w=lw, ln_b=lb, ln_eps=1e-8, ln_stats=st_r) if case == "fwd_ln" else {}
+        ops.gemm_tn(A, W1, out_bf16=mid_r, bias=b1, relu=True, drop_p=p, drop_seed=7, drop_stream=11, drop_step=step)
+        ops.gemm_tn(mid_r, W2, out_bf16=out_r, bias=b2, residual=A, row_ids=ids, drop_p=p, drop_seed=7, drop_stream=12,
+                    drop_step=step, **lnk)
+        lnk2 = dict(ln_out=ln, ln_w=lw, ln_b=lb, ln_eps=1e-8, ln_stats=st) if case == "fwd_ln" else {}
+        ops.mlp2_tn(A, W1, W2, mid, out, bias1=b1, bias2=b2, relu1=True, drop1_p=p, drop2_p=p, drop1_stream=11, drop2_stream=12,
+                    drop_seed=7, drop_step=step, residual_is_a=True, row_ids=ids, **lnk2)
+    else:
+        gate = torch.randn(M, N, generator=g).to(bf).cuda()
+        res = A if p == 0.0 else (torch.randn(M, N, generator=g) * 0.5).to(bf).cuda()
+        ops.gemm_tn(A, W1, out_bf16=mid_r, gate=gate, drop_p=p, drop_seed=7, drop_stream=11, drop_step=step)
+        ops.gemm_tn(mid_r, W2, out_bf16=out_r, residual=res)
+        ops.mlp2_tn(A, W1, W2, mid, out, gate=gate, drop1_p=p, drop1_stream=11, drop_seed=7, drop_step=step, residual=res)
+    assert torch.equal(mid, mid_r), float((mid.float() - mid_r.float()).abs().max())
+    torch.testing.assert_close(out.float(), out_r.float(), rtol=1.6e-2, atol=1e-3)
+    assert float((out.float() - out_r.float()).abs().mean()) < 1e-3
+    if case == "fwd_ln":
+        torch.testing.assert_close(st, st_r, rtol=1e-3, atol=1e-4)
+        torch.testing.assert_close(ln.float(), ln_r.float(), rtol=1.6e-2, atol=2e-2)
