@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsrfrd_b200.so")
+# SRFRD_B200_LIB: load another build of the same ABI (A/B timing of a kernel change; never a different product path)
+LIB_PATH = os.environ.get("SRFRD_B200_LIB") or os.path.join(_HERE, "lib", "libsrfrd_b200.so")
 
 vp, i32, i64, f32, u32, u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint32, C.c_uint64
 

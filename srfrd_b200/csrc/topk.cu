@@ -18,6 +18,7 @@
 //    warp-wide OR of compare masks and re-read from TMEM one column at a time, so insertion code runs rarely.
 // n_split = 2/3 feeds hi/lo bf16 splits of the fp32 user features as extra K (near-fp32 scores).
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -43,6 +44,7 @@ struct TopkShape {
   int slots;              // tile-maxima lists per row = 2 epilogue sets x max pieces a user group is cut into
   int stages;
   int debug;              // SRFRD_TOPK_DEBUG (profiling experiments only): 1 = never insert
+  long long* trace;       // SRFRD_TOPK_TRACE (profiling only): clock64 stamps of CTA 0's work units [unit][12]
   const bf16* feats; int ld_feats;
   const bf16* table; int ld_table;
   float* out_scores;      // (U, slots, TK)  phase 1: tile maxima; phase 2 writes the row's exact top-10 into slot 0
@@ -355,6 +357,299 @@ catalogue_tilemax_kernel(const __grid_constant__ CUtensorMap tmE, TopkShape s) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Phase 1, unit form (two user tiles; item tiles of MT = (512 - 2 * a_cols) / 4 rows rounded down to 16: 112 at D = 64).
+//
+// The tile form above is bound by the SERIAL cost of its MMA issuers: per 64-item tile an issuer pays ~250 cycles of
+// barrier tests, 8 x ~80 cycles of tcgen05.mma issue and 2 x ~200 cycles of tcgen05.commit for 256 cycles of tensor work
+// (8 MMAs of 128 x 64 x 16).  Here an MMA is 128 users x MT ITEMS x 16 (same issue cost, MT / 2 tensor cycles), a work
+// unit is (one MT-item tile) x (ONE user tile), and tensor memory holds FOUR accumulator stages of MT columns.  Unit
+// q = 2 * tile + user_tile always uses stage q % 4 = user_tile + 2 * (tile parity), so the kernel is four independent
+// pipelines  stage w -> epilogue group w  (w = user_tile + 2 * tile parity) fed by one issuer warp per user tile (it
+// alternates between its two stages); they share the item tiles and the tensor pipe:
+//   * every barrier has one waiter that consumes every phase (tfull[w]: group w; tempty[w]: issuer w & 1; full[stage]: both
+//     issuers, every phase; empty[stage]: the producer);
+//   * the issuer pays ONE commit per unit: the item tile's smem stage is handed back by the epilogue (one software
+//     arrive from each of the two groups that saw the tile's accumulators complete);
+//   * a thread reads its row's MT scores as two halves of MT / 2 columns (the ranking unit: list entries are
+//     2 * tile + half, phase 2 re-scores 10 x MT / 2 items per row).
+// What bounds it (clock64 stamps of one CTA, SRFRD_TOPK_TRACE, tools/topk_trace.py): a stage's round trip -- 4 MMA
+// issues ~330 cycles, ~310 until the epilogue sees the commit, two rounds of tcgen05.ld at ~450 cycles each while the
+// tensor pipe is busy, ~180 until the issuer sees the release -- against MT / 2 * 4 = 224 cycles of tensor work per unit.
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+template <int MT, bool TRACE>
+__global__ void __launch_bounds__(640, 1)
+catalogue_unitmax_kernel(const __grid_constant__ CUtensorMap tmE, TopkShape s) {
+  constexpr int UBS = 2, NEPI = 16, NACC = 4;
+  constexpr int HALF = MT / 2;                        // ranking unit (items) = columns one thread reads per round
+  constexpr int B_TILE_BYTES = MT * KB * 2;
+  constexpr int LSTR = NEPI * 32;
+  constexpr int TR0 = 2000, TRN = 256;                // traced tiles of CTA 0
+  static_assert(MT % 16 == 0 && HALF >= 32 && HALF < 64, "unit form: MT in {64 .. 112}");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smB = smem;
+  float* lthr = reinterpret_cast<float*>(smB + s.stages * B_TILE_BYTES);      // [LSTR] current TK-th best per thread
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lthr + LSTR);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + s.stages;
+  uint64_t* tfull = bars + 2 * s.stages;              // [NACC]
+  uint64_t* tempty = tfull + NACC;                    // [NACC]
+  uint64_t* afull = tempty + NACC;
+  uint64_t* aempty = afull + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int a_cols = s.n_split * (s.D / 2);
+  const int64_t total = (int64_t)s.ugroups * s.tiles_total;
+  const int64_t lin0 = (int64_t)blockIdx.x * s.share, lin1 = min(total, lin0 + s.share);
+
+  if (warp == NEPI && lane == 0) {
+    tma_prefetch_desc(&tmE);
+    for (int i = 0; i < s.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], UBS); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    mbar_init(afull, 4 * UBS);
+    mbar_init(aempty, UBS);
+    fence_barrier_init();
+  }
+  if (warp == NEPI + 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tA = tmem_base + NACC * MT;
+
+  if (warp == NEPI) {
+    // ------------------------------------------------------------------ TMA producer (item tiles)
+    int stage = 0; uint32_t phase = 0;
+    for (int64_t lin = lin0; lin < lin1;) {
+      const int t0 = (int)(lin % s.tiles_total);
+      const int t1 = (int)min((int64_t)s.tiles_total, t0 + (lin1 - lin));
+      for (int t = t0; t < t1; ++t) {
+        for (int kb = 0; kb < s.kblocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(&full[stage], B_TILE_BYTES);
+            tma_load_2d(smB + stage * B_TILE_BYTES, &tmE, &full[stage], kb * KB, s.row_lo + t * MT, SRFRD_EVICT_NORMAL);
+          }
+          __syncwarp();
+          if (++stage == s.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+      lin += t1 - t0;
+    }
+  } else if (warp > NEPI + UBS) {
+    // spare warp: pads the block to 20 warps (the register allocation granularity), no work
+  } else if (warp > NEPI) {
+    // ------------------------------------------------------------------ MMA issuer of user tile ub: stages ub, ub + 2
+    const int ub = warp - NEPI - 1;
+    const uint32_t idesc = umma_idesc_bf16(TILE_U, MT, 0, 0);
+    const uint64_t bdesc0 = umma_smem_desc(smem_u32(smB), 0, 1024);
+    const bool fast = s.D == 64 && s.n_split == 1;
+    int stage = 0; uint32_t phase = 0, uphase = 0, aphase0 = 0, aphase1 = 0;
+    int n = 0;                                          // tiles seen by this CTA so far
+    for (int64_t lin = lin0; lin < lin1;) {
+      const int t0 = (int)(lin % s.tiles_total);
+      const int t1 = (int)min((int64_t)s.tiles_total, t0 + (lin1 - lin));
+      mbar_wait(afull, uphase);                         // user tiles of this piece are in TMEM
+      uphase ^= 1;
+      tc_fence_after();
+      for (int t = t0; t < t1; ++t, ++n) {
+        {
+          const int w = ub + 2 * (n & 1);
+          const uint32_t tacc = tmem_base + w * MT;
+          const uint32_t aphase = (n & 1) ? aphase1 : aphase0;
+          if (n & 1) aphase1 ^= 1; else aphase0 ^= 1;
+          const bool tr = TRACE && blockIdx.x == 0 && n >= TR0 && n < TR0 + TRN;
+          long long* trq = s.trace + (size_t)(2 * (n - TR0) + ub) * 12;
+          if (tr && lane == 0) trq[0] = clock64();
+          mbar_wait2(&tempty[w], aphase ^ 1, &full[stage], phase);   // both tests in flight together
+          tc_fence_after();
+          if (tr && lane == 0) trq[1] = clock64();
+          for (int kb = 0; kb < s.kblocks; ++kb) {
+            int st = stage + kb; uint32_t ph = phase;
+            if (st >= s.stages) { st -= s.stages; ph ^= 1; }
+            if (kb > 0) { mbar_wait(&full[st], ph); tc_fence_after(); }
+            const uint64_t bd = bdesc0 + (uint64_t)(st * (B_TILE_BYTES >> 4));
+            if (elect_one()) {
+              if (fast) {                                   // D == 64, one split: 4 K-steps
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  if (k == 0 || s.debug != 4) umma_bf16_ts(tacc, tA + ub * 32 + k * 8, bd + 2 * k, idesc, k != 0);
+              } else {
+                const int ksteps = min(KB / 16, (s.D - kb * KB + 15) / 16);
+                for (int sp = 0; sp < s.n_split; ++sp)
+                  for (int k = 0; k < ksteps; ++k)
+                    umma_bf16_ts(tacc, tA + ub * a_cols + sp * (s.D / 2) + (kb * (KB / 16) + k) * 8, bd + 2 * k, idesc,
+                                 (kb | sp | k) != 0);
+              }
+              if (tr) trq[2] = clock64();
+              if (kb == s.kblocks - 1) umma_commit(&tfull[w]);
+              if (tr) trq[3] = clock64();
+            }
+            __syncwarp();
+          }
+        }
+        stage += s.kblocks;
+        if (stage >= s.stages) { stage -= s.stages; phase ^= 1; }
+      }
+      if (elect_one()) umma_commit(aempty);             // this warp's MMAs of the piece are done with the user tiles
+      __syncwarp();
+      lin += t1 - t0;
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue group w = ub + 2 * (tile parity)
+    const int quarter = warp & 3, ub = (warp >> 2) % UBS, set = warp / (4 * UBS);
+    const int w = ub + 2 * set;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const uint32_t taddr = tmem_base + lane_off + w * MT;
+    float* thr_mine = lthr + warp * 32 + lane;
+    const float* thr_other = lthr + ((warp + 4 * UBS) % NEPI) * 32 + lane;   // same user row, other set
+    uint32_t uphase = 0, tphase = 0;
+    int n = 0, rstage = 0;                              // rstage: smem ring position of tile n
+    for (int64_t lin = lin0; lin < lin1;) {
+      const int ug = (int)(lin / s.tiles_total);
+      const int t0 = (int)(lin % s.tiles_total);
+      const int t1 = (int)min((int64_t)s.tiles_total, t0 + (lin1 - lin));
+      const int piece = (int)(lin / s.share - ((int64_t)ug * s.tiles_total) / s.share);
+      const int urow = (ug * UBS + ub) * TILE_U + quarter * 32 + lane;
+      if (set == 0) {
+        // ---- stage this thread's user row into tensor memory (A operand, K-major, 2 bf16 per column) ----
+        mbar_wait(aempty, uphase ^ 1);                    // previous piece's MMAs no longer read the user tiles
+        uphase ^= 1;
+        tc_fence_after();
+        for (int sp = 0; sp < s.n_split; ++sp) {
+          const uint4* src = reinterpret_cast<const uint4*>(s.feats + ((size_t)sp * s.u_pad + urow) * s.ld_feats);
+          for (int c = 0; c < s.D / 2; c += 8) {            // 8 columns = 16 features = one UMMA K step
+            uint32_t v[8];
+            uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+            if (urow < s.U) { lo = __ldg(src + c / 4); hi = __ldg(src + c / 4 + 1); }
+            v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+            tmem_st8(tA + lane_off + ub * a_cols + sp * (s.D / 2) + c, v);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(afull);
+      }
+      float ts[TK]; int ti[TK];                       // this thread's TK best (unit maximum, unit index), sorted
+#pragma unroll
+      for (int r = 0; r < TK; ++r) { ts[r] = -INFINITY; ti[r] = -1; }
+      float thr = -INFINITY;
+      *thr_mine = -INFINITY;
+      // both threads of a row start the piece together: the partner's published threshold always belongs to THIS piece
+      named_bar_sync_t(1 + ub * 4 + quarter, 64);
+      auto offer = [&](float v, int id) {               // rare after warm-up, thread-divergent
+        if (v > thr && s.debug != 1) {
+          ts[TK - 1] = v; ti[TK - 1] = id;
+#pragma unroll
+          for (int r = TK - 1; r > 0; --r) {            // strict: an equal maximum never overtakes an earlier unit
+            if (ts[r] > ts[r - 1]) {
+              const float fs = ts[r]; ts[r] = ts[r - 1]; ts[r - 1] = fs;
+              const int is = ti[r]; ti[r] = ti[r - 1]; ti[r - 1] = is;
+            }
+          }
+          thr = fmaxf(thr, ts[TK - 1]);
+          *thr_mine = thr;
+        }
+      };
+      // one half: HALF = 32 + (16) + (8) columns -> maximum; `limit` = number of columns that are real items
+      auto half_max = [&](uint32_t col, int limit) {
+        uint32_t r0[32], r1[16], r2[8];
+        tmem_ld32(taddr + col, r0);
+        if constexpr ((HALF - 32) & 16) tmem_ld16(taddr + col + 32, r1);
+        if constexpr ((HALF - 32) & 8) tmem_ld8(taddr + col + 32 + ((HALF - 32) & 16), r2);
+        tmem_ld_wait();
+        if (limit < HALF) {                             // last tile of the table: columns past row_hi are not items
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (j >= limit) r0[j] = 0xff800000u;
+          if constexpr ((HALF - 32) & 16) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (32 + j >= limit) r1[j] = 0xff800000u;
+          }
+          if constexpr ((HALF - 32) & 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (32 + ((HALF - 32) & 16) + j >= limit) r2[j] = 0xff800000u;
+          }
+        }
+        // FMNMX3: two scores folded per ALU instruction, four independent chains
+        float m[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) m[c] = fmaxf(__uint_as_float(r0[2 * c]), __uint_as_float(r0[2 * c + 1]));
+#pragma unroll
+        for (int j = 8; j < 32; j += 8) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) m[c] = fmax3(m[c], __uint_as_float(r0[j + 2 * c]), __uint_as_float(r0[j + 2 * c + 1]));
+        }
+        if constexpr ((HALF - 32) & 16) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 8) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) m[c] = fmax3(m[c], __uint_as_float(r1[j + 2 * c]), __uint_as_float(r1[j + 2 * c + 1]));
+          }
+        }
+        if constexpr ((HALF - 32) & 8) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) m[c] = fmax3(m[c], __uint_as_float(r2[2 * c]), __uint_as_float(r2[2 * c + 1]));
+        }
+        return fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
+      };
+      for (int t = t0; t < t1; ++t, ++n) {
+        const int my_stage = rstage;
+        rstage += s.kblocks;
+        if (rstage >= s.stages) rstage -= s.stages;
+        if ((n & 1) != set) continue;                     // the other set's tile
+        const float thr_p = *thr_other;
+        const bool tr = TRACE && blockIdx.x == 0 && n >= TR0 && n < TR0 + TRN && quarter == 0 && lane == 0;
+        long long* trq = s.trace + (size_t)(2 * (n - TR0) + ub) * 12;
+        if (tr) trq[4] = clock64();
+        mbar_wait(&tfull[w], tphase);
+        tphase ^= 1;
+        tc_fence_after();
+        if (tr) trq[5] = clock64();
+        if (quarter == 0 && lane == 0) {                  // this unit's MMAs no longer read the item tile
+          for (int kb = 0; kb < s.kblocks; ++kb) {
+            int st = my_stage + kb;
+            if (st >= s.stages) st -= s.stages;
+            mbar_arrive(&empty[st]);
+          }
+        }
+        const int valid = s.row_hi - (s.row_lo + t * MT);  // real items in this tile (>= MT except in the last tile)
+        const float mA = s.debug == 5 ? 0.f : half_max(0, valid);
+        if (tr) trq[6] = clock64();
+        const float mB = (s.debug == 3 || s.debug == 5) ? mA : half_max(HALF, valid - HALF);
+        tc_fence_before();                                // all MT scores read: hand the accumulator back
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[w]);
+        if (tr) trq[7] = clock64();
+        thr = fmaxf(thr, thr_p);
+        offer(mA, 2 * t);
+        offer(mB, 2 * t + 1);
+        if (tr) trq[8] = clock64();
+      }
+      if (urow < s.U) {
+        const size_t o = ((size_t)urow * s.slots + piece * 2 + set) * TK;
+#pragma unroll
+        for (int r = 0; r < TK; ++r) {
+          s.out_scores[o + r] = ts[r];
+          s.out_ids[o + r] = ti[r];
+        }
+      }
+      lin += t1 - t0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == NEPI + 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Phase 2: one warp per user row.  Merge the row's tile-maxima lists into the TK best tiles (max desc, tile asc),
 // re-score their TK x NT items with the same bf16 operands (fp32 accumulation), keep the exact top TK by
 // (score desc, id asc) and write it into slot 0 of the row's list buffer (global ids); the other slots are emptied
@@ -531,13 +826,18 @@ using namespace srfrd;
 
 // tile configuration: UBS user tiles x NT item columns x NACC accumulator stages;
 // TMEM: NACC * UBS * NT accumulator + UBS * a_cols operand columns <= 512
-struct TopkCfg { int ubs, nt, nacc; };
+struct TopkCfg { int ubs, nt, nacc, ru; };   // nt: item rows per MMA / smem tile; ru: rows per ranking unit (phase 2's "tile")
 static TopkCfg pick_cfg(int D, int n_split) {
   const int a_cols = n_split * (D / 2);
-  const TopkCfg cands[] = {{2, 64, 3}, {1, 64, 3}, {1, 64, 2}, {1, 32, 2}};
+  // unit form (catalogue_unitmax_kernel): 4 stages x MT columns + 2 user tiles x a_cols; SRFRD_TOPK_UNIT=0 keeps the
+  // tile form for A/B timing
+  static const bool unit_form = [] { const char* e = getenv("SRFRD_TOPK_UNIT"); return !(e && e[0] == '0'); }();
+  const int mt = (512 - 2 * a_cols) / 4 / 16 * 16;
+  if (unit_form && mt >= 64 && mt <= 112) return TopkCfg{2, mt, 4, mt / 2};
+  const TopkCfg cands[] = {{2, 64, 3, 64}, {1, 64, 3, 64}, {1, 64, 2, 64}, {1, 32, 2, 32}};
   for (const TopkCfg& c : cands)
     if (c.nacc * c.ubs * c.nt + c.ubs * a_cols <= 512) return c;
-  return TopkCfg{0, 0, 0};
+  return TopkCfg{0, 0, 0, 0};
 }
 
 struct TopkPlan { int ugroups, tiles_total, grid, slots; int64_t share; };
@@ -549,8 +849,9 @@ static TopkPlan make_plan(const TopkCfg& c, int64_t U, int64_t n_rows, int64_t r
   int64_t grid = num_sms();
   if (grid > total) grid = total;
   // A piece restarts its lists cold (about 10 ln(n/10) insertions per row over n tiles): never cut a user group into
-  // pieces shorter than 64 tiles just to occupy more SMs.
-  const int64_t min_share = p.tiles_total < 64 ? p.tiles_total : 64;
+  // pieces shorter than 4096 items just to occupy more SMs.
+  const int64_t min_tiles = 4096 / c.nt < 1 ? 1 : 4096 / c.nt;
+  const int64_t min_share = p.tiles_total < min_tiles ? p.tiles_total : min_tiles;
   p.share = (total + grid - 1) / grid;
   if (p.share < min_share) p.share = min_share;
   p.grid = (int)((total + p.share - 1) / p.share);
@@ -588,6 +889,25 @@ static int launch_tilemax(const CUtensorMap& tmE, TopkShape& s, int grid, cudaSt
   return 0;
 }
 
+template <int MT>
+static int launch_unitmax(const CUtensorMap& tmE, TopkShape& s, int grid, cudaStream_t stream) {
+  const int b_tile = MT * KB * 2;
+  const int unit = 2 * s.kblocks;                       // ring length: a multiple of 2 * kblocks (see kernel comment)
+  s.stages = ((216 * 1024) / b_tile) / unit * unit;
+  SRFRD_REQUIRE(s.stages >= unit, "catalogue_topk: item tile ring does not fit shared memory");
+  const size_t smem = (size_t)s.stages * b_tile + 16 * 32 * 4 + (2 * s.stages + 32) * 8 + 1024 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SRFRD_CUDA(cudaFuncSetAttribute(catalogue_unitmax_kernel<MT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SRFRD_CUDA(cudaFuncSetAttribute(catalogue_unitmax_kernel<MT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  if (s.trace) catalogue_unitmax_kernel<MT, true><<<grid, 640, smem, stream>>>(tmE, s);
+  else catalogue_unitmax_kernel<MT, false><<<grid, 640, smem, stream>>>(tmE, s);
+  SRFRD_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int srfrd_catalogue_topk(const void* feats_bf16, int64_t U, int64_t u_pad, int n_split, const void* table_bf16,
                                     int64_t n_rows, int64_t row_lo, int64_t id_base, int D, int ld_feats, int ld_table,
                                     int chunks, float* part_scores, int* part_ids, float* packed_out, void* stream_) {
@@ -607,22 +927,45 @@ extern "C" int srfrd_catalogue_topk(const void* feats_bf16, int64_t U, int64_t u
   s.U = (int)U; s.D = D; s.n_split = n_split; s.u_pad = (int)u_pad;
   s.row_lo = (int)row_lo; s.row_hi = (int)n_rows; s.id_base = id_base;
   s.kblocks = (D + KB - 1) / KB;
-  s.nt = c.nt;
+  s.nt = c.ru;
   s.tiles_total = pl.tiles_total; s.ugroups = pl.ugroups; s.share = pl.share; s.slots = pl.slots;
   s.feats = (const bf16*)feats_bf16; s.ld_feats = ld_feats;
   s.table = (const bf16*)table_bf16; s.ld_table = ld_table;
   s.out_scores = part_scores; s.out_ids = part_ids; s.packed = packed_out;
   { const char* dbg = getenv("SRFRD_TOPK_DEBUG"); s.debug = dbg ? atoi(dbg) : 0; }
+  s.trace = nullptr;
+  const char* trace_path = getenv("SRFRD_TOPK_TRACE");
+  const size_t trace_bytes = 512 * 12 * sizeof(long long);
+  if (trace_path) {
+    SRFRD_CUDA(cudaMalloc(&s.trace, trace_bytes));
+    SRFRD_CUDA(cudaMemsetAsync(s.trace, 0, trace_bytes, stream));
+  }
   // list slots a user group does not use stay empty (index -1)
   SRFRD_CUDA(cudaMemsetAsync(part_ids, 0xFF, (size_t)U * pl.slots * TK * sizeof(int), stream));
   CUtensorMap tmE;
   if (int rc = make_tmap_bf16_2d(&tmE, table_bf16, n_rows, D, ld_table, c.nt, KB)) return rc;
   int rc;
-  if (c.ubs == 2 && c.nt == 64 && c.nacc == 3) rc = launch_tilemax<2, 64, 3>(tmE, s, pl.grid, stream);
+  if (c.nacc == 4 && c.nt == 112) rc = launch_unitmax<112>(tmE, s, pl.grid, stream);
+  else if (c.nacc == 4 && c.nt == 96) rc = launch_unitmax<96>(tmE, s, pl.grid, stream);
+  else if (c.nacc == 4 && c.nt == 80) rc = launch_unitmax<80>(tmE, s, pl.grid, stream);
+  else if (c.nacc == 4 && c.nt == 64) rc = launch_unitmax<64>(tmE, s, pl.grid, stream);
+  else if (c.ubs == 2 && c.nt == 64 && c.nacc == 3) rc = launch_tilemax<2, 64, 3>(tmE, s, pl.grid, stream);
   else if (c.ubs == 1 && c.nt == 64 && c.nacc == 3) rc = launch_tilemax<1, 64, 3>(tmE, s, pl.grid, stream);
   else if (c.ubs == 1 && c.nt == 64 && c.nacc == 2) rc = launch_tilemax<1, 64, 2>(tmE, s, pl.grid, stream);
   else rc = launch_tilemax<1, 32, 2>(tmE, s, pl.grid, stream);
   if (rc) return rc;
+  if (trace_path) {                                     // profiling only: synchronous dump of CTA 0's stamps
+    static long long host_trace[512 * 12];
+    SRFRD_CUDA(cudaMemcpyAsync(host_trace, s.trace, trace_bytes, cudaMemcpyDeviceToHost, stream));
+    SRFRD_CUDA(cudaStreamSynchronize(stream));
+    SRFRD_CUDA(cudaFree(s.trace));
+    if (FILE* f = fopen(trace_path, "w")) {
+      for (int q = 0; q < 512; ++q) {
+        for (int j = 0; j < 12; ++j) fprintf(f, "%lld%c", host_trace[q * 12 + j], j == 11 ? '\n' : ' ');
+      }
+      fclose(f);
+    }
+  }
   if (s.debug == 2) return 0;                           // profiling: phase 1 only
   catalogue_refine_kernel<<<(unsigned)((U + 7) / 8), 256, 0, stream>>>(s);
   SRFRD_LAUNCH_CHECK();
