@@ -359,22 +359,31 @@ catalogue_tilemax_kernel(const __grid_constant__ CUtensorMap tmE, TopkShape s) {
 // ---------------------------------------------------------------------------------------------------------------
 // Phase 1, unit form (two user tiles; item tiles of MT = (512 - 2 * a_cols) / 4 rows rounded down to 16: 112 at D = 64).
 //
-// The tile form above is bound by the SERIAL cost of its MMA issuers: per 64-item tile an issuer pays ~250 cycles of
-// barrier tests, 8 x ~80 cycles of tcgen05.mma issue and 2 x ~200 cycles of tcgen05.commit for 256 cycles of tensor work
-// (8 MMAs of 128 x 64 x 16).  Here an MMA is 128 users x MT ITEMS x 16 (same issue cost, MT / 2 tensor cycles), a work
-// unit is (one MT-item tile) x (ONE user tile), and tensor memory holds FOUR accumulator stages of MT columns.  Unit
-// q = 2 * tile + user_tile always uses stage q % 4 = user_tile + 2 * (tile parity), so the kernel is four independent
-// pipelines  stage w -> epilogue group w  (w = user_tile + 2 * tile parity) fed by one issuer warp per user tile (it
-// alternates between its two stages); they share the item tiles and the tensor pipe:
-//   * every barrier has one waiter that consumes every phase (tfull[w]: group w; tempty[w]: issuer w & 1; full[stage]: both
-//     issuers, every phase; empty[stage]: the producer);
-//   * the issuer pays ONE commit per unit: the item tile's smem stage is handed back by the epilogue (one software
-//     arrive from each of the two groups that saw the tile's accumulators complete);
-//   * a thread reads its row's MT scores as two halves of MT / 2 columns (the ranking unit: list entries are
-//     2 * tile + half, phase 2 re-scores 10 x MT / 2 items per row).
-// What bounds it (clock64 stamps of one CTA, SRFRD_TOPK_TRACE, tools/topk_trace.py): a stage's round trip -- 4 MMA
-// issues ~330 cycles, ~310 until the epilogue sees the commit, two rounds of tcgen05.ld at ~450 cycles each while the
-// tensor pipe is busy, ~180 until the issuer sees the release -- against MT / 2 * 4 = 224 cycles of tensor work per unit.
+// Tensor memory holds 448 accumulator columns = 896 cycles of tensor work, so the pipe's share is bounded by
+// 896 / (one accumulator round trip): release -> issuer sees it ~200 cycles, four tcgen05.mma issues ~330, commit ->
+// epilogue sees it ~350, every round of tcgen05.ld ~330 while the tensor pipe is busy.  The tile form above adds the
+// SERIAL cost of issuers that each serve several stages.  Here (clock64 stamps of one CTA: SRFRD_TOPK_TRACE,
+// tools/topk_trace.py):
+//   * an MMA is 128 users x MT ITEMS x 16; a work unit is (one MT-item tile) x (ONE user tile); unit q = 2 * tile +
+//     user_tile uses accumulator stage w = user_tile + 2 * (tile parity).  ONE ISSUER WARP PER STAGE: an issuer that
+//     alternates between two stages in order holds the ready one back behind the late one (measured +8 %).
+//   * a unit is read by EIGHT epilogue warps in ONE round of tcgen05.ld: per lane quarter one warp takes columns
+//     [0, MT / 2) and one [MT / 2, MT) (56 registers each), and the accumulator goes back after that single round (with four
+//     warps reading two rounds the round trip was ~1 900 cycles).  The eight warps of user tile ub serve all of its units,
+//     alternating between its two stages; a thread is one (user row, column half) and keeps that half's running list:
+//     the ranking unit is a half (list entries are 2 * tile + half, phase 2 re-scores 10 x MT / 2 items per row).
+//   * no producer warp (a block is 16 epilogue + 4 control warps = 5 per scheduler, the most that leaves 96 registers a
+//     thread): passing tempty[w] for tile n tells issuer w that ITS MMAs on tile n - 2 are complete; the second of the
+//     two issuers of a tile parity to get there (shared-memory counter) re-fills that tile's ring slot, after its own
+//     MMAs for tile n are issued.  (The same hand-over done by epilogue threads cost ~550 cycles on the accumulator's
+//     critical path.)
+//   * every barrier has one waiter group that consumes every phase (tfull[w]: the warps of user tile w & 1;
+//     tempty[w]: issuer w; full[slot]: the two issuers of the slot's parity -- the ring length is even).
+//   * per-thread lists stay in REGISTERS and are offered to after the release: with the lists in shared memory, or with
+//     the offer placed under the next load's latency, the rare insertion (a warp takes it when any of its 32 rows
+//     inserts) delayed the release and cost 0.7 ms instead of 0.1 ms at 1 M items.
+//   * measured and rejected: MMAs of MT / 2 columns with a barrier pair per half (eight round trips in flight): twice the
+//     commits and barrier tests, 2.77 ms against 2.18 ms.
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -382,11 +391,11 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                : "memory");
 }
 
-template <int MT, bool TRACE>
-__global__ void __launch_bounds__(640, 1)
+template <int MT, bool TRACE, bool WIDE>
+__global__ void __launch_bounds__(WIDE ? 384 : 640, 1)
 catalogue_unitmax_kernel(const __grid_constant__ CUtensorMap tmE, TopkShape s) {
-  constexpr int UBS = 2, NEPI = 16, NACC = 4;
-  constexpr int HALF = MT / 2;                        // ranking unit (items) = columns one thread reads per round
+  constexpr int UBS = 2, NEPI = WIDE ? 8 : 16, NACC = 4;
+  constexpr int HALF = MT / 2;                        // ranking unit (items) = columns one thread reads
   constexpr int B_TILE_BYTES = MT * KB * 2;
   constexpr int LSTR = NEPI * 32;
   constexpr int TR0 = 2000, TRN = 256;                // traced tiles of CTA 0
@@ -397,12 +406,13 @@ catalogue_unitmax_kernel(const __grid_constant__ CUtensorMap tmE, TopkShape s) {
   float* lthr = reinterpret_cast<float*>(smB + s.stages * B_TILE_BYTES);      // [LSTR] current TK-th best per thread
   uint64_t* bars = reinterpret_cast<uint64_t*>(lthr + LSTR);
   uint64_t* full = bars;
-  uint64_t* empty = bars + s.stages;
+  int* rcnt = reinterpret_cast<int*>(bars + s.stages); // [stages] issuers done with the slot's tile (0..2)
   uint64_t* tfull = bars + 2 * s.stages;              // [NACC]
   uint64_t* tempty = tfull + NACC;                    // [NACC]
   uint64_t* afull = tempty + NACC;
   uint64_t* aempty = afull + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 1);
+  const int ring_tiles = s.stages / s.kblocks;        // item tiles the ring holds
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int a_cols = s.n_split * (s.D / 2);
@@ -411,10 +421,10 @@ catalogue_unitmax_kernel(const __grid_constant__ CUtensorMap tmE, TopkShape s) {
 
   if (warp == NEPI && lane == 0) {
     tma_prefetch_desc(&tmE);
-    for (int i = 0; i < s.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], UBS); }
-    for (int i = 0; i < NACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < s.stages; ++i) { mbar_init(&full[i], 1); rcnt[i] = 0; }
+    for (int i = 0; i < NACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], WIDE ? 4 : 8); }
     mbar_init(afull, 4 * UBS);
-    mbar_init(aempty, UBS);
+    mbar_init(aempty, NACC);
     fence_barrier_init();
   }
   if (warp == NEPI + 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -424,35 +434,28 @@ catalogue_unitmax_kernel(const __grid_constant__ CUtensorMap tmE, TopkShape s) {
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tA = tmem_base + NACC * MT;
 
-  if (warp == NEPI) {
-    // ------------------------------------------------------------------ TMA producer (item tiles)
-    int stage = 0; uint32_t phase = 0;
-    for (int64_t lin = lin0; lin < lin1;) {
-      const int t0 = (int)(lin % s.tiles_total);
-      const int t1 = (int)min((int64_t)s.tiles_total, t0 + (lin1 - lin));
-      for (int t = t0; t < t1; ++t) {
+  if (warp >= NEPI) {
+    // ------------------------------------------------------------------ MMA issuer of stage w = user tile + 2 * tile parity
+    const int w = warp - NEPI, ub = w & 1, par = w >> 1;
+    if (w == 0 && elect_one()) {                        // fill the ring; afterwards the issuers refill a slot as it frees
+      for (int64_t m = 0; m < ring_tiles && lin0 + m < lin1; ++m) {
+        const int t = (int)((lin0 + m) % s.tiles_total);
+        const int st0 = (int)(m * s.kblocks);
         for (int kb = 0; kb < s.kblocks; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          if (elect_one()) {
-            mbar_expect_tx(&full[stage], B_TILE_BYTES);
-            tma_load_2d(smB + stage * B_TILE_BYTES, &tmE, &full[stage], kb * KB, s.row_lo + t * MT, SRFRD_EVICT_NORMAL);
-          }
-          __syncwarp();
-          if (++stage == s.stages) { stage = 0; phase ^= 1; }
+          mbar_expect_tx(&full[st0 + kb], B_TILE_BYTES);
+          tma_load_2d(smB + (st0 + kb) * B_TILE_BYTES, &tmE, &full[st0 + kb], kb * KB, s.row_lo + t * MT, SRFRD_EVICT_NORMAL);
         }
       }
-      lin += t1 - t0;
     }
-  } else if (warp > NEPI + UBS) {
-    // spare warp: pads the block to 20 warps (the register allocation granularity), no work
-  } else if (warp > NEPI) {
-    // ------------------------------------------------------------------ MMA issuer of user tile ub: stages ub, ub + 2
-    const int ub = warp - NEPI - 1;
+    __syncwarp();
     const uint32_t idesc = umma_idesc_bf16(TILE_U, MT, 0, 0);
     const uint64_t bdesc0 = umma_smem_desc(smem_u32(smB), 0, 1024);
     const bool fast = s.D == 64 && s.n_split == 1;
-    int stage = 0; uint32_t phase = 0, uphase = 0, aphase0 = 0, aphase1 = 0;
+    const uint32_t tacc = tmem_base + w * MT;
+    int stage = 0; uint32_t phase = 0, uphase = 0, aphase = 0;
     int n = 0;                                          // tiles seen by this CTA so far
+    const int ntiles = (int)(lin1 - lin0);
+    int rt = (int)((lin0 + ring_tiles - 2) % s.tiles_total);   // table tile that follows tile n - 2 in its ring slot
     for (int64_t lin = lin0; lin < lin1;) {
       const int t0 = (int)(lin % s.tiles_total);
       const int t1 = (int)min((int64_t)s.tiles_total, t0 + (lin1 - lin));
@@ -460,15 +463,14 @@ catalogue_unitmax_kernel(const __grid_constant__ CUtensorMap tmE, TopkShape s) {
       uphase ^= 1;
       tc_fence_after();
       for (int t = t0; t < t1; ++t, ++n) {
-        {
-          const int w = ub + 2 * (n & 1);
-          const uint32_t tacc = tmem_base + w * MT;
-          const uint32_t aphase = (n & 1) ? aphase1 : aphase0;
-          if (n & 1) aphase1 ^= 1; else aphase0 ^= 1;
+        const int rt_now = rt;
+        if (++rt == s.tiles_total) rt = 0;
+        if ((n & 1) == par) {
           const bool tr = TRACE && blockIdx.x == 0 && n >= TR0 && n < TR0 + TRN;
           long long* trq = s.trace + (size_t)(2 * (n - TR0) + ub) * 12;
           if (tr && lane == 0) trq[0] = clock64();
           mbar_wait2(&tempty[w], aphase ^ 1, &full[stage], phase);   // both tests in flight together
+          aphase ^= 1;
           tc_fence_after();
           if (tr && lane == 0) trq[1] = clock64();
           for (int kb = 0; kb < s.kblocks; ++kb) {
@@ -494,6 +496,19 @@ catalogue_unitmax_kernel(const __grid_constant__ CUtensorMap tmE, TopkShape s) {
             }
             __syncwarp();
           }
+          if (n >= 2 && n - 2 + ring_tiles < ntiles && elect_one()) {
+            int ps = stage - 2 * s.kblocks;
+            if (ps < 0) ps += s.stages;
+            if (atomicAdd(&rcnt[ps], 1) == 1) {
+              rcnt[ps] = 0;
+              __threadfence_block();
+              for (int kb = 0; kb < s.kblocks; ++kb) {
+                mbar_expect_tx(&full[ps + kb], B_TILE_BYTES);
+                tma_load_2d(smB + (ps + kb) * B_TILE_BYTES, &tmE, &full[ps + kb], kb * KB, s.row_lo + rt_now * MT, SRFRD_EVICT_NORMAL);
+              }
+            }
+          }
+          __syncwarp();
         }
         stage += s.kblocks;
         if (stage >= s.stages) { stage -= s.stages; phase ^= 1; }
@@ -502,23 +517,22 @@ catalogue_unitmax_kernel(const __grid_constant__ CUtensorMap tmE, TopkShape s) {
       __syncwarp();
       lin += t1 - t0;
     }
-  } else {
-    // ------------------------------------------------------------------ epilogue group w = ub + 2 * (tile parity)
-    const int quarter = warp & 3, ub = (warp >> 2) % UBS, set = warp / (4 * UBS);
-    const int w = ub + 2 * set;
+  } else if constexpr (!WIDE) {
+    // ------------------------------------------------------------------ epilogue: warp = (user tile, column half, lane quarter)
+    const int quarter = warp & 3, ch = (warp >> 2) & 1, ub = warp >> 3;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const uint32_t taddr = tmem_base + lane_off + w * MT;
+    const uint32_t taddr0 = tmem_base + lane_off + ub * MT + ch * HALF;      // stage ub (even tiles); + 2 * MT: odd tiles
     float* thr_mine = lthr + warp * 32 + lane;
-    const float* thr_other = lthr + ((warp + 4 * UBS) % NEPI) * 32 + lane;   // same user row, other set
-    uint32_t uphase = 0, tphase = 0;
-    int n = 0, rstage = 0;                              // rstage: smem ring position of tile n
+    const float* thr_other = lthr + (warp ^ 4) * 32 + lane;                  // same user row, other column half
+    uint32_t uphase = 0, tph0 = 0, tph1 = 0;
+    int n = 0;
     for (int64_t lin = lin0; lin < lin1;) {
       const int ug = (int)(lin / s.tiles_total);
       const int t0 = (int)(lin % s.tiles_total);
       const int t1 = (int)min((int64_t)s.tiles_total, t0 + (lin1 - lin));
       const int piece = (int)(lin / s.share - ((int64_t)ug * s.tiles_total) / s.share);
       const int urow = (ug * UBS + ub) * TILE_U + quarter * 32 + lane;
-      if (set == 0) {
+      if (ch == 0) {
         // ---- stage this thread's user row into tensor memory (A operand, K-major, 2 bf16 per column) ----
         mbar_wait(aempty, uphase ^ 1);                    // previous piece's MMAs no longer read the user tiles
         uphase ^= 1;
@@ -545,6 +559,132 @@ catalogue_unitmax_kernel(const __grid_constant__ CUtensorMap tmE, TopkShape s) {
       *thr_mine = -INFINITY;
       // both threads of a row start the piece together: the partner's published threshold always belongs to THIS piece
       named_bar_sync_t(1 + ub * 4 + quarter, 64);
+      for (int t = t0; t < t1; ++t, ++n) {
+        const int odd = n & 1, w = ub + 2 * odd;
+        const float thr_p = *thr_other;
+        const bool tr = TRACE && blockIdx.x == 0 && n >= TR0 && n < TR0 + TRN && quarter == 0 && lane == 0 && ch == 0;
+        long long* trq = s.trace + (size_t)(2 * (n - TR0) + ub) * 12;
+        if (tr) trq[4] = clock64();
+        mbar_wait(&tfull[w], odd ? tph1 : tph0);
+        if (odd) tph1 ^= 1; else tph0 ^= 1;
+        tc_fence_after();
+        if (tr) trq[5] = clock64();
+        const int limit = s.row_hi - (s.row_lo + t * MT) - ch * HALF;   // real items among this thread's columns
+        float tmax = 0.f;
+        if (s.debug == 5) {                               // ablation: hand the accumulator back unread
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[w]);
+        } else {
+          const uint32_t taddr = taddr0 + odd * (2 * MT);
+          uint32_t r0[32], r1[16], r2[8];
+          tmem_ld32(taddr, r0);
+          if constexpr ((HALF - 32) & 16) tmem_ld16(taddr + 32, r1);
+          if constexpr ((HALF - 32) & 8) tmem_ld8(taddr + 32 + ((HALF - 32) & 16), r2);
+          tmem_ld_wait();
+          tc_fence_before();                              // scores are in registers: hand the accumulator back now
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[w]);
+          if (tr) trq[6] = clock64();
+          if (limit < HALF) {                             // last tile of the table: columns past row_hi are not items
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j >= limit) r0[j] = 0xff800000u;
+            if constexpr ((HALF - 32) & 16) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) if (32 + j >= limit) r1[j] = 0xff800000u;
+            }
+            if constexpr ((HALF - 32) & 8) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) if (32 + ((HALF - 32) & 16) + j >= limit) r2[j] = 0xff800000u;
+            }
+          }
+          // FMNMX3: two scores folded per ALU instruction, four independent chains
+          float m[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) m[c] = fmaxf(__uint_as_float(r0[2 * c]), __uint_as_float(r0[2 * c + 1]));
+#pragma unroll
+          for (int j = 8; j < 32; j += 8) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) m[c] = fmax3(m[c], __uint_as_float(r0[j + 2 * c]), __uint_as_float(r0[j + 2 * c + 1]));
+          }
+          if constexpr ((HALF - 32) & 16) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 8) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) m[c] = fmax3(m[c], __uint_as_float(r1[j + 2 * c]), __uint_as_float(r1[j + 2 * c + 1]));
+            }
+          }
+          if constexpr ((HALF - 32) & 8) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) m[c] = fmax3(m[c], __uint_as_float(r2[2 * c]), __uint_as_float(r2[2 * c + 1]));
+          }
+          tmax = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
+        }
+        if (tr) trq[7] = clock64();
+        thr = fmaxf(thr, thr_p);
+        if (tmax > thr && s.debug != 1) {                 // rare after warm-up, thread-divergent
+          ts[TK - 1] = tmax; ti[TK - 1] = 2 * t + ch;
+#pragma unroll
+          for (int r = TK - 1; r > 0; --r) {              // strict: an equal maximum never overtakes an earlier unit
+            if (ts[r] > ts[r - 1]) {
+              const float fs = ts[r]; ts[r] = ts[r - 1]; ts[r - 1] = fs;
+              const int is = ti[r]; ti[r] = ti[r - 1]; ti[r - 1] = is;
+            }
+          }
+          thr = fmaxf(thr, ts[TK - 1]);
+          *thr_mine = thr;
+        }
+        if (tr) trq[8] = clock64();
+      }
+      if (urow < s.U) {
+        const size_t o = ((size_t)urow * s.slots + piece * 2 + ch) * TK;
+#pragma unroll
+        for (int r = 0; r < TK; ++r) {
+          s.out_scores[o + r] = ts[r];
+          s.out_ids[o + r] = ti[r];
+        }
+      }
+      lin += t1 - t0;
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue, wide form: warp = (user tile, lane quarter)
+    // 12 warps a block -> 168 registers a thread: a thread reads its row's whole MT scores in ONE round of tcgen05.ld
+    // (MT registers), so a unit is one barrier test + one load round for FOUR warps.
+    const int quarter = warp & 3, ub = warp >> 2;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const uint32_t taddr0 = tmem_base + lane_off + ub * MT;                  // stage ub (even tiles); + 2 * MT: odd tiles
+    uint32_t uphase = 0, tph0 = 0, tph1 = 0;
+    int n = 0;
+    for (int64_t lin = lin0; lin < lin1;) {
+      const int ug = (int)(lin / s.tiles_total);
+      const int t0 = (int)(lin % s.tiles_total);
+      const int t1 = (int)min((int64_t)s.tiles_total, t0 + (lin1 - lin));
+      const int piece = (int)(lin / s.share - ((int64_t)ug * s.tiles_total) / s.share);
+      const int urow = (ug * UBS + ub) * TILE_U + quarter * 32 + lane;
+      {
+        // ---- stage this thread's user row into tensor memory (A operand, K-major, 2 bf16 per column) ----
+        mbar_wait(aempty, uphase ^ 1);                    // previous piece's MMAs no longer read the user tiles
+        uphase ^= 1;
+        tc_fence_after();
+        for (int sp = 0; sp < s.n_split; ++sp) {
+          const uint4* src = reinterpret_cast<const uint4*>(s.feats + ((size_t)sp * s.u_pad + urow) * s.ld_feats);
+          for (int c = 0; c < s.D / 2; c += 8) {            // 8 columns = 16 features = one UMMA K step
+            uint32_t v[8];
+            uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+            if (urow < s.U) { lo = __ldg(src + c / 4); hi = __ldg(src + c / 4 + 1); }
+            v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+            tmem_st8(tA + lane_off + ub * a_cols + sp * (s.D / 2) + c, v);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(afull);
+      }
+      float ts[TK]; int ti[TK];                       // this row's TK best (unit maximum, unit index), sorted
+#pragma unroll
+      for (int r = 0; r < TK; ++r) { ts[r] = -INFINITY; ti[r] = -1; }
+      float thr = -INFINITY;
       auto offer = [&](float v, int id) {               // rare after warm-up, thread-divergent
         if (v > thr && s.debug != 1) {
           ts[TK - 1] = v; ti[TK - 1] = id;
@@ -555,17 +695,10 @@ catalogue_unitmax_kernel(const __grid_constant__ CUtensorMap tmE, TopkShape s) {
               const int is = ti[r]; ti[r] = ti[r - 1]; ti[r - 1] = is;
             }
           }
-          thr = fmaxf(thr, ts[TK - 1]);
-          *thr_mine = thr;
+          thr = ts[TK - 1];
         }
       };
-      // one half: HALF = 32 + (16) + (8) columns -> maximum; `limit` = number of columns that are real items
-      auto half_max = [&](uint32_t col, int limit) {
-        uint32_t r0[32], r1[16], r2[8];
-        tmem_ld32(taddr + col, r0);
-        if constexpr ((HALF - 32) & 16) tmem_ld16(taddr + col + 32, r1);
-        if constexpr ((HALF - 32) & 8) tmem_ld8(taddr + col + 32 + ((HALF - 32) & 16), r2);
-        tmem_ld_wait();
+      auto reduce_half = [&](uint32_t (&r0)[32], uint32_t (&r1)[16], uint32_t (&r2)[8], int limit) {
         if (limit < HALF) {                             // last tile of the table: columns past row_hi are not items
 #pragma unroll
           for (int j = 0; j < 32; ++j) if (j >= limit) r0[j] = 0xff800000u;
@@ -578,8 +711,7 @@ catalogue_unitmax_kernel(const __grid_constant__ CUtensorMap tmE, TopkShape s) {
             for (int j = 0; j < 8; ++j) if (32 + ((HALF - 32) & 16) + j >= limit) r2[j] = 0xff800000u;
           }
         }
-        // FMNMX3: two scores folded per ALU instruction, four independent chains
-        float m[4];
+        float m[4];                                     // FMNMX3: two scores folded per ALU instruction, four chains
 #pragma unroll
         for (int c = 0; c < 4; ++c) m[c] = fmaxf(__uint_as_float(r0[2 * c]), __uint_as_float(r0[2 * c + 1]));
 #pragma unroll
@@ -601,40 +733,44 @@ catalogue_unitmax_kernel(const __grid_constant__ CUtensorMap tmE, TopkShape s) {
         return fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
       };
       for (int t = t0; t < t1; ++t, ++n) {
-        const int my_stage = rstage;
-        rstage += s.kblocks;
-        if (rstage >= s.stages) rstage -= s.stages;
-        if ((n & 1) != set) continue;                     // the other set's tile
-        const float thr_p = *thr_other;
+        const int odd = n & 1, w = ub + 2 * odd;
         const bool tr = TRACE && blockIdx.x == 0 && n >= TR0 && n < TR0 + TRN && quarter == 0 && lane == 0;
         long long* trq = s.trace + (size_t)(2 * (n - TR0) + ub) * 12;
         if (tr) trq[4] = clock64();
-        mbar_wait(&tfull[w], tphase);
-        tphase ^= 1;
+        mbar_wait(&tfull[w], odd ? tph1 : tph0);
+        if (odd) tph1 ^= 1; else tph0 ^= 1;
         tc_fence_after();
         if (tr) trq[5] = clock64();
-        if (quarter == 0 && lane == 0) {                  // this unit's MMAs no longer read the item tile
-          for (int kb = 0; kb < s.kblocks; ++kb) {
-            int st = my_stage + kb;
-            if (st >= s.stages) st -= s.stages;
-            mbar_arrive(&empty[st]);
-          }
+        const int valid = s.row_hi - (s.row_lo + t * MT);   // real items in this tile (>= MT except in the last tile)
+        float mA = 0.f, mB = 0.f;
+        if (s.debug == 5) {                               // ablation: hand the accumulator back unread
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[w]);
+        } else {
+          const uint32_t taddr = taddr0 + odd * (2 * MT);
+          uint32_t a0[32], a1[16], a2[8], b0[32], b1[16], b2[8];
+          tmem_ld32(taddr, a0);
+          if constexpr ((HALF - 32) & 16) tmem_ld16(taddr + 32, a1);
+          if constexpr ((HALF - 32) & 8) tmem_ld8(taddr + 32 + ((HALF - 32) & 16), a2);
+          tmem_ld32(taddr + HALF, b0);
+          if constexpr ((HALF - 32) & 16) tmem_ld16(taddr + HALF + 32, b1);
+          if constexpr ((HALF - 32) & 8) tmem_ld8(taddr + HALF + 32 + ((HALF - 32) & 16), b2);
+          tmem_ld_wait();
+          tc_fence_before();                              // scores are in registers: hand the accumulator back now
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[w]);
+          if (tr) trq[6] = clock64();
+          mA = reduce_half(a0, a1, a2, valid);
+          mB = reduce_half(b0, b1, b2, valid - HALF);
         }
-        const int valid = s.row_hi - (s.row_lo + t * MT);  // real items in this tile (>= MT except in the last tile)
-        const float mA = s.debug == 5 ? 0.f : half_max(0, valid);
-        if (tr) trq[6] = clock64();
-        const float mB = (s.debug == 3 || s.debug == 5) ? mA : half_max(HALF, valid - HALF);
-        tc_fence_before();                                // all MT scores read: hand the accumulator back
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[w]);
         if (tr) trq[7] = clock64();
-        thr = fmaxf(thr, thr_p);
         offer(mA, 2 * t);
         offer(mB, 2 * t + 1);
         if (tr) trq[8] = clock64();
       }
       if (urow < s.U) {
-        const size_t o = ((size_t)urow * s.slots + piece * 2 + set) * TK;
+        const size_t o = ((size_t)urow * s.slots + piece * 2) * TK;     // the piece's second list slot stays empty
 #pragma unroll
         for (int r = 0; r < TK; ++r) {
           s.out_scores[o + r] = ts[r];
@@ -753,6 +889,182 @@ __global__ void __launch_bounds__(256) catalogue_refine_kernel(TopkShape s) {
 #pragma unroll
       for (int k = 0; k < TK - 1; ++k) { ts[k] = ts[k + 1]; ti[k] = ti[k + 1]; }
       ts[TK - 1] = -INFINITY; ti[TK - 1] = -1;
+    }
+  }
+}
+
+// Phase 2, fast form (D = 64, one split, table rows contiguous): same contract as catalogue_refine_kernel.
+//   * A ranking unit is RU CONSECUTIVE table rows = RU * 128 contiguous bytes, so the warp reads it as RU / 4 fully
+//     coalesced 512-byte requests (lane l, request i -> 16-byte piece i * 32 + l = row i * 4 + l / 8, features
+//     8 (l % 8) .. + 8): every lane only ever needs ITS eighth of the user's features (4 registers), all RU / 4 loads of
+//     a unit are in flight before the first is used, and a row's score is an 8-lane butterfly of 8-term partial sums.
+//     The general kernel above walks one row per lane with two loads in flight (0.44 ms at 16 384 users: as long as
+//     the whole streaming phase of a 125 k-row shard).
+//   * Lane (l & ~7) + (i & 7) keeps row i * 4 + l / 8's score (static register index i >> 3), so the TK * RU exact scores
+//     of a user sit in registers across the warp.
+//   * Each of the TK units holds an item whose EXACT score is the unit's exact maximum, so the TK-th best exact score is
+//     at least tau = min over units of that maximum: only scores >= tau survive (typically TK .. 2 TK of 560), they are
+//     compacted into shared memory, and their order is found by counting (one pass for <= 32 survivors; the selection
+//     rounds of step 1 otherwise -- dyadic test data with hundreds of exact ties takes that path).
+template <int RU>
+__global__ void __launch_bounds__(256, 2) catalogue_refine64_kernel(TopkShape s) {
+  constexpr int NI = RU / 4;                          // 512-byte requests per unit
+  constexpr int NK = (NI + 7) / 8;                    // scores a lane keeps per unit
+  constexpr int CAP = TK * RU;                        // survivors per user, worst case
+  static_assert(RU % 4 == 0 && NK <= 2, "refine64: ranking unit of 4 .. 64 rows in multiples of 4");
+  __shared__ float sv_s[8][CAP];
+  __shared__ int sv_i[8][CAP];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t u = (int64_t)blockIdx.x * 8 + wib;
+  if (u >= s.U) return;
+  float* osc = s.out_scores + (size_t)u * s.slots * TK;
+  int* oid = s.out_ids + (size_t)u * s.slots * TK;
+  const int nent = s.slots * TK;
+  // this lane's eighth of the user's features
+  float f[8];
+  {
+    const uint4 fv = __ldg(reinterpret_cast<const uint4*>(s.feats + (size_t)u * s.ld_feats) + (lane & 7));
+    const uint32_t fw[4] = {fv.x, fv.y, fv.z, fv.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&fw[q]));
+      f[2 * q] = x.x; f[2 * q + 1] = x.y;
+    }
+  }
+  // ---- 1. the TK best units (max desc, unit asc): entries cached in registers (4 per lane covers 12 list slots)
+  int tiles[TK];
+  {
+    float ev[4]; int et[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = lane + 32 * q;
+      et[q] = e < nent ? oid[e] : -1;
+      ev[q] = e < nent ? osc[e] : -INFINITY;
+    }
+    float last_v = INFINITY; int last_t = -1;
+#pragma unroll 1
+    for (int r = 0; r < TK; ++r) {
+      float bv = -INFINITY; int bt = -1;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const bool after_last = (last_t < 0) || ev[q] < last_v || (ev[q] == last_v && et[q] > last_t);
+        if (et[q] >= 0 && after_last && better(ev[q], et[q], bv, bt)) { bv = ev[q]; bt = et[q]; }
+      }
+      for (int e = lane + 128; e < nent; e += 32) {     // more than 12 slots: the rest straight from memory
+        const float v = osc[e]; const int t = oid[e];
+        if (t < 0) continue;
+        const bool after_last = (last_t < 0) || v < last_v || (v == last_v && t > last_t);
+        if (after_last && better(v, t, bv, bt)) { bv = v; bt = t; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int ot = __shfl_xor_sync(0xffffffffu, bt, o);
+        if (better(ov, ot, bv, bt)) { bv = ov; bt = ot; }
+      }
+#pragma unroll
+      for (int q = 0; q < TK; ++q) if (q == r) tiles[q] = bt;
+      if (bt >= 0) { last_v = bv; last_t = bt; }
+    }
+  }
+  __syncwarp();
+  for (int e = lane; e < nent; e += 32) oid[e] = -1;    // empty every slot (phase-1 entries are consumed)
+  // ---- 2. exact scores of the TK units
+  float sc[TK][NK];
+  float tau = INFINITY;
+#pragma unroll
+  for (int r = 0; r < TK; ++r) {
+#pragma unroll
+    for (int k = 0; k < NK; ++k) sc[r][k] = -INFINITY;
+    const int t = tiles[r];
+    if (t < 0) { tau = -INFINITY; continue; }           // warp-uniform
+    const int row0 = s.row_lo + t * RU + (lane >> 3);
+    const uint4* e0 = reinterpret_cast<const uint4*>(s.table + (size_t)row0 * 64) + (lane & 7);
+    uint4 ev[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i)
+      ev[i] = (row0 + 4 * i < s.row_hi) ? __ldg(e0 + i * 32) : make_uint4(0, 0, 0, 0);
+    float um = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const uint32_t ew[4] = {ev[i].x, ev[i].y, ev[i].z, ev[i].w};
+      float a = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ew[q]));
+        a = fmaf(f[2 * q], y.x, a);
+        a = fmaf(f[2 * q + 1], y.y, a);
+      }
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      a += __shfl_xor_sync(0xffffffffu, a, 4);
+      if (row0 + 4 * i >= s.row_hi) a = -INFINITY;       // past the table: not an item
+      um = fmaxf(um, a);
+      if ((i & 7) == (lane & 7)) sc[r][i >> 3] = a;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) um = fmaxf(um, __shfl_xor_sync(0xffffffffu, um, o));
+    tau = fminf(tau, um);
+  }
+  // ---- 3. survivors (score >= tau) -> shared memory, in any order
+  float* mv = sv_s[wib];
+  int* mi = sv_i[wib];
+  int ns = 0;
+#pragma unroll
+  for (int r = 0; r < TK; ++r) {
+    if (tiles[r] < 0) continue;
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      const float a = sc[r][k];
+      const bool keep = a >= tau && a > -INFINITY;
+      const uint32_t m = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const int i = k * 8 + (lane & 7);
+        mv[ns + __popc(m & ((1u << lane) - 1))] = a;
+        mi[ns + __popc(m & ((1u << lane) - 1))] = s.row_lo + tiles[r] * RU + 4 * i + (lane >> 3);
+      }
+      ns += __popc(m);
+    }
+  }
+  __syncwarp();
+  // ---- 4. order them: (score desc, row asc)
+  float my_v = -INFINITY; int my_i = -1; int my_rank = TK;
+  if (ns <= 32) {
+    if (lane < ns) { my_v = mv[lane]; my_i = mi[lane]; }
+    int rank = 0;
+    for (int j = 0; j < ns; ++j) {
+      const float ov = __shfl_sync(0xffffffffu, my_v, j);
+      const int oi = __shfl_sync(0xffffffffu, my_i, j);
+      rank += (ov > my_v || (ov == my_v && oi < my_i)) ? 1 : 0;
+    }
+    if (lane < ns) my_rank = rank;
+    if (lane >= ns && lane < TK) my_rank = lane;         // fewer than TK candidates: the tail is empty (-inf, -1)
+  } else {
+    float last_v = INFINITY; int last_i = -1;
+#pragma unroll 1
+    for (int r = 0; r < TK; ++r) {
+      float bv = -INFINITY; int bi = -1;
+      for (int e = lane; e < ns; e += 32) {
+        const float v = mv[e]; const int id = mi[e];
+        const bool after_last = (last_i < 0) || v < last_v || (v == last_v && id > last_i);
+        if (after_last && better(v, id, bv, bi)) { bv = v; bi = id; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == r) { my_v = bv; my_i = bi; my_rank = r; }
+      if (bi >= 0) { last_v = bv; last_i = bi; }
+    }
+  }
+  if (my_rank < TK) {
+    const int gid = my_i < 0 ? -1 : (int)(s.id_base + my_i);
+    osc[my_rank] = my_v; oid[my_rank] = gid;
+    if (s.packed) {
+      s.packed[(size_t)u * 2 * TK + my_rank] = my_v;
+      reinterpret_cast<int*>(s.packed)[(size_t)u * 2 * TK + TK + my_rank] = gid;
     }
   }
 }
@@ -893,17 +1205,27 @@ template <int MT>
 static int launch_unitmax(const CUtensorMap& tmE, TopkShape& s, int grid, cudaStream_t stream) {
   const int b_tile = MT * KB * 2;
   const int unit = 2 * s.kblocks;                       // ring length: a multiple of 2 * kblocks (see kernel comment)
-  s.stages = ((216 * 1024) / b_tile) / unit * unit;
+  const int list_bytes = 16 * 32 * 4;                   // published thresholds
+  s.stages = ((216 * 1024 - list_bytes) / b_tile) / unit * unit;
   SRFRD_REQUIRE(s.stages >= unit, "catalogue_topk: item tile ring does not fit shared memory");
-  const size_t smem = (size_t)s.stages * b_tile + 16 * 32 * 4 + (2 * s.stages + 32) * 8 + 1024 + 1024;
+  const size_t smem = (size_t)s.stages * b_tile + list_bytes + (2 * s.stages + 32) * 8 + 1024 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    SRFRD_CUDA(cudaFuncSetAttribute(catalogue_unitmax_kernel<MT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SRFRD_CUDA(cudaFuncSetAttribute(catalogue_unitmax_kernel<MT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SRFRD_CUDA(cudaFuncSetAttribute(catalogue_unitmax_kernel<MT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SRFRD_CUDA(cudaFuncSetAttribute(catalogue_unitmax_kernel<MT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SRFRD_CUDA(cudaFuncSetAttribute(catalogue_unitmax_kernel<MT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SRFRD_CUDA(cudaFuncSetAttribute(catalogue_unitmax_kernel<MT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  if (s.trace) catalogue_unitmax_kernel<MT, true><<<grid, 640, smem, stream>>>(tmE, s);
-  else catalogue_unitmax_kernel<MT, false><<<grid, 640, smem, stream>>>(tmE, s);
+  const char* wide_env = getenv("SRFRD_TOPK_WIDE");      // 0: sixteen epilogue warps, a column half each (A/B timing)
+  const bool wide = !(wide_env && wide_env[0] == '0');
+  if (wide) {
+    if (s.trace) catalogue_unitmax_kernel<MT, true, true><<<grid, 384, smem, stream>>>(tmE, s);
+    else catalogue_unitmax_kernel<MT, false, true><<<grid, 384, smem, stream>>>(tmE, s);
+  } else {
+    if (s.trace) catalogue_unitmax_kernel<MT, true, false><<<grid, 640, smem, stream>>>(tmE, s);
+    else catalogue_unitmax_kernel<MT, false, false><<<grid, 640, smem, stream>>>(tmE, s);
+  }
   SRFRD_LAUNCH_CHECK();
   return 0;
 }
@@ -967,7 +1289,13 @@ extern "C" int srfrd_catalogue_topk(const void* feats_bf16, int64_t U, int64_t u
     }
   }
   if (s.debug == 2) return 0;                           // profiling: phase 1 only
-  catalogue_refine_kernel<<<(unsigned)((U + 7) / 8), 256, 0, stream>>>(s);
+  // SRFRD_TOPK_REFINE=0: the general one-row-per-lane kernel everywhere (A/B timing)
+  const char* refine_env = getenv("SRFRD_TOPK_REFINE");
+  const bool fast_refine = !(refine_env && refine_env[0] == '0');
+  const bool fast = fast_refine && D == 64 && n_split == 1 && ld_table == 64;
+  if (fast && c.ru == 56) catalogue_refine64_kernel<56><<<(unsigned)((U + 7) / 8), 256, 0, stream>>>(s);
+  else if (fast && c.ru == 64) catalogue_refine64_kernel<64><<<(unsigned)((U + 7) / 8), 256, 0, stream>>>(s);
+  else catalogue_refine_kernel<<<(unsigned)((U + 7) / 8), 256, 0, stream>>>(s);
   SRFRD_LAUNCH_CHECK();
   return 0;
 }
