@@ -359,31 +359,36 @@ catalogue_tilemax_kernel(const __grid_constant__ CUtensorMap tmE, TopkShape s) {
 // ---------------------------------------------------------------------------------------------------------------
 // Phase 1, unit form (two user tiles; item tiles of MT = (512 - 2 * a_cols) / 4 rows rounded down to 16: 112 at D = 64).
 //
-// Tensor memory holds 448 accumulator columns = 896 cycles of tensor work, so the pipe's share is bounded by
-// 896 / (one accumulator round trip): release -> issuer sees it ~200 cycles, four tcgen05.mma issues ~330, commit ->
-// epilogue sees it ~350, every round of tcgen05.ld ~330 while the tensor pipe is busy.  The tile form above adds the
-// SERIAL cost of issuers that each serve several stages.  Here (clock64 stamps of one CTA: SRFRD_TOPK_TRACE,
-// tools/topk_trace.py):
+// Tensor memory holds 448 accumulator columns = 896 cycles of tensor work, so the tensor pipe's share is bounded by
+// 896 / (one accumulator round trip) -- release -> issuer sees it ~250 cycles, four tcgen05.mma issues ~320, commit ->
+// epilogue sees it ~350, one round of tcgen05.ld ~200-340 -- and by the epilogue warps' own serial time per unit.  With
+// K = 64 a score costs only four K steps, so this kernel is an epilogue / latency problem, not a tensor-throughput one
+// (a quarter of the MMAs, SRFRD_TOPK_DEBUG=4, changes the time by 2 %).  Structure (clock64 stamps of one CTA:
+// SRFRD_TOPK_TRACE, tools/topk_trace.py; A/B timings: tools/topk_ab.py):
 //   * an MMA is 128 users x MT ITEMS x 16; a work unit is (one MT-item tile) x (ONE user tile); unit q = 2 * tile +
 //     user_tile uses accumulator stage w = user_tile + 2 * (tile parity).  ONE ISSUER WARP PER STAGE: an issuer that
-//     alternates between two stages in order holds the ready one back behind the late one (measured +8 %).
-//   * a unit is read by EIGHT epilogue warps in ONE round of tcgen05.ld: per lane quarter one warp takes columns
-//     [0, MT / 2) and one [MT / 2, MT) (56 registers each), and the accumulator goes back after that single round (with four
-//     warps reading two rounds the round trip was ~1 900 cycles).  The eight warps of user tile ub serve all of its units,
-//     alternating between its two stages; a thread is one (user row, column half) and keeps that half's running list:
-//     the ranking unit is a half (list entries are 2 * tile + half, phase 2 re-scores 10 x MT / 2 items per row).
-//   * no producer warp (a block is 16 epilogue + 4 control warps = 5 per scheduler, the most that leaves 96 registers a
-//     thread): passing tempty[w] for tile n tells issuer w that ITS MMAs on tile n - 2 are complete; the second of the
-//     two issuers of a tile parity to get there (shared-memory counter) re-fills that tile's ring slot, after its own
-//     MMAs for tile n are issued.  (The same hand-over done by epilogue threads cost ~550 cycles on the accumulator's
-//     critical path.)
+//     alternates between two stages in order holds the ready one back behind the late one.
+//   * 8 epilogue + 4 issuer warps = 3 per scheduler -> 168 registers a thread: a thread owns one user row and reads
+//     its whole MT scores in ONE round of tcgen05.ld (MT registers), hands the accumulator back, and only then reduces
+//     them (FMNMX3, eight independent chains) to the maxima of the tile's two halves -- the ranking unit is a half
+//     (list entries are 2 * tile + half, phase 2 re-scores 10 x MT / 2 items per row).  The four warps of user tile
+//     ub serve all of its units, alternating between its two stages; the next unit's barrier is tested before the
+//     reduction so that the test's latency hides under it.
+//   * no producer warp: passing tempty[w] for tile n tells issuer w that ITS MMAs on tile n - 2 are complete; the
+//     second of the two issuers of a tile parity to get there (shared-memory counter) re-fills that tile's ring slot,
+//     after its own MMAs for tile n are issued.  (The same hand-over done by epilogue threads cost ~550 cycles on the
+//     accumulator's critical path.)
 //   * every barrier has one waiter group that consumes every phase (tfull[w]: the warps of user tile w & 1;
 //     tempty[w]: issuer w; full[slot]: the two issuers of the slot's parity -- the ring length is even).
-//   * per-thread lists stay in REGISTERS and are offered to after the release: with the lists in shared memory, or with
-//     the offer placed under the next load's latency, the rare insertion (a warp takes it when any of its 32 rows
-//     inserts) delayed the release and cost 0.7 ms instead of 0.1 ms at 1 M items.
-//   * measured and rejected: MMAs of MT / 2 columns with a barrier pair per half (eight round trips in flight): twice the
-//     commits and barrier tests, 2.77 ms against 2.18 ms.
+//   * per-row lists stay in REGISTERS and are offered to after the release.
+// Measured at 16 384 users x 1 M items, streaming phase only (tools/topk_ab.py, same box, same data):
+//     round-2 form (two issuers + producer, 16 epilogue warps x 96 registers, two ld rounds per unit)        2.18 ms
+//     + one issuer per stage, lists in shared memory, offer under the next load's latency                   2.63 ms
+//       (without insertions 1.92: the insertion of ~30 % of a warp's units delays the release)
+//     MMAs of MT / 2 columns with a barrier pair per half (eight round trips in flight)                      2.77 ms
+//     16 epilogue warps, a column half each, one ld round                                                    2.40 ms
+//     this form                                                                                              1.93 ms
+//     this form with quarter-tile ranking units (phase 2 halves, but four offers per unit: insertions 0.30)  2.10 ms
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -391,20 +396,18 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                : "memory");
 }
 
-template <int MT, bool TRACE, bool WIDE>
-__global__ void __launch_bounds__(WIDE ? 384 : 640, 1)
+template <int MT, bool TRACE>
+__global__ void __launch_bounds__(384, 1)
 catalogue_unitmax_kernel(const __grid_constant__ CUtensorMap tmE, TopkShape s) {
-  constexpr int UBS = 2, NEPI = WIDE ? 8 : 16, NACC = 4;
+  constexpr int UBS = 2, NEPI = 8, NACC = 4;
   constexpr int HALF = MT / 2;                        // ranking unit (items) = columns one thread reads
   constexpr int B_TILE_BYTES = MT * KB * 2;
-  constexpr int LSTR = NEPI * 32;
   constexpr int TR0 = 2000, TRN = 256;                // traced tiles of CTA 0
   static_assert(MT % 16 == 0 && HALF >= 32 && HALF < 64, "unit form: MT in {64 .. 112}");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smB = smem;
-  float* lthr = reinterpret_cast<float*>(smB + s.stages * B_TILE_BYTES);      // [LSTR] current TK-th best per thread
-  uint64_t* bars = reinterpret_cast<uint64_t*>(lthr + LSTR);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + s.stages * B_TILE_BYTES);
   uint64_t* full = bars;
   int* rcnt = reinterpret_cast<int*>(bars + s.stages); // [stages] issuers done with the slot's tile (0..2)
   uint64_t* tfull = bars + 2 * s.stages;              // [NACC]
@@ -422,7 +425,7 @@ catalogue_unitmax_kernel(const __grid_constant__ CUtensorMap tmE, TopkShape s) {
   if (warp == NEPI && lane == 0) {
     tma_prefetch_desc(&tmE);
     for (int i = 0; i < s.stages; ++i) { mbar_init(&full[i], 1); rcnt[i] = 0; }
-    for (int i = 0; i < NACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], WIDE ? 4 : 8); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
     mbar_init(afull, 4 * UBS);
     mbar_init(aempty, NACC);
     fence_barrier_init();
@@ -517,139 +520,8 @@ catalogue_unitmax_kernel(const __grid_constant__ CUtensorMap tmE, TopkShape s) {
       __syncwarp();
       lin += t1 - t0;
     }
-  } else if constexpr (!WIDE) {
-    // ------------------------------------------------------------------ epilogue: warp = (user tile, column half, lane quarter)
-    const int quarter = warp & 3, ch = (warp >> 2) & 1, ub = warp >> 3;
-    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const uint32_t taddr0 = tmem_base + lane_off + ub * MT + ch * HALF;      // stage ub (even tiles); + 2 * MT: odd tiles
-    float* thr_mine = lthr + warp * 32 + lane;
-    const float* thr_other = lthr + (warp ^ 4) * 32 + lane;                  // same user row, other column half
-    uint32_t uphase = 0, tph0 = 0, tph1 = 0;
-    int n = 0;
-    for (int64_t lin = lin0; lin < lin1;) {
-      const int ug = (int)(lin / s.tiles_total);
-      const int t0 = (int)(lin % s.tiles_total);
-      const int t1 = (int)min((int64_t)s.tiles_total, t0 + (lin1 - lin));
-      const int piece = (int)(lin / s.share - ((int64_t)ug * s.tiles_total) / s.share);
-      const int urow = (ug * UBS + ub) * TILE_U + quarter * 32 + lane;
-      if (ch == 0) {
-        // ---- stage this thread's user row into tensor memory (A operand, K-major, 2 bf16 per column) ----
-        mbar_wait(aempty, uphase ^ 1);                    // previous piece's MMAs no longer read the user tiles
-        uphase ^= 1;
-        tc_fence_after();
-        for (int sp = 0; sp < s.n_split; ++sp) {
-          const uint4* src = reinterpret_cast<const uint4*>(s.feats + ((size_t)sp * s.u_pad + urow) * s.ld_feats);
-          for (int c = 0; c < s.D / 2; c += 8) {            // 8 columns = 16 features = one UMMA K step
-            uint32_t v[8];
-            uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
-            if (urow < s.U) { lo = __ldg(src + c / 4); hi = __ldg(src + c / 4 + 1); }
-            v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
-            tmem_st8(tA + lane_off + ub * a_cols + sp * (s.D / 2) + c, v);
-          }
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(afull);
-      }
-      float ts[TK]; int ti[TK];                       // this thread's TK best (unit maximum, unit index), sorted
-#pragma unroll
-      for (int r = 0; r < TK; ++r) { ts[r] = -INFINITY; ti[r] = -1; }
-      float thr = -INFINITY;
-      *thr_mine = -INFINITY;
-      // both threads of a row start the piece together: the partner's published threshold always belongs to THIS piece
-      named_bar_sync_t(1 + ub * 4 + quarter, 64);
-      for (int t = t0; t < t1; ++t, ++n) {
-        const int odd = n & 1, w = ub + 2 * odd;
-        const float thr_p = *thr_other;
-        const bool tr = TRACE && blockIdx.x == 0 && n >= TR0 && n < TR0 + TRN && quarter == 0 && lane == 0 && ch == 0;
-        long long* trq = s.trace + (size_t)(2 * (n - TR0) + ub) * 12;
-        if (tr) trq[4] = clock64();
-        mbar_wait(&tfull[w], odd ? tph1 : tph0);
-        if (odd) tph1 ^= 1; else tph0 ^= 1;
-        tc_fence_after();
-        if (tr) trq[5] = clock64();
-        const int limit = s.row_hi - (s.row_lo + t * MT) - ch * HALF;   // real items among this thread's columns
-        float tmax = 0.f;
-        if (s.debug == 5) {                               // ablation: hand the accumulator back unread
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[w]);
-        } else {
-          const uint32_t taddr = taddr0 + odd * (2 * MT);
-          uint32_t r0[32], r1[16], r2[8];
-          tmem_ld32(taddr, r0);
-          if constexpr ((HALF - 32) & 16) tmem_ld16(taddr + 32, r1);
-          if constexpr ((HALF - 32) & 8) tmem_ld8(taddr + 32 + ((HALF - 32) & 16), r2);
-          tmem_ld_wait();
-          tc_fence_before();                              // scores are in registers: hand the accumulator back now
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[w]);
-          if (tr) trq[6] = clock64();
-          if (limit < HALF) {                             // last tile of the table: columns past row_hi are not items
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j >= limit) r0[j] = 0xff800000u;
-            if constexpr ((HALF - 32) & 16) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) if (32 + j >= limit) r1[j] = 0xff800000u;
-            }
-            if constexpr ((HALF - 32) & 8) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) if (32 + ((HALF - 32) & 16) + j >= limit) r2[j] = 0xff800000u;
-            }
-          }
-          // FMNMX3: two scores folded per ALU instruction, four independent chains
-          float m[4];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) m[c] = fmaxf(__uint_as_float(r0[2 * c]), __uint_as_float(r0[2 * c + 1]));
-#pragma unroll
-          for (int j = 8; j < 32; j += 8) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) m[c] = fmax3(m[c], __uint_as_float(r0[j + 2 * c]), __uint_as_float(r0[j + 2 * c + 1]));
-          }
-          if constexpr ((HALF - 32) & 16) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 8) {
-#pragma unroll
-              for (int c = 0; c < 4; ++c) m[c] = fmax3(m[c], __uint_as_float(r1[j + 2 * c]), __uint_as_float(r1[j + 2 * c + 1]));
-            }
-          }
-          if constexpr ((HALF - 32) & 8) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) m[c] = fmax3(m[c], __uint_as_float(r2[2 * c]), __uint_as_float(r2[2 * c + 1]));
-          }
-          tmax = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
-        }
-        if (tr) trq[7] = clock64();
-        thr = fmaxf(thr, thr_p);
-        if (tmax > thr && s.debug != 1) {                 // rare after warm-up, thread-divergent
-          ts[TK - 1] = tmax; ti[TK - 1] = 2 * t + ch;
-#pragma unroll
-          for (int r = TK - 1; r > 0; --r) {              // strict: an equal maximum never overtakes an earlier unit
-            if (ts[r] > ts[r - 1]) {
-              const float fs = ts[r]; ts[r] = ts[r - 1]; ts[r - 1] = fs;
-              const int is = ti[r]; ti[r] = ti[r - 1]; ti[r - 1] = is;
-            }
-          }
-          thr = fmaxf(thr, ts[TK - 1]);
-          *thr_mine = thr;
-        }
-        if (tr) trq[8] = clock64();
-      }
-      if (urow < s.U) {
-        const size_t o = ((size_t)urow * s.slots + piece * 2 + ch) * TK;
-#pragma unroll
-        for (int r = 0; r < TK; ++r) {
-          s.out_scores[o + r] = ts[r];
-          s.out_ids[o + r] = ti[r];
-        }
-      }
-      lin += t1 - t0;
-    }
   } else {
-    // ------------------------------------------------------------------ epilogue, wide form: warp = (user tile, lane quarter)
-    // 12 warps a block -> 168 registers a thread: a thread reads its row's whole MT scores in ONE round of tcgen05.ld
-    // (MT registers), so a unit is one barrier test + one load round for FOUR warps.
+    // ------------------------------------------------------------------ epilogue: warp = (user tile, lane quarter)
     const int quarter = warp & 3, ub = warp >> 2;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const uint32_t taddr0 = tmem_base + lane_off + ub * MT;                  // stage ub (even tiles); + 2 * MT: odd tiles
@@ -732,12 +604,13 @@ catalogue_unitmax_kernel(const __grid_constant__ CUtensorMap tmE, TopkShape s) {
         }
         return fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
       };
+      bool ready = false;                               // this unit's tfull was already seen complete (tested a unit ahead)
       for (int t = t0; t < t1; ++t, ++n) {
         const int odd = n & 1, w = ub + 2 * odd;
         const bool tr = TRACE && blockIdx.x == 0 && n >= TR0 && n < TR0 + TRN && quarter == 0 && lane == 0;
         long long* trq = s.trace + (size_t)(2 * (n - TR0) + ub) * 12;
         if (tr) trq[4] = clock64();
-        mbar_wait(&tfull[w], odd ? tph1 : tph0);
+        if (!ready) mbar_wait(&tfull[w], odd ? tph1 : tph0);
         if (odd) tph1 ^= 1; else tph0 ^= 1;
         tc_fence_after();
         if (tr) trq[5] = clock64();
@@ -747,6 +620,7 @@ catalogue_unitmax_kernel(const __grid_constant__ CUtensorMap tmE, TopkShape s) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[w]);
+          ready = false;
         } else {
           const uint32_t taddr = taddr0 + odd * (2 * MT);
           uint32_t a0[32], a1[16], a2[8], b0[32], b1[16], b2[8];
@@ -761,6 +635,8 @@ catalogue_unitmax_kernel(const __grid_constant__ CUtensorMap tmE, TopkShape s) {
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[w]);
           if (tr) trq[6] = clock64();
+          // the next unit's barrier is tested now, its ~100-cycle answer is looked at after the maxima
+          ready = t + 1 < t1 && mbar_try_wait(&tfull[ub + 2 * (odd ^ 1)], odd ? tph0 : tph1);
           mA = reduce_half(a0, a1, a2, valid);
           mB = reduce_half(b0, b1, b2, valid - HALF);
         }
@@ -1205,27 +1081,17 @@ template <int MT>
 static int launch_unitmax(const CUtensorMap& tmE, TopkShape& s, int grid, cudaStream_t stream) {
   const int b_tile = MT * KB * 2;
   const int unit = 2 * s.kblocks;                       // ring length: a multiple of 2 * kblocks (see kernel comment)
-  const int list_bytes = 16 * 32 * 4;                   // published thresholds
-  s.stages = ((216 * 1024 - list_bytes) / b_tile) / unit * unit;
+  s.stages = ((216 * 1024) / b_tile) / unit * unit;
   SRFRD_REQUIRE(s.stages >= unit, "catalogue_topk: item tile ring does not fit shared memory");
-  const size_t smem = (size_t)s.stages * b_tile + list_bytes + (2 * s.stages + 32) * 8 + 1024 + 1024;
+  const size_t smem = (size_t)s.stages * b_tile + (2 * s.stages + 32) * 8 + 1024 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    SRFRD_CUDA(cudaFuncSetAttribute(catalogue_unitmax_kernel<MT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SRFRD_CUDA(cudaFuncSetAttribute(catalogue_unitmax_kernel<MT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SRFRD_CUDA(cudaFuncSetAttribute(catalogue_unitmax_kernel<MT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SRFRD_CUDA(cudaFuncSetAttribute(catalogue_unitmax_kernel<MT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SRFRD_CUDA(cudaFuncSetAttribute(catalogue_unitmax_kernel<MT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SRFRD_CUDA(cudaFuncSetAttribute(catalogue_unitmax_kernel<MT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const char* wide_env = getenv("SRFRD_TOPK_WIDE");      // 0: sixteen epilogue warps, a column half each (A/B timing)
-  const bool wide = !(wide_env && wide_env[0] == '0');
-  if (wide) {
-    if (s.trace) catalogue_unitmax_kernel<MT, true, true><<<grid, 384, smem, stream>>>(tmE, s);
-    else catalogue_unitmax_kernel<MT, false, true><<<grid, 384, smem, stream>>>(tmE, s);
-  } else {
-    if (s.trace) catalogue_unitmax_kernel<MT, true, false><<<grid, 640, smem, stream>>>(tmE, s);
-    else catalogue_unitmax_kernel<MT, false, false><<<grid, 640, smem, stream>>>(tmE, s);
-  }
+  if (s.trace) catalogue_unitmax_kernel<MT, true><<<grid, 384, smem, stream>>>(tmE, s);
+  else catalogue_unitmax_kernel<MT, false><<<grid, 384, smem, stream>>>(tmE, s);
   SRFRD_LAUNCH_CHECK();
   return 0;
 }

@@ -44,11 +44,11 @@ for N in (1_000_000, 125_000):
     idx = EV.CatalogueIndex(table, 0)
     base = None
     quick = os.environ.get("AB_QUICK") == "1"
-    for name, env in [("default", {}), ("phase 1 only", {"SRFRD_TOPK_DEBUG": "2"}), ("no insertions", {"SRFRD_TOPK_DEBUG": "1"})] if quick else [("default", {}), ("general refine", {"SRFRD_TOPK_REFINE": "0"}), ("phase 1 only", {"SRFRD_TOPK_DEBUG": "2"}),
-                      ("no insertions", {"SRFRD_TOPK_DEBUG": "1"}), ("second half not read", {"SRFRD_TOPK_DEBUG": "3"}),
-                      ("one K step", {"SRFRD_TOPK_DEBUG": "4"}), ("no tcgen05.ld", {"SRFRD_TOPK_DEBUG": "5"}),
-                      ("narrow: default", {"SRFRD_TOPK_WIDE": "0"}), ("narrow: phase 1 only", {"SRFRD_TOPK_WIDE": "0", "SRFRD_TOPK_DEBUG": "2"}),
-                      ("narrow: no insertions", {"SRFRD_TOPK_WIDE": "0", "SRFRD_TOPK_DEBUG": "1"})]:
+    variants = [("default", {}), ("phase 1 only", {"SRFRD_TOPK_DEBUG": "2"}), ("no insertions", {"SRFRD_TOPK_DEBUG": "1"})]
+    if not quick:
+        variants += [("general refine", {"SRFRD_TOPK_REFINE": "0"}), ("one K step", {"SRFRD_TOPK_DEBUG": "4"}),
+                     ("no tcgen05.ld", {"SRFRD_TOPK_DEBUG": "5"})]
+    for name, env in variants:
         ms, sc, ids = timed(idx, env)
         note = ""
         if name == "default":
