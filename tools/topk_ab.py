@@ -18,7 +18,7 @@ def run(idx, fb, u_pad, chunks, ps, pi, packed=None):
 
 
 def timed(idx, env, iters=10):
-    for k in ("SRFRD_TOPK_DEBUG", "SRFRD_TOPK_REFINE"):
+    for k in ("SRFRD_TOPK_DEBUG", "SRFRD_TOPK_REFINE", "SRFRD_TOPK_ALIGN"):
         os.environ.pop(k, None)
     os.environ.update(env)
     fb, u_pad = EV._split_feats(feats, idx.Dp, 1)
@@ -44,7 +44,8 @@ for N in (1_000_000, 125_000):
     idx = EV.CatalogueIndex(table, 0)
     base = None
     quick = os.environ.get("AB_QUICK") == "1"
-    variants = [("default", {}), ("phase 1 only", {"SRFRD_TOPK_DEBUG": "2"}), ("no insertions", {"SRFRD_TOPK_DEBUG": "1"})]
+    variants = [("default", {}), ("phase 1 only", {"SRFRD_TOPK_DEBUG": "2"}), ("no insertions", {"SRFRD_TOPK_DEBUG": "1"}),
+                ("plain split", {"SRFRD_TOPK_ALIGN": "0"}), ("plain split: phase 1 only", {"SRFRD_TOPK_ALIGN": "0", "SRFRD_TOPK_DEBUG": "2"})]
     if not quick:
         variants += [("general refine", {"SRFRD_TOPK_REFINE": "0"}), ("one K step", {"SRFRD_TOPK_DEBUG": "4"}),
                      ("no tcgen05.ld", {"SRFRD_TOPK_DEBUG": "5"})]
