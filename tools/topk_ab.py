@@ -45,7 +45,7 @@ for N in (1_000_000, 125_000):
     base = None
     quick = os.environ.get("AB_QUICK") == "1"
     variants = [("default", {}), ("phase 1 only", {"SRFRD_TOPK_DEBUG": "2"}), ("no insertions", {"SRFRD_TOPK_DEBUG": "1"}),
-                ("plain split", {"SRFRD_TOPK_ALIGN": "0"}), ("plain split: phase 1 only", {"SRFRD_TOPK_ALIGN": "0", "SRFRD_TOPK_DEBUG": "2"})]
+                ("plain split", {"SRFRD_TOPK_ALIGN": "0"}), ("default again", {})]
     if not quick:
         variants += [("general refine", {"SRFRD_TOPK_REFINE": "0"}), ("one K step", {"SRFRD_TOPK_DEBUG": "4"}),
                      ("no tcgen05.ld", {"SRFRD_TOPK_DEBUG": "5"})]
