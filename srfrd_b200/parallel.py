@@ -55,6 +55,15 @@ def allgather_packed_topk(packed: torch.Tensor, group=None) -> torch.Tensor:
     return out.view(G, U, W)
 
 
+def allgather_rows(rows: torch.Tensor, group=None) -> torch.Tensor:
+    """(n, W) per rank (same n everywhere) -> (G * n, W) on every rank, rank-major: the user-sharded encode's exchange."""
+    G = dist.get_world_size(group)
+    n, W = rows.shape
+    out = torch.empty(G * n, W, dtype=rows.dtype, device=rows.device)
+    dist.all_gather_into_tensor(out, rows.contiguous(), group=group)
+    return out
+
+
 def merge_packed_topk_host(gathered: torch.Tensor, k: int = 10):
     """Host restatement of srfrd_merge_topk_packed (tie-break: score desc, id asc) for the CPU protocol tests."""
     import numpy as np

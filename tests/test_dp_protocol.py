@@ -105,6 +105,35 @@ def test_sharded_topk_equals_unsharded():
         np.testing.assert_array_equal(mi, ref)
 
 
+class _RowwiseEncoder:
+    """Stands in for the model: every user's representation depends on that user's row only (as the encoder's does)."""
+
+    def __init__(self):
+        g = torch.Generator().manual_seed(3)
+        self.w = torch.randn(50, 80, generator=g)
+
+    def encode_last(self, seq, rsq):
+        return torch.tanh(seq.float() @ self.w) + (0 if rsq is None else rsq.float().sum(1, keepdim=True))
+
+
+def _encode_job(rank, world):
+    from srfrd_b200 import evaluation as EV
+    g = torch.Generator().manual_seed(11)
+    seq = torch.randint(0, 9, (37, 50), generator=g)                # 37 users over 2 ranks: 19 + 18, one padded row
+    rsq = torch.randint(0, 3, (37, 50), generator=g)
+    return EV.encode_users(_RowwiseEncoder(), seq, rsq, dist.group.WORLD).numpy()
+
+
+def test_user_sharded_encode_equals_the_replicated_one():
+    """evaluation.encode_users: users split over the ranks + ONE all-gather == every rank encoding everybody."""
+    g = torch.Generator().manual_seed(11)
+    seq = torch.randint(0, 9, (37, 50), generator=g)
+    rsq = torch.randint(0, 3, (37, 50), generator=g)
+    ref = _RowwiseEncoder().encode_last(seq, rsq).numpy()
+    for out in _run(_encode_job, port=29613):
+        np.testing.assert_array_equal(out, ref)
+
+
 def test_shard_bounds_partition_the_table():
     from srfrd_b200 import parallel as P
     from srfrd_b200.evaluation import CatalogueIndex

@@ -13,6 +13,8 @@ for r in rows[hdr + 1:]:
     unit = r[mu]
     us = v / 1e3 if unit in ("ns", "nsecond") else (v if unit.startswith("us") else v * 1e3 if unit.startswith("ms") else v)
     name = re.sub(r"\(.*", "", r[kn]).replace("srfrd::", "")
+    if "spin_kernel" in name:          # torch.cuda._sleep: bench.py parks the GPU behind it while the host enqueues
+        continue
     a = agg.setdefault(name, [0, 0.0])
     a[0] += 1; a[1] += us
 tot = sum(a[1] for a in agg.values())
