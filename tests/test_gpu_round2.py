@@ -338,7 +338,8 @@ def _ragged_batch(B, L, N, seed, interior=True):
 
 def test_pack_plan_matches_host_restatement():
     from srfrd_b200 import ops
-    for B, L, seed in ((37, 50, 1), (300, 20, 2), (64, 127, 3), (1, 5, 4)):
+    # 4096 / 2500 sequences: 64 / 63 blocks of the one-launch plan kernel (cross-block prefix, last-block tile plan)
+    for B, L, seed in ((37, 50, 1), (300, 20, 2), (64, 127, 3), (1, 5, 4), (4096, 50, 5), (2500, 30, 6), (600, 160, 7)):
         b = _ragged_batch(B, L, 500, seed)
         plan = ops.PackedPlan(B, L, "cuda")
         for keep in (None, b["pos"]):
@@ -346,16 +347,18 @@ def test_pack_plan_matches_host_restatement():
             ref = _plan_reference(b["seq"].cpu().numpy(), None if keep is None else keep.cpu().numpy())
             rows = plan.rows.cpu().numpy()
             M = ref["M"]
-            assert rows[0] == M and rows[1] == ref["Tp"] and rows[2] == len(ref["tiles"]) - 1
+            assert rows[0] == M and rows[1] == ref["Tp"]
+            assert rows[2] == (len(ref["tiles"]) - 1 if L + 1 <= 128 else 0)       # longer sequences: row maps only
             assert np.array_equal(plan.seq_first.cpu().numpy(), ref["first"])
             assert np.array_equal(plan.row_tok.cpu().numpy()[:M], ref["row_tok"])
             assert np.array_equal(plan.row_ids.cpu().numpy()[:M], ref["row_ids"])
             assert np.array_equal(plan.row_info.cpu().numpy().reshape(-1, 4)[:M], ref["info"])
             assert np.array_equal(plan.tok_row.cpu().numpy().reshape(B, L), ref["tok_row"])
             assert np.array_equal(plan.last_row.cpu().numpy(), ref["last_row"])
-            assert np.array_equal(plan.tile_row0.cpu().numpy()[:rows[2] + 1], ref["tiles"])
-            t = ref["tiles"]
-            assert (np.diff(t) <= 128).all() and (np.diff(t) > 0).all()
+            if L + 1 <= 128:
+                assert np.array_equal(plan.tile_row0.cpu().numpy()[:rows[2] + 1], ref["tiles"])
+                t = ref["tiles"]
+                assert (np.diff(t) <= 128).all() and (np.diff(t) > 0).all()
 
 
 @pytest.mark.parametrize("kind,heads,drop,L", [("SRFR", 1, 0.0, 50), ("SRFRN", 1, 0.0, 50), ("SASRec", 1, 0.0, 50),
