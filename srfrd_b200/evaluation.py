@@ -32,7 +32,8 @@ class CatalogueIndex:
         self.Dp = (self.D + 15) // 16 * 16          # zero-padded K (tcgen05 K step / 16-byte rows)
         self.row_lo = 1 if self.id_base == 0 else 0
         self.table = torch.zeros(self.n_rows, self.Dp, dtype=bf16, device=table_f32.device)
-        ops.f32_to_bf16_split(table_f32.contiguous(), self.table[:, :self.D], None)
+        if self.n_rows > 0:                           # (more ranks than table rows: an empty shard is legal)
+            ops.f32_to_bf16_split(table_f32.contiguous(), self.table[:, :self.D], None)
 
     @staticmethod
     def shard_bounds(n_rows_total: int, rank: int, world: int) -> Tuple[int, int]:
