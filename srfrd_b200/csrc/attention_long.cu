@@ -35,6 +35,12 @@ struct AttnLong {
   const bf16* dout; int lddo;                  // backward: delta pre-pass
   bf16* dx; int lddx;                          // backward output of this pass (dq, dk or dv)
   uint64_t drop_seed; uint32_t drop_thresh, drop_stream; float drop_scale; const float* drop_step;
+  // Dead query tiles (srfrd_set_attention_live; hybrid packed layout only, where nothing reads a pad query's o / dq):
+  // q_lo[b] = first query tile of sequence b that holds a kept token.  Query tiles below it are all dropped padding: their
+  // outputs are dead and their dO is zero, so (query tile, key tile) pairs with a dead query tile contribute exactly
+  // nothing.  The forward and the dQ pass walk `items` (the n_live[0] live (sequence, head, query tile) items, in order)
+  // instead of all of them; the dK / dV passes start each key tile's pair loop at max(key tile, q_lo[b]).
+  const int* q_lo; const int* items; const int* n_live;
 };
 
 __device__ __forceinline__ uint32_t lsw128(int r, int c) {     // byte offset of (row r, column c) in a swizzled tile
@@ -91,7 +97,8 @@ attn_long_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* o_empty = s_full + 7;                          // [4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 11);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_items = p.B * p.heads * p.nq;
+  const int n_items = p.items ? __ldg(p.n_live) : p.B * p.heads * p.nq;
+#define LIVE_ITEM(k) (p.items ? __ldg(p.items + (k)) : (k))
 
   if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -121,7 +128,8 @@ attn_long_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       __syncwarp();
       if (++slot == p.ring) { slot = 0; ph ^= 1; }
     };
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    for (int k = blockIdx.x; k < n_items; k += gridDim.x) {
+      const int it = LIVE_ITEM(k);
       const int bh = it / p.nq, i = it % p.nq, b = bh / p.heads, h = bh % p.heads;
       const int seq0 = b * p.L, col0 = h * p.hd;
       for (int kb = 0; kb < p.kblocks; ++kb) {
@@ -140,8 +148,8 @@ attn_long_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     int slot = 0; uint32_t ph = 0;
     uint32_t iph = 0;                                                     // per-item phase (s_full, p_full)
     uint32_t ocnt = 0;                                                    // accumulator slot uses so far
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x, iph ^= 1) {
-      const int i = it % p.nq;
+    for (int k = blockIdx.x; k < n_items; k += gridDim.x, iph ^= 1) {
+      const int i = LIVE_ITEM(k) % p.nq;
       for (int kb = 0; kb < p.kblocks; ++kb) {
         const int ksteps = min(4, (p.hd - kb * 64) / 16);
         mbar_wait(&full[slot], ph);
@@ -197,7 +205,8 @@ attn_long_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const int r = quarter * 32 + lane;
     uint32_t iph = 0, ocnt = 0;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x, iph ^= 1) {
+    for (int k = blockIdx.x; k < n_items; k += gridDim.x, iph ^= 1) {
+      const int it = LIVE_ITEM(k);
       const int bh = it / p.nq, i = it % p.nq, b = bh / p.heads, h = bh % p.heads;
       const int l = i * LT + r;                      // position inside the sequence
       const bool own = l < p.L;
@@ -238,7 +247,7 @@ attn_long_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         s0[j] = __float_as_uint(e0); s1[j] = __float_as_uint(e1);
       }
       xsum[part * LT + r] = sum;
-      if (it != (int)blockIdx.x) mbar_wait(pv_done, iph ^ 1);     // the previous item's P V MMAs no longer read P
+      if (k != (int)blockIdx.x) mbar_wait(pv_done, iph ^ 1);      // the previous item's P V MMAs no longer read P
       if (c0 <= c_hi) lstore32(Ps, r, c0, s0);
       if (c1 <= c_hi) lstore32(Ps, r, c1, s1);
       for (int c = part; c < 4 * (i + 1); c += 4)                   // chunks of the attended key tiles beyond the window
@@ -282,6 +291,7 @@ attn_long_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       ocnt += p.kblocks;
     }
   }
+#undef LIVE_ITEM
   tc_fence_before();
   __syncthreads();
   if (warp == 17) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
@@ -326,7 +336,9 @@ attn_long_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
            *acc_full = s_full + 6, *acc_free = s_full + 7;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_items = p.B * p.heads * p.nq;
+  const bool listed = MODE == MODE_DQ && p.items != nullptr;                // dQ pass: live query tiles only
+  const int n_items = listed ? __ldg(p.n_live) : p.B * p.heads * p.nq;
+#define LIVE_ITEM(k) (listed ? __ldg(p.items + (k)) : (k))
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
@@ -345,12 +357,15 @@ attn_long_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   if (DROP) p.drop_seed = mix_seed(p.drop_seed, p.drop_step);
 
   // pairs of an item: dQ pass: fixed query tile t, key tiles 0..t;  dK / dV passes: fixed key tile t, query tiles t..nq-1
+  // (dK / dV with q_lo: the pairs of key tile t start at its first LIVE query tile)
 #define PAIR_LOOP_BEGIN                                                                             \
+  const int it = LIVE_ITEM(k);                                                                      \
   const int bh = it / p.nq, tt = it % p.nq, b = bh / p.heads, h = bh % p.heads;                     \
   const int seq0 = b * p.L, col0 = h * p.hd;                                                        \
-  const int np_item = (MODE == MODE_DQ) ? tt + 1 : p.nq - tt;                                       \
+  const int q0 = (MODE != MODE_DQ && p.q_lo) ? max(tt, __ldg(p.q_lo + b)) : tt;                     \
+  const int np_item = (MODE == MODE_DQ) ? tt + 1 : p.nq - q0;                                       \
   for (int pr = 0; pr < np_item; ++pr) {                                                            \
-    const int qi = (MODE == MODE_DQ) ? tt : tt + pr, kj = (MODE == MODE_DQ) ? pr : tt;
+    const int qi = (MODE == MODE_DQ) ? tt : q0 + pr, kj = (MODE == MODE_DQ) ? pr : tt;
 #define PAIR_LOOP_END }
 
   if (warp == 8) {
@@ -365,7 +380,7 @@ attn_long_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       __syncwarp();
       if (++slot == p.ring) { slot = 0; ph ^= 1; }
     };
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    for (int k = blockIdx.x; k < n_items; k += gridDim.x) {
       PAIR_LOOP_BEGIN
         for (int kb = 0; kb < p.kblocks; ++kb) {
           push(&tmQ, col0 + kb * 64, seq0 + qi * LT);
@@ -392,9 +407,9 @@ attn_long_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint64_t mX = umma_smem_desc(smem_u32(Xs), LTB, 1024);          // X^T as MN-major A (dK, dV)
     int slot = 0; uint32_t ph = 0;
     uint32_t np = 0, ni = 0;                                              // pairs / items so far
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++ni) {
+    for (int k = blockIdx.x; k < n_items; k += gridDim.x, ++ni) {
       PAIR_LOOP_BEGIN
-        (void)qi; (void)kj;
+        (void)qi; (void)kj; (void)seq0; (void)col0; (void)h;
         const uint32_t pp = np & 1;
         mbar_wait(sd_free, pp ^ 1);                  // previous pair's S / dP have been read out
         tc_fence_after();
@@ -460,7 +475,7 @@ attn_long_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int r = quarter * 32 + lane;
     const int c0 = part, c1 = part + 2;              // this warp's 32-key chunks of the pair
     uint32_t np = 0, ni = 0;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++ni) {
+    for (int k = blockIdx.x; k < n_items; k += gridDim.x, ++ni) {
       PAIR_LOOP_BEGIN
         const uint32_t pp = np & 1;
         const int l = qi * LT + r;                   // query position inside the sequence
@@ -527,6 +542,7 @@ attn_long_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_wait(acc_full, ni & 1);
       tc_fence_after();
       {
+        const int it = LIVE_ITEM(k);
         const int bh2 = it / p.nq, tt2 = it % p.nq, b2 = bh2 / p.heads, h2 = bh2 % p.heads;
         const int lo = tt2 * LT + r;
         const bool oown = lo < p.L;
@@ -558,13 +574,65 @@ attn_long_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
 #undef PAIR_LOOP_BEGIN
 #undef PAIR_LOOP_END
+#undef LIVE_ITEM
   tc_fence_before();
   __syncthreads();
   if (warp == 9) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+// ---- live query tiles of the hybrid packed layout (see AttnLong)
+static thread_local const int* g_live_qlo = nullptr;
+static thread_local const int* g_live_items = nullptr;
+static thread_local const int* g_live_n = nullptr;
+void attn_long_set_live(const int* q_lo, const int* items, const int* n_live) {
+  g_live_qlo = q_lo; g_live_items = items; g_live_n = n_live;
+}
+
+// q_lo[b] = tile of the first position of sequence b whose token is kept (tok_row >= 0), at most nq - 1; one warp a sequence
+__global__ void __launch_bounds__(256) attn_qlo_kernel(const int* tok_row, int64_t B, int L, int nq, int* q_lo) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  int first = L;
+  for (int l0 = 0; l0 < L && first == L; l0 += 32) {
+    const int l = l0 + lane;
+    const unsigned m = __ballot_sync(0xffffffffu, l < L && __ldg(tok_row + b * L + l) >= 0);
+    if (m) first = l0 + __ffs(m) - 1;
+  }
+  if (lane == 0) q_lo[b] = min(first / LT, nq - 1);
+}
+// items[] = the live (sequence, head, query tile) items in increasing order, n_live[0] = their number.  ONE block.
+__global__ void __launch_bounds__(1024) attn_items_kernel(const int* q_lo, int64_t B, int heads, int nq, int* items, int* n_live) {
+  __shared__ int wsum[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (int)((B + 1023) / 1024);
+  const int64_t b0 = (int64_t)tid * per, b1 = min(B, b0 + per);
+  int local = 0;
+  for (int64_t b = b0; b < b1; ++b) local += heads * (nq - q_lo[b]);
+  int incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int v = wsum[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+    wsum[lane] = v;
+    if (lane == 31) n_live[0] = v;
+  }
+  __syncthreads();
+  int at = incl - local + (warp ? wsum[warp - 1] : 0);
+  for (int64_t b = b0; b < b1; ++b) {
+    const int lo = q_lo[b];
+    for (int h = 0; h < heads; ++h)
+      for (int t = lo; t < nq; ++t) items[at++] = (int)((b * heads + h) * nq + t);
+  }
+}
+
 static int fill_long(AttnLong& p, int64_t B, int L, int H, int heads, float drop_p, uint64_t seed, uint32_t stream_id,
                      const float* drop_step) {
+  p.q_lo = g_live_qlo; p.items = g_live_items; p.n_live = g_live_n;
   p.B = (int)B; p.T = B * L; p.L = L; p.heads = heads; p.hd = H / heads;
   p.kblocks = (p.hd + 63) / 64;
   p.nq = (L + LT - 1) / LT;
@@ -661,3 +729,22 @@ int attn_long_bwd(const void* dout, int lddo, const void* q, int ldq, const void
 }
 
 }  // namespace srfrd
+
+extern "C" int srfrd_set_attention_live(const int* q_lo, const int* items, const int* n_live) {
+  SRFRD_REQUIRE((q_lo && items && n_live) || (!q_lo && !items && !n_live), "set_attention_live: all three pointers or none");
+  srfrd::attn_long_set_live(q_lo, items, n_live);
+  return 0;
+}
+
+extern "C" int srfrd_attention_live_items(const int* tok_row, int64_t B, int L, int heads, int* q_lo, int* items, int* n_live,
+                                          void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SRFRD_REQUIRE(tok_row && q_lo && items && n_live, "attention_live_items: null pointer");
+  SRFRD_REQUIRE(B >= 1 && B <= 16384 * 64 && L >= 1 && heads >= 1, "attention_live_items: bad shape");
+  const int nq = (L + srfrd::LT - 1) / srfrd::LT;
+  srfrd::attn_qlo_kernel<<<(unsigned)((B + 7) / 8), 256, 0, stream>>>(tok_row, B, L, nq, q_lo);
+  SRFRD_LAUNCH_CHECK();
+  srfrd::attn_items_kernel<<<1, 1024, 0, stream>>>(q_lo, B, heads, nq, items, n_live);
+  SRFRD_LAUNCH_CHECK();
+  return 0;
+}

@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import math
 import os
-from contextlib import contextmanager
+from contextlib import contextmanager, nullcontext
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
@@ -350,6 +350,18 @@ class HotPath:
         self.ws_generation += 1
         return hw
 
+    def _live_tiles(self, B: int, L: int) -> "ops.LiveTiles":
+        key = (B, L)
+        lt = getattr(self, "_lives", None)
+        if lt is None:
+            lt = self._lives = {}
+        if key not in lt:
+            if len(lt) >= 4:                          # a captured graph may hold pointers into these: bump the generation
+                lt.clear()
+                self.ws_generation += 1
+            lt[key] = ops.LiveTiles(B, L, self.spec.num_heads, self.device)
+        return lt[key]
+
     def _plan(self, B: int, L: int) -> "ops.PackedPlan":
         key = (B, L)
         if key not in self._plans:
@@ -576,6 +588,12 @@ class HotPath:
         aux_table = P.view(s.aux_key) if s.aux_key else None
         plan.build(seq, None if keep is None else keep.contiguous())
         hyb = self._hybrid_ws(B * L) if self.packed_mode(B, L) == "hybrid" else None
+        live = None
+        if hyb is not None and os.environ.get("SRFRD_LIVE_TILES", "1") != "0":
+            # query tiles whose 128 positions are all dropped padding (C4: the first tile of 58 % of the sequences): the
+            # dense-layout attention kernels skip them -- nothing reads a pad query's o / dq and its dO is zero
+            live = self._live_tiles(B, L)
+            live.build(plan)
         x = [ws[f"x{i}"][:T] for i in range(nb + 1)]
         row_ids = plan.row_ids
         fuse_ln = Hp <= 128 and os.environ.get("SRFRD_FUSE_LN", "1") != "0"
@@ -598,8 +616,9 @@ class HotPath:
                 else:       # dense-layout attention between an unpack and a pack copy
                     qd, kvd, od = hyb[f"qd{i}"][:B * L], hyb[f"kvd{i}"][:B * L], hyb[f"od{i}"][:B * L]
                     ops.unpack_rows([(q, qd, Hp, 0), (kv, kvd, 2 * Hp, 0)], plan)
-                    ops.attention_fwd(qd, kvd[:, :Hp], kvd[:, Hp:], od, B, L, H, s.num_heads, p_drop, seed, 10 + 4 * i, step,
-                                      stats=ws.get(f"ast{i}"))
+                    with (live.active() if live is not None else nullcontext()):
+                        ops.attention_fwd(qd, kvd[:, :Hp], kvd[:, Hp:], od, B, L, H, s.num_heads, p_drop, seed, 10 + 4 * i, step,
+                                          stats=ws.get(f"ast{i}"))
                     ops.pack_rows([(od, o, Hp, 0)], plan)
                 if fuse_ln:
                     ops.gemm_tn(o, self.sh[f"wo{i}"], out_bf16=r, bias=self.bias("bo", i), residual=Q, ln_out=y,
@@ -638,12 +657,12 @@ class HotPath:
             return out[:, :s.Dout]
         if training if save is None else save:
             self.saved = dict(seq=seq, aux_ids=aux_ids, B=B, L=L, p_drop=p_drop, seed=seed, step=step,
-                              version=self.fwd_version, plan=plan, hyb=hyb)
+                              version=self.fwd_version, plan=plan, hyb=hyb, live=live)
         return ws["hfin"][:T]
 
     def _backward_packed(self, dh: torch.Tensor) -> None:
         s, P, sv = self.spec, self.P, self.saved
-        plan, hyb = sv["plan"], sv.get("hyb")
+        plan, hyb, live = sv["plan"], sv.get("hyb"), sv.get("live")
         B, L = sv["B"], sv["L"]
         T, H, Hp, nb = plan.cap, s.H, s.Hp, s.num_blocks
         ws = self._ws
@@ -702,8 +721,9 @@ class HotPath:
                     qd, kvd, od = hyb[f"qd{i}"][:Td], hyb[f"kvd{i}"][:Td], hyb[f"od{i}"][:Td]
                     dod, dqd, dkvd = hyb["dod"][:Td], hyb["dqd"][:Td], hyb["dkvd"][:Td]
                     ops.unpack_rows([(gC, dod, Hp, 1)], plan)                  # a pad query's output is dead: dO = 0
-                    ops.attention_bwd(dod, qd, kvd[:, :Hp], kvd[:, Hp:], dqd, dkvd[:, :Hp], dkvd[:, Hp:], B, L, H, s.num_heads,
-                                      p_drop, seed, 10 + 4 * i, step, o=od, stats=ws.get(f"ast{i}"))
+                    with (live.active() if live is not None else nullcontext()):
+                        ops.attention_bwd(dod, qd, kvd[:, :Hp], kvd[:, Hp:], dqd, dkvd[:, :Hp], dkvd[:, Hp:], B, L, H,
+                                          s.num_heads, p_drop, seed, 10 + 4 * i, step, o=od, stats=ws.get(f"ast{i}"))
                     # dk, dv of the pad representative = the sum over its sequence's pad slots (every copy of the pad key)
                     ops.pack_rows([(dqd, dq, Hp, 0), (dkvd, dkv, 2 * Hp, 1)], plan)
                 gin = GM(f"attention_layers.{i}.in_proj_weight")

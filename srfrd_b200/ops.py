@@ -315,6 +315,33 @@ def row_limit(rows_dev):
         call("srfrd_set_row_limit", None)
 
 
+class LiveTiles:
+    """Live query tiles of the hybrid packed layout (srfrd_attention_live_items): which 128-position query tiles of the dense
+    (B, L) attention tensors hold a kept token.  `build(plan, heads)` after the pack plan; `with live.active():` around the
+    maxlen > 128 attention calls makes them skip the dead tiles."""
+
+    def __init__(self, B: int, L: int, heads: int, device):
+        nq = (L + 127) // 128
+        self.B, self.L, self.heads = B, L, heads
+        self.q_lo = torch.zeros(B, dtype=torch.int32, device=device)
+        self.items = torch.zeros(B * heads * nq, dtype=torch.int32, device=device)
+        self.n_live = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def build(self, plan: "PackedPlan"):
+        _lib.require_device()
+        assert (plan.B, plan.L) == (self.B, self.L)
+        call("srfrd_attention_live_items", _p(plan.tok_row), self.B, self.L, self.heads, _p(self.q_lo), _p(self.items),
+             _p(self.n_live), _stream())
+
+    @contextmanager
+    def active(self):
+        call("srfrd_set_attention_live", _p(self.q_lo), _p(self.items), _p(self.n_live))
+        try:
+            yield
+        finally:
+            call("srfrd_set_attention_live", None, None, None)
+
+
 def attention_packed_supported(L: int, H: int, heads: int) -> bool:
     return bool(_lib.load().srfrd_attention_packed_supported(int(L), int(H), int(heads)))
 

@@ -510,3 +510,91 @@ def test_mlp2_equals_two_gemm_tn_launches(M, N, case):
     if case == "fwd_ln":
         torch.testing.assert_close(st, st_r, rtol=1e-3, atol=1e-4)
         torch.testing.assert_close(ln.float(), ln_r.float(), rtol=1.6e-2, atol=2e-2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H,heads,drop", [(80, 1, 0.0), (128, 2, 0.0), (272, 1, 0.0), (80, 1, 0.3)])
+def test_long_attention_skips_dead_query_tiles_exactly(H, heads, drop):
+    """The maxlen > 128 attention kernels with the live-tile set of the hybrid packed layout (srfrd_attention_live_items /
+    srfrd_set_attention_live): mostly SHORT sequences (their first 128 positions are dropped padding, as in 58 % of C4's
+    sequences), some long ones, empty rows, an interior pad and a kept pad slot far to the left.  With dO = 0 on dropped pad
+    slots (what srfrd_unpack_rows writes) everything a dead query tile would have contributed is exactly zero: o and dq of
+    every kept token and ALL rows of dk, dv are BIT-IDENTICAL to the full loops, dropout included (the mask is a function
+    of the position, not of the loop order)."""
+    from srfrd_b200 import ops
+    B, L = 40, 200
+    rng = np.random.default_rng(21)
+    seq = np.zeros((B, L), np.int64); keep = np.zeros((B, L), np.int64)
+    for b in range(B):
+        n = 0 if b % 11 == 0 else (int(rng.integers(1, 70)) if b % 4 else int(rng.integers(90, 200)))
+        if n:
+            seq[b, L - n:] = rng.integers(1, 500, n)
+    seq[5, L - 3] = 0                                   # an interior pad
+    keep[7, 10] = 3                                     # a loss term on a pad input far left of a short sequence: tile 0 is live
+    plan = ops.PackedPlan(B, L, "cuda")
+    plan.build(torch.from_numpy(seq).cuda(), torch.from_numpy(keep).cuda())
+    live = ops.LiveTiles(B, L, heads, "cuda")
+    live.build(plan)
+    kept = (seq != 0) | (keep != 0)
+    first = np.where(kept.any(1), kept.argmax(1), L)
+    q_lo = live.q_lo.cpu().numpy()
+    assert np.array_equal(q_lo, np.minimum(first // 128, 1))
+    n_live = int(live.n_live)
+    assert n_live == int((heads * (2 - q_lo)).sum()) < B * heads * 2
+    assert np.array_equal(live.items.cpu().numpy()[:n_live],
+                          [(b * heads + h) * 2 + t for b in range(B) for h in range(heads) for t in range(q_lo[b], 2)])
+    T = B * L
+    g = torch.Generator(device="cuda").manual_seed(4)
+    rnd_ = lambda w: (torch.randn(T, w, generator=g, device="cuda") * 0.5).to(torch.bfloat16)
+    q, kv, dO = rnd_(H), rnd_(2 * H), rnd_(H)
+    live_rows = torch.from_numpy(kept.reshape(-1)).cuda()
+    dO = dO * live_rows[:, None].to(torch.bfloat16)      # dropped pad slots: dO = 0
+    out = {}
+    for mode in ("live", "full"):
+        o, dq, dkv = (torch.zeros(T, w, dtype=torch.bfloat16, device="cuda") for w in (H, H, 2 * H))
+        stats = torch.zeros(T * heads, 4, device="cuda")
+        ctx = live.active() if mode == "live" else ops.row_limit(None)
+        with ctx:
+            ops.attention_fwd(q, kv[:, :H], kv[:, H:], o, B, L, H, heads, drop, 77, 3, None, stats=stats)
+            ops.attention_bwd(dO, q, kv[:, :H], kv[:, H:], dq, dkv[:, :H], dkv[:, H:], B, L, H, heads, drop, 77, 3, None, o=o,
+                              stats=stats)
+        torch.cuda.synchronize()
+        out[mode] = (o, dq, dkv)
+    assert torch.equal(out["live"][0][live_rows], out["full"][0][live_rows])
+    assert torch.equal(out["live"][1][live_rows], out["full"][1][live_rows])
+    assert torch.equal(out["live"][2], out["full"][2])
+    assert float(out["full"][2].float().abs().max()) > 0 and torch.isfinite(out["live"][2].float()).all()
+    # the skipped tiles were really left alone: some dropped-pad rows of o still hold the zeros they were allocated with
+    assert bool((out["live"][0][~live_rows].float().abs().sum(1) == 0).any())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,heads,drop", [("SRFR", 1, 0.0), ("SASRec", 2, 0.0)])
+def test_hybrid_training_step_with_and_without_dead_tile_skipping(kind, heads, drop, monkeypatch):
+    """The same through FusedTrainer on the hybrid layout (maxlen 200): two steps with SRFRD_LIVE_TILES=1 / 0 agree to the
+    noise of the fp32 atomics in K4 / K5 (the attention kernels themselves are bit-identical, see above)."""
+    from srfrd_b200 import SRFR_model as M
+    from srfrd_b200.trainer import FusedTrainer
+    B, L, N = 48, 200, 700
+    rng = np.random.default_rng(21)
+    seq = np.zeros((B, L), np.int64); pos = np.zeros((B, L), np.int64); neg = np.zeros((B, L), np.int64)
+    for b in range(B):
+        n = 0 if b % 11 == 0 else (int(rng.integers(1, 70)) if b % 4 else int(rng.integers(90, 200)))
+        if n:
+            seq[b, L - n:] = rng.integers(1, N + 1, n); pos[b, L - n:] = rng.integers(1, N + 1, n); neg[b, L - n:] = rng.integers(1, N + 1, n)
+    rsq = (seq != 0) * rng.integers(1, 3, (B, L)); prs = (pos != 0) * rng.integers(1, 3, (B, L)); nrs = (neg != 0) * rng.integers(1, 3, (B, L))
+    b_ = {k: torch.from_numpy(v).cuda() for k, v in dict(seq=seq, rsq=rsq, pos=pos, prs=prs, neg=neg, nrs=nrs).items()}
+    w = (torch.rand(B, L, device="cuda") * (b_["pos"] != 0)).contiguous()
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("SRFRD_LIVE_TILES", flag)
+        torch.manual_seed(3)
+        m = (M.SRFR(N, L, 64, 16, drop, 2, heads, "cuda") if kind == "SRFR" else M.SASRec(N, L, 128, drop, 2, heads, "cuda"))
+        for _, p in m.named_parameters():
+            if p.dim() >= 2:
+                torch.nn.init.xavier_normal_(p.data)
+        m = m.to("cuda").train()
+        tr = FusedTrainer(m, use_graph=False, packed=True)
+        assert tr.eng.packed_mode(B, L) == "hybrid"
+        res[flag] = [float(tr.step(b_, w_pos=w)) for _ in range(3)]
+    np.testing.assert_allclose(res["1"], res["0"], rtol=2e-4)
