@@ -1,21 +1,23 @@
-// K8: full-catalogue scoring  feats (U, D) x table (N, D)^T  on tcgen05 with a streaming per-row top-10
-// in the epilogue; logits never reach HBM.  K9: merge of partial / per-shard candidate lists.
+// K8: full-catalogue scoring  feats (U, D) x table (N, D)^T  on tcgen05 with a streaming per-row top-10; logits never
+// reach HBM.  K9: merge of partial / per-shard candidate lists.
 // (SURVEY.md rows A9/A10 + full-catalogue extension: == predict(..., label = arange(1, N+1)) + stable top-k
 //  with the tie-break (score desc, item id asc).)
 //
-// A work unit is (UBS x 128 users) x (a chunk of the item rows).
-//  * The user tiles are STATIONARY IN TENSOR MEMORY: at the start of a unit the epilogue warps copy their rows
-//    (bf16, packed two per 32-bit column) into TMEM with tcgen05.st and every MMA takes its A operand from there
-//    (tcgen05.mma TS form).  With A in shared memory the SS-form MMA of a 128 x N x 16 step reads 4 KB of A plus
-//    N*32 B of B, which saturates the 128 B/clk shared-memory port while TMA is also writing tiles (measured:
-//    the MMA pipe sat at 35 % with the epilogue switched off entirely).
-//  * Every item tile (NT rows, streamed through a TMA ring) is multiplied against ALL UBS user tiles, which
-//    divides the L2 -> SM traffic per score by UBS (one user tile per CTA means every CTA streams the whole
-//    table: 16 GB per pass at C3, L2-bound).
-//  * Accumulators (UBS x NT columns) are double-buffered in TMEM so the tensor pipe runs ahead of the scan.
-//  * Each epilogue thread owns one user row x NT columns and keeps that row's running top-10 in registers:
-//    group maxima (FMNMX3) are compared with the current 10th best first; candidate columns are found with a
-//    warp-wide OR of compare masks and re-read from TMEM one column at a time, so insertion code runs rarely.
+// Two phases.
+//  1. Streaming (catalogue_unitmax_kernel; catalogue_tilemax_kernel is the round-1 form, kept for widths whose operands do
+//     not fit the unit form and behind SRFRD_TOPK_UNIT=0): every CTA owns a run of (user group, item tile) pairs.
+//     * The user tiles are STATIONARY IN TENSOR MEMORY: at the start of a run the epilogue warps copy their rows (bf16,
+//       packed two per 32-bit column) into TMEM with tcgen05.st and every MMA takes its A operand from there
+//       (tcgen05.mma TS form).  With A in shared memory the SS-form MMA of a 128 x N x 16 step reads 4 KB of A plus
+//       N * 32 B of B, which saturates the 128 B/clk shared-memory port while TMA is also writing tiles.
+//     * Every item tile (streamed through a TMA ring) is multiplied against both user tiles of the group, which halves
+//       the L2 -> SM traffic per score; CTAs sweep the table in time-aligned windows so that it crosses the HBM bus
+//       ~4 times per pass instead of ~28 (make_plan).
+//     * The epilogue keeps, per user row, only the ten best RANKING UNITS (half an item tile: 56 consecutive rows at
+//       D = 64) by their maximum score: the exact top-10 items provably live in them (see the proof at the kernel).
+//  2. Exact re-scoring (catalogue_refine64_kernel / catalogue_refine_kernel): the 10 x 56 candidate rows of every user,
+//     same bf16 operands, fp32 accumulation, order (score desc, id asc); writes the row's final list (and, for the
+//     row-sharded protocol, the 80-byte wire format of the all-gather).
 // n_split = 2/3 feeds hi/lo bf16 splits of the fp32 user features as extra K (near-fp32 scores).
 #include <math.h>
 #include <stdio.h>
