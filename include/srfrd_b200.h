@@ -333,13 +333,14 @@ SRFRD_API int srfrd_mlp2_tn(const void* A_bf16, int lda, const void* W1_bf16, in
  * (query tile, key tile) pair with such a query tile contributes exactly nothing (SRFR_model.py:98-99, :121 re-mask those
  * rows).  srfrd_attention_live_items derives from the pack plan's tok_row (B * L) the first live query tile of every
  * sequence (q_lo, B ints) and the list of live (sequence, head, query tile) items (items, up to B * heads * ceil(L / 128)
- * ints; n_live[0] = their number).  After srfrd_set_attention_live(q_lo, items, n_live) the maxlen > 128 attention
+ * ints; n_live[0] = their number).  After srfrd_set_attention_live(q_lo, items, n_live, tok_row) the maxlen > 128 attention
  * kernels launched from THIS host thread skip the dead tiles (forward and dQ: listed items only; dK / dV: pair loops
- * start at the first live query tile); (NULL, NULL, NULL) restores the full loops.  Thread-local; captured into CUDA
+ * start at the first live query tile; the delta pre-pass writes 0 for dropped pad slots, whose dO is zero, without reading
+ * them); four NULLs restore the full loops.  Thread-local; captured into CUDA
  * graphs by value.  Only valid while nothing reads the dense o / dq rows of dropped pad slots. */
 SRFRD_API int srfrd_attention_live_items(const int* tok_row, int64_t B, int L, int heads, int* q_lo, int* items, int* n_live,
                                void* stream);
-SRFRD_API int srfrd_set_attention_live(const int* q_lo, const int* items, const int* n_live);
+SRFRD_API int srfrd_set_attention_live(const int* q_lo, const int* items, const int* n_live, const int* tok_row);
 
 /* Packed <-> dense row movement for sequence lengths whose attention kernels work on the dense (B, L) layout
  * (128 < maxlen <= 256): the row-wise bulk of a block runs on packed rows, attention on dense tensors.

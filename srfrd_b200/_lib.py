@@ -83,7 +83,7 @@ SIGNATURES = {
     "srfrd_catalogue_topk": [vp, i64, i64, i32, vp, i64, i64, i64, i32, i32, i32, i32, vp, vp, vp, vp],
     "srfrd_merge_topk_packed": [vp, i64, i32, i32, vp, vp, vp],
     "srfrd_attention_live_items": [vp, i64, i32, i32, vp, vp, vp, vp],
-    "srfrd_set_attention_live": [vp, vp, vp],
+    "srfrd_set_attention_live": [vp, vp, vp, vp],
     "srfrd_merge_topk": [vp, vp, i64, i32, i32, vp, vp, vp],
     "srfrd_unpack_rows": [C.POINTER(RepackPart), i32, C.POINTER(PackDesc), i64, i32, vp],
     "srfrd_pack_rows": [C.POINTER(RepackPart), i32, C.POINTER(PackDesc), i64, i32, vp],

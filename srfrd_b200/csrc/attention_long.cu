@@ -41,6 +41,7 @@ struct AttnLong {
   // nothing.  The forward and the dQ pass walk `items` (the n_live[0] live (sequence, head, query tile) items, in order)
   // instead of all of them; the dK / dV passes start each key tile's pair loop at max(key tile, q_lo[b]).
   const int* q_lo; const int* items; const int* n_live;
+  const int* tok_row;   // (B * L) packed row of each dense position, -1 = dropped pad slot (its dO is zero): delta pre-pass
 };
 
 __device__ __forceinline__ uint32_t lsw128(int r, int c) {     // byte offset of (row r, column c) in a swizzled tile
@@ -300,12 +301,16 @@ attn_long_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 // ----------------------------------------------------------------------------------------------------------- backward
 // delta_i = sum_c dO[i, c] * O[i, c] per (token, head): one warp per row, written into stats[...].z
 __global__ void __launch_bounds__(256) attn_long_delta_kernel(const bf16* dout, int lddo, const bf16* o, int ldo, float4* stats,
-                                                              int64_t T, int heads, int hd) {
+                                                              int64_t T, int heads, int hd, const int* tok_row) {
   pdl_prologue_done();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= T * heads) return;
   const int64_t t = row / heads; const int h = (int)(row % heads);
+  if (tok_row && __ldg(tok_row + t) < 0) {      // hybrid layout: a dropped pad slot has dO = 0 (srfrd_unpack_rows), so delta = 0
+    if (lane == 0) reinterpret_cast<float*>(stats + row)[2] = 0.f;      // without reading 2 x hd values (64 % of C4's rows)
+    return;
+  }
   const __nv_bfloat162* a = reinterpret_cast<const __nv_bfloat162*>(dout + t * lddo + h * hd);
   const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(o + t * ldo + h * hd);
   float acc = 0.f;
@@ -584,8 +589,9 @@ attn_long_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 static thread_local const int* g_live_qlo = nullptr;
 static thread_local const int* g_live_items = nullptr;
 static thread_local const int* g_live_n = nullptr;
-void attn_long_set_live(const int* q_lo, const int* items, const int* n_live) {
-  g_live_qlo = q_lo; g_live_items = items; g_live_n = n_live;
+static thread_local const int* g_live_tok_row = nullptr;
+void attn_long_set_live(const int* q_lo, const int* items, const int* n_live, const int* tok_row) {
+  g_live_qlo = q_lo; g_live_items = items; g_live_n = n_live; g_live_tok_row = tok_row;
 }
 
 // q_lo[b] = tile of the first position of sequence b whose token is kept (tok_row >= 0), at most nq - 1; one warp a sequence
@@ -632,7 +638,7 @@ __global__ void __launch_bounds__(1024) attn_items_kernel(const int* q_lo, int64
 
 static int fill_long(AttnLong& p, int64_t B, int L, int H, int heads, float drop_p, uint64_t seed, uint32_t stream_id,
                      const float* drop_step) {
-  p.q_lo = g_live_qlo; p.items = g_live_items; p.n_live = g_live_n;
+  p.q_lo = g_live_qlo; p.items = g_live_items; p.n_live = g_live_n; p.tok_row = g_live_tok_row;
   p.B = (int)B; p.T = B * L; p.L = L; p.heads = heads; p.hd = H / heads;
   p.kblocks = (p.hd + 63) / 64;
   p.nq = (L + LT - 1) / LT;
@@ -719,7 +725,7 @@ int attn_long_bwd(const void* dout, int lddo, const void* q, int ldq, const void
   if (int rc = make_tmap_bf16_2d(&tmDO, dout, p.T, H, lddo, LT, 64)) return rc;
   const int64_t rows = p.T * heads;
   SRFRD_CUDA(launch_pdl(attn_long_delta_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, stream, (const bf16*)dout, lddo,
-                        (const bf16*)o, ldo, p.stats, p.T, heads, p.hd));
+                        (const bf16*)o, ldo, p.stats, p.T, heads, p.hd, p.tok_row));
   p.dx = (bf16*)dq; p.lddx = lddq;
   if (int rc = launch_long_bwd<MODE_DQ>(tmQ, tmK, tmV, tmDO, p, stream)) return rc;
   p.dx = (bf16*)dk; p.lddx = lddkv;
@@ -730,9 +736,10 @@ int attn_long_bwd(const void* dout, int lddo, const void* q, int ldq, const void
 
 }  // namespace srfrd
 
-extern "C" int srfrd_set_attention_live(const int* q_lo, const int* items, const int* n_live) {
-  SRFRD_REQUIRE((q_lo && items && n_live) || (!q_lo && !items && !n_live), "set_attention_live: all three pointers or none");
-  srfrd::attn_long_set_live(q_lo, items, n_live);
+extern "C" int srfrd_set_attention_live(const int* q_lo, const int* items, const int* n_live, const int* tok_row) {
+  SRFRD_REQUIRE((q_lo && items && n_live && tok_row) || (!q_lo && !items && !n_live && !tok_row),
+                "set_attention_live: all four pointers or none");
+  srfrd::attn_long_set_live(q_lo, items, n_live, tok_row);
   return 0;
 }
 

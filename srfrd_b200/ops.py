@@ -330,16 +330,17 @@ class LiveTiles:
     def build(self, plan: "PackedPlan"):
         _lib.require_device()
         assert (plan.B, plan.L) == (self.B, self.L)
+        self.tok_row = plan.tok_row
         call("srfrd_attention_live_items", _p(plan.tok_row), self.B, self.L, self.heads, _p(self.q_lo), _p(self.items),
              _p(self.n_live), _stream())
 
     @contextmanager
     def active(self):
-        call("srfrd_set_attention_live", _p(self.q_lo), _p(self.items), _p(self.n_live))
+        call("srfrd_set_attention_live", _p(self.q_lo), _p(self.items), _p(self.n_live), _p(self.tok_row))
         try:
             yield
         finally:
-            call("srfrd_set_attention_live", None, None, None)
+            call("srfrd_set_attention_live", None, None, None, None)
 
 
 def attention_packed_supported(L: int, H: int, heads: int) -> bool:
