@@ -296,6 +296,10 @@ def top_kernel_roofline(agg, nsteps, pk, traffic_key=None):
                 traffic=measured_traffic(traffic_key or tname), algorithmic_bytes_per_launch=round(td["bytes"] / td["n"]),
                 peak_source=pk["src"] + ", sustained figure not needed for HBM", avg_launch_ms=round(per_ms, 4),
                 share_of_step=round(td["ms"] / tot, 3),
+                note=("algorithmic bytes counted over the rows the launch actually processed; when a launch moves a few MB "
+                      "(packed token layout: every operand is L2-resident, traffic << algorithmic) its duration is the fixed "
+                      "cost of a launch, not HBM time -- DESIGN.md section 6; the HBM-bound kernels are measured beyond L2 in "
+                      "`gather` and `scale_kernels`"),
                 kernels={k: dict(ms_per_step=round(v["ms"] / nsteps, 4), launches_per_step=v["n"] // nsteps,
                                  gbs=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None,
                                  tflops=round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["flops"] else None)
